@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""Headline benchmark: kinematic env-steps/s with the policy in the loop (BASELINE.json `metric`).
+
+Workload (BASELINE.json configs[1]): Stage 5 Approach -> Finisher evaluation, 65,536 parallel episodes per GPU,
+official approach config (128 steps) + finisher config (36 steps), bundled checkpoints, suite built like
+`build_curriculum_local_eval_suite(seed=700001+5*1009, stage_index=5)`.  One "step" = one full pass of the hot path
+over the suite = 65,536 episodes x 164 env-steps, each with a policy forward.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+N > 1 is launched by torchrun (one rank per GPU, NCCL); episodes shard by index with no data-path collective
+(weak scaling: 65,536 episodes per GPU), one all-reduce of the eval statistics after the timed region.
+`--impl reference` times the CPU implementation of the same path (the oracle port of the reference's pure-Python
+env, all host threads) on a bounded sample of the same workload.
+
+Keys beyond the base contract: `roofline` (fused rollout kernel), `step_kernel_roofline` (the standalone fused
+env-step kernel K1 measured at an HBM-resident size), `cpu_baseline`, `e2e`, `clocks`, `gpu_launches`, `parity`.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+METRIC = "kinematic_env_steps_per_sec_policy_in_loop"
+UNIT = "env-steps/s"
+EPISODES_PER_GPU = 65536
+STAGE = 5
+SUITE_SEED = 700001 + STAGE * 1009
+# algorithmic work per env-step (DESIGN.md / SURVEY 8d)
+STEP_BYTES_APPROACH = 532
+ACTOR_FLOPS = 2 * (56 * 64 + 64 * 64 + 64 * 7)   # 16256
+ENV_FLOPS = 1800
+
+
+def peaks() -> dict:
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        d["source"] = "measured"
+        return d
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "sm_max_mhz": 1965.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled every 200 ms while the timed region runs."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int) -> None:
+        self.gpu = gpu_index
+        self.rows: list[list[str]] = []
+        self._stop = threading.Event()
+        self._t: threading.Thread | None = None
+
+    def _run(self) -> None:
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=6)
+
+    def summary(self) -> dict:
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) >= 7 and r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(self.rows)}
+
+
+def _oracle_setup():
+    from oracle import kin_oracle as ko
+    from rl_brain_trainer_b200 import config as kcfg
+
+    acfg, fcfg = kcfg.load_preset("approach_dynamic_scale_big"), kcfg.load_preset("finisher_noop_ft")
+    w = lambda name: dict(np.load(kcfg.PRESET_DIR / "policies" / f"{name}.npz"))  # noqa: E731
+    return ko, acfg, fcfg, ko.params_from_config(acfg), ko.params_from_config(fcfg), ko.OracleMlp(w("approach_stage8_11")), ko.OracleMlp(w("finisher"))
+
+
+def cpu_reference_steps_per_sec(n_episodes: int, threads: int, offset: int = 0):
+    """Oracle port of the reference CPU path on `n_episodes` of the same suite -> (env-steps/s, env_steps, seconds, success_rate)."""
+    from rl_brain_trainer_b200.samplers import build_curriculum_local_eval_suite
+
+    ko, acfg, fcfg, pa, pf, A, F = _oracle_setup()
+    suite = build_curriculum_local_eval_suite(acfg, seed=SUITE_SEED + offset, stage_index=STAGE, n_episodes=n_episodes)
+    t0 = time.perf_counter()
+    res, steps = ko.eval_approach_finisher(pa, pf, A, F, initial_q=suite.initial_q, goal_q=suite.goal_q, n_threads=threads)
+    dt = time.perf_counter() - t0
+    return steps / dt, steps, dt, float(res["success"].mean())
+
+
+def run_reference_arm(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import kin_oracle as ko
+
+    ko.build()
+    threads = os.cpu_count() or 1
+    pilot_rate, _, _, _ = cpu_reference_steps_per_sec(256, threads)
+    budget_s = 90.0 / max(args.steps + args.warmup, 1)
+    n_ep = int(np.clip(pilot_rate * budget_s / 164.0, 256, 8192)) // 64 * 64
+    for w in range(args.warmup):
+        cpu_reference_steps_per_sec(n_ep, threads, offset=w + 1)
+    total_steps, total_s, succ = 0, 0.0, []
+    for k in range(args.steps):
+        _, steps, dt, sr = cpu_reference_steps_per_sec(n_ep, threads, offset=100 + k)
+        total_steps += steps
+        total_s += dt
+        succ.append(sr)
+    value = total_steps / total_s
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total_s / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "stage5_approach_finisher_eval", "episodes_per_step": n_ep, "env_steps_per_episode": 164,
+                   "note": "bounded sample of the 65,536-episode suite; CPU port (C, fp64) of the reference's pure-Python env + fp32 MLP"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{args.steps} x {n_ep} episodes x 164 env-steps, {threads} host threads"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "success_rate": float(np.mean(succ)) if succ else None,
+    }
+    print(json.dumps(line))
+
+
+def measure_step_kernel(torch, device, pk, n_envs: int = 1 << 21, launches: int = 20) -> dict:
+    """K1 standalone at an HBM-resident size (working set >> 126 MB L2): achieved GB/s = 532 B x n_envs / event time."""
+    from rl_brain_trainer_b200 import config as kcfg
+    from rl_brain_trainer_b200.env import BatchedArmKinematicEnv
+
+    acfg = kcfg.load_preset("approach_dynamic_scale_big")
+    env = BatchedArmKinematicEnv(acfg, n_envs, device, with_aux=False, seed=3, host_sampler=False)
+    env.set_curriculum_stage(STAGE)
+    env.reset()
+    g = torch.Generator(device=device)
+    g.manual_seed(1)
+    actions = torch.rand((n_envs, 7), device=device, generator=g) * 2 - 1
+    for _ in range(3):
+        env.step(actions)
+    torch.cuda.synchronize(device)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(launches)]
+    for a, b in ev:
+        a.record()
+        env.step(actions)
+        b.record()
+    torch.cuda.synchronize(device)
+    ms = np.array([a.elapsed_time(b) for a, b in ev])
+    t = float(np.mean(ms)) * 1e-3
+    gbs = STEP_BYTES_APPROACH * n_envs / t / 1e9
+    del env
+    return {"kernel": "kin_step_kernel<approach>", "bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
+            "frac": gbs / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"], "n_envs": n_envs, "launches": launches,
+            "us_per_launch": t * 1e6, "env_steps_per_sec": n_envs / t, "bytes_per_env_step": STEP_BYTES_APPROACH,
+            "note": "working set %.0f MB per launch (> L2), CUDA events on the launching stream" % (STEP_BYTES_APPROACH * n_envs / 1e6)}
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--episodes", type=int, default=EPISODES_PER_GPU, help="episodes per GPU (default: the BASELINE config)")
+    ap.add_argument("--variant", default=os.environ.get("KIN_ROLLOUT_VARIANT", "auto"), choices=["auto", "ffma", "tc"])
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-step-kernel", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from rl_brain_trainer_b200 import config as kcfg
+    from rl_brain_trainer_b200.policy import PolicyWeights
+    from rl_brain_trainer_b200.rollout import VARIANT_FFMA, VARIANT_TC, ApproachFinisherRollout, RolloutResult
+    from rl_brain_trainer_b200.samplers import EvalSuite, build_curriculum_local_eval_suite
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+    pk = peaks()
+
+    acfg, fcfg = kcfg.load_preset("approach_dynamic_scale_big"), kcfg.load_preset("finisher_noop_ft")
+    pol_a, pol_f = PolicyWeights.preset("approach_stage8_11", device), PolicyWeights.preset("finisher", device)
+    n = int(args.episodes)
+    # every rank evaluates its own shard of one long suite: episodes [rank*n, (rank+1)*n)
+    full = build_curriculum_local_eval_suite(acfg, seed=SUITE_SEED, stage_index=STAGE, n_episodes=n * world)
+    sl = slice(rank * n, (rank + 1) * n)
+    suite = EvalSuite(initial_q=full.initial_q[sl], goal_q=full.goal_q[sl])
+
+    variant = {"ffma": VARIANT_FFMA, "tc": VARIANT_TC}.get(args.variant)
+    if variant is None:
+        variant = VARIANT_TC
+        try:
+            probe = ApproachFinisherRollout(acfg, pol_a, fcfg, pol_f, device=device, variant=VARIANT_TC)
+            probe.evaluate_suite(EvalSuite(initial_q=suite.initial_q[:128], goal_q=suite.goal_q[:128]))
+            torch.cuda.synchronize(device)
+        except Exception:
+            variant = VARIANT_FFMA
+    ro = ApproachFinisherRollout(acfg, pol_a, fcfg, pol_f, device=device, variant=variant)
+    dev_in = ro.upload(suite)
+    stride = (n + 31) // 32 * 32
+    out = RolloutResult(raw=torch.zeros((24, stride), dtype=torch.int32, device=device), n=n, env_steps=torch.zeros(1, dtype=torch.int64, device=device))
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=device)  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    # ---- device-resident leg ----------------------------------------------------------------------
+    for _ in range(args.warmup):
+        ro.run(dev_in, out=out)
+    barrier()
+    out.env_steps.zero_()
+    events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches = 0
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        t_wall0 = time.perf_counter()
+        for a, b in events:
+            flush.fill_(0.0)          # L2 flush between timed iterations (outside the event pair)
+            a.record()
+            ro.run(dev_in, out=out)
+            b.record()
+            launches += 1
+        barrier()
+        t_wall = time.perf_counter() - t_wall0
+    ms = np.array([a.elapsed_time(b) for a, b in events])
+    dev_s = float(ms.sum()) * 1e-3
+    env_steps = int(out.env_steps.item())
+    res = out.to_numpy()
+    success = float(res["success"].mean())
+
+    # ---- end-to-end leg: host buffers, pinned H2D + D2H inside the timed region ----------------------
+    pinned = {k: torch.as_tensor(np.ascontiguousarray(getattr(suite, k), dtype=np.float32)).pin_memory() for k in ("initial_q", "goal_q")}
+    dev_e2e = {k: torch.empty_like(v, device=device) for k, v in pinned.items()}
+    dev_e2e.update({"initial_dq": None, "initial_prev_action": None, "goal_pose6": None})
+    host_out = torch.empty((24, stride), dtype=torch.int32).pin_memory()
+    h2d = sum(v.numel() * 4 for v in pinned.values())
+    d2h = host_out.numel() * 4
+
+    def e2e_step():
+        for k, v in pinned.items():
+            dev_e2e[k].copy_(v, non_blocking=True)
+        ro.run(dev_e2e, out=out)
+        host_out.copy_(out.raw, non_blocking=True)
+
+    for _ in range(args.warmup):
+        e2e_step()
+    barrier()
+    out.env_steps.zero_()
+    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for a, b in ev2:
+        flush.fill_(0.0)
+        a.record()
+        e2e_step()
+        b.record()
+    barrier()
+    e2e_s = float(np.sum([a.elapsed_time(b) for a, b in ev2])) * 1e-3
+    e2e_steps = int(out.env_steps.item())
+    e2e_success = float((host_out[0, :n] != 0).float().mean())
+
+    # ---- reductions over ranks (the only collective: eval statistics) --------------------------------
+    stats = torch.tensor([dev_s, e2e_s], dtype=torch.float64, device=device)
+    sums = torch.tensor([env_steps, e2e_steps, success * n, n], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    dev_s_max, e2e_s_max = float(stats[0]), float(stats[1])
+    value = float(sums[0]) / dev_s_max
+    e2e_value = float(sums[1]) / e2e_s_max
+    success_all = float(sums[2] / sums[3])
+
+    step_roof = None
+    cpu_base = None
+    parity = None
+    if rank == 0:
+        if not args.skip_step_kernel:
+            step_roof = measure_step_kernel(torch, device, pk)
+        if world == 1 and not args.skip_cpu_baseline:
+            threads = os.cpu_count() or 1
+            n_cpu = 4096
+            rate, steps_cpu, dt, sr = cpu_reference_steps_per_sec(n_cpu, threads)
+            cpu_base = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                        "sample": f"first {n_cpu} episodes of the same suite x 164 env-steps ({steps_cpu} env-steps in {dt:.2f} s), "
+                                  f"C port (fp64) of the reference's Python env + fp32 MLP, {threads} host threads"}
+            ko, _, _, pa, pf, A, F = _oracle_setup()
+            ref, _ = ko.eval_approach_finisher(pa, pf, A, F, initial_q=suite.initial_q[:n_cpu].astype(np.float32).astype(float),
+                                               goal_q=suite.goal_q[:n_cpu].astype(np.float32).astype(float), n_threads=threads)
+            parity = {"episodes_checked": n_cpu, "success_flag_mismatches": int(np.sum(res["success"][:n_cpu].astype(int) != ref["success"])),
+                      "gpu_success_rate": float(res["success"][:n_cpu].mean()), "oracle_success_rate": float(ref["success"].mean()),
+                      "mean_final_pos_err_gpu": float(res["final_position_error"][:n_cpu].mean()),
+                      "mean_final_pos_err_oracle": float(ref["final_position_error"].mean())}
+
+    if rank == 0:
+        steps_per_launch = env_steps / max(args.steps, 1)
+        t_launch = dev_s / max(args.steps, 1)
+        tc = variant == VARIANT_TC
+        flops = (ACTOR_FLOPS + (0 if tc else ENV_FLOPS)) * steps_per_launch
+        if tc:
+            peak_tf = pk["bf16_tflops_sustained"] / 2.0   # kind::tf32 runs at half the bf16 rate
+            roof = {"kernel": "kin_rollout_tc_kernel", "bound": "tensor", "achieved": flops / t_launch / 1e12, "peak": peak_tf,
+                    "unit": "TFLOP/s", "frac": flops / t_launch / 1e12 / peak_tf, "traffic": None, "peak_source": pk["source"],
+                    "note": "actor MLP 16,256 FLOP/env-step on tcgen05 kind::tf32; peak = measured sustained bf16 / 2"}
+        else:
+            fp32_peak = 148 * 128 * 2 * pk["sm_max_mhz"] * 1e6 / 1e12
+            roof = {"kernel": "kin_rollout_ffma_kernel", "bound": "fp32", "achieved": flops / t_launch / 1e12, "peak": fp32_peak,
+                    "unit": "TFLOP/s", "frac": flops / t_launch / 1e12 / fp32_peak, "traffic": None, "peak_source": "148 SM x 128 lanes x 2 x sm_max_mhz",
+                    "note": "strict-fp32 variant: 16,256 (MLP) + 1,800 (env) FP32 FLOP per env-step on the FP32 pipe"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dev_s_max / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if not tc else "f32 env + tf32 MLP (f32 accumulate)", "data": "synthetic",
+            "config": {"workload": "stage5_approach_finisher_eval_65536env", "episodes_per_gpu": n, "env_steps_per_episode": 164,
+                       "approach_config": "workspace_expansion_dynamic_scale_big", "finisher_config": "dock_workspace_handoff_noop_ft_12env",
+                       "policies": "bundled approach stage8-11 + finisher checkpoints", "rollout_variant": "tc" if tc else "ffma",
+                       "parallelism": f"env-sharded x{world}", "l2": "256 MB flush between timed iterations"},
+            "env_steps_per_step": env_steps / max(args.steps, 1), "success_rate": success_all, "wall_s_timed_region": t_wall,
+            "roofline": roof, "step_kernel_roofline": step_roof, "cpu_baseline": cpu_base, "parity": parity,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "success_rate": e2e_success},
+            "clocks": clocks.summary(), "gpu_launches": launches,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

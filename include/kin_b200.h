@@ -1,0 +1,463 @@
+/*
+ * kin_b200.h -- C ABI of the B200-native kinematic env rollout (libkin_b200.so).
+ *
+ * Drop-in boundary for the hot path of jerry102102102/RL_brain_trainer's kinematic
+ * Approach -> Finisher stack.  The reference has no FFI: its boundary is the Gymnasium-style
+ * Python class `ArmKinematicEnv` (hrl_ws/src/hrl_trainer/hrl_trainer/kinematic_phase1/envs/
+ * arm_kinematic_env.py:69-365, below "AKE") plus the eval orchestrators that loop over it.
+ * Each entry point here states which reference call it replaces.  The Python host side
+ * (rl_brain_trainer_b200/env.py) binds these with ctypes and mirrors the reference's class API.
+ *
+ * Conventions
+ *  - plain C, no torch types; every pointer is a DEVICE pointer unless named host_*.
+ *  - the caller owns every buffer; no hidden allocation, no hidden synchronisation.
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *  - return value: 0 = KIN_OK, otherwise a KIN_ERR_* code; kin_last_error_string() explains
+ *    (thread-local).  Functions are thread-compatible, not thread-safe per handle.
+ *  - all arithmetic is fp32 on the device (the reference is fp64 on the CPU and casts the
+ *    observation to fp32); counters are integers, flags are bits.
+ *
+ * The python binding parses the structs in this header (one field per line:
+ * `float name;`, `float name[N];`, `int name;`), so the header is the single source of truth.
+ */
+#ifndef KIN_B200_H
+#define KIN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KIN_ABI_VERSION 1
+#define KIN_NJ 7
+#define KIN_OBS_DIM 56
+#define KIN_ROUTE_OBS_DIM 80
+#define KIN_MAX_MILESTONES 4
+#define KIN_MAX_STAGES 16
+#define KIN_MAX_COMPONENTS 64
+
+#define KIN_OK 0
+#define KIN_ERR_INVALID_ARG 1
+#define KIN_ERR_CUDA 2
+#define KIN_ERR_NO_DEVICE 3
+#define KIN_ERR_UNSUPPORTED 4
+
+/* policy mode == index of the one-hot in obs["mode_flag"] (AKE:544-551) */
+#define KIN_MODE_APPROACH 0
+#define KIN_MODE_DOCK 1
+/* kernel specialisation hint: every env in the batch is in this mode, or per-env (read from flags) */
+#define KIN_MODE_PER_ENV (-1)
+
+/* ---- per-env state: struct-of-arrays, one 32-bit word per row, env index fastest -----------
+ * state[row * stride + env]; stride >= n, stride % 32 == 0.  Rows (== private fields of AKE:80-100):   */
+#define KIN_ROW_Q 0            /* 7  joint positions                                              */
+#define KIN_ROW_DQ 7           /* 7  last executed joint delta                                    */
+#define KIN_ROW_PREV_ACTION 14 /* 7  last (clipped) action                                        */
+#define KIN_ROW_GOAL_POSE 21   /* 6  goal [x y z roll pitch yaw]                                  */
+#define KIN_ROW_EE_POSE 27     /* 6  cached FK(q)                                                 */
+#define KIN_ROW_MIN_POS 33     /* 1  running min position error                                   */
+#define KIN_ROW_CNT0 34        /* 1  u32: episode_step | dwell_count << 16                        */
+#define KIN_ROW_CNT1 35        /* 1  u32: near_goal_entry_count | near_goal_drift_count << 16     */
+#define KIN_ROW_FLAGS 36       /* 1  u32: KIN_FLAG_* bits                                         */
+#define KIN_ROW_ENTRY 37       /* 4  entry pos err, ori err, action l2, dq norm (dock reward)     */
+#define KIN_ROW_GOAL_Q 41      /* 7  goal joint vector (info only; the step never reads it)       */
+#define KIN_ROW_EPISODE 48     /* 1  u32: episodes completed by this slot (auto-reset RNG counter)*/
+#define KIN_ROW_ROUTE 49       /* 1  u32: route_index | ready_streak << 16 (route wrappers)       */
+#define KIN_ROW_ROUTE_PREV 50  /* 14 prev_q, prev_dq as seen by the route wrapper                 */
+#define KIN_STATE_ROWS 64
+
+#define KIN_FLAG_PRE_NEAR_HIT 0x1u
+#define KIN_FLAG_NEAR_HIT 0x2u
+#define KIN_FLAG_MODE_SHIFT 4 /* 2 bits */
+#define KIN_FLAG_STAGE_SHIFT 8 /* 4 bits: curriculum stage the episode was sampled from */
+
+/* ---- per-step result byte (done[env]) ------------------------------------------------------ */
+#define KIN_DONE_TERMINATED 0x1u
+#define KIN_DONE_TRUNCATED 0x2u
+#define KIN_DONE_SUCCESS 0x4u
+#define KIN_DONE_PRE_NEAR 0x8u      /* info["curr_in_pre_near_goal"] */
+#define KIN_DONE_NEAR 0x10u         /* info["curr_in_near_goal"]     */
+#define KIN_DONE_REASON_SHIFT 5     /* 2 bits: 0 running, 1 success, 2 max_steps, 3 invalid_state */
+#define KIN_DONE_AUTORESET 0x80u    /* slot was re-seeded in this call (obs is the new episode's) */
+
+/* ---- optional per-step scalars: aux[row * stride + env] (AKE:353-364 info keys) ------------- */
+#define KIN_AUX_POS_ERR 0         /* position_error_norm    */
+#define KIN_AUX_ORI_ERR 1         /* orientation_error_norm */
+#define KIN_AUX_ACTION_L2 2       /* action_l2              */
+#define KIN_AUX_DQ_L2 3           /* executed_delta_q_l2    */
+#define KIN_AUX_DQ_CHANGE_L2 4    /* delta_q_change_l2      */
+#define KIN_AUX_DOCK_LIMIT 5      /* dock_action_limit      */
+#define KIN_AUX_DQC_SCALE 6       /* dock_delta_q_change_limit_scale */
+#define KIN_AUX_MARGIN_MIN 7      /* joint_limit_margin_min */
+#define KIN_AUX_ROWS 8
+
+/* Flattened Phase1EnvConfig (AKE:32-66) + the precomputed FK chain.  Field names follow the
+ * reference's config keys: ar_* = ApproachRewardConfig (reward_approach.py:13-72),
+ * dr_* = DockRewardConfig (reward_dock.py:13-102), term_* = TerminationConfig
+ * (termination.py:11-17), obs_* = ObservationBuilderConfig (observation_builder.py:18-21),
+ * rr_* = RouteRewardConfig (route/reward_route.py:14-33).                                     */
+typedef struct KinEnvParams {
+    /* joint specs (kinematics/joint_limits.py:37-47) */
+    float joint_lower[7];
+    float joint_upper[7];
+    float joint_delta_limit[7];
+    /* FK chain of v5_1/ee_fk.py:98-134 with the constant transforms pre-multiplied on the host in
+     * fp64 (rl_brain_trainer_b200/kinematics.py): p = fk_pbase + fk_pq0*q0; R = fk_C[0]*Rz(q1);
+     * for j=2..6: p += R*fk_t[j-2]; R = R*fk_C[j-1]*Rz(qj);  R_ee = R*fk_AT                     */
+    float fk_pbase[3];
+    float fk_pq0[3];
+    float fk_C[54];
+    float fk_t[15];
+    float fk_AT[9];
+    /* env */
+    float action_delta_scale;
+    int dynamic_action_delta_scale_enabled;
+    float dynamic_action_delta_scale_near_pos_threshold_m;
+    float dynamic_action_delta_scale_far_pos_threshold_m;
+    float dynamic_action_delta_scale_near_multiplier;
+    float dynamic_action_delta_scale_far_multiplier;
+    float dock_action_delta_scale;
+    float dock_residual_action_limit;
+    float dock_delta_q_change_limit_scale;
+    float dock_dynamic_action_limit_near_pos_threshold_m;
+    float dock_dynamic_action_limit_far_pos_threshold_m;
+    float dock_dynamic_residual_action_limit_near;
+    float dock_dynamic_residual_action_limit_far;
+    float dock_dynamic_delta_q_change_limit_scale_near;
+    float dock_dynamic_delta_q_change_limit_scale_far;
+    int episode_length;
+    int dwell_steps_target;
+    /* termination */
+    int term_max_episode_steps;
+    float term_success_pos_threshold_m;
+    float term_success_ori_threshold_rad;
+    int term_success_dwell_steps;
+    int term_require_orientation;
+    int term_terminate_on_success;
+    /* observation */
+    float obs_pos_err_scale_m;
+    float obs_ori_err_scale_rad;
+    /* approach reward */
+    float ar_position_progress_weight;
+    float ar_orientation_progress_weight;
+    float ar_near_field_orientation_progress_weight;
+    float ar_pre_near_goal_pos_threshold_m;
+    float ar_near_goal_pos_threshold_m;
+    float ar_near_goal_ori_threshold_rad;
+    float ar_coarse_orientation_bonus_threshold_rad;
+    int ar_n_milestones;
+    float ar_orientation_milestone_thresholds_rad[4];
+    float ar_orientation_milestone_bonuses[4];
+    float ar_near_field_orientation_center_weight;
+    int ar_use_orientation_gate;
+    float ar_pre_near_goal_bonus;
+    float ar_near_goal_bonus;
+    float ar_near_goal_bonus_decay;
+    float ar_pre_near_to_near_progress_weight;
+    float ar_coarse_orientation_bonus;
+    float ar_handover_pos_threshold_m;
+    float ar_handover_ori_threshold_rad;
+    float ar_handover_bonus;
+    float ar_handover_retention_bonus;
+    float ar_handover_dwell_bonus;
+    float ar_handover_leave_penalty;
+    float ar_handover_regression_weight;
+    float ar_handover_smoothness_multiplier;
+    float ar_dock_coarse_ready_pos_threshold_m;
+    float ar_dock_coarse_ready_ori_threshold_rad;
+    float ar_dock_coarse_ready_action_threshold;
+    float ar_dock_coarse_ready_dq_threshold;
+    float ar_dock_coarse_ready_bonus;
+    float ar_dock_coarse_ready_retention_bonus;
+    float ar_dock_coarse_ready_dwell_bonus;
+    float ar_dock_coarse_ready_leave_penalty;
+    float ar_dock_coarse_ready_regression_weight;
+    float ar_finisher_ready_pos_threshold_m;
+    float ar_finisher_ready_ori_threshold_rad;
+    float ar_finisher_ready_action_threshold;
+    float ar_finisher_ready_dq_threshold;
+    float ar_finisher_ready_bonus;
+    float ar_finisher_ready_retention_bonus;
+    float ar_finisher_ready_dwell_bonus;
+    float ar_finisher_ready_leave_penalty;
+    float ar_finisher_ready_regression_weight;
+    float ar_near_handoff_pos_threshold_m;
+    float ar_near_handoff_ori_threshold_rad;
+    float ar_near_handoff_action_weight;
+    float ar_near_handoff_dq_weight;
+    float ar_near_handoff_motion_bonus_weight;
+    float ar_near_handoff_settle_bonus_weight;
+    float ar_same_step_alignment_bonus;
+    float ar_dwell_bonus;
+    float ar_drift_penalty_weight;
+    int ar_drift_penalty_escalation_start;
+    float ar_drift_penalty_escalation_per_count;
+    float ar_near_goal_leave_penalty;
+    float ar_action_magnitude_weight;
+    float ar_action_delta_weight;
+    float ar_joint_limit_penalty_weight;
+    float ar_success_bonus;
+    /* dock (Finisher) reward */
+    float dr_position_progress_weight;
+    float dr_orientation_progress_weight;
+    float dr_stay_in_zone_bonus;
+    float dr_dwell_bonus;
+    float dr_leave_zone_penalty;
+    float dr_working_range_bonus;
+    float dr_working_range_dwell_bonus;
+    int dr_working_range_dwell_start;
+    float dr_working_range_exit_penalty;
+    float dr_drift_penalty_position_weight;
+    float dr_drift_penalty_orientation_weight;
+    float dr_action_magnitude_weight;
+    float dr_action_delta_weight;
+    float dr_joint_limit_penalty_weight;
+    float dr_success_bonus;
+    float dr_tight_pose_pos_threshold_m;
+    float dr_tight_pose_ori_threshold_rad;
+    float dr_tight_pose_bonus;
+    float dr_tight_pose_dwell_bonus;
+    float dr_strict_pose_leave_penalty;
+    float dr_strict_center_reward_weight;
+    float dr_strict_center_position_weight;
+    float dr_strict_center_orientation_weight;
+    float dr_strict_center_small_action_bonus_weight;
+    float dr_strict_center_small_action_pos_radius_m;
+    float dr_strict_center_small_action_ori_radius_rad;
+    float dr_strict_center_small_action_scale;
+    float dr_strict_center_small_action_power;
+    float dr_strict_center_dwell_bonus_weight;
+    int dr_strict_center_dwell_start;
+    int dr_strict_center_dwell_escalation_start;
+    float dr_strict_center_dwell_escalation_per_step;
+    float dr_strict_zone_drift_penalty_multiplier;
+    float dr_strict_zone_action_penalty_multiplier;
+    float dr_tight_position_shaping_radius_m;
+    float dr_tight_position_shaping_weight;
+    float dr_tight_orientation_shaping_radius_rad;
+    float dr_tight_orientation_shaping_weight;
+    float dr_convergence_position_radius_m;
+    float dr_convergence_position_progress_weight;
+    float dr_convergence_orientation_radius_rad;
+    float dr_convergence_orientation_progress_weight;
+    float dr_position_first_orientation_pos_threshold_m;
+    float dr_position_first_orientation_pre_scale;
+    float dr_action_delta_violation_threshold;
+    float dr_action_delta_violation_weight;
+    float dr_delta_q_change_penalty_threshold;
+    float dr_delta_q_change_penalty_weight;
+    float dr_entry_action_penalty_near_pos_threshold_m;
+    float dr_entry_action_penalty_far_pos_threshold_m;
+    float dr_entry_action_penalty_near_multiplier;
+    float dr_entry_action_penalty_far_multiplier;
+    float dr_basin_outer_radius_m;
+    float dr_basin_inner_radius_m;
+    float dr_basin_dwell_radius_m;
+    float dr_basin_outer_bonus;
+    float dr_basin_inner_bonus;
+    float dr_basin_dwell_bonus;
+    float dr_basin_outer_exit_penalty;
+    float dr_basin_inner_exit_penalty;
+    float dr_basin_dwell_break_penalty;
+    float dr_basin_drift_penalty_weight;
+    float dr_near_strict_pos_threshold_m;
+    float dr_near_strict_ori_threshold_rad;
+    float dr_preserve_state_bonus;
+    float dr_preserve_position_tolerance_m;
+    float dr_preserve_orientation_tolerance_rad;
+    float dr_strict_hold_bonus;
+    float dr_low_motion_bonus;
+    float dr_low_motion_action_threshold;
+    float dr_low_motion_dq_threshold;
+    float dr_tiny_correction_bonus;
+    float dr_tiny_correction_action_threshold;
+    float dr_worse_than_entry_position_weight;
+    float dr_worse_than_entry_orientation_weight;
+    float dr_worse_than_entry_position_tolerance_m;
+    float dr_worse_than_entry_orientation_tolerance_rad;
+    float dr_near_strict_regression_multiplier;
+    float dr_aggressive_action_weight;
+    float dr_aggressive_action_threshold;
+    float dr_dq_penalty_weight;
+    float dr_dq_penalty_threshold;
+    float dr_near_strict_action_penalty_multiplier;
+    float dr_near_strict_dq_penalty_multiplier;
+    /* route reward (route wrappers only) */
+    float rr_q_goal_progress_weight;
+    float rr_ee_position_progress_weight;
+    float rr_ee_orientation_progress_weight;
+    float rr_route_tangent_progress_weight;
+    float rr_same_step_route_ready_bonus;
+    float rr_route_ready_dwell_bonus;
+    float rr_low_motion_near_waypoint_bonus;
+    float rr_orientation_regression_penalty_weight;
+    float rr_q_route_regression_penalty_weight;
+    float rr_off_route_penalty_weight;
+    float rr_action_magnitude_weight;
+    float rr_action_delta_weight;
+    float rr_dq_penalty_weight;
+    float rr_no_progress_penalty;
+    float rr_route_ready_pos_threshold_m;
+    float rr_route_ready_ori_threshold_rad;
+    float rr_route_ready_q_threshold;
+    float rr_route_ready_action_threshold;
+    float rr_route_ready_dq_threshold;
+} KinEnvParams;
+
+/* Device-side reset sampler: the Stage 0-11 curriculum shells and the random-start pair sampler
+ * (envs/curriculum.py:90-101, envs/reset_samplers.py:168-420).  Counter-based Philox4x32-10,
+ * key = (seed, env), counter = (episode, draw); validated distributionally against the
+ * reference's numpy PCG64 samplers (bit-identical streams are a host-side feature, samplers.py). */
+typedef struct KinSamplerParams {
+    int n_stages;
+    int current_stage;
+    int curriculum_enabled;
+    int stage_mix_enabled;
+    float start_q[112];
+    float start_noise[112];
+    float goal_q[112];
+    float goal_noise[112];
+    float start_sample_margin_fraction;
+    float goal_sample_margin_fraction;
+    /* workspace_stage_sampling (reset_samplers.py:344-389) */
+    float current_stage_ratio;
+    float previous_stage_ratio;
+    float old_workspace_replay_ratio;
+    float failure_replay_ratio;
+    int previous_stage_min_index;
+    int old_workspace_max_stage_index;
+    /* random_start_pair_sampling (reset_samplers.py:213-309) */
+    int random_start_enabled;
+    float source_ratio[6];
+    int home_stage_index;
+    int known_target_max_stage_index;
+    int mixed_target_max_stage_index;
+    int frontier_min_stage_index;
+    int frontier_max_stage_index;
+    int frontier_target_min_stage_index;
+    int frontier_target_max_stage_index;
+    int stress_target_min_stage_index;
+    int stress_target_max_stage_index;
+    int old_success_max_stage_index;
+    float random_valid_start_margin_fraction;
+    float stress_start_margin_fraction;
+    float failure_recovery_q_noise[7];
+    float initial_dq_noise[7];
+    float initial_prev_action_noise[7];
+    float min_pair_joint_l2;
+    /* dock resets (reset_samplers.py:426-471): goal shell + init noise around the goal */
+    int dock_use_stage_goal;
+    float dock_goal_q[7];
+    float dock_goal_noise[7];
+    float dock_init_q_noise[7];
+} KinSamplerParams;
+
+/* SB3 MultiInputPolicy weights, fp32, row-major [out][in] exactly as in policy.pth:
+ * x[in_dim] -> tanh(W0 x + b0)[64] -> tanh(W1 h + b1)[64] -> Wa h + ba [7]; value head likewise -> [1]. */
+typedef struct KinPolicyWeights {
+    int in_dim;
+    int has_value;
+    const float *pi_w0;
+    const float *pi_b0;
+    const float *pi_w1;
+    const float *pi_b1;
+    const float *act_w;
+    const float *act_b;
+    const float *vf_w0;
+    const float *vf_b0;
+    const float *vf_w1;
+    const float *vf_b1;
+    const float *val_w;
+    const float *val_b;
+    const float *log_std;
+} KinPolicyWeights;
+
+/* per-episode rows of the fused Approach -> Finisher evaluation: result[row * stride + episode] */
+#define KIN_RES_SUCCESS 0             /* u32 pipeline success (last finisher step, else approach) */
+#define KIN_RES_FLAGS 1               /* u32 bit0 approach_success, bit1 ready_hit, bit2 ready_dwell, bit3 final_ready, bits 4-5 handoff_kind */
+#define KIN_RES_HANDOFF_STEP 2        /* i32, -1 if none */
+#define KIN_RES_FIRST_READY_STEP 3    /* i32, -1 if none */
+#define KIN_RES_MAX_READY_STREAK 4    /* i32 */
+#define KIN_RES_STEPS 5               /* u32 approach_steps | finisher_steps << 16 */
+#define KIN_RES_FINAL_POS 6           /* f32 final_position_error (pipeline) */
+#define KIN_RES_FINAL_ORI 7
+#define KIN_RES_APPROACH_POS 8        /* f32 approach_final_position_error */
+#define KIN_RES_APPROACH_ORI 9
+#define KIN_RES_MIN_POS 10
+#define KIN_RES_MIN_ORI 11
+#define KIN_RES_FINAL_ACTION 12       /* f32 final_action_magnitude */
+#define KIN_RES_FINAL_DQ 13           /* f32 final_dq_norm */
+#define KIN_RES_FINAL_Q 14            /* 7 x f32 */
+#define KIN_RES_ROWS 24
+
+/* ---------------------------------------------------------------------------------------------
+ * library
+ * ------------------------------------------------------------------------------------------- */
+int kin_abi_version(void);
+const char *kin_last_error_string(void);
+/* number of SMs / device name of the current device (for grid sizing and bench metadata) */
+int kin_device_info(int *sm_count, int *cc_major, int *cc_minor, char *name, int name_len);
+
+/* Replaces: ArmKinematicEnv.__init__(config) -- validates and stores a host copy of the params.   */
+int kin_params_create(const KinEnvParams *host_params, void **handle);
+int kin_params_set_sampler(void *handle, const KinSamplerParams *host_sampler);
+int kin_params_destroy(void *handle);
+
+/* Replaces: compute_ee_pose6 / ee_pose6_from_q (kinematics/fk_interface.py:21, v5_1/ee_fk.py:120).
+ * q [n,7] row-major -> pose6 [n,6] row-major.                                                    */
+int kin_fk_pose6(void *handle, const float *q, float *pose6, int n, void *stream);
+
+/* Replaces: ArmKinematicEnv.reset(options={initial_q, initial_dq, initial_prev_action, goal_q,
+ * goal_pose6, policy_mode}) (AKE:102-211, explicit-options branch) for a batch.
+ * env_ids: NULL = envs [0, n_reset) else int32 [n_reset] slots; option arrays are [n_reset,7|6]
+ * row-major; initial_dq / initial_prev_action / goal_pose6 may be NULL (zeros / FK(clip(goal_q))).
+ * goal_q may be NULL only if goal_pose6 is given.  obs (nullable) is [n_reset,56].               */
+int kin_env_reset(void *handle, float *state, int stride, int n_envs, const int *env_ids, int n_reset,
+                  int mode, const float *initial_q, const float *initial_dq, const float *initial_prev_action,
+                  const float *goal_q, const float *goal_pose6, float *obs, void *stream);
+
+/* Replaces: sample_approach_reset / sample_dock_reset + reset (AKE:157-176) on the device, for the
+ * slots whose mask byte is non-zero (mask NULL = all).  Requires kin_params_set_sampler.          */
+int kin_env_reset_sampled(void *handle, float *state, int stride, int n_envs, const uint8_t *mask, int mode,
+                          uint64_t seed, float *obs, void *stream);
+
+/* Replaces: ArmKinematicEnv.step(action) (AKE:213-365) for n envs -- the fused env-step kernel.
+ * action [n,7] row-major; obs [n,56] row-major; reward [n]; done [n] (KIN_DONE_* bits);
+ * aux (nullable) [KIN_AUX_ROWS][stride]; components (nullable) [KIN_MAX_COMPONENTS][stride] =
+ * info["reward_components"] in the reference's dict order.  mode_hint: KIN_MODE_APPROACH /
+ * KIN_MODE_DOCK when the whole batch is in one mode (specialised kernel), else KIN_MODE_PER_ENV.
+ * auto_reset != 0: finished slots are re-seeded in the same kernel by the device sampler
+ * (VecEnv semantics: obs is the first observation of the next episode, KIN_DONE_AUTORESET set,
+ * terminal_obs (nullable, [n,56]) receives the last observation of the finished episode).        */
+int kin_env_step(void *handle, float *state, int stride, int n_envs, int mode_hint, const float *action,
+                 float *obs, float *reward, uint8_t *done, float *aux, float *components, int auto_reset,
+                 uint64_t seed, float *terminal_obs, void *stream);
+
+/* Replaces: ArmKinematicEnv.current_observation() (AKE:381) -> obs [n,56].                        */
+int kin_env_observe(void *handle, const float *state, int stride, int n_envs, float *obs, void *stream);
+
+/* Replaces: `model.predict(obs, deterministic=True)` of the SB3 MultiInputPolicy
+ * (eval/eval_three_stage.py:25-27) for a batch: obs [n,in_dim] -> action [n,7] (clipped to +-1),
+ * value [n] (nullable).                                                                           */
+int kin_policy_forward(const KinPolicyWeights *host_weights, const float *obs, float *action, float *value,
+                       int n, void *stream);
+
+/* Replaces: the per-episode loop of evaluate_workspace_expansion_checkpoint / _run_pairs
+ * (eval/eval_workspace_expansion.py:126-147, eval/eval_full_workspace_coverage.py:120-164):
+ * _run_approach_with_handoff + _finisher_ready + _run_policy(dock), fused into ONE persistent
+ * kernel with the policy in the loop, one thread per episode, state in registers.
+ * episode inputs are [n,7|6] row-major (initial_dq / initial_prev_action nullable);
+ * result is [KIN_RES_ROWS][stride] words; env_steps (nullable, device u64) += steps executed.     */
+int kin_rollout_approach_finisher(void *approach_handle, void *finisher_handle,
+                                  const KinPolicyWeights *host_approach, const KinPolicyWeights *host_finisher,
+                                  const float *initial_q, const float *initial_dq, const float *initial_prev_action,
+                                  const float *goal_q, const float *goal_pose6, int n, int stride,
+                                  int handoff_confirm_steps, int variant, uint32_t *result,
+                                  unsigned long long *env_steps, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KIN_B200_H */

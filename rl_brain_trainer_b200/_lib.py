@@ -1,0 +1,109 @@
+"""Loader of ``libkin_b200.so`` (the C ABI in ``include/kin_b200.h``) and ctypes views of its structs.
+
+There is deliberately no fallback: if the library has not been built (``__graft_entry__.build()`` /
+``python -m rl_brain_trainer_b200.build``) or cannot be loaded, :func:`lib` raises.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import re
+from pathlib import Path
+from typing import Any
+
+PKG_DIR = Path(__file__).resolve().parent
+REPO_ROOT = PKG_DIR.parent
+HEADER = REPO_ROOT / "include" / "kin_b200.h"
+LIB_PATH = PKG_DIR / "libkin_b200.so"
+
+_SCALARS = {"float": ctypes.c_float, "int": ctypes.c_int, "double": ctypes.c_double}
+_structs: dict[str, type] = {}
+_defines: dict[str, int] = {}
+
+
+def _header_text() -> str:
+    return HEADER.read_text()
+
+
+def c_struct(name: str) -> type:
+    """ctypes.Structure for ``typedef struct <name> {...} <name>;`` parsed from the header."""
+    if name in _structs:
+        return _structs[name]
+    m = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), _header_text(), re.S)
+    if m is None:
+        raise RuntimeError(f"struct {name} not found in {HEADER}")
+    body = re.sub(r"/\*.*?\*/", "", m.group(1), flags=re.S)
+    fields: list[tuple[str, Any]] = []
+    for raw in body.split(";"):
+        line = raw.strip()
+        if not line:
+            continue
+        mm = re.match(r"(const\s+)?(\w+)\s*(\*)?\s*(\w+)(?:\[(\d+)\])?$", line)
+        if mm is None:
+            raise RuntimeError(f"cannot parse field {line!r} of {name}")
+        _, ctype, ptr, fname, arr = mm.groups()
+        t: Any = ctypes.c_void_p if ptr else _SCALARS[ctype]
+        if arr:
+            t = t * int(arr)
+        fields.append((fname, t))
+    cls = type(name, (ctypes.Structure,), {"_fields_": fields})
+    _structs[name] = cls
+    return cls
+
+
+def define(name: str) -> int:
+    """Integer value of a ``#define KIN_*`` constant in the header."""
+    if not _defines:
+        for m in re.finditer(r"^#define\s+(KIN_\w+)\s+\(?(-?(?:0x[0-9a-fA-F]+|\d+))u?\)?", _header_text(), re.M):
+            _defines[m.group(1)] = int(m.group(2), 0)
+    return _defines[name]
+
+
+def declared_functions() -> list[str]:
+    """Names of every function the header declares (used by the CPU-side symbol test)."""
+    text = re.sub(r"/\*.*?\*/", "", _header_text(), flags=re.S)
+    return sorted(set(re.findall(r"\b(kin_\w+)\s*\(", text)))
+
+
+_lib: ctypes.CDLL | None = None
+
+
+class KinError(RuntimeError):
+    """A C-ABI call returned a non-zero code (message from kin_last_error_string)."""
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise KinError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(nvcc, sm_100a). There is no CPU fallback.")
+    L = ctypes.CDLL(str(LIB_PATH))
+    vp, i32, u64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64
+    L.kin_abi_version.restype = i32
+    L.kin_last_error_string.restype = ctypes.c_char_p
+    L.kin_device_info.argtypes = [ctypes.POINTER(i32)] * 3 + [ctypes.c_char_p, i32]
+    L.kin_params_create.argtypes = [vp, ctypes.POINTER(vp)]
+    L.kin_params_set_sampler.argtypes = [vp, vp]
+    L.kin_params_destroy.argtypes = [vp]
+    L.kin_fk_pose6.argtypes = [vp, vp, vp, i32, vp]
+    L.kin_env_reset.argtypes = [vp, vp, i32, i32, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp]
+    L.kin_env_reset_sampled.argtypes = [vp, vp, i32, i32, vp, i32, u64, vp, vp]
+    L.kin_env_step.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, i32, u64, vp, vp]
+    L.kin_env_observe.argtypes = [vp, vp, i32, i32, vp, vp]
+    L.kin_policy_forward.argtypes = [vp, vp, vp, vp, i32, vp]
+    L.kin_rollout_approach_finisher.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp]
+    for name in declared_functions():
+        fn = getattr(L, name)  # raises AttributeError if the .so lacks a declared symbol
+        if name not in ("kin_last_error_string",):
+            fn.restype = i32
+    if L.kin_abi_version() != define("KIN_ABI_VERSION"):
+        raise KinError("libkin_b200.so ABI version does not match include/kin_b200.h; rebuild")
+    _lib = L
+    return L
+
+
+def check(code: int) -> None:
+    if code != 0:
+        raise KinError(f"[{code}] {lib().kin_last_error_string().decode()}")

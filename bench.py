@@ -66,7 +66,34 @@ class ClockSampler:
         self._stop = threading.Event()
         self._t: threading.Thread | None = None
 
+    def _run_nvml(self) -> bool:
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.gpu]) if vis and vis.split(",")[self.gpu].isdigit() else self.gpu
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            return False
+        bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
+        while not self._stop.is_set():
+            try:
+                sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                reasons = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                pw = pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0
+                flags = ["Active" if reasons & bits[k] else "Not Active" for k in ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")]
+                self.rows.append([str(sm), str(mx), f"{pw:.1f}", *flags])
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+        return True
+
     def _run(self) -> None:
+        if self._run_nvml():
+            return
         while not self._stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits"],
@@ -163,12 +190,12 @@ def measure_step_kernel(torch, device, pk, n_envs: int = 1 << 21, launches: int 
     g.manual_seed(1)
     actions = torch.rand((n_envs, 7), device=device, generator=g) * 2 - 1
     for _ in range(3):
-        env.step(actions)
+        env.step_raw(actions)
     torch.cuda.synchronize(device)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(launches)]
     for a, b in ev:
         a.record()
-        env.step(actions)
+        env.step_raw(actions)   # exactly one kin_step_kernel launch between the events
         b.record()
     torch.cuda.synchronize(device)
     ms = np.array([a.elapsed_time(b) for a, b in ev])
@@ -252,17 +279,18 @@ def main() -> None:
     out.env_steps.zero_()
     events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     launches = 0
-    with ClockSampler(local_rank) as clocks:
-        barrier()
-        t_wall0 = time.perf_counter()
-        for a, b in events:
-            flush.fill_(0.0)          # L2 flush between timed iterations (outside the event pair)
-            a.record()
-            ro.run(dev_in, out=out)
-            b.record()
-            launches += 1
-        barrier()
-        t_wall = time.perf_counter() - t_wall0
+    clocks = ClockSampler(local_rank)   # samples through the device leg, the e2e leg and the step-kernel measurement
+    clocks.__enter__()
+    barrier()
+    t_wall0 = time.perf_counter()
+    for a, b in events:
+        flush.fill_(0.0)          # L2 flush between timed iterations (outside the event pair)
+        a.record()
+        ro.run(dev_in, out=out)
+        b.record()
+        launches += 1
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
     ms = np.array([a.elapsed_time(b) for a, b in events])
     dev_s = float(ms.sum()) * 1e-3
     env_steps = int(out.env_steps.item())
@@ -313,9 +341,10 @@ def main() -> None:
     step_roof = None
     cpu_base = None
     parity = None
+    if rank == 0 and not args.skip_step_kernel:
+        step_roof = measure_step_kernel(torch, device, pk)
+    clocks.__exit__(None, None, None)
     if rank == 0:
-        if not args.skip_step_kernel:
-            step_roof = measure_step_kernel(torch, device, pk)
         if world == 1 and not args.skip_cpu_baseline:
             threads = os.cpu_count() or 1
             n_cpu = 4096

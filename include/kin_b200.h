@@ -111,6 +111,15 @@ typedef struct KinEnvParams {
     float fk_C[54];
     float fk_t[15];
     float fk_AT[9];
+    /* derived on the host in fp64 (params.py) so the kernels multiply instead of divide:
+     * 1/max(span,1e-9), 1/max(delta_limit,1e-9), 1/pos_err_scale, 1/ori_err_scale, 1/max(episode_length,1),
+     * 1/max(dwell_steps_target,1)                                                                */
+    float k_inv_span[7];
+    float k_inv_delta_limit[7];
+    float k_inv_pos_err_scale;
+    float k_inv_ori_err_scale;
+    float k_inv_episode_length;
+    float k_inv_dwell_steps_target;
     /* env */
     float action_delta_scale;
     int dynamic_action_delta_scale_enabled;

@@ -46,6 +46,8 @@ struct StepOut {
     float dq_change_l2;
     float dock_limit, dqc_scale;
     float margin_min;
+    float pe[3], oe[3];      // pose error components after the step (reused by the observation)
+    float margin[NJ];        // per-joint limit margins after the step (reused by the observation)
     unsigned done;           // KIN_DONE_* bits
 };
 
@@ -65,12 +67,35 @@ __device__ __forceinline__ float wrap_to_pi(float v) {
     return fmaf(-k, kTwoPi, v);
 }
 
+// sin and cos of a joint angle.  Joint values are clipped to their limits (|q| <= pi), so the argument reduction is
+// a 3-term Cody-Waite by k*pi/2 with |k| <= 2 and no large-argument path; minimax polynomials on [-pi/4, pi/4]
+// (errors ~1 ulp, the same polynomials the fast path of sinf/cosf uses).
+__device__ __forceinline__ void sincos_joint(float x, float* sp, float* cp) {
+    const float kf = rintf(x * 0.63661977236758134f);
+    const int k = (int)kf;
+    float r = fmaf(kf, -1.57079601287841796875f, x);
+    r = fmaf(kf, -3.1391647326017846353e-07f, r);
+    r = fmaf(kf, -5.3903029534742383927e-15f, r);
+    const float r2 = r * r;
+    float ps = fmaf(r2, -1.9515295891e-4f, 8.3321608736e-3f);
+    ps = fmaf(ps, r2, -1.6666654611e-1f);
+    ps = fmaf(ps * r2, r, r);
+    float pc = fmaf(r2, 2.4433157117e-5f, -1.3887316255e-3f);
+    pc = fmaf(pc, r2, 4.1666645683e-2f);
+    pc = fmaf(pc, r2, -0.5f);
+    pc = fmaf(pc, r2, 1.0f);
+    const float s0 = (k & 1) ? pc : ps;
+    const float c0 = (k & 1) ? ps : pc;
+    *sp = (k & 2) ? -s0 : s0;
+    *cp = ((k + 1) & 2) ? -c0 : c0;
+}
+
 // ee_fk.py:98-134 with the constant transforms folded on the host (see KinEnvParams::fk_*):
 // one sincos + 12 flops per revolute joint for the Rz, 27 for the constant 3x3, 9 for the offset.
 __device__ __forceinline__ void fk_pose6(const KinEnvParams& P, const float* q, float* pose) {
     float s, c;
     float R[9], M[9];
-    sincosf(q[1], &s, &c);
+    sincos_joint(q[1], &s, &c);
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
         float m0 = P.fk_C[3 * r], m1 = P.fk_C[3 * r + 1];
@@ -93,7 +118,7 @@ __device__ __forceinline__ void fk_pose6(const KinEnvParams& P, const float* q, 
 #pragma unroll
             for (int k = 0; k < 3; ++k)
                 M[3 * r + k] = fmaf(R[3 * r], C[k], fmaf(R[3 * r + 1], C[3 + k], R[3 * r + 2] * C[6 + k]));
-        sincosf(q[j], &s, &c);
+        sincos_joint(q[j], &s, &c);
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
             R[3 * r] = fmaf(c, M[3 * r], s * M[3 * r + 1]);
@@ -126,10 +151,8 @@ __device__ __forceinline__ void pose_error(const float* curr, const float* goal,
 
 // joint_limits.py:165-174
 __device__ __forceinline__ float joint_margin(const KinEnvParams& P, float q, int i) {
-    float span = fmaxf(P.joint_upper[i] - P.joint_lower[i], 1e-9f);
-    float left = (q - P.joint_lower[i]) / span;
-    float right = (P.joint_upper[i] - q) / span;
-    return clampf(2.0f * fminf(left, right), 0.0f, 1.0f);
+    float nearest = fminf(q - P.joint_lower[i], P.joint_upper[i] - q);
+    return clampf(2.0f * nearest * P.k_inv_span[i], 0.0f, 1.0f);
 }
 
 // AKE:432-444 -- thresholds always come from reward_config (ar_*), also in dock mode
@@ -194,34 +217,41 @@ __device__ __forceinline__ void reset_core(const KinEnvParams& P, EnvRegs& s, in
 // dq 0:7 | goal_ori_err 7:10 | goal_pos_err 10:13 | joint_limit_margin 13:20 | mode_flag 20:24 |
 // next_wp_ori_err 24:27 | next_wp_pos_err 27:30 | prev_action 30:37 | progress 37:40 | q 40:47 |
 // task_type 47:50 | wp_ori_err 50:53 | wp_pos_err 53:56
-__device__ __forceinline__ void build_obs(const KinEnvParams& P, const EnvRegs& s, int mode, float* o) {
-    float pe[3], oe[3];
-    pose_error(s.ee, s.goal, pe, oe);
+// pe/oe = pose error of the CURRENT state, margin = per-joint limit margins (both already computed by the step)
+__device__ __forceinline__ void build_obs_from(const KinEnvParams& P, const EnvRegs& s, int mode, const float* pe, const float* oe,
+                                               const float* margin, float* o) {
 #pragma unroll
     for (int i = 0; i < NJ; ++i) {
-        float span = fmaxf(P.joint_upper[i] - P.joint_lower[i], 1e-9f);
-        o[i] = clampf(s.dq[i] / fmaxf(P.joint_delta_limit[i], 1e-9f), -1.0f, 1.0f);
-        o[13 + i] = joint_margin(P, s.q[i], i);
+        o[i] = clampf(s.dq[i] * P.k_inv_delta_limit[i], -1.0f, 1.0f);
+        o[13 + i] = margin[i];
         o[30 + i] = clampf(s.pa[i], -1.0f, 1.0f);
-        o[40 + i] = clampf(fmaf(2.0f, (s.q[i] - P.joint_lower[i]) / span, -1.0f), -1.0f, 1.0f);
+        o[40 + i] = clampf(fmaf(2.0f * P.k_inv_span[i], s.q[i] - P.joint_lower[i], -1.0f), -1.0f, 1.0f);
     }
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        o[7 + k] = clampf(oe[k] / P.obs_ori_err_scale_rad, -1.0f, 1.0f);
-        o[10 + k] = clampf(pe[k] / P.obs_pos_err_scale_m, -1.0f, 1.0f);
+        o[7 + k] = clampf(oe[k] * P.k_inv_ori_err_scale, -1.0f, 1.0f);
+        o[10 + k] = clampf(pe[k] * P.k_inv_pos_err_scale, -1.0f, 1.0f);
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) o[20 + k] = (k == mode) ? 1.0f : 0.0f;
 #pragma unroll
     for (int k = 24; k < 30; ++k) o[k] = 0.0f;
-    o[37] = clampf((float)s.step / (float)max(P.episode_length, 1), 0.0f, 1.0f);
-    o[38] = clampf((float)s.dwell / (float)max(P.dwell_steps_target, 1), 0.0f, 1.0f);
+    o[37] = clampf((float)s.step * P.k_inv_episode_length, 0.0f, 1.0f);
+    o[38] = clampf((float)s.dwell * P.k_inv_dwell_steps_target, 0.0f, 1.0f);
     o[39] = 0.0f;
     o[47] = 1.0f;
     o[48] = 0.0f;
     o[49] = 0.0f;
 #pragma unroll
     for (int k = 50; k < 56; ++k) o[k] = 0.0f;
+}
+
+__device__ __forceinline__ void build_obs(const KinEnvParams& P, const EnvRegs& s, int mode, float* o) {
+    float pe[3], oe[3], margin[NJ];
+    pose_error(s.ee, s.goal, pe, oe);
+#pragma unroll
+    for (int i = 0; i < NJ; ++i) margin[i] = joint_margin(P, s.q[i], i);
+    build_obs_from(P, s, mode, pe, oe, margin, o);
 }
 
 struct RewardIn {
@@ -578,7 +608,8 @@ __device__ __forceinline__ void step_core(const KinEnvParams& P, EnvRegs& s, con
         dmsq = fmaf(da, da, dmsq);
         dq_sq = fmaf(dqi, dqi, dq_sq);
         dchg_sq = fmaf(dch, dch, dchg_sq);
-        margin = fminf(margin, joint_margin(P, qn[i], i));
+        out.margin[i] = joint_margin(P, qn[i], i);
+        margin = fminf(margin, out.margin[i]);
         s.q[i] = qn[i];
         s.dq[i] = dqi;
         s.pa[i] = a[i];
@@ -629,6 +660,8 @@ __device__ __forceinline__ void step_core(const KinEnvParams& P, EnvRegs& s, con
     s.step = step_count;
     if (curr_near) s.flags |= KIN_FLAG_NEAR_HIT;
     out.pos = curr_pos; out.ori = curr_ori;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { out.pe[k] = pe[k]; out.oe[k] = oe[k]; }
     out.action_l2 = in.action_norm; out.dq_l2 = in.dq_norm; out.dq_change_l2 = in.dq_change_l2;
     out.dock_limit = dock_limit; out.dqc_scale = dqc_scale; out.margin_min = margin;
     out.done = (terminated ? KIN_DONE_TERMINATED : 0u) | (truncated ? KIN_DONE_TRUNCATED : 0u) | (success ? KIN_DONE_SUCCESS : 0u) |

@@ -75,7 +75,7 @@ kin_step_kernel(const __grid_constant__ KinEnvParams P, const KinSamplerParams* 
         const unsigned any = __ballot_sync(0xffffffffu, finished);
         if (any) {
             if (terminal_obs) {  // VecEnv "terminal_observation": the last observation of the finished episode
-                build_obs(P, s, mode, o);
+                build_obs_from(P, s, mode, out.pe, out.oe, out.margin, o);
                 stage_obs_row(tile, lane, o);
                 if (BULK) {
                     bulk_store_tile(terminal_obs + (size_t)env0 * OBS, tile, tile_bytes, lane);
@@ -103,7 +103,8 @@ kin_step_kernel(const __grid_constant__ KinEnvParams P, const KinSamplerParams* 
     }
     if (active) done[env] = (uint8_t)done_bits;
 
-    build_obs(P, s, mode, o);
+    if (AUTORESET && (done_bits & KIN_DONE_AUTORESET)) build_obs(P, s, mode, o);   // fresh episode: recompute errors / margins
+    else build_obs_from(P, s, mode, out.pe, out.oe, out.margin, o);
     stage_obs_row(tile, lane, o);
     if (BULK) {
         bulk_store_tile(obs + (size_t)env0 * OBS, tile, tile_bytes, lane);

@@ -284,6 +284,17 @@ class BatchedArmKinematicEnv:
         truncated = (self.done & _D("KIN_DONE_TRUNCATED")) != 0
         return self.obs, self.reward, terminated, truncated, self._info(reset=False)
 
+    def step_raw(self, actions: torch.Tensor) -> None:
+        """One fused-kernel step with no host-side post-processing: results land in ``self.obs / reward / done / aux``.
+
+        ``actions`` must already be a contiguous float32 ``[num_envs, 7]`` tensor on this device.  This is the call a
+        device-resident rollout loop makes (policy kernel -> step_raw -> policy kernel ...).
+        """
+        hint = _D("KIN_MODE_PER_ENV") if self._mode_all is None else self._mode_all
+        _lib.check(self._L.kin_env_step(self._params.handle, self.state.data_ptr(), self.stride, self.num_envs, hint, actions.data_ptr(),
+                                        self.obs.data_ptr(), self.reward.data_ptr(), self.done.data_ptr(), _ptr(self.aux), _ptr(self.components),
+                                        int(self.auto_reset), self._seed, _ptr(self.terminal_obs), _stream()))
+
     def current_observation(self) -> torch.Tensor:
         out = torch.empty_like(self.obs)
         with torch.cuda.device(self.device):

@@ -31,7 +31,7 @@ def env_params(cfg: Phase1EnvConfig, route_reward: Any | None = None):
               "obs_": cfg.observation_config, "rr_": route_reward}
     skip = {"ar_n_milestones", "ar_orientation_milestone_thresholds_rad", "ar_orientation_milestone_bonuses"}
     for fname, ftype in cls._fields_:
-        if fname.startswith(("joint_", "fk_")) or fname in skip:
+        if fname.startswith(("joint_", "fk_", "k_")) or fname in skip:
             continue
         src, key = cfg, fname
         for prefix, sub in groups.items():
@@ -42,6 +42,13 @@ def env_params(cfg: Phase1EnvConfig, route_reward: Any | None = None):
             continue
         value = getattr(src, key)
         setattr(p, fname, int(value) if ftype is ctypes.c_int else float(value))
+    for i, spec in enumerate(cfg.joint_specs):
+        p.k_inv_span[i] = 1.0 / max(spec.upper - spec.lower, 1e-9)
+        p.k_inv_delta_limit[i] = 1.0 / max(spec.delta_limit, 1e-9)
+    p.k_inv_pos_err_scale = 1.0 / cfg.observation_config.pos_err_scale_m
+    p.k_inv_ori_err_scale = 1.0 / cfg.observation_config.ori_err_scale_rad
+    p.k_inv_episode_length = 1.0 / max(cfg.episode_length, 1)
+    p.k_inv_dwell_steps_target = 1.0 / max(cfg.dwell_steps_target, 1)
     thr = tuple(cfg.reward_config.orientation_milestone_thresholds_rad or ())
     bon = tuple(cfg.reward_config.orientation_milestone_bonuses or ())
     n = min(len(thr), len(bon))  # zip(strict=False), reward_approach.py:111

@@ -203,3 +203,61 @@ def test_single_env_adapter_seeded_reset_matches_reference_stream():
         assert np.abs(info["q"] - g["approach_s5_q"][i]).max() < 1e-7
         assert np.abs(info["goal_q"] - g["approach_s5_goal_q"][i]).max() < 1e-7
         assert np.abs(info["goal_pose6"] - g["approach_s5_goal_pose6"][i]).max() < 1e-5
+
+
+# ---- tensor-core variant (tcgen05 kind::tf32): statistical parity, the strict path is the FFMA variant above -------------------
+def test_fused_rollout_tc_close_to_strict_fp32():
+    from rl_brain_trainer_b200.rollout import VARIANT_FFMA, VARIANT_TC
+    from rl_brain_trainer_b200.samplers import build_curriculum_local_eval_suite
+
+    cfg = env_config("approach_dynamic_scale_big")
+    for n in (100, 8192):   # ragged (partial tile / partial CTA) and multi-CTA sizes
+        suite = build_curriculum_local_eval_suite(cfg, seed=700001 + 5 * 1009, stage_index=5, n_episodes=n)
+        a = _rollout(VARIANT_FFMA).evaluate_suite(suite).to_numpy()
+        b = _rollout(VARIANT_TC).evaluate_suite(suite).to_numpy()
+        flips = int((a["success"] != b["success"]).sum())
+        assert flips <= max(1, 0.005 * n), f"{flips} of {n} success flags differ between tf32 and fp32 MLP"
+        assert abs(a["success"].mean() - b["success"].mean()) <= max(0.005, 1.0 / n)
+        assert np.array_equal(a["approach_steps"], b["approach_steps"])
+        assert float(np.abs(a["final_q"] - b["final_q"]).mean()) < 5e-4      # TF32 operands: O(1e-3) action differences
+        assert abs(a["final_position_error"].mean() - b["final_position_error"].mean()) < 2e-5
+        assert abs(a["final_orientation_error"].mean() - b["final_orientation_error"].mean()) < 2e-4
+
+
+def test_fused_rollout_tc_reference_anchors():
+    """Stage 5 (61/64) and random-start known split (77/96) with the tensor-core MLP: within +-3 episodes."""
+    from rl_brain_trainer_b200 import workspace
+    from rl_brain_trainer_b200.rollout import VARIANT_TC
+    from rl_brain_trainer_b200.samplers import EvalSuite
+
+    g = golden("eval_stage5.npz")
+    res = _rollout(VARIANT_TC).evaluate_suite(EvalSuite(initial_q=g["initial_q"], goal_q=g["goal_q"], goal_pose6=g["goal_pose6"])).to_numpy()
+    assert abs(int(res["success"].sum()) - 61) <= 3
+    assert abs(res["final_position_error"].mean() - g["final_position_error"].mean()) < 1e-4
+    suites = workspace.build_randomstart_eval(env_config("randomstart_overnight"), seed=940001)
+    res = _rollout(VARIANT_TC, approach="randomstart_overnight", policy="randomstart").evaluate_suite(suites["known"]).to_numpy()
+    assert abs(int(res["success"].sum()) - 77) <= 4
+
+
+def test_fused_rollout_terminate_on_success_early_exit():
+    """A config that terminates on success: lanes finish at different steps (per-lane predication, tile-uniform loop exit)."""
+    import json
+    from dataclasses import replace
+
+    from rl_brain_trainer_b200.rollout import VARIANT_FFMA, VARIANT_TC, ApproachFinisherRollout
+    from rl_brain_trainer_b200.samplers import build_curriculum_local_eval_suite
+
+    cfg = env_config("approach_dynamic_scale_big")
+    cfg_t = replace(cfg, termination_config=replace(cfg.termination_config, terminate_on_success=True))
+    suite = build_curriculum_local_eval_suite(cfg, seed=11, stage_index=3, n_episodes=1000)
+    pa, pf = oracle_params(cfg_t), oracle_params(env_config("finisher_noop_ft"))
+    ref, _ = ko.eval_approach_finisher(pa, pf, oracle_policy("approach_stage8_11"), oracle_policy("finisher"),
+                                       initial_q=suite.initial_q.astype(np.float32).astype(float),
+                                       goal_q=suite.goal_q.astype(np.float32).astype(float), n_threads=8)
+    assert ref["approach_steps"].min() < 128 and len(set(ref["approach_steps"].tolist())) > 5
+    for variant, tol in ((VARIANT_FFMA, 0.01), (VARIANT_TC, 0.03)):
+        ro = ApproachFinisherRollout(cfg_t, _policy("approach_stage8_11"), env_config("finisher_noop_ft"), _policy("finisher"), variant=variant)
+        res = ro.evaluate_suite(suite).to_numpy()
+        assert np.mean(res["approach_steps"] != ref["approach_steps"]) <= tol * 3
+        assert np.mean(res["success"].astype(int) != ref["success"]) <= tol
+    assert json is not None

@@ -65,7 +65,7 @@ extern "C" {
 #define KIN_ROW_GOAL_Q 41      /* 7  goal joint vector (info only; the step never reads it)       */
 #define KIN_ROW_EPISODE 48     /* 1  u32: episodes completed by this slot (auto-reset RNG counter)*/
 #define KIN_ROW_ROUTE 49       /* 1  u32: route_index | ready_streak << 16 (route wrappers)       */
-#define KIN_ROW_ROUTE_PREV 50  /* 14 prev_q, prev_dq as seen by the route wrapper                 */
+#define KIN_ROW_ROUTE2 50      /* 1  u32: last_route_index | completed_waypoints << 16 (sequence) */
 #define KIN_STATE_ROWS 64
 
 #define KIN_FLAG_PRE_NEAR_HIT 0x1u
@@ -401,6 +401,27 @@ typedef struct KinPolicyWeights {
 #define KIN_RES_FINAL_Q 14            /* 7 x f32 */
 #define KIN_RES_ROWS 24
 
+/* Dense q-goal route (route/route_dataset.py:16-99): device arrays, one row per waypoint. */
+typedef struct KinRouteTable {
+    int n_waypoints;
+    int pad0;
+    const float *q_goal;
+    const float *pose6;
+    const float *next_q_delta;
+    const float *progress_m;
+} KinRouteTable;
+
+/* per-step scalars of the route wrappers: raux[row * stride + env] (route/route_env.py:175-190 info keys) */
+#define KIN_RAUX_Q_ERR 0        /* route_q_error_norm        */
+#define KIN_RAUX_NEAREST 1      /* nearest_route_q_distance  */
+#define KIN_RAUX_POS_ERR 2      /* position_error_norm       */
+#define KIN_RAUX_ORI_ERR 3      /* orientation_error_norm    */
+#define KIN_RAUX_FLAGS 4        /* u32: bit0 route_ready, bit1 route_regression, bit2 route_orientation_hit, bit3 waypoint_success */
+#define KIN_RAUX_ROUTE_INDEX 5  /* u32 route_index after the step (advanced in sequence mode) */
+#define KIN_RAUX_STREAK 6       /* u32 route_ready_streak    */
+#define KIN_RAUX_COMPLETED 7    /* u32 route_completed_waypoints (sequence mode) */
+#define KIN_RAUX_ROWS 8
+
 /* ---------------------------------------------------------------------------------------------
  * library
  * ------------------------------------------------------------------------------------------- */
@@ -465,6 +486,31 @@ int kin_rollout_approach_finisher(void *approach_handle, void *finisher_handle,
                                   const float *goal_q, const float *goal_pose6, int n, int stride,
                                   int handoff_confirm_steps, int variant, uint32_t *result,
                                   unsigned long long *env_steps, void *stream);
+
+/* Replaces: RouteKinematicEnv.reset(options={route_index, start_route_index}) / RouteSequenceKinematicEnv.reset and
+ * the evaluator's state override (route/route_env.py:49-97, route/route_sequence_env.py:96-137,
+ * eval/eval_route_curriculum.py:67-87).  route_index [n_reset] int32; last_route_index (nullable, sequence mode);
+ * initial_q (nullable -> waypoint(start_route_index[i]) with start_route_index nullable -> route_index-1);
+ * obs [n_reset,80] nullable.                                                                                     */
+int kin_route_reset(void *handle, const KinRouteTable *host_route, float *state, int stride, int n_envs, const int *env_ids,
+                    int n_reset, const int *route_index, const int *start_route_index, const int *last_route_index,
+                    const float *initial_q, const float *initial_dq, const float *initial_prev_action, float *obs, void *stream);
+
+/* Replaces: RouteKinematicEnv.step (route/route_env.py:124-192; sequence_mode = 0) and RouteSequenceKinematicEnv.step
+ * with the in-episode waypoint advance (route/route_sequence_env.py:139-257; sequence_mode = 1).
+ * obs [n,80]; reward = route reward (route/reward_route.py:54-143); done = KIN_DONE_* with route semantics;
+ * raux (nullable) [KIN_RAUX_ROWS][stride]; rcomp (nullable) [17][stride] = route reward components.            */
+int kin_route_step(void *handle, const KinRouteTable *host_route, float *state, int stride, int n_envs, const float *action,
+                   float *obs, float *reward, uint8_t *done, float *raux, float *rcomp, int sequence_mode,
+                   int reset_ready_streak_on_advance, void *stream);
+
+/* Replaces: evaluate_sequential_route / _roll_one (eval/eval_route_curriculum.py:55-125,188-218) for n independent
+ * replicas, fused with the 80-input route policy: replica r starts at start_q[r] (nullable -> waypoint(start_index-1))
+ * and chains waypoints start_index..end_index, each from the actual final state of the previous one.
+ * prefix [n] int32 = longest_success_prefix; success_bits (nullable) [n][ceil((end-start+1)/32)] u32 bitmask.     */
+int kin_route_probe(void *handle, const KinRouteTable *host_route, const KinPolicyWeights *host_policy, const float *start_q,
+                    int start_index, int end_index, int n, int *prefix, uint32_t *success_bits, unsigned long long *env_steps,
+                    void *stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,243 @@
+"""Dense holder-route wrappers on the GPU: route dataset, batched Route(Sequence)KinematicEnv, sequential probe.
+
+Mirrors ``kinematic_phase1/route/route_dataset.py:16-99``, ``route/route_env.py:27-212``,
+``route/route_sequence_env.py:29-278`` and ``eval/eval_route_curriculum.py:55-246``.  The 483-waypoint route file of
+the reference (``tray1_holder1_to_8_route_q_dense.json``) is not in its snapshot: ``load_route_dataset``
+reads that JSON format when a user supplies the file, ``synthetic_route`` builds a seeded stand-in with similar
+statistics for tests and benchmarks.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import json
+from dataclasses import dataclass
+from pathlib import Path
+from typing import Any, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib, kinematics
+from .config import RouteEnvConfig, RouteSequenceConfig
+from .env import ParamsHandle, _D, _ptr, _stream
+from .policy import PolicyWeights
+
+ROUTE_OBS_DIM = 80
+ROUTE_OBS_SLICES: dict[str, slice] = {
+    "dq": slice(0, 7), "goal_ori_err": slice(7, 10), "goal_pos_err": slice(10, 13), "joint_limit_margin": slice(13, 20),
+    "mode_flag": slice(20, 24), "next_wp_ori_err": slice(24, 27), "next_wp_pos_err": slice(27, 30), "prev_action": slice(30, 37),
+    "progress": slice(37, 40), "q": slice(40, 47), "route_q_error": slice(47, 54), "route_q_goal": slice(54, 61),
+    "route_scalar": slice(61, 64), "route_tangent": slice(64, 71), "task_type": slice(71, 74), "wp_ori_err": slice(74, 77),
+    "wp_pos_err": slice(77, 80),
+}
+
+
+def default_chunk_bounds(max_index: int) -> tuple[tuple[int, int], ...]:
+    """route_dataset.py:60-70."""
+    edges = ((1, 40), (41, 80), (81, 120), (121, 180), (181, 260), (261, 360))
+    return tuple((lo, min(hi, max_index)) for lo, hi in edges) + ((361, max_index),)
+
+
+@dataclass
+class RouteDataset:
+    """Waypoint table: ``q_goal [n,7]``, FK ``pose6 [n,6]``, ``next_q_delta [n,7]``, cumulative EE path ``progress_m [n]``, chunk ids."""
+
+    q_goal: np.ndarray
+    pose6: np.ndarray
+    next_q_delta: np.ndarray
+    progress_m: np.ndarray
+    chunk_id: np.ndarray
+    path: Path | None = None
+
+    def __len__(self) -> int:
+        return int(self.q_goal.shape[0])
+
+    @classmethod
+    def from_q(cls, q_goals: np.ndarray, path: Path | None = None, chunk_bounds: Sequence[tuple[int, int]] | None = None) -> "RouteDataset":
+        q = np.asarray(q_goals, dtype=float).reshape(-1, 7)
+        if q.shape[0] < 1:
+            raise ValueError("Route dataset must contain a non-empty list")
+        pose = np.array([kinematics.fk_pose6_folded(x) for x in q])
+        steps = np.linalg.norm(np.diff(pose[:, :3], axis=0), axis=1) if len(q) > 1 else np.zeros(0)
+        progress = np.concatenate([[0.0], np.cumsum(steps)])
+        nxt = q[np.minimum(np.arange(len(q)) + 1, len(q) - 1)] - q
+        bounds = tuple(chunk_bounds) if chunk_bounds is not None else default_chunk_bounds(len(q) - 1)
+        chunk = np.full(len(q), len(bounds) - 1, dtype=np.int64)
+        for i in range(len(q)):
+            for c, (lo, hi) in enumerate(bounds):
+                if lo <= i <= hi:
+                    chunk[i] = c
+                    break
+        return cls(q_goal=q, pose6=pose, next_q_delta=nxt, progress_m=progress, chunk_id=chunk, path=path)
+
+
+def load_route_dataset(path: str | Path, *, chunk_bounds: Sequence[tuple[int, int]] | None = None) -> RouteDataset:
+    """Reference JSON format: ``{"route_q": [...]}`` or a bare list; entries are 7-vectors or dicts with ``q`` / ``q_goal``."""
+    p = Path(path)
+    payload = json.loads(p.read_text(encoding="utf-8"))
+    entries = payload.get("route_q") if isinstance(payload, dict) else payload
+    if not isinstance(entries, list) or not entries:
+        raise ValueError(f"Route dataset must contain a non-empty list: {p}")
+
+    def q_of(e: Any) -> Any:
+        if isinstance(e, dict):
+            return e["q"] if "q" in e else e["q_goal"]
+        return e
+
+    return RouteDataset.from_q(np.asarray([q_of(e) for e in entries], dtype=float), path=p, chunk_bounds=chunk_bounds)
+
+
+def synthetic_route(n_waypoints: int = 483, *, seed: int = 7, n_knots: int = 9, knot_sigma: float = 0.22, target_spacing_m: float = 0.012) -> RouteDataset:
+    """Seeded dense q-route: smooth-step interpolation through random-walk joint knots inside the Stage-<=8 envelope.
+
+    The knot spread is rescaled so the mean EE spacing is ~``target_spacing_m`` (the reference route: 483 waypoints, ~5.8 m).
+    """
+    rng = np.random.default_rng(seed)
+    knots = np.cumsum(rng.normal(0.0, knot_sigma, size=(n_knots, 7)), axis=0) * np.array([0.2, 1, 1, 1, 1, 1, 1])
+    knots = np.clip(knots, [-0.30, -1.2, -1.2, -1.2, -1.0, -1.0, -1.0], [0.30, 1.2, 1.2, 1.2, 1.0, 1.0, 1.0])
+
+    def sample(k: np.ndarray) -> np.ndarray:
+        t = np.linspace(0, len(k) - 1, n_waypoints)
+        i0 = np.clip(np.floor(t).astype(int), 0, len(k) - 2)
+        w = (t - i0)[:, None]
+        w = w * w * (3 - 2 * w)
+        return k[i0] * (1 - w) + k[i0 + 1] * w
+
+    ds = RouteDataset.from_q(sample(knots))
+    spacing = ds.progress_m[-1] / max(n_waypoints - 1, 1)
+    if spacing > 0:
+        ds = RouteDataset.from_q(sample(knots * min(target_spacing_m / spacing, 1.0)))
+    return ds
+
+
+class DeviceRoute:
+    """Route table resident on one GPU + the ``KinRouteTable`` view."""
+
+    def __init__(self, route: RouteDataset, device: str | torch.device = "cuda") -> None:
+        self.route = route
+        self.device = torch.device(device)
+        f = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32)).to(self.device)  # noqa: E731
+        self.q, self.pose, self.tan, self.prog = f(route.q_goal), f(route.pose6), f(route.next_q_delta), f(route.progress_m)
+        t = _lib.c_struct("KinRouteTable")()
+        t.n_waypoints = len(route)
+        t.q_goal, t.pose6, t.next_q_delta, t.progress_m = self.q.data_ptr(), self.pose.data_ptr(), self.tan.data_ptr(), self.prog.data_ptr()
+        self.c = t
+
+
+class BatchedRouteKinematicEnv:
+    """``num_envs`` route replicas: ``RouteKinematicEnv`` (sequence disabled) or ``RouteSequenceKinematicEnv`` semantics.
+
+    ``reset(route_index=[M], start_route_index=None, initial_q=None, ...)`` -> obs [N,80]
+    ``step(actions [N,7])`` -> (obs [N,80], reward [N], terminated, truncated, info) with the route info keys.
+    """
+
+    def __init__(self, route: RouteDataset, config: RouteEnvConfig, num_envs: int, device: str | torch.device = "cuda", *,
+                 sequence_config: RouteSequenceConfig | None = None, with_components: bool = False) -> None:
+        if not torch.cuda.is_available():
+            raise _lib.KinError("BatchedRouteKinematicEnv needs a CUDA device; there is no CPU fallback")
+        self.config, self.route = config, route
+        self.sequence = sequence_config if (sequence_config is not None and sequence_config.enabled) else None
+        self.device = torch.device(device)
+        self.num_envs = int(num_envs)
+        self.stride = (self.num_envs + 31) // 32 * 32
+        self._L = _lib.lib()
+        with torch.cuda.device(self.device):
+            self._params = ParamsHandle(config.base_env_config, config.reward_config)
+            self.table = DeviceRoute(route, self.device)
+            self.state = torch.zeros((_D("KIN_STATE_ROWS"), self.stride), dtype=torch.float32, device=self.device)
+            self.obs = torch.zeros((self.num_envs, ROUTE_OBS_DIM), dtype=torch.float32, device=self.device)
+            self.reward = torch.zeros(self.num_envs, dtype=torch.float32, device=self.device)
+            self.done = torch.zeros(self.num_envs, dtype=torch.uint8, device=self.device)
+            self.raux = torch.zeros((_D("KIN_RAUX_ROWS"), self.stride), dtype=torch.float32, device=self.device)
+            self.rcomp = torch.zeros((17, self.stride), dtype=torch.float32, device=self.device) if with_components else None
+
+    def reset(self, *, route_index: Any, start_route_index: Any = None, initial_q: Any = None, initial_dq: Any = None,
+              initial_prev_action: Any = None, env_ids: Any = None) -> torch.Tensor:
+        ids = None if env_ids is None else torch.as_tensor(env_ids, dtype=torch.int32, device=self.device).contiguous()
+        m = self.num_envs if ids is None else int(ids.numel())
+        ri = torch.as_tensor(route_index, dtype=torch.int32, device=self.device).reshape(-1)
+        if ri.numel() == 1 and m > 1:
+            ri = ri.expand(m)
+        ri = ri.contiguous()
+        last = None
+        if self.sequence is not None:  # route_sequence_env.py:120-124
+            max_index = min(self.config.reset_config.max_route_index, len(self.route) - 1)
+            ri = ri.clamp(1, max_index).contiguous()
+            last = torch.clamp(ri + max(int(self.sequence.sequence_length), 1) - 1, max=max_index).to(torch.int32).contiguous()
+        st = None if start_route_index is None else torch.as_tensor(start_route_index, dtype=torch.int32, device=self.device).reshape(-1).expand(m).contiguous()
+        f = lambda x: None if x is None else torch.as_tensor(x, dtype=torch.float32, device=self.device).reshape(-1, 7).expand(m, 7).contiguous()  # noqa: E731
+        iq, idq, ipa = f(initial_q), f(initial_dq), f(initial_prev_action)
+        out = self.obs if ids is None else torch.empty((m, ROUTE_OBS_DIM), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.kin_route_reset(self._params.handle, ctypes.byref(self.table.c), _ptr(self.state), self.stride, self.num_envs,
+                                               _ptr(ids), m, _ptr(ri), _ptr(st), _ptr(last), _ptr(iq), _ptr(idq), _ptr(ipa), _ptr(out), _stream()))
+        if ids is not None:
+            self.obs[ids.long()] = out
+        return self.obs
+
+    def step(self, actions: torch.Tensor):
+        a = torch.as_tensor(actions, dtype=torch.float32, device=self.device)
+        if a.shape != (self.num_envs, 7):
+            raise ValueError(f"Expected action shape {(self.num_envs, 7)}, got {tuple(a.shape)}")
+        a = a.contiguous()
+        seq = self.sequence is not None
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.kin_route_step(self._params.handle, ctypes.byref(self.table.c), _ptr(self.state), self.stride, self.num_envs,
+                                              _ptr(a), _ptr(self.obs), _ptr(self.reward), _ptr(self.done), _ptr(self.raux), _ptr(self.rcomp),
+                                              int(seq), int(bool(self.sequence.reset_ready_streak_on_advance)) if seq else 1, _stream()))
+        d = self.done
+        n = self.num_envs
+        fl = self.raux[_D("KIN_RAUX_FLAGS"), :n].view(torch.int32)
+        info = {
+            "success": (d & _D("KIN_DONE_SUCCESS")) != 0, "route_ready": (fl & 1) != 0, "route_regression": (fl & 2) != 0,
+            "route_orientation_hit": (fl & 4) != 0, "route_waypoint_success": (fl & 8) != 0,
+            "route_ready_streak": self.raux[_D("KIN_RAUX_STREAK"), :n].view(torch.int32),
+            "route_index": self.raux[_D("KIN_RAUX_ROUTE_INDEX"), :n].view(torch.int32),
+            "route_completed_waypoints": self.raux[_D("KIN_RAUX_COMPLETED"), :n].view(torch.int32),
+            "route_q_error_norm": self.raux[_D("KIN_RAUX_Q_ERR"), :n], "nearest_route_q_distance": self.raux[_D("KIN_RAUX_NEAREST"), :n],
+            "position_error_norm": self.raux[_D("KIN_RAUX_POS_ERR"), :n], "orientation_error_norm": self.raux[_D("KIN_RAUX_ORI_ERR"), :n],
+            "q": self.state[_D("KIN_ROW_Q"):_D("KIN_ROW_Q") + 7, :n].t(), "dq": self.state[_D("KIN_ROW_DQ"):_D("KIN_ROW_DQ") + 7, :n].t(),
+        }
+        if self.rcomp is not None:
+            info["reward_components"] = self.rcomp[:, :n]
+        return self.obs, self.reward, (d & _D("KIN_DONE_TERMINATED")) != 0, (d & _D("KIN_DONE_TRUNCATED")) != 0, info
+
+
+def evaluate_sequential_route(route: RouteDataset, config: RouteEnvConfig, policy: PolicyWeights, *, n_replicas: int = 1, start_index: int = 1,
+                              end_index: int | None = None, start_q_noise_std: float = 0.0, seed: int = 0,
+                              device: str | torch.device = "cuda") -> dict[str, Any]:
+    """``evaluate_sequential_route`` (eval_route_curriculum.py:188-246) for ``n_replicas`` independent chains in one launch.
+
+    Replica 0 starts exactly at waypoint ``start_index - 1`` like the reference; the others add N(0, std) joint noise.
+    Returns per-replica ``longest_success_prefix``, the success bitmask, the prefix histogram and env-step count.
+    """
+    if not torch.cuda.is_available():
+        raise _lib.KinError("evaluate_sequential_route needs a CUDA device; there is no CPU fallback")
+    device = torch.device(device)
+    end = min(len(route) - 1, len(route) - 1 if end_index is None else int(end_index))
+    m = end - start_index + 1
+    words = (m + 31) // 32
+    with torch.cuda.device(device):
+        params = ParamsHandle(config.base_env_config, config.reward_config)
+        table = DeviceRoute(route, device)
+        base = torch.as_tensor(route.q_goal[max(start_index - 1, 0)], dtype=torch.float32, device=device).expand(n_replicas, 7).clone()
+        if start_q_noise_std > 0 and n_replicas > 1:
+            g = torch.Generator(device=device)
+            g.manual_seed(seed)
+            noise = torch.randn((n_replicas, 7), device=device, generator=g) * start_q_noise_std
+            noise[0] = 0.0
+            base = base + noise
+        prefix = torch.zeros(n_replicas, dtype=torch.int32, device=device)
+        bits = torch.zeros((n_replicas, words), dtype=torch.int32, device=device)
+        steps = torch.zeros(1, dtype=torch.int64, device=device)
+        _lib.check(_lib.lib().kin_route_probe(params.handle, ctypes.byref(table.c), ctypes.byref(policy.c), base.data_ptr(), int(start_index), end,
+                                              n_replicas, prefix.data_ptr(), bits.data_ptr(), steps.data_ptr(), _stream()))
+    hist = torch.bincount(prefix.long(), minlength=m + 1)
+    p0 = int(prefix[0].item())
+    return {
+        "longest_success_prefix": prefix, "success_bits": bits, "prefix_histogram": hist, "env_steps": steps,
+        "replica0_longest_success_prefix": p0,
+        "replica0_cumulative_successful_route_distance_m": float(route.progress_m[min(p0, len(route) - 1)] - route.progress_m[0]),
+        "start_index": int(start_index), "end_index": int(end),
+    }

@@ -1,0 +1,143 @@
+"""GPU parity of the dense holder-route wrappers (waypoint advance, route reward, 80-float obs, sequential probe) vs the oracle."""
+
+from __future__ import annotations
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import kin_oracle as ko
+
+from ._util import golden, oracle_params, oracle_policy
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup():
+    from rl_brain_trainer_b200 import config as kcfg
+    from rl_brain_trainer_b200.route import RouteDataset
+
+    g = golden("trace_route.npz")
+    renv, seq = kcfg.to_route_env_config(kcfg.preset_dict("route_prefix120"), max_route_index=len(g["route_q"]) - 1)
+    route = RouteDataset.from_q(g["route_q"])
+    return g, renv, seq, route, oracle_params(renv.base_env_config, renv.reward_config)
+
+
+def test_route_dataset_matches_reference():
+    g, _, _, route, _ = _setup()
+    assert np.abs(route.pose6 - g["route_pose6"]).max() < 1e-9
+    assert np.abs(route.progress_m - g["route_progress"]).max() < 1e-9
+
+
+def _compare_step(prefix, t, g, obs, reward, term, trunc, info, comps):
+    where = f"{prefix} step {t}"
+    flags = np.array([int(term[0]), int(trunc[0]), int(info["success"][0]), int(info["route_ready"][0]), int(info["route_ready_streak"][0]),
+                      int(info["route_regression"][0]), int(info["route_orientation_hit"][0]), int(info["route_index"][0])])
+    assert np.array_equal(flags, g[prefix + "flags"][t]), where
+    sc = np.array([float(info["route_q_error_norm"][0]), float(info["nearest_route_q_distance"][0]), float(info["position_error_norm"][0]),
+                   float(info["orientation_error_norm"][0])])
+    assert np.abs(sc - g[prefix + "scalars"][t]).max() < 1e-5, where
+    assert np.abs(obs[0].cpu().numpy() - g[prefix + "obs"][t]).max() < 5e-5, where
+    ref = g[prefix + "components"][t]
+    got = comps[:17, 0].cpu().numpy()
+    assert np.abs(got - ref).max() < 3e-4 * max(1.0, np.abs(ref).max()), (where, got - ref)
+    assert abs(float(reward[0]) - g[prefix + "reward"][t]) < 5e-4 * max(1.0, abs(g[prefix + "reward"][t])), where
+
+
+def test_route_env_golden_sequential_chain():
+    """RouteKinematicEnv with the evaluator's state override, 12 chained waypoints recorded from the reference."""
+    from rl_brain_trainer_b200.route import BatchedRouteKinematicEnv
+
+    g, renv, _, route, _ = _setup()
+    env = BatchedRouteKinematicEnv(route, renv, 1, with_components=True)
+    starts = g["seq_episode_start"]
+    for e in range(len(starts) - 1):
+        obs = env.reset(route_index=[int(g["seq_reset_index"][e])], start_route_index=[0], initial_q=g["seq_reset_q"][e],
+                        initial_dq=g["seq_reset_dq"][e], initial_prev_action=g["seq_reset_pa"][e])
+        assert np.abs(obs[0].cpu().numpy() - g["seq_reset_obs"][e]).max() < 5e-5
+        for t in range(starts[e], starts[e + 1]):
+            obs, reward, term, trunc, info = env.step(torch.as_tensor(g["seq_action"][t][None], dtype=torch.float32))
+            _compare_step("seq_", t, g, obs, reward, term, trunc, info, info["reward_components"])
+
+
+def test_route_sequence_env_golden_waypoint_advance():
+    """RouteSequenceKinematicEnv: the target advances in place inside one episode (sequence_length 4)."""
+    from dataclasses import replace
+
+    from rl_brain_trainer_b200.route import BatchedRouteKinematicEnv
+
+    g, renv, seq, route, _ = _setup()
+    env = BatchedRouteKinematicEnv(route, renv, 1, sequence_config=replace(seq, enabled=True, sequence_length=4), with_components=True)
+    starts = g["adv_episode_start"]
+    for e in range(len(starts) - 1):
+        first = int(g["adv_reset_index"][e])
+        obs = env.reset(route_index=[first], start_route_index=[first - 1])
+        assert np.abs(obs[0].cpu().numpy() - g["adv_reset_obs"][e]).max() < 5e-5
+        for t in range(starts[e], starts[e + 1]):
+            obs, reward, term, trunc, info = env.step(torch.as_tensor(g["adv_action"][t][None], dtype=torch.float32))
+            _compare_step("adv_", t, g, obs, reward, term, trunc, info, info["reward_components"])
+            assert int(info["route_completed_waypoints"][0]) == int(g["adv_completed"][t])
+
+
+def test_route_batch_vs_oracle_random():
+    """256 replicas at random waypoints with noisy proportional actions, 40 steps, sequence mode, vs the oracle."""
+    from dataclasses import replace
+
+    from rl_brain_trainer_b200.route import BatchedRouteKinematicEnv
+
+    g, renv, seq, route, params = _setup()
+    rng = np.random.default_rng(3)
+    n, T = 256, 40
+    env = BatchedRouteKinematicEnv(route, renv, n, sequence_config=replace(seq, enabled=True, sequence_length=3))
+    oroute = ko.OracleRoute(g["route_q"])
+    first = rng.integers(1, len(route) - 4, size=n)
+    obs = env.reset(route_index=first, start_route_index=first - 1)
+    oenvs = []
+    for e in range(n):
+        oe = ko.OracleRouteEnv(params, oroute, sequence_length=3, max_route_index=len(route) - 1)
+        oe.reset(route_index=int(first[e]), start_route_index=int(first[e]) - 1)
+        oenvs.append(oe)
+    dl = np.array([s.delta_limit for s in renv.base_env_config.joint_specs]) * renv.base_env_config.action_delta_scale
+    alive = np.ones(n, dtype=bool)
+    mism = 0
+    for t in range(T):
+        q = env.state[0:7, :n].t().cpu().numpy().astype(float)
+        idx = env.raux[5, :n].view(torch.int32).cpu().numpy() if t else first
+        goal = g["route_q"][np.clip(idx, 0, len(route) - 1)]
+        a = np.clip((goal - q) / dl * 0.7 + rng.normal(0, 0.03, (n, 7)), -1, 1).astype(np.float32)
+        obs, reward, term, trunc, info = env.step(torch.as_tensor(a))
+        for e in range(n):
+            if not alive[e]:
+                continue
+            robs, ro = oenvs[e].step(a[e].astype(float))
+            same = (int(term[e]) == ro.terminated and int(info["success"][e]) == ro.success and int(info["route_index"][e]) == ro.route_index
+                    and int(info["route_ready"][e]) == ro.route_ready)
+            if not same:           # threshold-adjacent flip: stop comparing this replica (its trajectory of targets diverges)
+                mism += 1
+                alive[e] = False
+                continue
+            assert np.abs(obs[e].cpu().numpy() - robs).max() < 1e-4
+            assert abs(float(reward[e]) - ro.route_reward) < 1e-3 * max(1.0, abs(ro.route_reward))
+            if ro.terminated or ro.base.truncated:
+                alive[e] = False
+    assert mism <= 0.03 * n
+
+
+def test_route_sequential_probe_matches_oracle():
+    from rl_brain_trainer_b200.policy import PolicyWeights
+    from rl_brain_trainer_b200.route import evaluate_sequential_route, synthetic_route
+
+    g, renv, _, route, params = _setup()
+    pol = PolicyWeights.preset("route_prefix120", "cuda")
+    res = evaluate_sequential_route(route, renv, pol, n_replicas=64, start_index=1, end_index=len(route) - 1, start_q_noise_std=0.0008, seed=1)
+    prefix, flags, errs, steps = ko.route_sequential_probe(params, ko.OracleRoute(g["route_q"]), oracle_policy("route_prefix120"), start_index=1,
+                                                           end_index=len(route) - 1)
+    bits = res["success_bits"][0].cpu().numpy().view(np.uint32)
+    got = np.array([(bits[k >> 5] >> (k & 31)) & 1 for k in range(len(flags))])
+    assert np.mean(got != flags) <= 0.08, (got, flags)
+    assert abs(res["replica0_longest_success_prefix"] - prefix) <= 2
+    assert int(res["prefix_histogram"].sum()) == 64
+    # a longer seeded synthetic route in the reference's dimensions runs end to end
+    big = synthetic_route(483, seed=7)
+    res = evaluate_sequential_route(big, renv, pol, n_replicas=256, start_index=1, end_index=170, start_q_noise_std=0.0008)
+    assert int(res["env_steps"].item()) >= 170 * 256 and res["longest_success_prefix"].shape == (256,)

@@ -512,6 +512,71 @@ int kin_route_probe(void *handle, const KinRouteTable *host_route, const KinPoli
                     int start_index, int end_index, int n, int *prefix, uint32_t *success_bits, unsigned long long *env_steps,
                     void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * PPO agent update (third-party arithmetic: stable-baselines3 2.8.0 PPO, call sites
+ * kinematic_phase1/train_workspace_expansion.py:189-232; restated in DESIGN.md section 3 "K3").
+ * All parameters live in ONE flat fp32 buffer in this order (sizes for in_dim = 56):
+ *   pi_w0[64*in] pi_b0[64] pi_w1[64*64] pi_b1[64] act_w[7*64] act_b[7]
+ *   vf_w0[64*in] vf_b0[64] vf_w1[64*64] vf_b1[64] val_w[64] val_b[1] log_std[7]          = 16150 floats
+ * ------------------------------------------------------------------------------------------- */
+#define KIN_PPO_TILE 64          /* samples per tile; minibatches are unions of tiles */
+#define KIN_PPO_STATS 8          /* per-minibatch statistics, see KIN_PPO_STAT_* */
+#define KIN_PPO_STAT_POLICY_LOSS 0
+#define KIN_PPO_STAT_VALUE_LOSS 1
+#define KIN_PPO_STAT_ENTROPY 2
+#define KIN_PPO_STAT_APPROX_KL 3
+#define KIN_PPO_STAT_CLIP_FRACTION 4
+#define KIN_PPO_STAT_GRAD_NORM 5
+#define KIN_PPO_STAT_SAMPLES 6
+
+typedef struct KinPpoHyper {
+    float gamma;
+    float gae_lambda;
+    float clip_range;
+    float ent_coef;
+    float vf_coef;
+    float max_grad_norm;
+    float learning_rate;
+    float adam_beta1;
+    float adam_beta2;
+    float adam_eps;
+    int normalize_advantage;
+    int pad0;
+} KinPpoHyper;
+
+int kin_ppo_param_count(int in_dim);
+
+/* Replaces: policy.forward(obs) during collect_rollouts (SB3 on_policy_algorithm.py): a = mean + exp(log_std) * eps,
+ * value, log_prob.  obs [n,56]; action [n,7] (unclipped sample, what SB3 stores); the env clips it itself.
+ * eps is Philox4x32(seed, env, step).  deterministic != 0 -> action = mean.                                       */
+int kin_policy_act(const KinPolicyWeights *host_weights, const float *obs, float *action, float *logp, float *value, int n,
+                   uint64_t seed, uint32_t step, int deterministic, void *stream);
+
+/* Replaces: the TimeLimit bootstrap of collect_rollouts: reward += gamma * V(terminal_obs) where the episode was
+ * truncated (not terminated).  terminal_obs [n,56], done [n] KIN_DONE_* bytes.                                    */
+int kin_ppo_bootstrap(const KinPolicyWeights *host_weights, const float *terminal_obs, const uint8_t *done, float *reward, float gamma,
+                      int n, void *stream);
+
+/* Replaces: RolloutBuffer.compute_returns_and_advantage (GAE).  reward/value/episode_start are [T][n] (episode_start u8),
+ * last_value [n], last_done [n] u8 (KIN_DONE_* bytes of the last step) -> advantage, returns [T][n];
+ * tile_sums (nullable) [T*n/64][2] doubles = (sum adv, sum adv^2) per 64-sample tile.                            */
+int kin_ppo_gae(const float *reward, const float *value, const uint8_t *episode_start, const float *last_value, const uint8_t *last_done,
+                float gamma, float gae_lambda, int T, int n, float *advantage, float *returns, double *tile_sums, void *stream);
+
+/* One PPO minibatch gradient (SB3 ppo.py train(): clipped surrogate + vf_coef * MSE + ent_coef * entropy term, advantages
+ * normalised per minibatch).  The minibatch is the union of the 64-sample tiles tile_ids[0..n_tiles); sample s of tile j is
+ * row tile_ids[j]*64 + s of obs [S,56] / action [S,7] / old_logp / advantage / returns.  global_batch = samples in the
+ * whole (all-rank) minibatch.  grad [P] receives the SUM over local samples of d(loss*global_batch)/dparam / global_batch,
+ * i.e. ranks all-reduce (sum) grad and stats afterwards.  partials: scratch [grid][P + KIN_PPO_STATS] floats.           */
+int kin_ppo_grad(const float *params, int in_dim, const KinPpoHyper *host_hyper, const float *obs, const float *action, const float *old_logp,
+                 const float *advantage, const float *returns, const double *tile_sums, const int *tile_ids, int n_tiles,
+                 long long global_batch, float *partials, int grid, float *grad, float *stats, void *stream);
+
+/* clip_grad_norm_(max_grad_norm) + Adam step on the flat parameter buffer (torch.optim.Adam semantics, eps = 1e-5 in SB3).
+ * adam_m / adam_v [P]; step = 1-based update count.                                                                    */
+int kin_ppo_adam(float *params, const float *grad, float *adam_m, float *adam_v, int n_params, const KinPpoHyper *host_hyper, int step,
+                 float *stats, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

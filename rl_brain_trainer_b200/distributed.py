@@ -1,0 +1,106 @@
+"""Multi-GPU plumbing: envs / episodes shard by index, collectives only where the path has a real exchange.
+
+* evaluation: no data-path collective; one all-reduce (sum) of a small statistics vector at the end.
+* training: one all-reduce (sum) of the flat gradient (+ the statistics) per minibatch; every rank then applies the
+  identical Adam step.  Curriculum promotion uses an all-reduced (successes, episodes) pair so all ranks switch stage together.
+
+All helpers take plain tensors and an optional process group, so they run under NCCL (one rank per GPU) and under gloo on
+CPU tensors (tests/test_distributed_gloo.py, world_size 2).
+"""
+
+from __future__ import annotations
+
+from typing import Any
+
+import torch
+import torch.distributed as dist
+
+
+def world(group: Any = None) -> tuple[int, int]:
+    """(rank, world_size); (0, 1) when torch.distributed is not initialised."""
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def shard_slice(n_total: int, rank: int, world_size: int) -> slice:
+    """Contiguous shard of ``n_total`` independent units (episodes, envs, route replicas) owned by ``rank``.
+
+    The first ``n_total % world_size`` ranks get one extra unit, so every unit is owned exactly once.
+    """
+    base, extra = divmod(int(n_total), int(world_size))
+    start = rank * base + min(rank, extra)
+    return slice(start, start + base + (1 if rank < extra else 0))
+
+
+def allreduce_sum_(t: torch.Tensor, group: Any = None) -> torch.Tensor:
+    """In-place sum over ranks (no-op for a single process)."""
+    if world(group)[1] > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t
+
+
+def allreduce_max_(t: torch.Tensor, group: Any = None) -> torch.Tensor:
+    if world(group)[1] > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return t
+
+
+def reduce_eval_stats(success: torch.Tensor, final_pos: torch.Tensor, final_ori: torch.Tensor, env_steps: torch.Tensor | int,
+                      group: Any = None) -> dict[str, float]:
+    """Success rate / mean errors / env-steps over all ranks from per-rank episode rows (one small all-reduce)."""
+    v = torch.stack([success.double().sum(), torch.as_tensor(float(success.numel()), dtype=torch.float64, device=success.device),
+                     final_pos.double().sum(), final_ori.double().sum(),
+                     torch.as_tensor(env_steps, dtype=torch.float64, device=success.device).reshape(())])
+    allreduce_sum_(v, group)
+    n = max(float(v[1]), 1.0)
+    return {"episodes": float(v[1]), "success_rate": float(v[0]) / n, "mean_final_position_error": float(v[2]) / n,
+            "mean_final_orientation_error": float(v[3]) / n, "env_steps": float(v[4])}
+
+
+class CurriculumTracker:
+    """Windowed success-rate promotion (``PointCurriculumTracker`` / ``PointCurriculumCallback``, curriculum.py:104-154,
+    training/callbacks.py:54-92), fed with per-iteration (successes, episodes) counts that are summed over ranks first.
+
+    The reference keeps a deque of the last ``window_episodes`` episode outcomes; with tens of thousands of envs finishing
+    together the window is filled many times per iteration, so the rate of the latest batch of finished episodes is used
+    when that batch alone is at least a window long, otherwise batches are accumulated until it is.
+    """
+
+    def __init__(self, n_stages: int, success_rate_threshold: float, window_episodes: int, min_episodes_per_stage: int, stage_index: int = 0) -> None:
+        self.n_stages, self.threshold = int(n_stages), float(success_rate_threshold)
+        self.window, self.min_episodes = int(window_episodes), int(min_episodes_per_stage)
+        self.stage_index = int(stage_index)
+        self.stage_episode_count = 0
+        self._succ = 0.0
+        self._eps = 0.0
+        self.history: list[dict[str, float | int]] = []
+
+    def record(self, successes: torch.Tensor | float, episodes: torch.Tensor | float, group: Any = None) -> bool:
+        v = torch.as_tensor([float(successes), float(episodes)], dtype=torch.float64)
+        if world(group)[1] > 1:
+            dev = successes.device if isinstance(successes, torch.Tensor) else None
+            backend = dist.get_backend(group)
+            v = v.to(dev) if (backend == "nccl" and dev is not None) else v
+            allreduce_sum_(v, group)
+        s, e = float(v[0]), float(v[1])
+        if e <= 0:
+            return False
+        if e >= self.window:
+            self._succ, self._eps = s, e
+        else:
+            self._succ += s
+            self._eps += e
+        self.stage_episode_count += int(e)
+        if self.stage_index >= self.n_stages - 1 or self.stage_episode_count < self.min_episodes or self._eps < self.window:
+            return False
+        rate = self._succ / self._eps
+        if rate < self.threshold:
+            if self._eps >= 4 * self.window:
+                self._succ, self._eps = 0.0, 0.0
+            return False
+        self.history.append({"from_stage_index": self.stage_index, "to_stage_index": self.stage_index + 1, "trigger_success_rate": rate})
+        self.stage_index += 1
+        self.stage_episode_count = 0
+        self._succ, self._eps = 0.0, 0.0
+        return True

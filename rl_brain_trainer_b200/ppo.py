@@ -1,0 +1,276 @@
+"""PPO training of the Approach / Finisher policies on the GPU env (rollout collection + agent update + grad all-reduce).
+
+Replaces ``model.learn`` of the reference's trainers (``kinematic_phase1/train_workspace_expansion.py:144-270``), whose
+arithmetic is stable-baselines3 2.8.0 PPO (third-party, absent from the reference tree; restated in ``csrc/kin_ppo.cu`` and
+checked against a PyTorch autograd restatement in ``tests/test_gpu_ppo.py``).  Differences that are deliberate and
+documented in DESIGN.md: minibatches are random unions of 64-sample tiles (64 consecutive envs of one time step) instead
+of a per-sample permutation, and with several ranks the advantage normalisation is per rank-local minibatch.
+"""
+
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Any
+
+import numpy as np
+import torch
+
+from . import _lib
+from .config import Phase1EnvConfig
+from .distributed import CurriculumTracker, allreduce_sum_, world
+from .env import BatchedArmKinematicEnv, _D
+from .policy import KEYS, PolicyWeights
+
+PARAM_ORDER = ("pi_w0", "pi_b0", "pi_w1", "pi_b1", "act_w", "act_b", "vf_w0", "vf_b0", "vf_w1", "vf_b1", "val_w", "val_b", "log_std")
+
+
+@dataclass
+class PPOHyper:
+    """SB3 PPO hyper-parameters (defaults of ``configs/ppo_default.yaml`` + SB3's own)."""
+
+    learning_rate: float = 3e-4
+    n_steps: int = 128
+    batch_size: int = 256
+    n_epochs: int = 10
+    gamma: float = 0.99
+    gae_lambda: float = 0.95
+    clip_range: float = 0.2
+    ent_coef: float = 0.0
+    vf_coef: float = 0.5
+    max_grad_norm: float = 0.5
+    normalize_advantage: bool = True
+    adam_beta1: float = 0.9
+    adam_beta2: float = 0.999
+    adam_eps: float = 1e-5
+
+    @classmethod
+    def from_config(cls, cfg: dict[str, Any]) -> "PPOHyper":
+        """``algorithms.ppo`` section of a reference YAML."""
+        known = {k: cfg[k] for k in cls.__dataclass_fields__ if k in cfg}
+        return cls(**known)
+
+    def c(self):
+        h = _lib.c_struct("KinPpoHyper")()
+        for f in ("gamma", "gae_lambda", "clip_range", "ent_coef", "vf_coef", "max_grad_norm", "learning_rate", "adam_beta1", "adam_beta2", "adam_eps"):
+            setattr(h, f, float(getattr(self, f)))
+        h.normalize_advantage = int(self.normalize_advantage)
+        return h
+
+
+def flatten_policy_(policy: PolicyWeights) -> torch.Tensor:
+    """Move every parameter of ``policy`` into ONE flat fp32 buffer (``PARAM_ORDER``) and re-point its tensors at views of it."""
+    if not policy.has_value or "log_std" not in policy.tensors:
+        raise ValueError("training needs actor, critic and log_std")
+    sizes = [policy.tensors[k].numel() for k in PARAM_ORDER]
+    flat = torch.empty(sum(sizes), dtype=torch.float32, device=policy.device)
+    off = 0
+    for k, n in zip(PARAM_ORDER, sizes):
+        view = flat[off:off + n].view_as(policy.tensors[k])
+        view.copy_(policy.tensors[k])
+        policy.tensors[k] = view
+        off += n
+    policy._c = None   # rebuild the C view with the new pointers
+    expect = _lib.lib().kin_ppo_param_count(policy.in_dim)
+    if expect != flat.numel():
+        raise RuntimeError(f"flat parameter count {flat.numel()} != library layout {expect}")
+    return flat
+
+
+def random_policy(in_dim: int = 56, *, seed: int = 0, log_std_init: float = 0.0, device: str | torch.device = "cuda") -> PolicyWeights:
+    """Fresh ``MultiInputPolicy``-shaped weights (orthogonal init with SB3's gains: sqrt(2) hidden, 0.01 action, 1 value)."""
+    g = torch.Generator().manual_seed(seed)
+
+    def ortho(rows: int, cols: int, gain: float) -> torch.Tensor:
+        a = torch.randn(max(rows, cols), min(rows, cols), generator=g)
+        q, r = torch.linalg.qr(a)
+        q = q * torch.sign(torch.diagonal(r))
+        q = q.t() if rows < cols else q
+        return (gain * q[:rows, :cols]).contiguous()
+
+    sd = {}
+    for net, out_key, out_dim, gain in (("policy_net", "action_net", 7, 0.01), ("value_net", "value_net", 1, 1.0)):
+        sd[f"mlp_extractor.{net}.0.weight"] = ortho(64, in_dim, 2 ** 0.5)
+        sd[f"mlp_extractor.{net}.0.bias"] = torch.zeros(64)
+        sd[f"mlp_extractor.{net}.2.weight"] = ortho(64, 64, 2 ** 0.5)
+        sd[f"mlp_extractor.{net}.2.bias"] = torch.zeros(64)
+        sd[f"{out_key}.weight"] = ortho(out_dim, 64, gain)
+        sd[f"{out_key}.bias"] = torch.zeros(out_dim)
+    sd["log_std"] = torch.full((7,), float(log_std_init))
+    return PolicyWeights({k: v.numpy() for k, v in sd.items()}, device)
+
+
+class PPOTrainer:
+    """Batched on-device PPO: ``collect()`` fills the rollout buffer, ``update()`` runs the epochs, ``learn()`` loops."""
+
+    def __init__(self, config: Phase1EnvConfig, policy: PolicyWeights, *, num_envs: int, hyper: PPOHyper, device: str | torch.device = "cuda",
+                 seed: int = 0, stage_index: int = 0, process_group: Any = None, grad_ctas: int | None = None) -> None:
+        if not torch.cuda.is_available():
+            raise _lib.KinError("PPOTrainer needs a CUDA device; there is no CPU fallback")
+        if policy.in_dim != 56:
+            raise _lib.KinError("the on-device PPO update is built for the 56-input policies (the 80-input route policy is next)")
+        tile = _D("KIN_PPO_TILE")
+        if num_envs % tile:
+            raise ValueError(f"num_envs must be a multiple of {tile}")
+        self.device = torch.device(device)
+        self.group = process_group
+        self.rank, self.world = world(process_group)
+        self.cfg, self.hp, self.policy = config, hyper, policy
+        self.N, self.T = int(num_envs), int(hyper.n_steps)
+        self.S = self.N * self.T
+        self.local_batch = int(hyper.batch_size)
+        if self.local_batch % tile or self.S % self.local_batch:
+            raise ValueError("batch_size must be a multiple of 64 and divide num_envs * n_steps (per rank)")
+        self._L = _lib.lib()
+        self.seed = int(seed) + 7919 * self.rank
+        with torch.cuda.device(self.device):
+            self.params = flatten_policy_(policy)
+            self.P = self.params.numel()
+            self.adam_m = torch.zeros_like(self.params)
+            self.adam_v = torch.zeros_like(self.params)
+            self.grad = torch.zeros_like(self.params)
+            self.stats = torch.zeros(_D("KIN_PPO_STATS"), dtype=torch.float32, device=self.device)
+            props = torch.cuda.get_device_properties(self.device)
+            self.grad_ctas = int(grad_ctas or props.multi_processor_count)
+            self.partials = torch.zeros((self.grad_ctas, self.P + _D("KIN_PPO_STATS") + 8), dtype=torch.float32, device=self.device)
+            self.env = BatchedArmKinematicEnv(config, self.N, self.device, auto_reset=True, seed=self.seed, host_sampler=False, with_aux=False)
+            self.env.set_curriculum_stage(stage_index)
+            f32 = dict(dtype=torch.float32, device=self.device)
+            self.obs_buf = torch.zeros((self.T + 1, self.N, 56), **f32)
+            self.act_buf = torch.zeros((self.T, self.N, 7), **f32)
+            self.logp_buf = torch.zeros((self.T, self.N), **f32)
+            self.val_buf = torch.zeros((self.T, self.N), **f32)
+            self.rew_buf = torch.zeros((self.T, self.N), **f32)
+            self.done_buf = torch.zeros((self.T, self.N), dtype=torch.uint8, device=self.device)
+            self.start_buf = torch.zeros((self.T, self.N), dtype=torch.uint8, device=self.device)
+            self.adv_buf = torch.zeros((self.T, self.N), **f32)
+            self.ret_buf = torch.zeros((self.T, self.N), **f32)
+            self.last_val = torch.zeros(self.N, **f32)
+            self.tile_sums = torch.zeros((self.S // tile, 2), dtype=torch.float64, device=self.device)
+            self._gen = torch.Generator(device=self.device)
+            self._gen.manual_seed(self.seed)
+            self.env.reset()
+            self.obs_buf[0].copy_(self.env.obs)
+        self._next_start = torch.ones(self.N, dtype=torch.uint8, device=self.device)
+        self.num_timesteps = 0
+        self.update_count = 0
+        self.global_step = 0
+        cur = config.curriculum_config
+        self.curriculum = CurriculumTracker(len(cur.stages), cur.success_rate_threshold, cur.window_episodes, cur.min_episodes_per_stage,
+                                            stage_index) if cur.enabled else None
+        self.last_rollout: dict[str, float] = {}
+
+    # ------------------------------------------------------------------ rollout
+    def collect(self) -> dict[str, float]:
+        """``collect_rollouts``: T steps of (sample action, env step with auto-reset, TimeLimit bootstrap), then GAE."""
+        L, env, hp = self._L, self.env, self.hp
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        w = ctypes.byref(self.policy.c)
+        done_bits = _D("KIN_DONE_TERMINATED") | _D("KIN_DONE_TRUNCATED")
+        with torch.cuda.device(self.device):
+            for t in range(self.T):
+                env.obs = self.obs_buf[t + 1]      # the step kernel writes the next observation straight into the buffer
+                env.reward = self.rew_buf[t]
+                env.done = self.done_buf[t]
+                self.start_buf[t].copy_(self._next_start)
+                _lib.check(L.kin_policy_act(w, self.obs_buf[t].data_ptr(), self.act_buf[t].data_ptr(), self.logp_buf[t].data_ptr(),
+                                            self.val_buf[t].data_ptr(), self.N, self.seed, self.global_step, 0, stream))
+                env.step_raw(self.act_buf[t])
+                _lib.check(L.kin_ppo_bootstrap(w, env.terminal_obs.data_ptr(), self.done_buf[t].data_ptr(), self.rew_buf[t].data_ptr(),
+                                               float(hp.gamma), self.N, stream))
+                self._next_start = ((self.done_buf[t] & done_bits) != 0).to(torch.uint8)
+                self.global_step += 1
+            _lib.check(L.kin_policy_act(w, self.obs_buf[self.T].data_ptr(), self._scratch_act().data_ptr(),
+                                        self._scratch_logp().data_ptr(), self.last_val.data_ptr(), self.N, self.seed, self.global_step, 1, stream))
+            _lib.check(L.kin_ppo_gae(self.rew_buf.data_ptr(), self.val_buf.data_ptr(), self.start_buf.data_ptr(), self.last_val.data_ptr(),
+                                     self.done_buf[self.T - 1].data_ptr(), float(hp.gamma), float(hp.gae_lambda), self.T, self.N,
+                                     self.adv_buf.data_ptr(), self.ret_buf.data_ptr(), self.tile_sums.data_ptr(), stream))
+            self.obs_buf[0].copy_(self.obs_buf[self.T])
+        self.num_timesteps += self.S * self.world
+        finished = (self.done_buf & done_bits) != 0
+        succ = ((self.done_buf & _D("KIN_DONE_SUCCESS")) != 0) & finished
+        self.last_rollout = {"episodes": float(finished.sum()), "successes": float(succ.sum()), "mean_reward": float(self.rew_buf.mean())}
+        return self.last_rollout
+
+    def _scratch_act(self) -> torch.Tensor:
+        if not hasattr(self, "_sa"):
+            self._sa = torch.zeros((self.N, 7), dtype=torch.float32, device=self.device)
+            self._sl = torch.zeros(self.N, dtype=torch.float32, device=self.device)
+        return self._sa
+
+    def _scratch_logp(self) -> torch.Tensor:
+        self._scratch_act()
+        return self._sl
+
+    # ------------------------------------------------------------------ update
+    def minibatch_grad(self, tile_ids: torch.Tensor) -> None:
+        """Gradient of one minibatch (sum over local samples, already divided by the GLOBAL minibatch size) into ``self.grad``."""
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        hp = self.hp.c()
+        n_tiles = int(tile_ids.numel())
+        global_batch = n_tiles * _D("KIN_PPO_TILE") * self.world
+        _lib.check(self._L.kin_ppo_grad(self.params.data_ptr(), 56, ctypes.byref(hp), self.obs_buf.data_ptr(), self.act_buf.data_ptr(),
+                                        self.logp_buf.data_ptr(), self.adv_buf.data_ptr(), self.ret_buf.data_ptr(), self.tile_sums.data_ptr(),
+                                        tile_ids.data_ptr(), n_tiles, global_batch, self.partials.data_ptr(), self.grad_ctas,
+                                        self.grad.data_ptr(), self.stats.data_ptr(), stream))
+
+    def apply_update(self) -> None:
+        """All-reduce the gradient (sum over ranks), clip by global norm, Adam step -- identical on every rank."""
+        if self.world > 1:
+            allreduce_sum_(self.grad, self.group)
+            allreduce_sum_(self.stats[:5], self.group)
+        self.update_count += 1
+        hp = self.hp.c()
+        _lib.check(self._L.kin_ppo_adam(self.params.data_ptr(), self.grad.data_ptr(), self.adam_m.data_ptr(), self.adam_v.data_ptr(), self.P,
+                                        ctypes.byref(hp), self.update_count, self.stats.data_ptr(),
+                                        torch.cuda.current_stream(self.device).cuda_stream))
+
+    def update(self) -> dict[str, float]:
+        tile = _D("KIN_PPO_TILE")
+        n_tiles_total = self.S // tile
+        tiles_per_mb = self.local_batch // tile
+        agg = torch.zeros(_D("KIN_PPO_STATS"), dtype=torch.float64, device=self.device)
+        n_mb = 0
+        with torch.cuda.device(self.device):
+            for _ in range(self.hp.n_epochs):
+                perm = torch.randperm(n_tiles_total, generator=self._gen, device=self.device, dtype=torch.int64).to(torch.int32)
+                for start in range(0, n_tiles_total, tiles_per_mb):
+                    ids = perm[start:start + tiles_per_mb].contiguous()
+                    self.minibatch_grad(ids)
+                    self.apply_update()
+                    agg += self.stats.double()
+                    n_mb += 1
+        a = (agg / max(n_mb, 1)).cpu().numpy()
+        return {"policy_loss": float(a[0]), "value_loss": float(a[1]), "entropy": float(a[2]), "approx_kl": float(a[3]),
+                "clip_fraction": float(a[4]), "grad_norm": float(a[5]), "minibatches": n_mb}
+
+    def learn(self, iterations: int) -> list[dict[str, float]]:
+        log = []
+        for _ in range(int(iterations)):
+            r = self.collect()
+            u = self.update()
+            if self.curriculum is not None and self.curriculum.record(r["successes"], r["episodes"], self.group):
+                self.env.set_curriculum_stage(self.curriculum.stage_index)
+            log.append({**r, **u, "stage": float(self.env.get_curriculum_stage()), "timesteps": float(self.num_timesteps)})
+        return log
+
+    def state_dict(self) -> dict[str, torch.Tensor]:
+        """SB3 ``policy.pth`` key names, so a trained policy loads back into the reference (and vice versa)."""
+        return {KEYS[f]: t.detach().clone() for f, t in self.policy.tensors.items()}
+
+
+def numpy_gae(rewards: np.ndarray, values: np.ndarray, episode_starts: np.ndarray, last_values: np.ndarray, last_dones: np.ndarray,
+              gamma: float, gae_lambda: float) -> tuple[np.ndarray, np.ndarray]:
+    """Plain restatement of SB3 ``RolloutBuffer.compute_returns_and_advantage`` (host-side reference for tests)."""
+    T = rewards.shape[0]
+    adv = np.zeros_like(rewards, dtype=np.float64)
+    last = np.zeros(rewards.shape[1])
+    for step in reversed(range(T)):
+        if step == T - 1:
+            nnt, nv = 1.0 - last_dones.astype(np.float64), last_values.astype(np.float64)
+        else:
+            nnt, nv = 1.0 - episode_starts[step + 1].astype(np.float64), values[step + 1].astype(np.float64)
+        delta = rewards[step] + gamma * nv * nnt - values[step]
+        last = delta + gamma * gae_lambda * nnt * last
+        adv[step] = last
+    return adv, adv + values

@@ -1,0 +1,207 @@
+"""GPU tests of the PPO kernels against a PyTorch autograd restatement of stable-baselines3's formulas (test infrastructure)."""
+
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from ._util import env_config
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(seed=0, log_std=-0.5):
+    from rl_brain_trainer_b200 import ppo
+
+    pol = ppo.random_policy(56, seed=seed, log_std_init=log_std, device="cuda")
+    # make the action head non-trivial (SB3's 0.01 gain would hide errors in the actor gradient)
+    pol.tensors["act_w"].mul_(30.0)
+    pol.tensors["pi_b0"].normal_(0, 0.1)
+    pol.tensors["vf_b1"].normal_(0, 0.1)
+    flat = ppo.flatten_policy_(pol)
+    return ppo, pol, flat
+
+
+def _torch_forward(pol, obs):
+    t = pol.tensors
+    lin = torch.nn.functional.linear
+    h = torch.tanh(lin(torch.tanh(lin(obs, t["pi_w0"], t["pi_b0"])), t["pi_w1"], t["pi_b1"]))
+    mean = lin(h, t["act_w"], t["act_b"])
+    hv = torch.tanh(lin(torch.tanh(lin(obs, t["vf_w0"], t["vf_b0"])), t["vf_w1"], t["vf_b1"]))
+    value = lin(hv, t["val_w"], t["val_b"])[:, 0]
+    return mean, value
+
+
+def test_policy_act_matches_gaussian_policy():
+    from rl_brain_trainer_b200 import _lib
+
+    ppo, pol, _ = _setup()
+    n = 5000
+    obs = (torch.rand((n, 56), device="cuda") * 2 - 1).contiguous()
+    act, logp, val = (torch.zeros((n, 7), device="cuda"), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda"))
+    L = _lib.lib()
+    s = torch.cuda.current_stream().cuda_stream
+    _lib.check(L.kin_policy_act(ctypes.byref(pol.c), obs.data_ptr(), act.data_ptr(), logp.data_ptr(), val.data_ptr(), n, 11, 3, 1, s))
+    mean, value = _torch_forward(pol, obs)
+    assert torch.allclose(act, mean, atol=3e-6) and torch.allclose(val, value, atol=3e-5)
+    _lib.check(L.kin_policy_act(ctypes.byref(pol.c), obs.data_ptr(), act.data_ptr(), logp.data_ptr(), val.data_ptr(), n, 11, 3, 0, s))
+    dist = torch.distributions.Normal(mean, pol.tensors["log_std"].exp())
+    assert torch.allclose(logp, dist.log_prob(act).sum(-1), atol=2e-4)
+    z = ((act - mean) / pol.tensors["log_std"].exp()).cpu().numpy()
+    assert abs(z.mean()) < 0.02 and abs(z.std() - 1.0) < 0.02 and abs(np.mean(z ** 3)) < 0.06      # standard normal draws
+    act2 = torch.zeros_like(act)
+    _lib.check(L.kin_policy_act(ctypes.byref(pol.c), obs.data_ptr(), act2.data_ptr(), logp.data_ptr(), val.data_ptr(), n, 11, 4, 0, s))
+    assert not torch.equal(act, act2)                                                                 # new step -> new noise
+
+
+def test_gae_matches_sb3_restatement():
+    from rl_brain_trainer_b200 import _lib, ppo
+
+    rng = np.random.default_rng(0)
+    T, n = 37, 192
+    rew, val = rng.normal(0, 1, (T, n)).astype(np.float32), rng.normal(0, 1, (T, n)).astype(np.float32)
+    starts = (rng.random((T, n)) < 0.1).astype(np.uint8)
+    last_val = rng.normal(0, 1, n).astype(np.float32)
+    last_done_flag = (rng.random(n) < 0.3)
+    last_done = np.where(last_done_flag, 2, 0).astype(np.uint8)   # KIN_DONE_TRUNCATED
+    d = lambda a: torch.as_tensor(a).cuda().contiguous()  # noqa: E731
+    adv, ret = torch.zeros((T, n), device="cuda"), torch.zeros((T, n), device="cuda")
+    sums = torch.zeros((T * n // 64, 2), dtype=torch.float64, device="cuda")
+    tr, tv, ts, tl, td = d(rew), d(val), d(starts), d(last_val), d(last_done)
+    _lib.check(_lib.lib().kin_ppo_gae(tr.data_ptr(), tv.data_ptr(), ts.data_ptr(), tl.data_ptr(), td.data_ptr(), 0.98, 0.95, T, n, adv.data_ptr(),
+                                      ret.data_ptr(), sums.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    ra, rr = ppo.numpy_gae(rew, val, starts, last_val, last_done_flag, 0.98, 0.95)
+    assert np.abs(adv.cpu().numpy() - ra).max() < 2e-5 and np.abs(ret.cpu().numpy() - rr).max() < 2e-5
+    flat = adv.reshape(-1, 64).double()
+    assert torch.allclose(sums[:, 0], flat.sum(1), atol=1e-9) and torch.allclose(sums[:, 1], (flat * flat).sum(1), atol=1e-9)
+
+
+def _torch_ppo_loss(pol, hp, obs, act, old_logp, adv, ret):
+    mean, value = _torch_forward(pol, obs)
+    dist = torch.distributions.Normal(mean, pol.tensors["log_std"].exp().expand_as(mean))
+    logp = dist.log_prob(act).sum(-1)
+    entropy = dist.entropy().sum(-1)
+    a = (adv - adv.mean()) / (adv.std() + 1e-8) if hp.normalize_advantage else adv
+    ratio = torch.exp(logp - old_logp)
+    pl = -torch.min(a * ratio, a * torch.clamp(ratio, 1 - hp.clip_range, 1 + hp.clip_range)).mean()
+    vl = torch.nn.functional.mse_loss(ret, value)
+    loss = pl + hp.ent_coef * (-entropy.mean()) + hp.vf_coef * vl
+    with torch.no_grad():
+        lr = logp - old_logp
+        stats = dict(policy_loss=float(pl), value_loss=float(vl), entropy=float(entropy.mean()), approx_kl=float(((torch.exp(lr) - 1) - lr).mean()),
+                     clip_fraction=float(((ratio - 1).abs() > hp.clip_range).float().mean()))
+    return loss, stats
+
+
+def test_minibatch_gradient_matches_autograd():
+    from rl_brain_trainer_b200 import _lib
+
+    ppo, pol, flat = _setup(seed=3)
+    hp = ppo.PPOHyper(clip_range=0.15, ent_coef=0.01, vf_coef=0.5, normalize_advantage=True)
+    S = 64 * 40
+    g = torch.Generator(device="cuda").manual_seed(1)
+    obs = (torch.rand((S, 56), device="cuda", generator=g) * 2 - 1).contiguous()
+    with torch.no_grad():
+        mean, value = _torch_forward(pol, obs)
+    act = (mean + pol.tensors["log_std"].exp() * torch.randn((S, 7), device="cuda", generator=g)).contiguous()
+    old_logp = (torch.distributions.Normal(mean, pol.tensors["log_std"].exp()).log_prob(act).sum(-1)
+                + 0.3 * torch.randn(S, device="cuda", generator=g)).contiguous()        # ratios well away from 1: clipping is exercised
+    adv = torch.randn(S, device="cuda", generator=g).contiguous()
+    ret = (value + torch.randn(S, device="cuda", generator=g)).contiguous()
+    sums = torch.stack([adv.reshape(-1, 64).double().sum(1), (adv.reshape(-1, 64).double() ** 2).sum(1)], dim=1).contiguous()
+    tile_ids = torch.tensor([3, 17, 0, 39, 8, 21, 22, 5, 30, 11, 12, 1], dtype=torch.int32, device="cuda")
+    P = flat.numel()
+    ctas = 5
+    partials = torch.zeros((ctas, P + 16), device="cuda")
+    grad, stats = torch.zeros(P, device="cuda"), torch.zeros(8, device="cuda")
+    c_hp = hp.c()
+    _lib.check(_lib.lib().kin_ppo_grad(flat.data_ptr(), 56, ctypes.byref(c_hp), obs.data_ptr(), act.data_ptr(), old_logp.data_ptr(), adv.data_ptr(),
+                                       ret.data_ptr(), sums.data_ptr(), tile_ids.data_ptr(), tile_ids.numel(), tile_ids.numel() * 64,
+                                       partials.data_ptr(), ctas, grad.data_ptr(), stats.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    idx = (tile_ids.long()[:, None] * 64 + torch.arange(64, device="cuda")[None]).reshape(-1)
+    for t in pol.tensors.values():
+        t.requires_grad_(True)
+    loss, ref_stats = _torch_ppo_loss(pol, hp, obs[idx], act[idx], old_logp[idx], adv[idx], ret[idx])
+    grads = torch.autograd.grad(loss, [pol.tensors[k] for k in ppo.PARAM_ORDER])
+    ref = torch.cat([gk.reshape(-1) for gk in grads])
+    off = 0
+    for k, gk in zip(ppo.PARAM_ORDER, grads):
+        n = gk.numel()
+        got = grad[off:off + n]
+        scale = float(gk.abs().max()) + 1e-12
+        assert float((got - gk.reshape(-1)).abs().max()) < 2e-4 * scale + 1e-7, (k, float((got - gk.reshape(-1)).abs().max()), scale)
+        off += n
+    assert float((grad - ref).norm() / ref.norm()) < 1e-4
+    got_stats = stats.cpu().numpy()
+    for i, key in enumerate(("policy_loss", "value_loss", "entropy", "approx_kl", "clip_fraction")):
+        assert abs(got_stats[i] - ref_stats[key]) < 2e-4 * max(1.0, abs(ref_stats[key])), key
+    assert ref_stats["clip_fraction"] > 0.2
+    for t in pol.tensors.values():
+        t.requires_grad_(False)
+
+
+def test_adam_matches_torch():
+    from rl_brain_trainer_b200 import _lib, ppo
+
+    P = 16143
+    g = torch.Generator(device="cuda").manual_seed(5)
+    params = torch.randn(P, device="cuda", generator=g)
+    ref_p = params.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref_p], lr=3e-4, eps=1e-5)
+    m, v, stats = torch.zeros(P, device="cuda"), torch.zeros(P, device="cuda"), torch.zeros(8, device="cuda")
+    hp = ppo.PPOHyper(learning_rate=3e-4, max_grad_norm=0.5)
+    c_hp = hp.c()
+    for step in range(1, 6):
+        grad = torch.randn(P, device="cuda", generator=g) * (0.001 if step % 2 else 0.1)   # below and above the clip norm
+        ref_p.grad = grad.clone()
+        norm = torch.nn.utils.clip_grad_norm_([ref_p], 0.5)
+        opt.step()
+        _lib.check(_lib.lib().kin_ppo_adam(params.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(), P, ctypes.byref(c_hp), step, stats.data_ptr(),
+                                           torch.cuda.current_stream().cuda_stream))
+        assert abs(float(stats[5]) - float(norm)) < 1e-4 * float(norm)
+        assert float((params - ref_p.detach()).abs().max()) < 2e-6
+
+
+def test_bootstrap_adds_discounted_terminal_value():
+    from rl_brain_trainer_b200 import _lib
+
+    ppo, pol, _ = _setup(seed=2)
+    n = 300
+    obs = (torch.rand((n, 56), device="cuda") * 2 - 1).contiguous()
+    done = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    done[5] = 2          # truncated
+    done[6] = 3          # terminated and truncated -> no bootstrap
+    done[200] = 2
+    rew = torch.ones(n, device="cuda")
+    _lib.check(_lib.lib().kin_ppo_bootstrap(ctypes.byref(pol.c), obs.data_ptr(), done.data_ptr(), rew.data_ptr(), 0.9, n, torch.cuda.current_stream().cuda_stream))
+    _, value = _torch_forward(pol, obs)
+    exp = torch.ones(n, device="cuda")
+    exp[5] += 0.9 * value[5]
+    exp[200] += 0.9 * value[200]
+    assert torch.allclose(rew, exp, atol=3e-5)
+
+
+def test_trainer_runs_and_improves_value_fit():
+    """A short on-device PPO run on the Stage-0 shell: finite statistics, parameters move, the critic's loss falls."""
+    from rl_brain_trainer_b200 import ppo
+
+    cfg = env_config("approach_dynamic_scale_big")
+    pol = ppo.random_policy(56, seed=1, log_std_init=-1.0, device="cuda")
+    hp = ppo.PPOHyper(learning_rate=1e-3, n_steps=32, batch_size=2048, n_epochs=4, gamma=0.98, clip_range=0.2)
+    tr = ppo.PPOTrainer(cfg, pol, num_envs=1024, hyper=hp, seed=3)
+    p0 = tr.params.clone()
+    log = tr.learn(4)
+    assert all(np.isfinite(list(row.values())).all() for row in log)
+    assert float((tr.params - p0).abs().max()) > 1e-4
+    assert log[-1]["value_loss"] < log[0]["value_loss"]
+    assert log[0]["minibatches"] == 4 * (1024 * 32 // 2048)
+    sd = tr.state_dict()
+    assert "mlp_extractor.policy_net.0.weight" in sd and sd["log_std"].shape == (7,)
+    # lr = 0 leaves the parameters untouched
+    tr2 = ppo.PPOTrainer(cfg, ppo.random_policy(56, seed=1, device="cuda"), num_envs=256, hyper=ppo.PPOHyper(learning_rate=0.0, n_steps=8, batch_size=512, n_epochs=1))
+    q0 = tr2.params.clone()
+    tr2.learn(1)
+    assert torch.equal(tr2.params, q0)

@@ -49,7 +49,7 @@ struct TcSmem {
     float bo[8];
     unsigned long long mbar[TC_TILES];
     unsigned tmem_base;
-    int run_flags[TC_TILES][4];
+    int run_flags[2][TC_TILES][4];   // double-buffered by step parity: written before, read after the layer-1 barrier
 };
 
 struct DevPolicyTc {
@@ -171,13 +171,18 @@ __device__ __forceinline__ void issue_layer(unsigned a_saddr, unsigned w_saddr, 
 struct TileCtx {
     float* A;
     unsigned a_saddr, w0_saddr, w1_saddr, wo_saddr, mbar_saddr, tmem_d, tmem_row;
-    int tile, row;
+    int tile, row, flag_buf;
     unsigned parity;
     bool issuer;
 };
 
-// obs[56] -> act[7]; collective over the tile's 128 threads
-__device__ __forceinline__ void mlp_tc(const TcSmem& S, TileCtx& c, const float* o, float* act) {
+// obs[56] -> act[7]; collective over the tile's 128 threads.  Returns false (without running the MLP) once no episode
+// of the tile is still running: the vote rides on the layer-1 barrier, flags double-buffered by step parity.
+__device__ __forceinline__ bool mlp_tc(TcSmem& S, TileCtx& c, const float* o, float* act, bool running) {
+    const int fb = c.flag_buf;
+    c.flag_buf ^= 1;
+    const unsigned any = __any_sync(0xffffffffu, running);
+    if ((threadIdx.x & 31) == 0) S.run_flags[fb][c.tile][(threadIdx.x >> 5) & 3] = (int)any;
     // ---- layer 1: A = [obs | 1 | 0...]
 #pragma unroll
     for (int k4 = 0; k4 < KIN_OBS_DIM / 4; ++k4) a_store4(c.A, c.row, k4, to_tf32(o[4 * k4]), to_tf32(o[4 * k4 + 1]), to_tf32(o[4 * k4 + 2]), to_tf32(o[4 * k4 + 3]));
@@ -186,6 +191,7 @@ __device__ __forceinline__ void mlp_tc(const TcSmem& S, TileCtx& c, const float*
     fence_async_smem();
     tc_fence_before();
     tile_barrier(c.tile);
+    if (!(S.run_flags[fb][c.tile][0] | S.run_flags[fb][c.tile][1] | S.run_flags[fb][c.tile][2] | S.run_flags[fb][c.tile][3])) return false;
     if (c.issuer) issue_layer(c.a_saddr, c.w0_saddr, CHUNK_FLOATS_W * 4, c.tmem_d, umma_idesc(TC_TILE, TC_HID), c.mbar_saddr);
     mbar_wait(c.mbar_saddr, c.parity);
     c.parity ^= 1u;
@@ -230,20 +236,11 @@ __device__ __forceinline__ void mlp_tc(const TcSmem& S, TileCtx& c, const float*
     tc_fence_before();
 #pragma unroll
     for (int i = 0; i < KIN_NJ; ++i) act[i] = clampf(a8[i] + S.bo[i], -1.0f, 1.0f);
+    return true;
 }
 
 __device__ __forceinline__ bool ready_pred_tc(float pos_thr, float ori_thr, float a_thr, float dq_thr, float pos, float ori, float an, float dqn) {
     return pos_thr > 0.0f && ori_thr > 0.0f && pos <= pos_thr && ori <= ori_thr && (a_thr <= 0.0f || an <= a_thr) && (dq_thr <= 0.0f || dqn <= dq_thr);
-}
-
-// does any episode of this tile still run?  (flags written before, read after the tile barrier inside mlp_tc's caller)
-__device__ __forceinline__ bool tile_any(TcSmem& S, const TileCtx& c, bool running) {
-    const unsigned any = __any_sync(0xffffffffu, running);
-    if ((threadIdx.x & 31) == 0) S.run_flags[c.tile][(threadIdx.x >> 5) & 3] = (int)any;
-    tile_barrier(c.tile);
-    const bool r = S.run_flags[c.tile][0] | S.run_flags[c.tile][1] | S.run_flags[c.tile][2] | S.run_flags[c.tile][3];
-    tile_barrier(c.tile);   // flags may be rewritten only after everyone has read them
-    return r;
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 2)
@@ -261,6 +258,7 @@ kin_rollout_tc_kernel(const __grid_constant__ KinEnvParams PA, const __grid_cons
     c.A = S.A[c.tile];
     c.issuer = c.row == 0;
     c.parity = 0u;
+    c.flag_buf = 0;
 
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)), "r"(TMEM_COLS) : "memory");
@@ -318,10 +316,13 @@ kin_rollout_tc_kernel(const __grid_constant__ KinEnvParams PA, const __grid_cons
     StepOut so;
     so.done = 0u; so.pos = s.entry[0]; so.ori = s.entry[1]; so.dq_l2 = 0.0f;
     bool running = active;
-    while (tile_any(S, c, running)) {
+    pose_error(s.ee, s.goal, so.pe, so.oe);
+#pragma unroll
+    for (int i = 0; i < NJ; ++i) so.margin[i] = joint_margin(PA, s.q[i], i);
+    while (true) {
         float o[OBS], act[NJ];
-        build_obs(PA, s, KIN_MODE_APPROACH, o);
-        mlp_tc(S, c, o, act);
+        build_obs_from(PA, s, KIN_MODE_APPROACH, so.pe, so.oe, so.margin, o);
+        if (!mlp_tc(S, c, o, act, running)) break;
         if (running) {
             float an2 = 0.0f;
 #pragma unroll
@@ -382,10 +383,13 @@ kin_rollout_tc_kernel(const __grid_constant__ KinEnvParams PA, const __grid_cons
             reset_core(PF, s, KIN_MODE_DOCK, r_iq, r_idq, r_ipa, goal_q, r_gp, gq_out);
         }
         steps = 0;
-        while (tile_any(S, c, running)) {
+        pose_error(s.ee, s.goal, so.pe, so.oe);
+#pragma unroll
+        for (int i = 0; i < NJ; ++i) so.margin[i] = joint_margin(PF, s.q[i], i);
+        while (true) {
             float o[OBS], act[NJ];
-            build_obs(PF, s, KIN_MODE_DOCK, o);
-            mlp_tc(S, c, o, act);
+            build_obs_from(PF, s, KIN_MODE_DOCK, so.pe, so.oe, so.margin, o);
+            if (!mlp_tc(S, c, o, act, running)) break;
             if (running) {
                 float an2 = 0.0f;
 #pragma unroll

@@ -135,6 +135,58 @@ class ApproachFinisherRollout:
     def evaluate_suite(self, suite: EvalSuite) -> RolloutResult:
         return self.run(self.upload(suite))
 
+    def evaluate_stream(self, host_inputs: list[dict[str, torch.Tensor | None]], host_results: list[torch.Tensor]) -> list[torch.Tensor]:
+        """Evaluate a sequence of suites held in PINNED host memory, results into pinned host tensors, copies overlapped.
+
+        Three streams, two device slots: the H2D copy of suite k+1 and the D2H copy of result k-1 run while the rollout
+        kernel of suite k computes.  ``host_inputs[k]`` maps ``initial_q / goal_q / ...`` to pinned ``[n,7|6]`` float32
+        tensors (or None); ``host_results[k]`` is a pinned int32 ``[KIN_RES_ROWS, stride]`` tensor.  Returns per-suite
+        device ``env_steps`` counters; the caller synchronises (e.g. ``torch.cuda.synchronize``) before reading results.
+        """
+        dev = self.device
+        if not hasattr(self, "_streams"):
+            self._streams = [torch.cuda.Stream(dev) for _ in range(3)]
+        s_in, s_run, s_out = self._streams
+        cur = torch.cuda.current_stream(dev)
+        for st in self._streams:
+            st.wait_stream(cur)
+        n = int(host_inputs[0]["initial_q"].shape[0])
+        stride = (n + 31) // 32 * 32
+        slots = []
+        for _ in range(2):
+            d_in = {k: (None if v is None else torch.empty(v.shape, dtype=torch.float32, device=dev)) for k, v in host_inputs[0].items()}
+            res = RolloutResult(raw=torch.zeros((_D("KIN_RES_ROWS"), stride), dtype=torch.int32, device=dev), n=n,
+                                env_steps=torch.zeros(1, dtype=torch.int64, device=dev))
+            slots.append({"in": d_in, "res": res, "free": None})
+        counters = []
+        for k, (h_in, h_out) in enumerate(zip(host_inputs, host_results)):
+            slot = slots[k % 2]
+            with torch.cuda.stream(s_in):
+                if slot["free"] is not None:
+                    s_in.wait_event(slot["free"])            # the previous user of this slot has been copied out
+                for key, v in h_in.items():
+                    if v is not None:
+                        slot["in"][key].copy_(v, non_blocking=True)
+                ev_in = torch.cuda.Event()
+                ev_in.record(s_in)
+            with torch.cuda.stream(s_run):
+                s_run.wait_event(ev_in)
+                slot["res"].env_steps.zero_()
+                self.run(slot["in"], out=slot["res"])
+                ev_run = torch.cuda.Event()
+                ev_run.record(s_run)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_run)
+                h_out.copy_(slot["res"].raw, non_blocking=True)
+                steps = slot["res"].env_steps.clone()
+                ev_out = torch.cuda.Event()
+                ev_out.record(s_out)
+            slot["free"] = ev_out
+            counters.append(steps)
+        for st in self._streams:
+            cur.wait_stream(st)
+        return counters
+
 
 # ----------------------------------------------------------------------------------------------
 # summaries

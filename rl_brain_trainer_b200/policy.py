@@ -66,6 +66,19 @@ class PolicyWeights:
     def save_npz(self, path: str | Path) -> None:
         np.savez_compressed(path, **{k: v.detach().cpu().numpy() for k, v in self.state_dict().items()})
 
+    def save_sb3_zip(self, path: str | Path, data: dict | None = None) -> None:
+        """Write an SB3-style ``model.zip`` (``policy.pth`` with the reference's key names + a ``data`` JSON), so the
+        reference's ``PPO.load`` / its evaluators can pick a policy trained here back up (``training/callbacks.py:17-29``)."""
+        import json
+
+        buf = io.BytesIO()
+        torch.save({k: v.detach().cpu() for k, v in self.state_dict().items()}, buf)
+        with zipfile.ZipFile(Path(path), "w") as z:
+            z.writestr("policy.pth", buf.getvalue())
+            z.writestr("data", json.dumps(data or {"policy_class": "MultiInputPolicy", "n_envs": 1}))
+            z.writestr("_stable_baselines3_version", "2.8.0")
+            z.writestr("system_info.txt", "written by rl_brain_trainer_b200")
+
     @classmethod
     def load(cls, path: str | Path, device: str | torch.device = "cuda") -> "PolicyWeights":
         path = Path(path)

@@ -244,14 +244,20 @@ class PPOTrainer:
         return {"policy_loss": float(a[0]), "value_loss": float(a[1]), "entropy": float(a[2]), "approx_kl": float(a[3]),
                 "clip_fraction": float(a[4]), "grad_norm": float(a[5]), "minibatches": n_mb}
 
-    def learn(self, iterations: int) -> list[dict[str, float]]:
+    def learn(self, iterations: int, gate: Any = None) -> list[dict[str, float]]:
+        """``model.learn``: iterations of collect + update; curriculum promotion; optional eval gate (``gate.EvalGate``)."""
         log = []
         for _ in range(int(iterations)):
             r = self.collect()
             u = self.update()
             if self.curriculum is not None and self.curriculum.record(r["successes"], r["episodes"], self.group):
                 self.env.set_curriculum_stage(self.curriculum.stage_index)
-            log.append({**r, **u, "stage": float(self.env.get_curriculum_stage()), "timesteps": float(self.num_timesteps)})
+            row = {**r, **u, "stage": float(self.env.get_curriculum_stage()), "timesteps": float(self.num_timesteps)}
+            if gate is not None:
+                rec = gate.maybe_eval(self.num_timesteps, self.policy)
+                if rec is not None:
+                    row["gate_score"] = float(rec["score"])
+            log.append(row)
         return log
 
     def state_dict(self) -> dict[str, torch.Tensor]:

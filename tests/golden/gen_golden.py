@@ -616,6 +616,30 @@ def gen_samplers(cfgs) -> None:
     assert ref_samplers is not None
 
 
+def gen_gate() -> None:
+    """Gate-score known answers from the reference's workspace_curriculum.py on seeded random stage metrics."""
+    from hrl_trainer.kinematic_phase1.workspace.workspace_curriculum import gate_config_from_dict, gated_score
+
+    rng = np.random.default_rng(12)
+    cases = []
+    gate_cfgs = [None, {"score_stage_index": 9, "retention_stage0_4_success": 0.95, "retention_stage5_success": 0.85, "promotion_stage_success": 0.55,
+                        "promotion_ready_rate": 0.62, "max_mean_position_error_m": 0.024, "max_mean_orientation_error_rad": 0.16},
+                 {"retention_stage_thresholds": [0.98, 0.98, 0.98, 0.95, 0.90, 0.90, 0.85, 0.75], "promotion_stage_success": 0.55, "promotion_ready_rate": 0.60}]
+    for i in range(24):
+        gc = gate_cfgs[i % 3]
+        n = int(rng.integers(6, 13))
+        hi = i % 4 == 0
+        metrics = {s: {"success_rate": float(np.clip(rng.normal(0.99 if hi else 0.9 - 0.05 * s, 0.02 if hi else 0.1), 0, 1)),
+                       "finisher_ready_hit_rate": float(np.clip(rng.normal(0.9 - 0.03 * s, 0.1), 0, 1)),
+                       "mean_final_position_error": float(abs(rng.normal(0.003 + 0.002 * s, 0.002))),
+                       "mean_final_orientation_error": float(abs(rng.normal(0.02 + 0.01 * s, 0.01)))} for s in range(n)}
+        cur = int(rng.integers(0, n))
+        out = gated_score(metrics, cur, gate_config_from_dict(gc))
+        cases.append({"gate_config": gc, "stage_metrics": {str(k): v for k, v in metrics.items()}, "current_stage": cur, "expected": out})
+    (GOLD / "gate_cases.json").write_text(json.dumps(cases, indent=1))
+    print("gate_cases.json", len(cases))
+
+
 def write_presets(cfgs, policies, hyper) -> None:
     PRESETS.mkdir(parents=True, exist_ok=True)
     (PRESETS / "policies").mkdir(exist_ok=True)
@@ -633,6 +657,7 @@ def main() -> None:
     cfgs = merged_configs()
     write_presets(cfgs, policies, hyper)
     gen_fk()
+    gen_gate()
     gen_traces(cfgs, policies)
     gen_samplers(cfgs)
     gen_route(cfgs, policies)

@@ -205,3 +205,42 @@ def test_trainer_runs_and_improves_value_fit():
     q0 = tr2.params.clone()
     tr2.learn(1)
     assert torch.equal(tr2.params, q0)
+
+
+def test_gate_eval_and_finetune_retention():
+    """Multi-stage gate evaluation in one launch; a short fine-tune at the reference's learning rate keeps the gate's retention
+    (the acceptance SURVEY 8c asks for: a policy touched by the new trainer still passes when evaluated by the ORACLE env)."""
+    from oracle import kin_oracle as ko
+    from rl_brain_trainer_b200 import gate, ppo
+    from rl_brain_trainer_b200.policy import PolicyWeights
+    from rl_brain_trainer_b200.samplers import build_curriculum_local_eval_suite
+
+    from ._util import oracle_params
+
+    acfg, fcfg = env_config("approach_dynamic_scale_big"), env_config("finisher_noop_ft")
+    pol, fin = PolicyWeights.preset("approach_stage8_11", "cuda"), PolicyWeights.preset("finisher", "cuda")
+    gate_cfg = {"score_stage_index": 9, "retention_stage0_4_success": 0.95, "retention_stage5_success": 0.85, "promotion_stage_success": 0.55,
+                "promotion_ready_rate": 0.62, "max_mean_position_error_m": 0.024, "max_mean_orientation_error_rad": 0.16}
+    before = gate.evaluate_workspace_expansion(acfg, pol, fcfg, fin, episodes=256, seed=720001, gate_config=gate_cfg)
+    m = before["stage_metrics"]
+    assert set(m) == set(range(12)) and all(m[s]["episode_count"] == 256 for s in m)
+    assert m[0]["success_rate"] > 0.98 and m[5]["success_rate"] > 0.9 and m[11]["success_rate"] < m[5]["success_rate"]
+    assert before["best_model_selection"]["retention_ok"]
+    assert 12 * 256 * 128 <= before["env_steps"] <= 12 * 256 * 164      # episodes without a handoff skip the 36 finisher steps
+    hp = ppo.PPOHyper(learning_rate=4e-6, n_steps=128, batch_size=8192, n_epochs=2, gamma=0.995, clip_range=0.1, ent_coef=0.0003)
+    tr = ppo.PPOTrainer(acfg, pol, num_envs=1024, hyper=hp, seed=5, stage_index=8)
+    g = gate.EvalGate(acfg, fcfg, fin, eval_interval=1024 * 128, episodes=128, seed=720001, stage_indices=list(range(12)), gate_config=gate_cfg)
+    log = tr.learn(2, gate=g)
+    assert len(g.history) == 2 and "gate_score" in log[-1] and g.best_state is not None
+    after = gate.evaluate_workspace_expansion(acfg, pol, fcfg, fin, episodes=256, seed=720001, gate_config=gate_cfg)
+    assert after["best_model_selection"]["retention_ok"]
+    assert abs(after["stage_metrics"][5]["success_rate"] - m[5]["success_rate"]) < 0.05
+    # the fine-tuned weights, evaluated by the CPU oracle env on Stage 5
+    suite = build_curriculum_local_eval_suite(acfg, seed=720001 + 5 * 1009, stage_index=5, n_episodes=256)
+    w = {k: v.detach().cpu().numpy() for k, v in tr.state_dict().items()}
+    fw = {k: v.detach().cpu().numpy() for k, v in fin.state_dict().items()}
+    ref, _ = ko.eval_approach_finisher(oracle_params(acfg), oracle_params(fcfg), ko.OracleMlp(w), ko.OracleMlp(fw),
+                                       initial_q=suite.initial_q.astype(np.float32).astype(float), goal_q=suite.goal_q.astype(np.float32).astype(float),
+                                       n_threads=8)
+    assert ref["success"].mean() >= 0.85
+    assert abs(ref["success"].mean() - after["stage_metrics"][5]["success_rate"]) < 0.03

@@ -572,6 +572,16 @@ int kin_ppo_grad(const float *params, int in_dim, const KinPpoHyper *host_hyper,
                  const float *advantage, const float *returns, const double *tile_sums, const int *tile_ids, int n_tiles,
                  long long global_batch, float *partials, int grid, float *grad, float *stats, void *stream);
 
+/* Tensor-core variant of kin_ppo_grad: the same minibatch gradient with every GEMM (forward, data gradients and the
+ * sample-reduction weight-gradient GEMMs) on tcgen05.mma kind::f16 (bf16 operands, fp32 accumulation in TMEM).
+ * n_tiles must be even (two 64-sample tiles form one 128-row GEMM tile).  partials: scratch [grid][P + 16] floats.
+ * logp_out / value_out (nullable, [S]) receive this variant's own log-prob / value of every visited sample; with
+ * forward_only != 0 nothing else is computed (used to refresh old_logp with the same arithmetic the update uses). */
+int kin_ppo_grad_tc(const float *params, int in_dim, const KinPpoHyper *host_hyper, const float *obs, const float *action, const float *old_logp,
+                    const float *advantage, const float *returns, const double *tile_sums, const int *tile_ids, int n_tiles,
+                    long long global_batch, float *partials, int grid, float *grad, float *stats, float *logp_out, float *value_out,
+                    int forward_only, void *stream);
+
 /* clip_grad_norm_(max_grad_norm) + Adam step on the flat parameter buffer (torch.optim.Adam semantics, eps = 1e-5 in SB3).
  * adam_m / adam_v [P]; step = 1-based update count.                                                                    */
 int kin_ppo_adam(float *params, const float *grad, float *adam_m, float *adam_v, int n_params, const KinPpoHyper *host_hyper, int step,

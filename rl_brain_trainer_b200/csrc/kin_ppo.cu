@@ -18,6 +18,7 @@
 // register-tiled shared-memory SGEMMs.  The tcgen05 variant of the update is the next step.
 #include "kin_internal.h"
 #include "kin_mlp.cuh"
+#include "kin_ppo_layout.cuh"
 #include "kin_state.cuh"
 
 namespace kin {
@@ -26,29 +27,6 @@ constexpr int PPO_THREADS = 256;
 constexpr int TS = KIN_PPO_TILE;      // 64 samples per tile
 constexpr int HS = 132;               // row stride of the [TS][128] activation tiles (16-byte aligned rows)
 constexpr float kHalfLog2Pi = 0.91893853320467274178f;
-
-struct PpoOffsets {
-    int pi_w0, pi_b0, pi_w1, pi_b1, act_w, act_b, vf_w0, vf_b0, vf_w1, vf_b1, val_w, val_b, log_std, total;
-};
-__host__ __device__ inline PpoOffsets ppo_offsets(int in_dim) {
-    PpoOffsets o;
-    int p = 0;
-    o.pi_w0 = p; p += 64 * in_dim;
-    o.pi_b0 = p; p += 64;
-    o.pi_w1 = p; p += 4096;
-    o.pi_b1 = p; p += 64;
-    o.act_w = p; p += 7 * 64;
-    o.act_b = p; p += 7;
-    o.vf_w0 = p; p += 64 * in_dim;
-    o.vf_b0 = p; p += 64;
-    o.vf_w1 = p; p += 4096;
-    o.vf_b1 = p; p += 64;
-    o.val_w = p; p += 64;
-    o.val_b = p; p += 1;
-    o.log_std = p; p += 7;
-    o.total = p;
-    return o;
-}
 
 // ---------------------------------------------------------------------------------------------------------
 // rollout-side kernels
@@ -611,6 +589,11 @@ kin_ppo_adam_kernel(float* __restrict__ params, const float* __restrict__ grad, 
     }
 }
 
+int kin_ppo_reduce_launch(const float* partials, int n_cta, int P, float* grad, float* stats, float inv_global_batch, cudaStream_t st) {
+    kin_ppo_reduce_kernel<<<(P + 5 + 255) / 256, 256, 0, st>>>(partials, n_cta, P, grad, stats, inv_global_batch);
+    return KIN_OK;
+}
+
 static ActW actor_w(const KinPolicyWeights* w) { return ActW{w->pi_w0, w->pi_b0, w->pi_w1, w->pi_b1, w->act_w, w->act_b}; }
 static ActW critic_w(const KinPolicyWeights* w) { return ActW{w->vf_w0, w->vf_b0, w->vf_w1, w->vf_b1, w->val_w, w->val_b}; }
 
@@ -684,7 +667,7 @@ extern "C" int kin_ppo_grad(const float* params, int in_dim, const KinPpoHyper* 
     const int g = grid < n_tiles ? grid : n_tiles;
     const float inv = 1.0f / (float)global_batch;
     kin_ppo_grad_kernel<56><<<g, PPO_THREADS, smem, st>>>(params, *hp, obs, action, old_logp, advantage, returns, tile_sums, tile_ids, n_tiles, inv, partials);
-    kin_ppo_reduce_kernel<<<(P + 5 + 255) / 256, 256, 0, st>>>(partials, g, P, grad, stats, inv);
+    kin_ppo_reduce_launch(partials, g, P, grad, stats, inv, st);
     e = cudaGetLastError();
     return e == cudaSuccess ? KIN_OK : kin_fail_cuda(e, "kin_ppo_grad");
 }

@@ -104,7 +104,8 @@ class PPOTrainer:
     """Batched on-device PPO: ``collect()`` fills the rollout buffer, ``update()`` runs the epochs, ``learn()`` loops."""
 
     def __init__(self, config: Phase1EnvConfig, policy: PolicyWeights, *, num_envs: int, hyper: PPOHyper, device: str | torch.device = "cuda",
-                 seed: int = 0, stage_index: int = 0, process_group: Any = None, grad_ctas: int | None = None) -> None:
+                 seed: int = 0, stage_index: int = 0, process_group: Any = None, grad_ctas: int | None = None,
+                 update_variant: str = "tc") -> None:
         if not torch.cuda.is_available():
             raise _lib.KinError("PPOTrainer needs a CUDA device; there is no CPU fallback")
         if policy.in_dim != 56:
@@ -112,6 +113,9 @@ class PPOTrainer:
         tile = _D("KIN_PPO_TILE")
         if num_envs % tile:
             raise ValueError(f"num_envs must be a multiple of {tile}")
+        if update_variant not in ("tc", "fp32"):
+            raise ValueError("update_variant must be 'tc' (tcgen05 bf16 GEMMs, fp32 accumulate) or 'fp32' (strict FP32-pipe kernel)")
+        self.update_variant = update_variant
         self.device = torch.device(device)
         self.group = process_group
         self.rank, self.world = world(process_group)
@@ -121,6 +125,8 @@ class PPOTrainer:
         self.local_batch = int(hyper.batch_size)
         if self.local_batch % tile or self.S % self.local_batch:
             raise ValueError("batch_size must be a multiple of 64 and divide num_envs * n_steps (per rank)")
+        if update_variant == "tc" and (self.local_batch % (2 * tile) or self.S % (2 * tile)):
+            raise ValueError("the tensor-core update pairs 64-sample tiles: batch_size and num_envs * n_steps must be multiples of 128")
         self._L = _lib.lib()
         self.seed = int(seed) + 7919 * self.rank
         with torch.cuda.device(self.device):
@@ -209,10 +215,26 @@ class PPOTrainer:
         hp = self.hp.c()
         n_tiles = int(tile_ids.numel())
         global_batch = n_tiles * _D("KIN_PPO_TILE") * self.world
+        if self.update_variant == "tc":
+            _lib.check(self._L.kin_ppo_grad_tc(self.params.data_ptr(), 56, ctypes.byref(hp), self.obs_buf.data_ptr(), self.act_buf.data_ptr(),
+                                               self.logp_buf.data_ptr(), self.adv_buf.data_ptr(), self.ret_buf.data_ptr(), self.tile_sums.data_ptr(),
+                                               tile_ids.data_ptr(), n_tiles, global_batch, self.partials.data_ptr(), self.grad_ctas,
+                                               self.grad.data_ptr(), self.stats.data_ptr(), None, None, 0, stream))
+            return
         _lib.check(self._L.kin_ppo_grad(self.params.data_ptr(), 56, ctypes.byref(hp), self.obs_buf.data_ptr(), self.act_buf.data_ptr(),
                                         self.logp_buf.data_ptr(), self.adv_buf.data_ptr(), self.ret_buf.data_ptr(), self.tile_sums.data_ptr(),
                                         tile_ids.data_ptr(), n_tiles, global_batch, self.partials.data_ptr(), self.grad_ctas,
                                         self.grad.data_ptr(), self.stats.data_ptr(), stream))
+
+    def refresh_old_logp(self) -> None:
+        """Recompute the rollout's log-probs with the tensor-core kernel's own forward (bf16 operands), so that the probability
+        ratio of the first epoch is exactly 1 as in SB3 (the rollout sampled with the fp32 policy; the two forwards differ by O(1e-3))."""
+        if not hasattr(self, "_all_tiles"):
+            self._all_tiles = torch.arange(self.S // _D("KIN_PPO_TILE"), dtype=torch.int32, device=self.device)
+        hp = self.hp.c()
+        _lib.check(self._L.kin_ppo_grad_tc(self.params.data_ptr(), 56, ctypes.byref(hp), self.obs_buf.data_ptr(), self.act_buf.data_ptr(), None, None,
+                                           None, None, self._all_tiles.data_ptr(), int(self._all_tiles.numel()), 0, None, self.grad_ctas, None, None,
+                                           self.logp_buf.data_ptr(), None, 1, torch.cuda.current_stream(self.device).cuda_stream))
 
     def apply_update(self) -> None:
         """All-reduce the gradient (sum over ranks), clip by global norm, Adam step -- identical on every rank."""
@@ -232,6 +254,8 @@ class PPOTrainer:
         agg = torch.zeros(_D("KIN_PPO_STATS"), dtype=torch.float64, device=self.device)
         n_mb = 0
         with torch.cuda.device(self.device):
+            if self.update_variant == "tc":
+                self.refresh_old_logp()
             for _ in range(self.hp.n_epochs):
                 perm = torch.randperm(n_tiles_total, generator=self._gen, device=self.device, dtype=torch.int64).to(torch.int32)
                 for start in range(0, n_tiles_total, tiles_per_mb):

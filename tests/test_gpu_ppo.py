@@ -143,6 +143,79 @@ def test_minibatch_gradient_matches_autograd():
         t.requires_grad_(False)
 
 
+def test_minibatch_gradient_tc_matches_autograd():
+    """Tensor-core (bf16 operand, fp32 accumulate) variant of the minibatch gradient vs fp32 autograd: bf16-level agreement per
+    tensor, near-perfect direction overall; the forward-only pass reproduces log-prob / value to bf16 accuracy."""
+    from rl_brain_trainer_b200 import _lib
+
+    ppo, pol, flat = _setup(seed=4)
+    hp = ppo.PPOHyper(clip_range=0.15, ent_coef=0.01, vf_coef=0.5, normalize_advantage=True)
+    c_hp = hp.c()
+    S = 64 * 48
+    g = torch.Generator(device="cuda").manual_seed(2)
+    obs = (torch.rand((S, 56), device="cuda", generator=g) * 2 - 1).contiguous()
+    with torch.no_grad():
+        mean, value = _torch_forward(pol, obs)
+    sigma = pol.tensors["log_std"].exp()
+    act = (mean + sigma * torch.randn((S, 7), device="cuda", generator=g)).contiguous()
+    exact_logp = torch.distributions.Normal(mean, sigma).log_prob(act).sum(-1)
+    old_logp = (exact_logp + 0.3 * torch.randn(S, device="cuda", generator=g)).contiguous()
+    adv = torch.randn(S, device="cuda", generator=g).contiguous()
+    ret = (value + torch.randn(S, device="cuda", generator=g)).contiguous()
+    sums = torch.stack([adv.reshape(-1, 64).double().sum(1), (adv.reshape(-1, 64).double() ** 2).sum(1)], dim=1).contiguous()
+    tile_ids = torch.tensor([3, 17, 0, 39, 8, 21, 22, 5, 30, 11, 12, 1, 47, 40], dtype=torch.int32, device="cuda")
+    idx = (tile_ids.long()[:, None] * 64 + torch.arange(64, device="cuda")[None]).reshape(-1)
+    P = flat.numel()
+    c_hp = hp.c()
+    L = _lib.lib()
+    stream = torch.cuda.current_stream().cuda_stream
+    # forward only: log-prob and value of the visited samples
+    lp_out, v_out = torch.full((S,), 123.0, device="cuda"), torch.full((S,), 123.0, device="cuda")
+    _lib.check(L.kin_ppo_grad_tc(flat.data_ptr(), 56, ctypes.byref(c_hp), obs.data_ptr(), act.data_ptr(), None, None, None, None,
+                                 tile_ids.data_ptr(), tile_ids.numel(), 0, None, 3, None, None, lp_out.data_ptr(), v_out.data_ptr(), 1, stream))
+    torch.cuda.synchronize()
+    assert float((v_out[idx] - value[idx]).abs().max()) < 0.03 and float((lp_out[idx] - exact_logp[idx]).abs().max()) < 0.06
+    assert float((lp_out[idx] - exact_logp[idx]).abs().mean()) < 0.008
+    untouched = torch.ones(S, dtype=torch.bool, device="cuda")
+    untouched[idx] = False
+    assert bool((lp_out[untouched] == 123.0).all())
+    # (clip_range, per-tensor tolerance, whole-gradient tolerance, cosine): without clipping the only error is bf16 rounding; with the
+    # 0.3-sigma ratio noise of this case bf16-level log-prob errors flip the clip state of samples at the boundary (0.2 % of them)
+    for clip, tol_k, tol_all, min_cos in ((50.0, 5e-2, 1.2e-2, 0.9999), (0.15, 0.12, 8e-2, 0.998)):
+        hp = ppo.PPOHyper(clip_range=clip, ent_coef=0.01, vf_coef=0.5, normalize_advantage=True)
+        c_hp = hp.c()
+        for t in pol.tensors.values():
+            t.requires_grad_(True)
+        loss, ref_stats = _torch_ppo_loss(pol, hp, obs[idx], act[idx], old_logp[idx], adv[idx], ret[idx])
+        grads = torch.autograd.grad(loss, [pol.tensors[k] for k in ppo.PARAM_ORDER])
+        ref = torch.cat([gk.reshape(-1) for gk in grads])
+        for t in pol.tensors.values():
+            t.requires_grad_(False)
+        for ctas in (2, 7, 148):      # several GEMM tiles per CTA (TMEM accumulation across tiles), one per CTA, more CTAs than tiles
+            partials = torch.zeros((ctas, P + 16), device="cuda")
+            grad, stats = torch.zeros(P, device="cuda"), torch.zeros(8, device="cuda")
+            _lib.check(L.kin_ppo_grad_tc(flat.data_ptr(), 56, ctypes.byref(c_hp), obs.data_ptr(), act.data_ptr(), old_logp.data_ptr(), adv.data_ptr(),
+                                         ret.data_ptr(), sums.data_ptr(), tile_ids.data_ptr(), tile_ids.numel(), tile_ids.numel() * 64,
+                                         partials.data_ptr(), ctas, grad.data_ptr(), stats.data_ptr(), None, None, 0, stream))
+            torch.cuda.synchronize()
+            off = 0
+            for k, gk in zip(ppo.PARAM_ORDER, grads):
+                n = gk.numel()
+                rel = float((grad[off:off + n] - gk.reshape(-1)).norm() / (gk.norm() + 1e-12))
+                assert rel < tol_k, (clip, ctas, k, rel)
+                off += n
+            cos = float(torch.dot(grad, ref) / (grad.norm() * ref.norm()))
+            assert cos > min_cos and float((grad - ref).norm() / ref.norm()) < tol_all, (clip, ctas, cos)
+            got_stats = stats.cpu().numpy()
+            for i, key in enumerate(("policy_loss", "value_loss", "entropy", "approx_kl", "clip_fraction")):
+                assert abs(got_stats[i] - ref_stats[key]) < 3e-2 * max(1.0, abs(ref_stats[key])), (key, got_stats[i], ref_stats[key])
+    # odd tile counts are refused (two 64-sample tiles per GEMM tile)
+    rc = L.kin_ppo_grad_tc(flat.data_ptr(), 56, ctypes.byref(c_hp), obs.data_ptr(), act.data_ptr(), old_logp.data_ptr(), adv.data_ptr(),
+                           ret.data_ptr(), sums.data_ptr(), tile_ids.data_ptr(), 3, 192, partials.data_ptr(), 2, grad.data_ptr(), stats.data_ptr(),
+                           None, None, 0, stream)
+    assert rc != 0
+
+
 def test_adam_matches_torch():
     from rl_brain_trainer_b200 import _lib, ppo
 
@@ -184,14 +257,15 @@ def test_bootstrap_adds_discounted_terminal_value():
     assert torch.allclose(rew, exp, atol=3e-5)
 
 
-def test_trainer_runs_and_improves_value_fit():
+@pytest.mark.parametrize("variant", ["tc", "fp32"])
+def test_trainer_runs_and_improves_value_fit(variant):
     """A short on-device PPO run on the Stage-0 shell: finite statistics, parameters move, the critic's loss falls."""
     from rl_brain_trainer_b200 import ppo
 
     cfg = env_config("approach_dynamic_scale_big")
     pol = ppo.random_policy(56, seed=1, log_std_init=-1.0, device="cuda")
     hp = ppo.PPOHyper(learning_rate=1e-3, n_steps=32, batch_size=2048, n_epochs=4, gamma=0.98, clip_range=0.2)
-    tr = ppo.PPOTrainer(cfg, pol, num_envs=1024, hyper=hp, seed=3)
+    tr = ppo.PPOTrainer(cfg, pol, num_envs=1024, hyper=hp, seed=3, update_variant=variant)
     p0 = tr.params.clone()
     log = tr.learn(4)
     assert all(np.isfinite(list(row.values())).all() for row in log)
@@ -201,7 +275,8 @@ def test_trainer_runs_and_improves_value_fit():
     sd = tr.state_dict()
     assert "mlp_extractor.policy_net.0.weight" in sd and sd["log_std"].shape == (7,)
     # lr = 0 leaves the parameters untouched
-    tr2 = ppo.PPOTrainer(cfg, ppo.random_policy(56, seed=1, device="cuda"), num_envs=256, hyper=ppo.PPOHyper(learning_rate=0.0, n_steps=8, batch_size=512, n_epochs=1))
+    tr2 = ppo.PPOTrainer(cfg, ppo.random_policy(56, seed=1, device="cuda"), num_envs=256, hyper=ppo.PPOHyper(learning_rate=0.0, n_steps=8, batch_size=512, n_epochs=1),
+                         update_variant=variant)
     q0 = tr2.params.clone()
     tr2.learn(1)
     assert torch.equal(tr2.params, q0)

@@ -576,11 +576,32 @@ int kin_ppo_grad(const float *params, int in_dim, const KinPpoHyper *host_hyper,
  * sample-reduction weight-gradient GEMMs) on tcgen05.mma kind::f16 (bf16 operands, fp32 accumulation in TMEM).
  * n_tiles must be even (two 64-sample tiles form one 128-row GEMM tile).  partials: scratch [grid][P + 16] floats.
  * logp_out / value_out (nullable, [S]) receive this variant's own log-prob / value of every visited sample; with
- * forward_only != 0 nothing else is computed (used to refresh old_logp with the same arithmetic the update uses). */
-int kin_ppo_grad_tc(const float *params, int in_dim, const KinPpoHyper *host_hyper, const float *obs, const float *action, const float *old_logp,
+ * forward_only != 0 nothing else is computed (used to refresh old_logp with the same arithmetic the update uses).
+ * obs_is_image != 0: obs is the rollout buffer kin_ppo_collect wrote -- one 16 KB bf16 operand image per 128 consecutive
+ * samples -- and every pair (tile_ids[2j], tile_ids[2j+1]) must be (2m, 2m+1), i.e. one whole image.                      */
+int kin_ppo_grad_tc(const float *params, int in_dim, const KinPpoHyper *host_hyper, const void *obs, const float *action, const float *old_logp,
                     const float *advantage, const float *returns, const double *tile_sums, const int *tile_ids, int n_tiles,
                     long long global_batch, float *partials, int grid, float *grad, float *stats, float *logp_out, float *value_out,
-                    int forward_only, void *stream);
+                    int forward_only, int obs_is_image, void *stream);
+
+/* Replaces: OnPolicyAlgorithm.collect_rollouts (SB3 on_policy_algorithm.py) over a VecEnv of ArmKinematicEnv, fused into ONE
+ * launch: n_steps x (actor + critic forward on tcgen05, a = mean + exp(log_std) * eps, log-prob, env step with reward and
+ * termination, in-register auto-reset from the device sampler).  n_envs must be a multiple of 128.  Outputs, time-major:
+ * obs_tiles [n_steps][n_envs/128][16 KB] bf16 operand images ([obs | 1 | 0] rows, SWIZZLE_128B) consumed by
+ * kin_ppo_grad_tc(obs_is_image = 1); action [T][n][7]; logp / value / reward [T][n]; done / episode_start [T][n] u8;
+ * start_io [n] u8 (in: "previous step finished an episode" of step 0, out: the same for the next rollout); last_value [n].
+ * Episodes that hit the time limit append (t * n + env, terminal observation) to boot_index / boot_obs (capacity boot_cap,
+ * count in *boot_count, reset by this call); kin_ppo_bootstrap_list then adds gamma * V(terminal_obs) to their rewards.
+ * eps is Philox4x32(noise_seed, env, first_step + t) -- the draws of kin_policy_act; resets use Philox(reset_seed, env, episode).
+ * params: the flat PARAM_ORDER buffer.  tiles_per_cta: 0 (auto), 1, 2 or 4.                                               */
+int kin_ppo_collect(void *handle, float *state, int stride, int n_envs, int mode, const float *params, int in_dim, int n_steps,
+                    uint64_t noise_seed, uint32_t first_step, uint64_t reset_seed, void *obs_tiles, float *action, float *logp, float *value,
+                    float *reward, uint8_t *done, uint8_t *episode_start, uint8_t *start_io, float *last_value, int *boot_count,
+                    int *boot_index, float *boot_obs, int boot_cap, int tiles_per_cta, void *stream);
+
+/* reward[boot_index[i]] += gamma * V(boot_obs[i]) for i < min(*boot_count, boot_cap) (strict-fp32 critic of the flat params). */
+int kin_ppo_bootstrap_list(const float *params, int in_dim, const float *boot_obs, const int *boot_index, const int *boot_count, int boot_cap,
+                           float *reward, float gamma, void *stream);
 
 /* clip_grad_norm_(max_grad_norm) + Adam step on the flat parameter buffer (torch.optim.Adam semantics, eps = 1e-5 in SB3).
  * adam_m / adam_v [P]; step = 1-based update count.                                                                    */

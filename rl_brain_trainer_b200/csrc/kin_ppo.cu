@@ -35,17 +35,6 @@ struct ActW {
     const float *w0, *b0, *w1, *b1, *wo, *bo;
 };
 
-__device__ __forceinline__ float gauss_pair(Philox& rng, float* second) {
-    // Box-Muller on two 24-bit uniforms in (0, 1]
-    const float u1 = ((float)(rng.next_u32() >> 8) + 1.0f) * (1.0f / 16777216.0f);
-    const float u2 = (float)(rng.next_u32() >> 8) * (1.0f / 16777216.0f);
-    const float r = sqrtf(-2.0f * logf(u1));
-    float s, c;
-    sincosf(kTwoPi * u2, &s, &c);
-    *second = r * s;
-    return r * c;
-}
-
 template <int IN>
 __global__ void __launch_bounds__(128)
 kin_policy_act_kernel(ActW pi, ActW vf, const float* __restrict__ log_std, const float* __restrict__ obs, float* __restrict__ action,

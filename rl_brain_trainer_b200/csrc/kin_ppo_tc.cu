@@ -49,7 +49,7 @@ constexpr unsigned COL_W0 = 384;      // 2 x 64 (column 56 = db0)
 constexpr unsigned TMEM_COLS_G = 512;
 
 struct __align__(1024) TcGradSmem {
-    unsigned char X[TILE_BYTES];
+    unsigned char X[2][TILE_BYTES];      // double-buffered in image mode (the next tile's image is prefetched by the TMA engine)
     unsigned char H1[2][TILE_BYTES];
     unsigned char H2[2][TILE_BYTES];
     unsigned char G2[2][TILE_BYTES];
@@ -63,9 +63,15 @@ struct __align__(1024) TcGradSmem {
     float ls[8];
     float inv_sig[8];
     float scal[32];                      // 0 adv mean, 1 1/(std+eps), 2..6 statistics, 8..14 d log_std
-    unsigned long long mbar[2];
+    unsigned long long mbar[4];          // 0 forward/backward chain, 1 weight-gradient batch, 2/3 X image buffers
     unsigned tmem_base;
 };
+
+__device__ __forceinline__ void bulk_load_tile(unsigned dst_saddr, const void* src, unsigned mbar_saddr) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_saddr), "r"(TILE_BYTES) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_saddr), "l"(src), "r"(TILE_BYTES), "r"(mbar_saddr) : "memory");
+}
 
 __device__ __forceinline__ void st_bf16(unsigned char* tile, int row, int col, float v) {
     *reinterpret_cast<unsigned short*>(tile + sw_elem(row, col)) = (unsigned short)(pack_bf16(v, 0.0f) & 0xffffu);
@@ -105,6 +111,8 @@ __device__ __forceinline__ void epilogue64(unsigned tz, unsigned char* tile, int
     }
 }
 
+// IMG: obs is the rollout buffer of bf16 operand images written by kin_ppo_collect (one 16 KB image per 128 consecutive samples)
+template <bool IMG>
 __global__ void __launch_bounds__(TCG_THREADS, 1)
 kin_ppo_grad_tc_kernel(const float* __restrict__ params, KinPpoHyper hp, const float* __restrict__ obs, const float* __restrict__ action,
                        const float* __restrict__ old_logp, const float* __restrict__ advantage, const float* __restrict__ returns,
@@ -172,8 +180,8 @@ kin_ppo_grad_tc_kernel(const float* __restrict__ params, KinPpoHyper hp, const f
     }
     if (warp == 0) tmem_alloc(smem_u32(&S.tmem_base), TMEM_COLS_G);
     if (tid == 0) {
-        mbar_init(smem_u32(&S.mbar[0]), 1);
-        mbar_init(smem_u32(&S.mbar[1]), 1);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&S.mbar[i]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     fence_async_smem();
@@ -185,7 +193,12 @@ kin_ppo_grad_tc_kernel(const float* __restrict__ params, KinPpoHyper hp, const f
     const unsigned tlane = tb + ((unsigned)((warp & 3) * 32) << 16);     // this warp's lane quadrant, column 0
     const unsigned tz = tlane + COL_Z + net * 64;
     const unsigned mb_main = smem_u32(&S.mbar[0]), mb_wg = smem_u32(&S.mbar[1]);
-    const unsigned aX = smem_u32(S.X), aDO = smem_u32(S.DO), aW0 = smem_u32(S.W0);
+    const unsigned aXb[2] = {smem_u32(S.X[0]), smem_u32(S.X[1])}, aDO = smem_u32(S.DO), aW0 = smem_u32(S.W0);
+    const unsigned mb_x[2] = {smem_u32(&S.mbar[2]), smem_u32(&S.mbar[3])};
+    unsigned par_x[2] = {0u, 0u};
+    const unsigned char* img = reinterpret_cast<const unsigned char*>(obs);
+    if (IMG && tid == 0 && (int)blockIdx.x < n_pairs)
+        bulk_load_tile(aXb[0], img + (size_t)(tile_ids[2 * blockIdx.x] >> 1) * TILE_BYTES, mb_x[0]);
     const unsigned aH1[2] = {smem_u32(S.H1[0]), smem_u32(S.H1[1])}, aH2[2] = {smem_u32(S.H2[0]), smem_u32(S.H2[1])};
     const unsigned aG2[2] = {smem_u32(S.G2[0]), smem_u32(S.G2[1])}, aG1[2] = {smem_u32(S.G1[0]), smem_u32(S.G1[1])};
     const unsigned aW1[2] = {smem_u32(S.W1[0]), smem_u32(S.W1[1])}, aWO[2] = {smem_u32(S.WO[0]), smem_u32(S.WO[1])};
@@ -196,23 +209,48 @@ kin_ppo_grad_tc_kernel(const float* __restrict__ params, KinPpoHyper hp, const f
     int it = 0;
     for (int j = blockIdx.x; j < n_pairs; j += gridDim.x, ++it) {
         const int t0 = tile_ids[2 * j], t1 = tile_ids[2 * j + 1];
+        const int xb = IMG ? (it & 1) : 0;
+        const unsigned aX = aXb[xb];
+        // loss inputs of this thread's sample: issue the loads now, consume them after layer 3
+        const size_t g = (size_t)(row < 64 ? t0 : t1) * 64 + (row & 63);
+        float act_r[7], adv_r = 0.0f, olp_r = 0.0f, ret_r = 0.0f;
+        if (net == 0) {
+#pragma unroll
+            for (int d = 0; d < 7; ++d) act_r[d] = __ldg(action + g * 7 + d);
+            if (!forward_only) {
+                adv_r = __ldg(advantage + g);
+                olp_r = __ldg(old_logp + g);
+                ret_r = __ldg(returns + g);
+            }
+        }
         if (it > 0 && !forward_only) {      // the previous tile's weight-gradient GEMMs still read X / H / G / dO
             mbar_wait(mb_wg, par_wg);
             par_wg ^= 1u;
         }
-        // ---- X tile: obs fp32 -> bf16, coalesced float4 reads; column 56 = 1 carries the layer-1 bias ------------------
+        if (IMG) {
+            // the other buffer is free (its last readers were the previous tile's GEMMs): prefetch the next tile's image into it
+            const int jn = j + gridDim.x;
+            if (tid == 0 && jn < n_pairs) bulk_load_tile(aXb[xb ^ 1], img + (size_t)(tile_ids[2 * jn] >> 1) * TILE_BYTES, mb_x[xb ^ 1]);
+            mbar_wait(mb_x[xb], par_x[xb]);
+            par_x[xb] ^= 1u;
+            fence_before();
+            __syncthreads();
+        } else {
+            // ---- X tile: obs fp32 -> bf16, coalesced float4 reads; column 56 = 1 carries the layer-1 bias --------------
+            unsigned char* X = S.X[0];
 #pragma unroll
-        for (int i = 0; i < 7; ++i) {
-            const int idx = tid + TCG_THREADS * i;           // 0 .. 1791
-            const int half = idx >= 896, rem = idx - half * 896;
-            const int r = half * 64 + rem / 14, q = rem % 14;
-            const float4 v = __ldg(reinterpret_cast<const float4*>(obs + (size_t)(half ? t1 : t0) * 64 * IN) + rem);
-            *reinterpret_cast<uint2*>(S.X + sw_chunk(r, q >> 1) + ((q & 1) << 3)) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+            for (int i = 0; i < 7; ++i) {
+                const int idx = tid + TCG_THREADS * i;           // 0 .. 1791
+                const int half = idx >= 896, rem = idx - half * 896;
+                const int r = half * 64 + rem / 14, q = rem % 14;
+                const float4 v = __ldg(reinterpret_cast<const float4*>(obs + (size_t)(half ? t1 : t0) * 64 * IN) + rem);
+                *reinterpret_cast<uint2*>(X + sw_chunk(r, q >> 1) + ((q & 1) << 3)) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+            }
+            if (tid < 128) *reinterpret_cast<uint4*>(X + sw_chunk(tid, 7)) = make_uint4(0x00003F80u, 0u, 0u, 0u);
+            fence_async_smem();
+            fence_before();
+            __syncthreads();
         }
-        if (tid < 128) *reinterpret_cast<uint4*>(S.X + sw_chunk(tid, 7)) = make_uint4(0x00003F80u, 0u, 0u, 0u);
-        fence_async_smem();
-        fence_before();
-        __syncthreads();
         // ---- layer 1 ----------------------------------------------------------------------------------------------------
         if (tid == 0) {
             fence_after();
@@ -262,23 +300,22 @@ kin_ppo_grad_tc_kernel(const float* __restrict__ params, KinPpoHyper hp, const f
         if (net == 0) {
             float o[16];
             tmem_ld16(tlane + COL_O, o);
-            const size_t g = (size_t)(row < 64 ? t0 : t1) * 64 + (row & 63);
             float lp = 0.0f, z[7];
 #pragma unroll
             for (int d = 0; d < 7; ++d) {
-                z[d] = (__ldg(action + g * 7 + d) - (o[d] + S.bo[d])) * S.inv_sig[d];
+                z[d] = (act_r[d] - (o[d] + S.bo[d])) * S.inv_sig[d];
                 lp += -0.5f * z[d] * z[d] - S.ls[d] - kHalfLog2PiTc;
             }
             const float v = o[7] + S.bo[7];
             if (logp_out) logp_out[g] = lp;
             if (value_out) value_out[g] = v;
             if (!forward_only) {
-                const float adv_n = (__ldg(advantage + g) - S.scal[0]) * S.scal[1];
-                const float log_ratio = lp - __ldg(old_logp + g);
+                const float adv_n = (adv_r - S.scal[0]) * S.scal[1];
+                const float log_ratio = lp - olp_r;
                 const float ratio = expf(log_ratio);
                 const float pl1 = adv_n * ratio, pl2 = adv_n * fminf(fmaxf(ratio, 1.0f - hp.clip_range), 1.0f + hp.clip_range);
                 const float dpl_dlp = (pl1 <= pl2) ? -adv_n * ratio : 0.0f;
-                const float rt = __ldg(returns + g);
+                const float rt = ret_r;
                 float dm[8];
                 float ent = 0.0f;
 #pragma unroll
@@ -444,10 +481,11 @@ kin_ppo_grad_tc_kernel(const float* __restrict__ params, KinPpoHyper hp, const f
 
 using namespace kin;
 
-extern "C" int kin_ppo_grad_tc(const float* params, int in_dim, const KinPpoHyper* hp, const float* obs, const float* action, const float* old_logp,
+extern "C" int kin_ppo_grad_tc(const float* params, int in_dim, const KinPpoHyper* hp, const void* obs_any, const float* action, const float* old_logp,
                                const float* advantage, const float* returns, const double* tile_sums, const int* tile_ids, int n_tiles,
                                long long global_batch, float* partials, int grid, float* grad, float* stats, float* logp_out, float* value_out,
-                               int forward_only, void* stream) {
+                               int forward_only, int obs_is_image, void* stream) {
+    const float* obs = static_cast<const float*>(obs_any);
     if (!params || !hp || !obs || !action || !tile_ids || n_tiles <= 0 || grid <= 0)
         return kin_fail(KIN_ERR_INVALID_ARG, "kin_ppo_grad_tc: bad arguments");
     if (!forward_only && (!old_logp || !advantage || !returns || !tile_sums || !partials || !grad || global_batch <= 0))
@@ -460,7 +498,8 @@ extern "C" int kin_ppo_grad_tc(const float* params, int in_dim, const KinPpoHype
     const size_t smem = sizeof(TcGradSmem) + 1024;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kin_ppo_grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(kin_ppo_grad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(kin_ppo_grad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return kin_fail_cuda(e, "kin_ppo_grad_tc: smem attribute");
         attr_set = true;
     }
@@ -468,8 +507,12 @@ extern "C" int kin_ppo_grad_tc(const float* params, int in_dim, const KinPpoHype
     const int n_pairs = n_tiles / 2;
     const int g = grid < n_pairs ? grid : n_pairs;
     const float inv = forward_only ? 0.0f : 1.0f / (float)global_batch;
-    kin_ppo_grad_tc_kernel<<<g, TCG_THREADS, smem, st>>>(params, *hp, obs, action, old_logp, advantage, returns, tile_sums, tile_ids, n_pairs, inv,
-                                                         partials, logp_out, value_out, forward_only);
+    if (obs_is_image)
+        kin_ppo_grad_tc_kernel<true><<<g, TCG_THREADS, smem, st>>>(params, *hp, obs, action, old_logp, advantage, returns, tile_sums, tile_ids, n_pairs,
+                                                                   inv, partials, logp_out, value_out, forward_only);
+    else
+        kin_ppo_grad_tc_kernel<false><<<g, TCG_THREADS, smem, st>>>(params, *hp, obs, action, old_logp, advantage, returns, tile_sums, tile_ids, n_pairs,
+                                                                    inv, partials, logp_out, value_out, forward_only);
     if (!forward_only) kin_ppo_reduce_launch(partials, g, P, grad, stats, inv, st);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? KIN_OK : kin_fail_cuda(e, "kin_ppo_grad_tc");

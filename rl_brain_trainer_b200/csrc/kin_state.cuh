@@ -177,6 +177,18 @@ struct Philox {
     }
 };
 
+// two standard normals from one Philox pair (policy noise of the PPO rollout)
+__device__ __forceinline__ float gauss_pair(Philox& rng, float* second) {
+    // Box-Muller on two 24-bit uniforms in (0, 1]
+    const float u1 = ((float)(rng.next_u32() >> 8) + 1.0f) * (1.0f / 16777216.0f);
+    const float u2 = (float)(rng.next_u32() >> 8) * (1.0f / 16777216.0f);
+    const float r = sqrtf(-2.0f * logf(u1));
+    float s, c;
+    sincosf(kTwoPi * u2, &s, &c);
+    *second = r * s;
+    return r * c;
+}
+
 // curriculum.py:90-101: base + U(-noise, noise) (only if any noise > 0), clipped to the limits
 __device__ __forceinline__ void sample_shell(const KinEnvParams& P, Philox& rng, const float* base, const float* noise, float* q) {
     bool any = false;

@@ -105,7 +105,7 @@ class PPOTrainer:
 
     def __init__(self, config: Phase1EnvConfig, policy: PolicyWeights, *, num_envs: int, hyper: PPOHyper, device: str | torch.device = "cuda",
                  seed: int = 0, stage_index: int = 0, process_group: Any = None, grad_ctas: int | None = None,
-                 update_variant: str = "tc") -> None:
+                 update_variant: str = "tc", collect_variant: str | None = None) -> None:
         if not torch.cuda.is_available():
             raise _lib.KinError("PPOTrainer needs a CUDA device; there is no CPU fallback")
         if policy.in_dim != 56:
@@ -116,6 +116,13 @@ class PPOTrainer:
         if update_variant not in ("tc", "fp32"):
             raise ValueError("update_variant must be 'tc' (tcgen05 bf16 GEMMs, fp32 accumulate) or 'fp32' (strict FP32-pipe kernel)")
         self.update_variant = update_variant
+        # "fused": one kin_ppo_collect launch per rollout (tensor-core policy, bf16 observation images, needs the tc update);
+        # "steps": one policy / env-step / bootstrap launch per time step (strict fp32, fp32 observation buffer)
+        self.collect_variant = collect_variant or ("fused" if update_variant == "tc" and num_envs % 128 == 0 else "steps")
+        if self.collect_variant not in ("fused", "steps"):
+            raise ValueError("collect_variant must be 'fused' or 'steps'")
+        if self.collect_variant == "fused" and (update_variant != "tc" or num_envs % 128):
+            raise ValueError("the fused collection writes bf16 operand images: it needs update_variant='tc' and num_envs % 128 == 0")
         self.device = torch.device(device)
         self.group = process_group
         self.rank, self.world = world(process_group)
@@ -142,7 +149,15 @@ class PPOTrainer:
             self.env = BatchedArmKinematicEnv(config, self.N, self.device, auto_reset=True, seed=self.seed, host_sampler=False, with_aux=False)
             self.env.set_curriculum_stage(stage_index)
             f32 = dict(dtype=torch.float32, device=self.device)
-            self.obs_buf = torch.zeros((self.T + 1, self.N, 56), **f32)
+            fused = self.collect_variant == "fused"
+            self.obs_buf = None if fused else torch.zeros((self.T + 1, self.N, 56), **f32)
+            if fused:
+                self.obs_img = torch.zeros((self.T, self.N // 128, 128 * 128), dtype=torch.uint8, device=self.device)
+                limit = max(int(getattr(config.termination_config, "max_episode_steps", config.episode_length)), 1)
+                self.boot_cap = self.N * (self.T // limit + 2)     # an env hits the time limit at most once per `limit` steps
+                self.boot_count = torch.zeros(1, dtype=torch.int32, device=self.device)
+                self.boot_index = torch.zeros(self.boot_cap, dtype=torch.int32, device=self.device)
+                self.boot_obs = torch.zeros((self.boot_cap, 56), **f32)
             self.act_buf = torch.zeros((self.T, self.N, 7), **f32)
             self.logp_buf = torch.zeros((self.T, self.N), **f32)
             self.val_buf = torch.zeros((self.T, self.N), **f32)
@@ -156,8 +171,10 @@ class PPOTrainer:
             self._gen = torch.Generator(device=self.device)
             self._gen.manual_seed(self.seed)
             self.env.reset()
-            self.obs_buf[0].copy_(self.env.obs)
+            if not fused:
+                self.obs_buf[0].copy_(self.env.obs)
         self._next_start = torch.ones(self.N, dtype=torch.uint8, device=self.device)
+        self.tiles_per_cta = 0              # fused collection: 128-env tiles per CTA (0 = fewest that fit one wave)
         self.num_timesteps = 0
         self.update_count = 0
         self.global_step = 0
@@ -169,6 +186,9 @@ class PPOTrainer:
     # ------------------------------------------------------------------ rollout
     def collect(self) -> dict[str, float]:
         """``collect_rollouts``: T steps of (sample action, env step with auto-reset, TimeLimit bootstrap), then GAE."""
+        self.env._ensure_sampler()          # a curriculum promotion since the last rollout re-uploads the device sampler
+        if self.collect_variant == "fused":
+            return self._collect_fused()
         L, env, hp = self._L, self.env, self.hp
         stream = torch.cuda.current_stream(self.device).cuda_stream
         w = ctypes.byref(self.policy.c)
@@ -198,6 +218,30 @@ class PPOTrainer:
         self.last_rollout = {"episodes": float(finished.sum()), "successes": float(succ.sum()), "mean_reward": float(self.rew_buf.mean())}
         return self.last_rollout
 
+    def _collect_fused(self) -> dict[str, float]:
+        """The whole rollout in one launch (``kin_ppo_collect``), then the TimeLimit bootstrap of the listed episodes and GAE."""
+        L, env, hp = self._L, self.env, self.hp
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            mode = _D("KIN_MODE_APPROACH") if env._mode_all is None else env._mode_all
+            _lib.check(L.kin_ppo_collect(env._params.handle, env.state.data_ptr(), env.stride, self.N, mode, self.params.data_ptr(), 56, self.T,
+                                         self.seed, self.global_step, env._seed, self.obs_img.data_ptr(), self.act_buf.data_ptr(),
+                                         self.logp_buf.data_ptr(), self.val_buf.data_ptr(), self.rew_buf.data_ptr(), self.done_buf.data_ptr(),
+                                         self.start_buf.data_ptr(), self._next_start.data_ptr(), self.last_val.data_ptr(), self.boot_count.data_ptr(),
+                                         self.boot_index.data_ptr(), self.boot_obs.data_ptr(), self.boot_cap, int(self.tiles_per_cta), stream))
+            _lib.check(L.kin_ppo_bootstrap_list(self.params.data_ptr(), 56, self.boot_obs.data_ptr(), self.boot_index.data_ptr(),
+                                                self.boot_count.data_ptr(), self.boot_cap, self.rew_buf.data_ptr(), float(hp.gamma), stream))
+            _lib.check(L.kin_ppo_gae(self.rew_buf.data_ptr(), self.val_buf.data_ptr(), self.start_buf.data_ptr(), self.last_val.data_ptr(),
+                                     self.done_buf[self.T - 1].data_ptr(), float(hp.gamma), float(hp.gae_lambda), self.T, self.N,
+                                     self.adv_buf.data_ptr(), self.ret_buf.data_ptr(), self.tile_sums.data_ptr(), stream))
+        self.global_step += self.T
+        self.num_timesteps += self.S * self.world
+        done_bits = _D("KIN_DONE_TERMINATED") | _D("KIN_DONE_TRUNCATED")
+        finished = (self.done_buf & done_bits) != 0
+        succ = ((self.done_buf & _D("KIN_DONE_SUCCESS")) != 0) & finished
+        self.last_rollout = {"episodes": float(finished.sum()), "successes": float(succ.sum()), "mean_reward": float(self.rew_buf.mean())}
+        return self.last_rollout
+
     def _scratch_act(self) -> torch.Tensor:
         if not hasattr(self, "_sa"):
             self._sa = torch.zeros((self.N, 7), dtype=torch.float32, device=self.device)
@@ -216,10 +260,11 @@ class PPOTrainer:
         n_tiles = int(tile_ids.numel())
         global_batch = n_tiles * _D("KIN_PPO_TILE") * self.world
         if self.update_variant == "tc":
-            _lib.check(self._L.kin_ppo_grad_tc(self.params.data_ptr(), 56, ctypes.byref(hp), self.obs_buf.data_ptr(), self.act_buf.data_ptr(),
-                                               self.logp_buf.data_ptr(), self.adv_buf.data_ptr(), self.ret_buf.data_ptr(), self.tile_sums.data_ptr(),
-                                               tile_ids.data_ptr(), n_tiles, global_batch, self.partials.data_ptr(), self.grad_ctas,
-                                               self.grad.data_ptr(), self.stats.data_ptr(), None, None, 0, stream))
+            img = self.collect_variant == "fused"
+            _lib.check(self._L.kin_ppo_grad_tc(self.params.data_ptr(), 56, ctypes.byref(hp), (self.obs_img if img else self.obs_buf).data_ptr(),
+                                               self.act_buf.data_ptr(), self.logp_buf.data_ptr(), self.adv_buf.data_ptr(), self.ret_buf.data_ptr(),
+                                               self.tile_sums.data_ptr(), tile_ids.data_ptr(), n_tiles, global_batch, self.partials.data_ptr(),
+                                               self.grad_ctas, self.grad.data_ptr(), self.stats.data_ptr(), None, None, 0, int(img), stream))
             return
         _lib.check(self._L.kin_ppo_grad(self.params.data_ptr(), 56, ctypes.byref(hp), self.obs_buf.data_ptr(), self.act_buf.data_ptr(),
                                         self.logp_buf.data_ptr(), self.adv_buf.data_ptr(), self.ret_buf.data_ptr(), self.tile_sums.data_ptr(),
@@ -234,7 +279,7 @@ class PPOTrainer:
         hp = self.hp.c()
         _lib.check(self._L.kin_ppo_grad_tc(self.params.data_ptr(), 56, ctypes.byref(hp), self.obs_buf.data_ptr(), self.act_buf.data_ptr(), None, None,
                                            None, None, self._all_tiles.data_ptr(), int(self._all_tiles.numel()), 0, None, self.grad_ctas, None, None,
-                                           self.logp_buf.data_ptr(), None, 1, torch.cuda.current_stream(self.device).cuda_stream))
+                                           self.logp_buf.data_ptr(), None, 1, 0, torch.cuda.current_stream(self.device).cuda_stream))
 
     def apply_update(self) -> None:
         """All-reduce the gradient (sum over ranks), clip by global norm, Adam step -- identical on every rank."""
@@ -254,10 +299,15 @@ class PPOTrainer:
         agg = torch.zeros(_D("KIN_PPO_STATS"), dtype=torch.float64, device=self.device)
         n_mb = 0
         with torch.cuda.device(self.device):
-            if self.update_variant == "tc":
+            img = self.collect_variant == "fused"
+            if self.update_variant == "tc" and not img:   # the fused collection already sampled with the tensor-core forward
                 self.refresh_old_logp()
             for _ in range(self.hp.n_epochs):
-                perm = torch.randperm(n_tiles_total, generator=self._gen, device=self.device, dtype=torch.int64).to(torch.int32)
+                if img:   # minibatches are unions of whole 128-sample images: permute pairs of 64-sample tiles
+                    p2 = torch.randperm(n_tiles_total // 2, generator=self._gen, device=self.device, dtype=torch.int64)
+                    perm = torch.stack((2 * p2, 2 * p2 + 1), dim=1).reshape(-1).to(torch.int32)
+                else:
+                    perm = torch.randperm(n_tiles_total, generator=self._gen, device=self.device, dtype=torch.int64).to(torch.int32)
                 for start in range(0, n_tiles_total, tiles_per_mb):
                     ids = perm[start:start + tiles_per_mb].contiguous()
                     self.minibatch_grad(ids)
@@ -287,6 +337,18 @@ class PPOTrainer:
     def state_dict(self) -> dict[str, torch.Tensor]:
         """SB3 ``policy.pth`` key names, so a trained policy loads back into the reference (and vice versa)."""
         return {KEYS[f]: t.detach().clone() for f, t in self.policy.tensors.items()}
+
+
+def decode_obs_images(images: torch.Tensor) -> torch.Tensor:
+    """``[..., 16384]`` uint8 operand images written by ``kin_ppo_collect`` -> ``[..., 128, 64]`` float32 rows
+    (56 observation floats rounded to bf16, a constant 1 that carries the layer-1 bias, zero padding)."""
+    lead = images.shape[:-1]
+    chunks = images.reshape(*lead, 128, 8, 16)                       # row, 16-byte chunk slot, bytes
+    r = torch.arange(128, device=images.device)[:, None]
+    c = torch.arange(8, device=images.device)[None, :]
+    slot = (c ^ (r & 7)).reshape(*([1] * len(lead)), 128, 8, 1).expand(*lead, 128, 8, 16)
+    rows = torch.gather(chunks, -2, slot).reshape(*lead, 128, 128).contiguous()
+    return rows.view(torch.bfloat16).float()
 
 
 def numpy_gae(rewards: np.ndarray, values: np.ndarray, episode_starts: np.ndarray, last_values: np.ndarray, last_dones: np.ndarray,

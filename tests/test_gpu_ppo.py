@@ -172,7 +172,7 @@ def test_minibatch_gradient_tc_matches_autograd():
     # forward only: log-prob and value of the visited samples
     lp_out, v_out = torch.full((S,), 123.0, device="cuda"), torch.full((S,), 123.0, device="cuda")
     _lib.check(L.kin_ppo_grad_tc(flat.data_ptr(), 56, ctypes.byref(c_hp), obs.data_ptr(), act.data_ptr(), None, None, None, None,
-                                 tile_ids.data_ptr(), tile_ids.numel(), 0, None, 3, None, None, lp_out.data_ptr(), v_out.data_ptr(), 1, stream))
+                                 tile_ids.data_ptr(), tile_ids.numel(), 0, None, 3, None, None, lp_out.data_ptr(), v_out.data_ptr(), 1, 0, stream))
     torch.cuda.synchronize()
     assert float((v_out[idx] - value[idx]).abs().max()) < 0.03 and float((lp_out[idx] - exact_logp[idx]).abs().max()) < 0.06
     assert float((lp_out[idx] - exact_logp[idx]).abs().mean()) < 0.008
@@ -196,13 +196,14 @@ def test_minibatch_gradient_tc_matches_autograd():
             grad, stats = torch.zeros(P, device="cuda"), torch.zeros(8, device="cuda")
             _lib.check(L.kin_ppo_grad_tc(flat.data_ptr(), 56, ctypes.byref(c_hp), obs.data_ptr(), act.data_ptr(), old_logp.data_ptr(), adv.data_ptr(),
                                          ret.data_ptr(), sums.data_ptr(), tile_ids.data_ptr(), tile_ids.numel(), tile_ids.numel() * 64,
-                                         partials.data_ptr(), ctas, grad.data_ptr(), stats.data_ptr(), None, None, 0, stream))
+                                         partials.data_ptr(), ctas, grad.data_ptr(), stats.data_ptr(), None, None, 0, 0, stream))
             torch.cuda.synchronize()
             off = 0
             for k, gk in zip(ppo.PARAM_ORDER, grads):
                 n = gk.numel()
                 rel = float((grad[off:off + n] - gk.reshape(-1)).norm() / (gk.norm() + 1e-12))
-                assert rel < tol_k, (clip, ctas, k, rel)
+                # bias-like tensors are signed sums of bf16-rounded per-sample terms with heavy cancellation: looser bound
+                assert rel < (tol_k if n > 64 else 3 * tol_k), (clip, ctas, k, rel)
                 off += n
             cos = float(torch.dot(grad, ref) / (grad.norm() * ref.norm()))
             assert cos > min_cos and float((grad - ref).norm() / ref.norm()) < tol_all, (clip, ctas, cos)
@@ -212,7 +213,7 @@ def test_minibatch_gradient_tc_matches_autograd():
     # odd tile counts are refused (two 64-sample tiles per GEMM tile)
     rc = L.kin_ppo_grad_tc(flat.data_ptr(), 56, ctypes.byref(c_hp), obs.data_ptr(), act.data_ptr(), old_logp.data_ptr(), adv.data_ptr(),
                            ret.data_ptr(), sums.data_ptr(), tile_ids.data_ptr(), 3, 192, partials.data_ptr(), 2, grad.data_ptr(), stats.data_ptr(),
-                           None, None, 0, stream)
+                           None, None, 0, 0, stream)
     assert rc != 0
 
 
@@ -280,6 +281,86 @@ def test_trainer_runs_and_improves_value_fit(variant):
     q0 = tr2.params.clone()
     tr2.learn(1)
     assert torch.equal(tr2.params, q0)
+
+
+@pytest.mark.parametrize("tiles_per_cta,num_envs,trained", [(1, 256, False), (2, 512, False), (4, 640, True)])
+def test_fused_collection_replays_through_the_step_kernel(tiles_per_cta, num_envs, trained):
+    """kin_ppo_collect (one launch per rollout, tensor-core policy) against the per-step kernels: replaying its recorded actions
+    through kin_env_step from the same start state reproduces rewards, done flags, observations (as bf16 images) and the
+    auto-reset draws; its sampled actions / log-probs / values agree with the fp32 policy on the recorded observations."""
+    import dataclasses
+
+    from rl_brain_trainer_b200 import _lib, ppo
+    from rl_brain_trainer_b200.env import BatchedArmKinematicEnv
+
+    cfg = env_config("approach_dynamic_scale_big")      # short episodes: several time-limit truncations per rollout
+    cfg = dataclasses.replace(cfg, episode_length=24, termination_config=dataclasses.replace(cfg.termination_config, max_episode_steps=24))
+    T = 60
+    if trained:       # the bundled approach checkpoint on the easiest shell: success / near-goal flags and dwell counters are exercised
+        from rl_brain_trainer_b200.policy import PolicyWeights
+
+        pol, stage = PolicyWeights.preset("approach_stage8_11", "cuda"), 0
+    else:
+        pol, stage = ppo.random_policy(56, seed=2, log_std_init=-1.5, device="cuda"), 3
+        pol.tensors["act_w"].mul_(40.0)
+        pol.tensors["vf_b1"].normal_(0, 0.2)
+    hp = ppo.PPOHyper(n_steps=T, batch_size=num_envs * T // 4, n_epochs=1, gamma=0.97, learning_rate=0.0)
+    tr = ppo.PPOTrainer(cfg, pol, num_envs=num_envs, hyper=hp, seed=11, stage_index=stage, update_variant="tc", collect_variant="fused")
+    tr.tiles_per_cta = tiles_per_cta
+    replay = BatchedArmKinematicEnv(cfg, num_envs, "cuda", auto_reset=True, seed=tr.env._seed, host_sampler=False, with_aux=False)
+    replay.set_curriculum_stage(stage)
+    replay._ensure_sampler()
+    for rollout in range(2):                 # the second rollout starts mid-episode from the state the first one left
+        replay.state.copy_(tr.env.state)
+        start0 = tr._next_start.clone()
+        obs0 = replay.current_observation()
+        tr.collect()
+        torch.cuda.synchronize()
+        obs_img = ppo.decode_obs_images(tr.obs_img).reshape(T, num_envs, 64)
+        assert bool((obs_img[..., 56] == 1.0).all()) and bool((obs_img[..., 57:] == 0.0).all())
+        raw_rew = torch.zeros((T, num_envs), device="cuda")
+        obs_t = obs0
+        n_trunc = 0
+        for t in range(T):
+            # observation image of step t == bf16(observation the step kernel produced)
+            assert torch.equal(obs_img[t, :, :56], obs_t.bfloat16().float()), (rollout, t)
+            mean, value = _torch_forward(pol, obs_t)
+            sigma = pol.tensors["log_std"].exp()
+            z = (tr.act_buf[t] - mean) / sigma
+            lp = torch.distributions.Normal(mean, sigma).log_prob(tr.act_buf[t]).sum(-1)
+            assert float((tr.val_buf[t] - value).abs().max()) < 0.05 * max(1.0, float(value.abs().max()))
+            # the buffer holds log N(a) under the SAMPLING (bf16-operand) policy; against the fp32 policy it moves by z * d(mean) / sigma
+            smin = float(sigma.min())
+            assert float((tr.logp_buf[t] - lp).abs().max()) < 0.08 / smin and float((tr.logp_buf[t] - lp).abs().mean()) < 0.008 / smin
+            assert abs(float(z.mean())) < 0.15 and 0.8 < float(z.std()) < 1.2
+            replay.step_raw(tr.act_buf[t].contiguous())
+            torch.cuda.synchronize()
+            assert torch.equal(replay.done, tr.done_buf[t]), (rollout, t)
+            raw_rew[t] = replay.reward
+            trunc = ((replay.done & 2) != 0) & ((replay.done & 1) == 0)
+            expect = replay.reward.clone()
+            if bool(trunc.any()):
+                _, tv = _torch_forward(pol, replay.terminal_obs)
+                expect[trunc] += hp.gamma * tv[trunc]
+                n_trunc += int(trunc.sum())
+            assert torch.allclose(tr.rew_buf[t], expect, atol=2e-5), (rollout, t, float((tr.rew_buf[t] - expect).abs().max()))
+            exp_start = start0 if t == 0 else ((tr.done_buf[t - 1] & 3) != 0).to(torch.uint8)
+            assert torch.equal(tr.start_buf[t], exp_start)
+            obs_t = replay.obs.clone()
+        assert n_trunc == int(tr.boot_count) and n_trunc > 0
+        assert not trained or bool(((tr.done_buf & 4) != 0).any())           # the trained policy reaches the success zone
+        assert torch.equal(replay.state[:, :num_envs], tr.env.state[:, :num_envs])
+        _, v_last = _torch_forward(pol, obs_t)
+        assert float((tr.last_val - v_last).abs().max()) < 0.05 * max(1.0, float(v_last.abs().max()))
+        assert torch.equal(tr._next_start, ((tr.done_buf[T - 1] & 3) != 0).to(torch.uint8))
+        # GAE ran on the bootstrapped rewards
+        ra, rr = ppo.numpy_gae(tr.rew_buf.cpu().numpy(), tr.val_buf.cpu().numpy(), tr.start_buf.cpu().numpy(), tr.last_val.cpu().numpy(),
+                               ((tr.done_buf[T - 1] & 3) != 0).cpu().numpy(), hp.gamma, hp.gae_lambda)
+        assert np.abs(tr.adv_buf.cpu().numpy() - ra).max() < 5e-4
+    # the update consumes the images with the arithmetic that sampled them: with frozen parameters the probability ratio is 1
+    stats = tr.update()
+    assert stats["approx_kl"] < 1e-6 and stats["clip_fraction"] == 0.0 and np.isfinite(list(stats.values())).all()
+    assert stats["grad_norm"] > 0
 
 
 def test_gate_eval_and_finetune_retention():

@@ -567,10 +567,17 @@ int kin_ppo_gae(const float *reward, const float *value, const uint8_t *episode_
  * normalised per minibatch).  The minibatch is the union of the 64-sample tiles tile_ids[0..n_tiles); sample s of tile j is
  * row tile_ids[j]*64 + s of obs [S,56] / action [S,7] / old_logp / advantage / returns.  global_batch = samples in the
  * whole (all-rank) minibatch.  grad [P] receives the SUM over local samples of d(loss*global_batch)/dparam / global_batch,
- * i.e. ranks all-reduce (sum) grad and stats afterwards.  partials: scratch [grid][P + KIN_PPO_STATS] floats.           */
+ * i.e. ranks all-reduce (sum) grad and stats afterwards.  partials: scratch [grid][P + KIN_PPO_STATS + 8] floats.
+ * adv_stats (nullable): this minibatch's (mean, 1/(std+eps)) from kin_ppo_adv_stats; NULL -> computed from tile_sums.     */
 int kin_ppo_grad(const float *params, int in_dim, const KinPpoHyper *host_hyper, const float *obs, const float *action, const float *old_logp,
                  const float *advantage, const float *returns, const double *tile_sums, const int *tile_ids, int n_tiles,
-                 long long global_batch, float *partials, int grid, float *grad, float *stats, void *stream);
+                 long long global_batch, float *partials, int grid, float *grad, float *stats, const float *adv_stats, void *stream);
+
+/* (mean, 1 / (std + 1e-8)) of the advantages of n_minibatches minibatches at once (minibatch m = tile_ids[m * n .. (m + 1) * n),
+ * n = n_tiles_per_minibatch), torch semantics (unbiased std); normalize == 0 writes (0, 1).  adv_stats [n_minibatches][2]; pass
+ * adv_stats + 2 * m to the gradient kernels so they skip their own (serial) pass over the tile sums.                          */
+int kin_ppo_adv_stats(const double *tile_sums, const int *tile_ids, int n_tiles_per_minibatch, int n_minibatches, int normalize,
+                      float *adv_stats, void *stream);
 
 /* Tensor-core variant of kin_ppo_grad: the same minibatch gradient with every GEMM (forward, data gradients and the
  * sample-reduction weight-gradient GEMMs) on tcgen05.mma kind::f16 (bf16 operands, fp32 accumulation in TMEM).
@@ -582,7 +589,7 @@ int kin_ppo_grad(const float *params, int in_dim, const KinPpoHyper *host_hyper,
 int kin_ppo_grad_tc(const float *params, int in_dim, const KinPpoHyper *host_hyper, const void *obs, const float *action, const float *old_logp,
                     const float *advantage, const float *returns, const double *tile_sums, const int *tile_ids, int n_tiles,
                     long long global_batch, float *partials, int grid, float *grad, float *stats, float *logp_out, float *value_out,
-                    int forward_only, int obs_is_image, void *stream);
+                    int forward_only, int obs_is_image, const float *adv_stats, void *stream);
 
 /* Replaces: OnPolicyAlgorithm.collect_rollouts (SB3 on_policy_algorithm.py) over a VecEnv of ArmKinematicEnv, fused into ONE
  * launch: n_steps x (actor + critic forward on tcgen05, a = mean + exp(log_std) * eps, log-prob, env step with reward and
@@ -604,9 +611,10 @@ int kin_ppo_bootstrap_list(const float *params, int in_dim, const float *boot_ob
                            float *reward, float gamma, void *stream);
 
 /* clip_grad_norm_(max_grad_norm) + Adam step on the flat parameter buffer (torch.optim.Adam semantics, eps = 1e-5 in SB3).
- * adam_m / adam_v [P]; step = 1-based update count.                                                                    */
+ * adam_m / adam_v [P]; step = 1-based update count.  stats[5] receives the gradient norm; stats_accum (nullable, [8]) gets
+ * stats[0..5] added and slot 7 incremented: running sums over the minibatches of one update without host round trips.    */
 int kin_ppo_adam(float *params, const float *grad, float *adam_m, float *adam_v, int n_params, const KinPpoHyper *host_hyper, int step,
-                 float *stats, void *stream);
+                 float *stats, float *stats_accum, void *stream);
 
 #ifdef __cplusplus
 }

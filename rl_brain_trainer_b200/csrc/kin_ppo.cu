@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(PPO_THREADS, 1)
 kin_ppo_grad_kernel(const float* __restrict__ params, KinPpoHyper hp, const float* __restrict__ obs, const float* __restrict__ action,
                     const float* __restrict__ old_logp, const float* __restrict__ advantage, const float* __restrict__ returns,
                     const double* __restrict__ tile_sums, const int* __restrict__ tile_ids, int n_tiles, float inv_global_batch,
-                    float* __restrict__ partials) {
+                    float* __restrict__ partials, const float* __restrict__ adv_stats) {
     using L = GradSmem<IN>;
     extern __shared__ __align__(16) float sm[];
     const PpoOffsets O = ppo_offsets(IN);
@@ -209,8 +209,10 @@ kin_ppo_grad_kernel(const float* __restrict__ params, KinPpoHyper hp, const floa
         sm[L::LS + tid] = tid < 7 ? __ldg(params + O.log_std + tid) : 0.0f;
     }
     if (tid < 32) sm[L::SCAL + tid] = 0.0f;
-    // advantage statistics of this minibatch (torch: mean, unbiased std) from the per-tile sums
-    if (tid < 32) {
+    // advantage statistics of this minibatch (torch: mean, unbiased std): precomputed (kin_ppo_adv_stats) or from the per-tile sums
+    if (adv_stats) {
+        if (tid == 0) { sm[L::SCAL + 0] = adv_stats[0]; sm[L::SCAL + 1] = adv_stats[1]; }
+    } else if (tid < 32) {
         double s1 = 0.0, s2 = 0.0;
         for (int j = tid; j < n_tiles; j += 32) {
             const int t = tile_ids[j];
@@ -526,26 +528,68 @@ kin_ppo_grad_kernel(const float* __restrict__ params, KinPpoHyper hp, const floa
     }
 }
 
-// grad[p] = sum over CTAs of partials[c][p]; stats likewise
+// grad[p] = sum over CTAs of partials[c][p]; stats likewise.  A block owns 32 consecutive parameters (one 128-byte line per
+// partial row); its 8 warps take rows w, w + 8, ... with independent loads in flight, then fold in a fixed order (deterministic).
 __global__ void __launch_bounds__(256)
 kin_ppo_reduce_kernel(const float* __restrict__ partials, int n_cta, int P, float* __restrict__ grad, float* __restrict__ stats, float inv_global_batch) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ float part[8][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int p = blockIdx.x * 32 + lane;
     const int row = P + KIN_PPO_STATS + 8;
-    if (p < P) {
-        float a = 0.0f;
-        for (int c = 0; c < n_cta; ++c) a += partials[(size_t)c * row + p];
-        grad[p] = a;
-    } else if (p < P + 5 && stats) {
-        float a = 0.0f;
-        for (int c = 0; c < n_cta; ++c) a += partials[(size_t)c * row + p];
-        stats[p - P] = a * inv_global_batch;
+    float a0 = 0.0f, a1 = 0.0f;
+    if (p < P + 5) {
+        int c = w;
+        for (; c + 8 < n_cta; c += 16) {
+            a0 += __ldg(partials + (size_t)c * row + p);
+            a1 += __ldg(partials + (size_t)(c + 8) * row + p);
+        }
+        if (c < n_cta) a0 += __ldg(partials + (size_t)c * row + p);
+    }
+    part[w][lane] = a0 + a1;
+    __syncthreads();
+    if (w == 0 && p < P + 5) {
+        float a = part[0][lane];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) a += part[k][lane];
+        if (p < P) grad[p] = a;
+        else if (stats) stats[p - P] = a * inv_global_batch;
+    }
+}
+
+// (mean, 1 / (std + 1e-8)) of the advantages of each minibatch (torch: mean, unbiased std) from the per-tile fp64 sums;
+// one CTA per minibatch, minibatch m = tile_ids[m * n_tiles .. (m + 1) * n_tiles)
+__global__ void __launch_bounds__(256)
+kin_ppo_adv_stats_kernel(const double* __restrict__ tile_sums, const int* __restrict__ tile_ids, int n_tiles, int normalize, float* __restrict__ out) {
+    __shared__ double sh[2][8];
+    const int* ids = tile_ids + (size_t)blockIdx.x * n_tiles;
+    double s1 = 0.0, s2 = 0.0;
+    for (int j = threadIdx.x; j < n_tiles; j += 256) {
+        const int t = ids[j];
+        s1 += tile_sums[2 * t];
+        s2 += tile_sums[2 * t + 1];
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+    }
+    if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = s1; sh[1][threadIdx.x >> 5] = s2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        s1 = 0.0; s2 = 0.0;
+        for (int k = 0; k < 8; ++k) { s1 += sh[0][k]; s2 += sh[1][k]; }
+        const double nsamp = (double)n_tiles * TS;
+        const double mean = s1 / nsamp;
+        const double var = nsamp > 1.0 ? fmax((s2 - nsamp * mean * mean) / (nsamp - 1.0), 0.0) : 0.0;
+        out[2 * blockIdx.x] = normalize ? (float)mean : 0.0f;
+        out[2 * blockIdx.x + 1] = normalize ? (float)(1.0 / (sqrt(var) + 1e-8)) : 1.0f;
     }
 }
 
 // clip_grad_norm_ + Adam, one CTA
 __global__ void __launch_bounds__(1024)
 kin_ppo_adam_kernel(float* __restrict__ params, const float* __restrict__ grad, float* __restrict__ m, float* __restrict__ v, int P,
-                    KinPpoHyper hp, float bc1, float bc2, float* __restrict__ stats) {
+                    KinPpoHyper hp, float bc1, float bc2, float* __restrict__ stats, float* __restrict__ stats_accum) {
     __shared__ float red[32];
     __shared__ float coef;
     float ss = 0.0f;
@@ -563,6 +607,12 @@ kin_ppo_adam_kernel(float* __restrict__ params, const float* __restrict__ grad, 
             const float c = hp.max_grad_norm > 0.0f ? hp.max_grad_norm / (norm + 1e-6f) : 1.0f;
             coef = c < 1.0f ? c : 1.0f;
             if (stats) stats[KIN_PPO_STAT_GRAD_NORM] = norm;
+            if (stats && stats_accum) {          // running sums over the minibatches of an update (slot 7 counts them)
+#pragma unroll
+                for (int q = 0; q < 5; ++q) stats_accum[q] += stats[q];
+                stats_accum[KIN_PPO_STAT_GRAD_NORM] += norm;
+                stats_accum[7] += 1.0f;
+            }
         }
     }
     __syncthreads();
@@ -579,7 +629,7 @@ kin_ppo_adam_kernel(float* __restrict__ params, const float* __restrict__ grad, 
 }
 
 int kin_ppo_reduce_launch(const float* partials, int n_cta, int P, float* grad, float* stats, float inv_global_batch, cudaStream_t st) {
-    kin_ppo_reduce_kernel<<<(P + 5 + 255) / 256, 256, 0, st>>>(partials, n_cta, P, grad, stats, inv_global_batch);
+    kin_ppo_reduce_kernel<<<(P + 5 + 31) / 32, 256, 0, st>>>(partials, n_cta, P, grad, stats, inv_global_batch);
     return KIN_OK;
 }
 
@@ -643,8 +693,8 @@ extern "C" int kin_ppo_gae(const float* reward, const float* value, const uint8_
 
 extern "C" int kin_ppo_grad(const float* params, int in_dim, const KinPpoHyper* hp, const float* obs, const float* action, const float* old_logp,
                             const float* advantage, const float* returns, const double* tile_sums, const int* tile_ids, int n_tiles,
-                            long long global_batch, float* partials, int grid, float* grad, float* stats, void* stream) {
-    if (!params || !hp || !obs || !action || !old_logp || !advantage || !returns || !tile_sums || !tile_ids || !partials || !grad || n_tiles <= 0 ||
+                            long long global_batch, float* partials, int grid, float* grad, float* stats, const float* adv_stats, void* stream) {
+    if (!params || !hp || !obs || !action || !old_logp || !advantage || !returns || (!tile_sums && !adv_stats) || !tile_ids || !partials || !grad || n_tiles <= 0 ||
         grid <= 0 || global_batch <= 0)
         return kin_fail(KIN_ERR_INVALID_ARG, "kin_ppo_grad: bad arguments");
     if (in_dim != 56) return kin_fail(KIN_ERR_UNSUPPORTED, "kin_ppo_grad: in_dim must be 56 (the route policy's 80-input update is not built yet)");
@@ -655,17 +705,26 @@ extern "C" int kin_ppo_grad(const float* params, int in_dim, const KinPpoHyper* 
     cudaStream_t st = (cudaStream_t)stream;
     const int g = grid < n_tiles ? grid : n_tiles;
     const float inv = 1.0f / (float)global_batch;
-    kin_ppo_grad_kernel<56><<<g, PPO_THREADS, smem, st>>>(params, *hp, obs, action, old_logp, advantage, returns, tile_sums, tile_ids, n_tiles, inv, partials);
+    kin_ppo_grad_kernel<56><<<g, PPO_THREADS, smem, st>>>(params, *hp, obs, action, old_logp, advantage, returns, tile_sums, tile_ids, n_tiles, inv, partials, adv_stats);
     kin_ppo_reduce_launch(partials, g, P, grad, stats, inv, st);
     e = cudaGetLastError();
     return e == cudaSuccess ? KIN_OK : kin_fail_cuda(e, "kin_ppo_grad");
 }
 
+extern "C" int kin_ppo_adv_stats(const double* tile_sums, const int* tile_ids, int n_tiles_per_minibatch, int n_minibatches, int normalize,
+                                 float* adv_stats, void* stream) {
+    if (!tile_sums || !tile_ids || !adv_stats || n_tiles_per_minibatch <= 0 || n_minibatches <= 0)
+        return kin_fail(KIN_ERR_INVALID_ARG, "kin_ppo_adv_stats: bad arguments");
+    kin_ppo_adv_stats_kernel<<<n_minibatches, 256, 0, (cudaStream_t)stream>>>(tile_sums, tile_ids, n_tiles_per_minibatch, normalize, adv_stats);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? KIN_OK : kin_fail_cuda(e, "kin_ppo_adv_stats");
+}
+
 extern "C" int kin_ppo_adam(float* params, const float* grad, float* adam_m, float* adam_v, int n_params, const KinPpoHyper* hp, int step,
-                            float* stats, void* stream) {
+                            float* stats, float* stats_accum, void* stream) {
     if (!params || !grad || !adam_m || !adam_v || !hp || n_params <= 0 || step < 1) return kin_fail(KIN_ERR_INVALID_ARG, "kin_ppo_adam: bad arguments");
     const float bc1 = 1.0f - powf(hp->adam_beta1, (float)step), bc2 = 1.0f - powf(hp->adam_beta2, (float)step);
-    kin_ppo_adam_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(params, grad, adam_m, adam_v, n_params, *hp, bc1, bc2, stats);
+    kin_ppo_adam_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(params, grad, adam_m, adam_v, n_params, *hp, bc1, bc2, stats, stats_accum);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? KIN_OK : kin_fail_cuda(e, "kin_ppo_adam");
 }

@@ -143,6 +143,8 @@ class PPOTrainer:
             self.adam_v = torch.zeros_like(self.params)
             self.grad = torch.zeros_like(self.params)
             self.stats = torch.zeros(_D("KIN_PPO_STATS"), dtype=torch.float32, device=self.device)
+            self.stats_accum = torch.zeros(_D("KIN_PPO_STATS"), dtype=torch.float32, device=self.device)
+            self._adv_stats = torch.zeros((max(self.S // self.local_batch, 1), 2), dtype=torch.float32, device=self.device)
             props = torch.cuda.get_device_properties(self.device)
             self.grad_ctas = int(grad_ctas or props.multi_processor_count)
             self.partials = torch.zeros((self.grad_ctas, self.P + _D("KIN_PPO_STATS") + 8), dtype=torch.float32, device=self.device)
@@ -253,23 +255,26 @@ class PPOTrainer:
         return self._sl
 
     # ------------------------------------------------------------------ update
-    def minibatch_grad(self, tile_ids: torch.Tensor) -> None:
-        """Gradient of one minibatch (sum over local samples, already divided by the GLOBAL minibatch size) into ``self.grad``."""
+    def _grad_launch(self, tile_ptr: int, n_tiles: int, adv_ptr: int | None) -> None:
         stream = torch.cuda.current_stream(self.device).cuda_stream
-        hp = self.hp.c()
-        n_tiles = int(tile_ids.numel())
+        hp = self._c_hyper
         global_batch = n_tiles * _D("KIN_PPO_TILE") * self.world
         if self.update_variant == "tc":
             img = self.collect_variant == "fused"
             _lib.check(self._L.kin_ppo_grad_tc(self.params.data_ptr(), 56, ctypes.byref(hp), (self.obs_img if img else self.obs_buf).data_ptr(),
                                                self.act_buf.data_ptr(), self.logp_buf.data_ptr(), self.adv_buf.data_ptr(), self.ret_buf.data_ptr(),
-                                               self.tile_sums.data_ptr(), tile_ids.data_ptr(), n_tiles, global_batch, self.partials.data_ptr(),
-                                               self.grad_ctas, self.grad.data_ptr(), self.stats.data_ptr(), None, None, 0, int(img), stream))
+                                               self.tile_sums.data_ptr(), tile_ptr, n_tiles, global_batch, self.partials.data_ptr(),
+                                               self.grad_ctas, self.grad.data_ptr(), self.stats.data_ptr(), None, None, 0, int(img), adv_ptr, stream))
             return
         _lib.check(self._L.kin_ppo_grad(self.params.data_ptr(), 56, ctypes.byref(hp), self.obs_buf.data_ptr(), self.act_buf.data_ptr(),
                                         self.logp_buf.data_ptr(), self.adv_buf.data_ptr(), self.ret_buf.data_ptr(), self.tile_sums.data_ptr(),
-                                        tile_ids.data_ptr(), n_tiles, global_batch, self.partials.data_ptr(), self.grad_ctas,
-                                        self.grad.data_ptr(), self.stats.data_ptr(), stream))
+                                        tile_ptr, n_tiles, global_batch, self.partials.data_ptr(), self.grad_ctas,
+                                        self.grad.data_ptr(), self.stats.data_ptr(), adv_ptr, stream))
+
+    def minibatch_grad(self, tile_ids: torch.Tensor) -> None:
+        """Gradient of one minibatch (sum over local samples, already divided by the GLOBAL minibatch size) into ``self.grad``."""
+        self._c_hyper = self.hp.c()
+        self._grad_launch(tile_ids.data_ptr(), int(tile_ids.numel()), None)
 
     def refresh_old_logp(self) -> None:
         """Recompute the rollout's log-probs with the tensor-core kernel's own forward (bf16 operands), so that the probability
@@ -279,7 +284,7 @@ class PPOTrainer:
         hp = self.hp.c()
         _lib.check(self._L.kin_ppo_grad_tc(self.params.data_ptr(), 56, ctypes.byref(hp), self.obs_buf.data_ptr(), self.act_buf.data_ptr(), None, None,
                                            None, None, self._all_tiles.data_ptr(), int(self._all_tiles.numel()), 0, None, self.grad_ctas, None, None,
-                                           self.logp_buf.data_ptr(), None, 1, 0, torch.cuda.current_stream(self.device).cuda_stream))
+                                           self.logp_buf.data_ptr(), None, 1, 0, None, torch.cuda.current_stream(self.device).cuda_stream))
 
     def apply_update(self) -> None:
         """All-reduce the gradient (sum over ranks), clip by global norm, Adam step -- identical on every rank."""
@@ -287,34 +292,40 @@ class PPOTrainer:
             allreduce_sum_(self.grad, self.group)
             allreduce_sum_(self.stats[:5], self.group)
         self.update_count += 1
-        hp = self.hp.c()
+        hp = getattr(self, "_c_hyper", None) or self.hp.c()
         _lib.check(self._L.kin_ppo_adam(self.params.data_ptr(), self.grad.data_ptr(), self.adam_m.data_ptr(), self.adam_v.data_ptr(), self.P,
-                                        ctypes.byref(hp), self.update_count, self.stats.data_ptr(),
+                                        ctypes.byref(hp), self.update_count, self.stats.data_ptr(), self.stats_accum.data_ptr(),
                                         torch.cuda.current_stream(self.device).cuda_stream))
 
     def update(self) -> dict[str, float]:
+        """``PPO.train``: n_epochs passes over the rollout in random minibatches; no host synchronisation until the statistics are read."""
         tile = _D("KIN_PPO_TILE")
         n_tiles_total = self.S // tile
         tiles_per_mb = self.local_batch // tile
-        agg = torch.zeros(_D("KIN_PPO_STATS"), dtype=torch.float64, device=self.device)
-        n_mb = 0
+        mb_per_epoch = n_tiles_total // tiles_per_mb
+        self._c_hyper = self.hp.c()
         with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            self.stats_accum.zero_()
             img = self.collect_variant == "fused"
             if self.update_variant == "tc" and not img:   # the fused collection already sampled with the tensor-core forward
                 self.refresh_old_logp()
+            adv = self._adv_stats
             for _ in range(self.hp.n_epochs):
                 if img:   # minibatches are unions of whole 128-sample images: permute pairs of 64-sample tiles
                     p2 = torch.randperm(n_tiles_total // 2, generator=self._gen, device=self.device, dtype=torch.int64)
                     perm = torch.stack((2 * p2, 2 * p2 + 1), dim=1).reshape(-1).to(torch.int32)
                 else:
                     perm = torch.randperm(n_tiles_total, generator=self._gen, device=self.device, dtype=torch.int64).to(torch.int32)
-                for start in range(0, n_tiles_total, tiles_per_mb):
-                    ids = perm[start:start + tiles_per_mb].contiguous()
-                    self.minibatch_grad(ids)
+                self._perm = perm                          # keep the ids alive until the launches that read them have run
+                _lib.check(self._L.kin_ppo_adv_stats(self.tile_sums.data_ptr(), perm.data_ptr(), tiles_per_mb, mb_per_epoch,
+                                                     int(self.hp.normalize_advantage), adv.data_ptr(), stream))
+                for m in range(mb_per_epoch):
+                    self._grad_launch(perm.data_ptr() + 4 * m * tiles_per_mb, tiles_per_mb, adv.data_ptr() + 8 * m)
                     self.apply_update()
-                    agg += self.stats.double()
-                    n_mb += 1
-        a = (agg / max(n_mb, 1)).cpu().numpy()
+            a = self.stats_accum.cpu().numpy().astype(np.float64)
+        n_mb = max(int(round(a[7])), 1)
+        a = a / n_mb
         return {"policy_loss": float(a[0]), "value_loss": float(a[1]), "entropy": float(a[2]), "approx_kl": float(a[3]),
                 "clip_fraction": float(a[4]), "grad_norm": float(a[5]), "minibatches": n_mb}
 

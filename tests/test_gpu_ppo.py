@@ -120,7 +120,7 @@ def test_minibatch_gradient_matches_autograd():
     c_hp = hp.c()
     _lib.check(_lib.lib().kin_ppo_grad(flat.data_ptr(), 56, ctypes.byref(c_hp), obs.data_ptr(), act.data_ptr(), old_logp.data_ptr(), adv.data_ptr(),
                                        ret.data_ptr(), sums.data_ptr(), tile_ids.data_ptr(), tile_ids.numel(), tile_ids.numel() * 64,
-                                       partials.data_ptr(), ctas, grad.data_ptr(), stats.data_ptr(), torch.cuda.current_stream().cuda_stream))
+                                       partials.data_ptr(), ctas, grad.data_ptr(), stats.data_ptr(), None, torch.cuda.current_stream().cuda_stream))
     idx = (tile_ids.long()[:, None] * 64 + torch.arange(64, device="cuda")[None]).reshape(-1)
     for t in pol.tensors.values():
         t.requires_grad_(True)
@@ -172,7 +172,7 @@ def test_minibatch_gradient_tc_matches_autograd():
     # forward only: log-prob and value of the visited samples
     lp_out, v_out = torch.full((S,), 123.0, device="cuda"), torch.full((S,), 123.0, device="cuda")
     _lib.check(L.kin_ppo_grad_tc(flat.data_ptr(), 56, ctypes.byref(c_hp), obs.data_ptr(), act.data_ptr(), None, None, None, None,
-                                 tile_ids.data_ptr(), tile_ids.numel(), 0, None, 3, None, None, lp_out.data_ptr(), v_out.data_ptr(), 1, 0, stream))
+                                 tile_ids.data_ptr(), tile_ids.numel(), 0, None, 3, None, None, lp_out.data_ptr(), v_out.data_ptr(), 1, 0, None, stream))
     torch.cuda.synchronize()
     assert float((v_out[idx] - value[idx]).abs().max()) < 0.03 and float((lp_out[idx] - exact_logp[idx]).abs().max()) < 0.06
     assert float((lp_out[idx] - exact_logp[idx]).abs().mean()) < 0.008
@@ -196,7 +196,7 @@ def test_minibatch_gradient_tc_matches_autograd():
             grad, stats = torch.zeros(P, device="cuda"), torch.zeros(8, device="cuda")
             _lib.check(L.kin_ppo_grad_tc(flat.data_ptr(), 56, ctypes.byref(c_hp), obs.data_ptr(), act.data_ptr(), old_logp.data_ptr(), adv.data_ptr(),
                                          ret.data_ptr(), sums.data_ptr(), tile_ids.data_ptr(), tile_ids.numel(), tile_ids.numel() * 64,
-                                         partials.data_ptr(), ctas, grad.data_ptr(), stats.data_ptr(), None, None, 0, 0, stream))
+                                         partials.data_ptr(), ctas, grad.data_ptr(), stats.data_ptr(), None, None, 0, 0, None, stream))
             torch.cuda.synchronize()
             off = 0
             for k, gk in zip(ppo.PARAM_ORDER, grads):
@@ -213,7 +213,7 @@ def test_minibatch_gradient_tc_matches_autograd():
     # odd tile counts are refused (two 64-sample tiles per GEMM tile)
     rc = L.kin_ppo_grad_tc(flat.data_ptr(), 56, ctypes.byref(c_hp), obs.data_ptr(), act.data_ptr(), old_logp.data_ptr(), adv.data_ptr(),
                            ret.data_ptr(), sums.data_ptr(), tile_ids.data_ptr(), 3, 192, partials.data_ptr(), 2, grad.data_ptr(), stats.data_ptr(),
-                           None, None, 0, 0, stream)
+                           None, None, 0, 0, None, stream)
     assert rc != 0
 
 
@@ -233,7 +233,7 @@ def test_adam_matches_torch():
         ref_p.grad = grad.clone()
         norm = torch.nn.utils.clip_grad_norm_([ref_p], 0.5)
         opt.step()
-        _lib.check(_lib.lib().kin_ppo_adam(params.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(), P, ctypes.byref(c_hp), step, stats.data_ptr(),
+        _lib.check(_lib.lib().kin_ppo_adam(params.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(), P, ctypes.byref(c_hp), step, stats.data_ptr(), None,
                                            torch.cuda.current_stream().cuda_stream))
         assert abs(float(stats[5]) - float(norm)) < 1e-4 * float(norm)
         assert float((params - ref_p.detach()).abs().max()) < 2e-6

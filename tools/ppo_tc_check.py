@@ -38,11 +38,11 @@ def run(kind, tile_ids, ctas):
     if kind == "tc":
         _lib.check(L.kin_ppo_grad_tc(flat.data_ptr(), 56, ctypes.byref(c_hp), obs.data_ptr(), act.data_ptr(), old_logp.data_ptr(), adv.data_ptr(),
                                      ret.data_ptr(), sums.data_ptr(), tile_ids.data_ptr(), n, n * 64, partials.data_ptr(), ctas, grad.data_ptr(),
-                                     stats.data_ptr(), None, None, 0, 0, stream))
+                                     stats.data_ptr(), None, None, 0, 0, None, stream))
     else:
         _lib.check(L.kin_ppo_grad(flat.data_ptr(), 56, ctypes.byref(c_hp), obs.data_ptr(), act.data_ptr(), old_logp.data_ptr(), adv.data_ptr(),
                                   ret.data_ptr(), sums.data_ptr(), tile_ids.data_ptr(), n, n * 64, partials.data_ptr(), ctas, grad.data_ptr(),
-                                  stats.data_ptr(), stream))
+                                  stats.data_ptr(), None, stream))
     torch.cuda.synchronize()
     return grad, stats
 
@@ -51,7 +51,7 @@ tile_ids = torch.tensor([3, 17, 0, 39, 8, 21, 22, 5, 30, 11, 12, 1, 47, 40], dty
 idx = (tile_ids.long()[:, None] * 64 + torch.arange(64, device="cuda")[None]).reshape(-1)
 lp_out, v_out = torch.full((S,), 123.0, device="cuda"), torch.full((S,), 123.0, device="cuda")
 _lib.check(L.kin_ppo_grad_tc(flat.data_ptr(), 56, ctypes.byref(c_hp), obs.data_ptr(), act.data_ptr(), None, None, None, None,
-                             tile_ids.data_ptr(), tile_ids.numel(), 0, None, 3, None, None, lp_out.data_ptr(), v_out.data_ptr(), 1, 0, stream))
+                             tile_ids.data_ptr(), tile_ids.numel(), 0, None, 3, None, None, lp_out.data_ptr(), v_out.data_ptr(), 1, 0, None, stream))
 torch.cuda.synchronize()
 print("forward-only: value max err", float((v_out[idx] - value[idx]).abs().max()), "logp max/mean err",
       float((lp_out[idx] - exact_logp[idx]).abs().max()), float((lp_out[idx] - exact_logp[idx]).abs().mean()), flush=True)
@@ -75,8 +75,11 @@ for kind, ctas in (("fp32", 5), ("tc", 2), ("tc", 7), ("tc", 148)):
     print("   stats", [f"{float(x):.5f}" for x in stats[:5]], "ref", {k: round(v, 5) for k, v in ref_stats.items()}, flush=True)
 
 # timing on a realistic minibatch: 131072 samples = 2048 tiles
-perm = torch.randperm(S // 64, device="cuda", generator=g)[:2048].to(torch.int32).contiguous()
-for kind in ("fp32", "tc"):
+NT = int(os.environ.get("NT", "2048"))
+perm = torch.randperm(S // 64, device="cuda", generator=g)[:NT].to(torch.int32).contiguous()
+kinds = ("fp32", "tc") if "DBG" not in os.environ else ("tc",)
+c_hp.pad0 = int(os.environ.get("DBG", "0"))
+for kind in kinds:
     for _ in range(3):
         run(kind, perm, 148)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -87,11 +90,11 @@ for kind in ("fp32", "tc"):
     for _ in range(20):
         if kind == "tc":
             L.kin_ppo_grad_tc(flat.data_ptr(), 56, ctypes.byref(c_hp), obs.data_ptr(), act.data_ptr(), old_logp.data_ptr(), adv.data_ptr(), ret.data_ptr(),
-                              sums.data_ptr(), perm.data_ptr(), n, n * 64, partials.data_ptr(), 148, grad.data_ptr(), stats.data_ptr(), None, None, 0, 0, stream)
+                              sums.data_ptr(), perm.data_ptr(), n, n * 64, partials.data_ptr(), 148, grad.data_ptr(), stats.data_ptr(), None, None, 0, 0, None, stream)
         else:
             L.kin_ppo_grad(flat.data_ptr(), 56, ctypes.byref(c_hp), obs.data_ptr(), act.data_ptr(), old_logp.data_ptr(), adv.data_ptr(), ret.data_ptr(),
-                           sums.data_ptr(), perm.data_ptr(), n, n * 64, partials.data_ptr(), 148, grad.data_ptr(), stats.data_ptr(), stream)
+                           sums.data_ptr(), perm.data_ptr(), n, n * 64, partials.data_ptr(), 148, grad.data_ptr(), stats.data_ptr(), None, stream)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 20
-    print(f"{kind}: {ms * 1e3:.1f} us per 131072-sample minibatch = {131072 / ms / 1e3:.1f} M samples/s, {131072 * 95.2e3 / ms / 1e9:.1f} TFLOP/s")
+    print(f"dbg={c_hp.pad0} {kind}: {ms * 1e3:.1f} us per {NT * 64}-sample minibatch = {NT * 64 / ms / 1e3:.1f} M samples/s, {NT * 64 * 95.2e3 / ms / 1e9:.1f} TFLOP/s")

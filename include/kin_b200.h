@@ -585,11 +585,13 @@ int kin_ppo_adv_stats(const double *tile_sums, const int *tile_ids, int n_tiles_
  * logp_out / value_out (nullable, [S]) receive this variant's own log-prob / value of every visited sample; with
  * forward_only != 0 nothing else is computed (used to refresh old_logp with the same arithmetic the update uses).
  * obs_is_image != 0: obs is the rollout buffer kin_ppo_collect wrote -- one 16 KB bf16 operand image per 128 consecutive
- * samples -- and every pair (tile_ids[2j], tile_ids[2j+1]) must be (2m, 2m+1), i.e. one whole image.                      */
+ * samples -- and every pair (tile_ids[2j], tile_ids[2j+1]) must be (2m, 2m+1), i.e. one whole image.
+ * weight_image (nullable): the bf16 operand image of params (kin_ppo_pack_weights / kin_ppo_adam keep it current); each CTA then
+ * fetches its weights with bulk copies instead of converting them from fp32.                                               */
 int kin_ppo_grad_tc(const float *params, int in_dim, const KinPpoHyper *host_hyper, const void *obs, const float *action, const float *old_logp,
                     const float *advantage, const float *returns, const double *tile_sums, const int *tile_ids, int n_tiles,
                     long long global_batch, float *partials, int grid, float *grad, float *stats, float *logp_out, float *value_out,
-                    int forward_only, int obs_is_image, const float *adv_stats, void *stream);
+                    int forward_only, int obs_is_image, const float *adv_stats, const void *weight_image, void *stream);
 
 /* Replaces: OnPolicyAlgorithm.collect_rollouts (SB3 on_policy_algorithm.py) over a VecEnv of ArmKinematicEnv, fused into ONE
  * launch: n_steps x (actor + critic forward on tcgen05, a = mean + exp(log_std) * eps, log-prob, env step with reward and
@@ -600,8 +602,8 @@ int kin_ppo_grad_tc(const float *params, int in_dim, const KinPpoHyper *host_hyp
  * Episodes that hit the time limit append (t * n + env, terminal observation) to boot_index / boot_obs (capacity boot_cap,
  * count in *boot_count, reset by this call); kin_ppo_bootstrap_list then adds gamma * V(terminal_obs) to their rewards.
  * eps is Philox4x32(noise_seed, env, first_step + t) -- the draws of kin_policy_act; resets use Philox(reset_seed, env, episode).
- * params: the flat PARAM_ORDER buffer.  tiles_per_cta: 0 (auto), 1, 2 or 4.                                               */
-int kin_ppo_collect(void *handle, float *state, int stride, int n_envs, int mode, const float *params, int in_dim, int n_steps,
+ * params: the flat PARAM_ORDER buffer; weight_image (nullable): its bf16 operand image.  tiles_per_cta: 0 (auto), 1, 2 or 4. */
+int kin_ppo_collect(void *handle, float *state, int stride, int n_envs, int mode, const float *params, const void *weight_image, int in_dim, int n_steps,
                     uint64_t noise_seed, uint32_t first_step, uint64_t reset_seed, void *obs_tiles, float *action, float *logp, float *value,
                     float *reward, uint8_t *done, uint8_t *episode_start, uint8_t *start_io, float *last_value, int *boot_count,
                     int *boot_index, float *boot_obs, int boot_cap, int tiles_per_cta, void *stream);
@@ -612,9 +614,14 @@ int kin_ppo_bootstrap_list(const float *params, int in_dim, const float *boot_ob
 
 /* clip_grad_norm_(max_grad_norm) + Adam step on the flat parameter buffer (torch.optim.Adam semantics, eps = 1e-5 in SB3).
  * adam_m / adam_v [P]; step = 1-based update count.  stats[5] receives the gradient norm; stats_accum (nullable, [8]) gets
- * stats[0..5] added and slot 7 incremented: running sums over the minibatches of one update without host round trips.    */
+ * stats[0..5] added and slot 7 incremented: running sums over the minibatches of one update without host round trips.
+ * weight_image (nullable, in_dim 56): the bf16 operand image is rewritten in step with the parameters.                   */
 int kin_ppo_adam(float *params, const float *grad, float *adam_m, float *adam_v, int n_params, const KinPpoHyper *host_hyper, int step,
-                 float *stats, float *stats_accum, void *stream);
+                 float *stats, float *stats_accum, void *weight_image, int in_dim, void *stream);
+
+/* Build the 36 KB bf16 operand image of the flat parameters (the B operands of the tensor-core kernels: W0 | W1 | WO of both
+ * nets as SWIZZLE_128B tiles, layer-1 bias folded in as column 56).  kin_ppo_adam(weight_image != NULL) keeps it current.   */
+int kin_ppo_pack_weights(const float *params, int in_dim, void *weight_image, void *stream);
 
 #ifdef __cplusplus
 }

@@ -42,6 +42,7 @@ struct __align__(1024) CollectSmem {
     float ls[8];
     float sig[8];
     unsigned long long mbar[TILES][2];           // [0]: layer 1 (MMA commit + image store drained), [1]: layers 2 / 3
+    unsigned long long mbar_w;                   // weight image bulk copy
     unsigned tmem_base;
 };
 
@@ -173,7 +174,8 @@ __device__ __forceinline__ void policy_forward_tc(CollectSmem<TILES>& S, TileSta
 template <int TILES, int MODE>
 __global__ void __launch_bounds__(TILES * CT_ROWS, 1)
 kin_collect_kernel(const __grid_constant__ KinEnvParams P, const KinSamplerParams* __restrict__ SP, float* __restrict__ state, int stride, int n,
-                   const float* __restrict__ params, int T, uint64_t noise_seed, uint32_t step0, uint64_t reset_seed, CollectOut out) {
+                   const float* __restrict__ params, const unsigned char* __restrict__ wimg, int T, uint64_t noise_seed, uint32_t step0,
+                   uint64_t reset_seed, CollectOut out) {
     constexpr int IN = 56;
     extern __shared__ unsigned char smem_raw[];
     CollectSmem<TILES>& S = *reinterpret_cast<CollectSmem<TILES>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -181,26 +183,39 @@ kin_collect_kernel(const __grid_constant__ KinEnvParams P, const KinSamplerParam
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     constexpr int NT = TILES * CT_ROWS;
 
-    // ---- weights -> bf16 operand tiles (both nets) -------------------------------------------------------------------
-    {
-        uint4* zw = reinterpret_cast<uint4*>(S.WO);
-        for (int i = tid; i < 2 * 16 * 128 / 16; i += NT) zw[i] = make_uint4(0u, 0u, 0u, 0u);
+    // ---- weights -> bf16 operand tiles (both nets): one bulk copy of the prebuilt image, or converted here ---------------
+    if (wimg) {
+        static_assert(offsetof(CollectSmem<TILES>, W1) == offsetof(CollectSmem<TILES>, W0) + 16384 &&
+                      offsetof(CollectSmem<TILES>, WO) == offsetof(CollectSmem<TILES>, W0) + 32768, "W0 | W1 | WO must be laid out like the image");
+        if (tid == 0) {
+            const unsigned mbw = smem_u32(&S.mbar_w);
+            mbar_init(mbw, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbw), "r"(KIN_WIMG_BYTES) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_u32(S.W0)), "l"(wimg), "r"(KIN_WIMG_BYTES), "r"(mbw) : "memory");
+        }
+    } else {
+        {
+            uint4* zw = reinterpret_cast<uint4*>(S.WO);
+            for (int i = tid; i < 2 * 16 * 128 / 16; i += NT) zw[i] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        for (int i = tid; i < 128 * 64; i += NT) {
+            const int nn = i >> 6, k = i & 63, u = nn & 63;
+            const int wbase = (nn < 64) ? O.pi_w0 : O.vf_w0, bbase = (nn < 64) ? O.pi_b0 : O.vf_b0;
+            const float v = k < IN ? __ldg(params + wbase + u * IN + k) : (k == IN ? __ldg(params + bbase + u) : 0.0f);
+            *reinterpret_cast<unsigned short*>(S.W0 + sw_elem(nn, k)) = (unsigned short)(pack_bf16(v, 0.0f) & 0xffffu);
+        }
+        for (int i = tid; i < 2 * 4096; i += NT) {
+            const int nt = i >> 12, u = (i >> 6) & 63, k = i & 63;
+            *reinterpret_cast<unsigned short*>(S.W1[nt] + sw_elem(u, k)) =
+                (unsigned short)(pack_bf16(__ldg(params + (nt ? O.vf_w1 : O.pi_w1) + u * 64 + k), 0.0f) & 0xffffu);
+        }
+        __syncthreads();
+        for (int i = tid; i < 7 * 64; i += NT)
+            *reinterpret_cast<unsigned short*>(S.WO[0] + sw_elem(i >> 6, i & 63)) = (unsigned short)(pack_bf16(__ldg(params + O.act_w + i), 0.0f) & 0xffffu);
+        if (tid < 64) *reinterpret_cast<unsigned short*>(S.WO[1] + sw_elem(7, tid)) = (unsigned short)(pack_bf16(__ldg(params + O.val_w + tid), 0.0f) & 0xffffu);
     }
-    for (int i = tid; i < 128 * 64; i += NT) {
-        const int nn = i >> 6, k = i & 63, u = nn & 63;
-        const int wbase = (nn < 64) ? O.pi_w0 : O.vf_w0, bbase = (nn < 64) ? O.pi_b0 : O.vf_b0;
-        const float v = k < IN ? __ldg(params + wbase + u * IN + k) : (k == IN ? __ldg(params + bbase + u) : 0.0f);
-        *reinterpret_cast<unsigned short*>(S.W0 + sw_elem(nn, k)) = (unsigned short)(pack_bf16(v, 0.0f) & 0xffffu);
-    }
-    for (int i = tid; i < 2 * 4096; i += NT) {
-        const int nt = i >> 12, u = (i >> 6) & 63, k = i & 63;
-        *reinterpret_cast<unsigned short*>(S.W1[nt] + sw_elem(u, k)) =
-            (unsigned short)(pack_bf16(__ldg(params + (nt ? O.vf_w1 : O.pi_w1) + u * 64 + k), 0.0f) & 0xffffu);
-    }
-    __syncthreads();
-    for (int i = tid; i < 7 * 64; i += NT)
-        *reinterpret_cast<unsigned short*>(S.WO[0] + sw_elem(i >> 6, i & 63)) = (unsigned short)(pack_bf16(__ldg(params + O.act_w + i), 0.0f) & 0xffffu);
-    if (tid < 64) *reinterpret_cast<unsigned short*>(S.WO[1] + sw_elem(7, tid)) = (unsigned short)(pack_bf16(__ldg(params + O.val_w + tid), 0.0f) & 0xffffu);
     if (tid < 128) S.b1[tid] = __ldg(params + (tid < 64 ? O.pi_b1 + tid : O.vf_b1 + tid - 64));
     if (tid < 8) {
         const float ls = tid < 7 ? __ldg(params + O.log_std + tid) : 0.0f;
@@ -218,6 +233,7 @@ kin_collect_kernel(const __grid_constant__ KinEnvParams P, const KinSamplerParam
     fence_before();
     __syncthreads();
     fence_after();
+    if (wimg) mbar_wait(smem_u32(&S.mbar_w), 0u);
 
     TileState<TILES> c;
     c.tile = tid >> 7;
@@ -365,7 +381,8 @@ kin_bootstrap_list_kernel(const float* __restrict__ params, const float* __restr
 }
 
 template <int TILES>
-static cudaError_t launch_collect(const KinHandle* h, float* state, int stride, int n, int mode, const float* params, int T, uint64_t noise_seed,
+static cudaError_t launch_collect(const KinHandle* h, float* state, int stride, int n, int mode, const float* params, const unsigned char* wimg, int T,
+                                  uint64_t noise_seed,
                                   uint32_t step0, uint64_t reset_seed, const CollectOut& out, cudaStream_t st) {
     const size_t smem = sizeof(CollectSmem<TILES>) + 1024;
     const int n_tiles = n / CT_ROWS;
@@ -374,13 +391,13 @@ static cudaError_t launch_collect(const KinHandle* h, float* state, int stride, 
     if (mode == KIN_MODE_APPROACH) {
         e = cudaFuncSetAttribute(kin_collect_kernel<TILES, KIN_MODE_APPROACH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        kin_collect_kernel<TILES, KIN_MODE_APPROACH><<<grid, TILES * CT_ROWS, smem, st>>>(h->params, h->d_sampler, state, stride, n, params, T, noise_seed,
-                                                                                        step0, reset_seed, out);
+        kin_collect_kernel<TILES, KIN_MODE_APPROACH><<<grid, TILES * CT_ROWS, smem, st>>>(h->params, h->d_sampler, state, stride, n, params, wimg, T,
+                                                                                        noise_seed, step0, reset_seed, out);
     } else {
         e = cudaFuncSetAttribute(kin_collect_kernel<TILES, KIN_MODE_DOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        kin_collect_kernel<TILES, KIN_MODE_DOCK><<<grid, TILES * CT_ROWS, smem, st>>>(h->params, h->d_sampler, state, stride, n, params, T, noise_seed, step0,
-                                                                                    reset_seed, out);
+        kin_collect_kernel<TILES, KIN_MODE_DOCK><<<grid, TILES * CT_ROWS, smem, st>>>(h->params, h->d_sampler, state, stride, n, params, wimg, T, noise_seed,
+                                                                                    step0, reset_seed, out);
     }
     return cudaGetLastError();
 }
@@ -389,7 +406,7 @@ static cudaError_t launch_collect(const KinHandle* h, float* state, int stride, 
 
 using namespace kin;
 
-extern "C" int kin_ppo_collect(void* handle, float* state, int stride, int n_envs, int mode, const float* params, int in_dim, int n_steps,
+extern "C" int kin_ppo_collect(void* handle, float* state, int stride, int n_envs, int mode, const float* params, const void* weight_image, int in_dim, int n_steps,
                                uint64_t noise_seed, uint32_t first_step, uint64_t reset_seed, void* obs_tiles, float* action, float* logp, float* value,
                                float* reward, uint8_t* done, uint8_t* episode_start, uint8_t* start_io, float* last_value, int* boot_count,
                                int* boot_index, float* boot_obs, int boot_cap, int tiles_per_cta, void* stream) {
@@ -415,9 +432,9 @@ extern "C" int kin_ppo_collect(void* handle, float* state, int stride, int n_env
     CollectOut out{(unsigned char*)obs_tiles, action, logp, value, reward, done, episode_start, start_io, last_value, boot_count, boot_index, boot_obs, boot_cap};
     cudaError_t e = cudaMemsetAsync(boot_count, 0, sizeof(int), st);
     if (e != cudaSuccess) return kin_fail_cuda(e, "kin_ppo_collect: memset");
-    if (tiles == 1) e = launch_collect<1>(h, state, stride, n_envs, mode, params, n_steps, noise_seed, first_step, reset_seed, out, st);
-    else if (tiles == 2) e = launch_collect<2>(h, state, stride, n_envs, mode, params, n_steps, noise_seed, first_step, reset_seed, out, st);
-    else if (tiles == 4) e = launch_collect<4>(h, state, stride, n_envs, mode, params, n_steps, noise_seed, first_step, reset_seed, out, st);
+    if (tiles == 1) e = launch_collect<1>(h, state, stride, n_envs, mode, params, static_cast<const unsigned char*>(weight_image), n_steps, noise_seed, first_step, reset_seed, out, st);
+    else if (tiles == 2) e = launch_collect<2>(h, state, stride, n_envs, mode, params, static_cast<const unsigned char*>(weight_image), n_steps, noise_seed, first_step, reset_seed, out, st);
+    else if (tiles == 4) e = launch_collect<4>(h, state, stride, n_envs, mode, params, static_cast<const unsigned char*>(weight_image), n_steps, noise_seed, first_step, reset_seed, out, st);
     else return kin_fail(KIN_ERR_INVALID_ARG, "kin_ppo_collect: tiles_per_cta must be 0 (auto), 1, 2 or 4");
     return e == cudaSuccess ? KIN_OK : kin_fail_cuda(e, "kin_ppo_collect");
 }

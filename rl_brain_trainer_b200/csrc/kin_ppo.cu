@@ -16,6 +16,8 @@
 //
 // This is the FP32-pipe variant (the strict-parity path north_star asks to keep); the GEMM-shaped parts are classic
 // register-tiled shared-memory SGEMMs.  The tcgen05 variant of the update is the next step.
+#include <cuda_bf16.h>
+
 #include "kin_internal.h"
 #include "kin_mlp.cuh"
 #include "kin_ppo_layout.cuh"
@@ -589,7 +591,8 @@ kin_ppo_adv_stats_kernel(const double* __restrict__ tile_sums, const int* __rest
 // clip_grad_norm_ + Adam, one CTA
 __global__ void __launch_bounds__(1024)
 kin_ppo_adam_kernel(float* __restrict__ params, const float* __restrict__ grad, float* __restrict__ m, float* __restrict__ v, int P,
-                    KinPpoHyper hp, float bc1, float bc2, float* __restrict__ stats, float* __restrict__ stats_accum) {
+                    KinPpoHyper hp, float bc1, float bc2, float* __restrict__ stats, float* __restrict__ stats_accum,
+                    unsigned short* __restrict__ wimg, int in_dim) {
     __shared__ float red[32];
     __shared__ float coef;
     float ss = 0.0f;
@@ -624,7 +627,23 @@ kin_ppo_adam_kernel(float* __restrict__ params, const float* __restrict__ grad, 
         m[p] = mm;
         v[p] = vv;
         const float denom = sqrtf(vv) / sqrtf(bc2) + hp.adam_eps;
-        params[p] -= (hp.learning_rate / bc1) * (mm / denom);
+        const float np = params[p] - (hp.learning_rate / bc1) * (mm / denom);
+        params[p] = np;
+        if (wimg) {      // keep the bf16 operand image of the weights in step with the parameters
+            const int off = wimg_offset(ppo_offsets(in_dim), in_dim, p);
+            if (off >= 0) wimg[off >> 1] = __bfloat16_as_ushort(__float2bfloat16_rn(np));
+        }
+    }
+}
+
+// full (re)build of the bf16 operand image from the flat parameters
+__global__ void __launch_bounds__(256)
+kin_ppo_pack_weights_kernel(const float* __restrict__ params, int in_dim, unsigned short* __restrict__ wimg) {
+    const PpoOffsets O = ppo_offsets(in_dim);
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i < O.total) {
+        const int off = wimg_offset(O, in_dim, i);
+        if (off >= 0) wimg[off >> 1] = __bfloat16_as_ushort(__float2bfloat16_rn(params[i]));
     }
 }
 
@@ -720,11 +739,25 @@ extern "C" int kin_ppo_adv_stats(const double* tile_sums, const int* tile_ids, i
     return e == cudaSuccess ? KIN_OK : kin_fail_cuda(e, "kin_ppo_adv_stats");
 }
 
+extern "C" int kin_ppo_pack_weights(const float* params, int in_dim, void* weight_image, void* stream) {
+    if (!params || !weight_image) return kin_fail(KIN_ERR_INVALID_ARG, "kin_ppo_pack_weights: bad arguments");
+    if (in_dim != 56) return kin_fail(KIN_ERR_UNSUPPORTED, "kin_ppo_pack_weights: in_dim must be 56");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(weight_image, 0, KIN_WIMG_BYTES, st);
+    if (e != cudaSuccess) return kin_fail_cuda(e, "kin_ppo_pack_weights: memset");
+    const int P = ppo_offsets(in_dim).total;
+    kin_ppo_pack_weights_kernel<<<(P + 255) / 256, 256, 0, st>>>(params, in_dim, static_cast<unsigned short*>(weight_image));
+    e = cudaGetLastError();
+    return e == cudaSuccess ? KIN_OK : kin_fail_cuda(e, "kin_ppo_pack_weights");
+}
+
 extern "C" int kin_ppo_adam(float* params, const float* grad, float* adam_m, float* adam_v, int n_params, const KinPpoHyper* hp, int step,
-                            float* stats, float* stats_accum, void* stream) {
+                            float* stats, float* stats_accum, void* weight_image, int in_dim, void* stream) {
+    if (weight_image && in_dim != 56) return kin_fail(KIN_ERR_UNSUPPORTED, "kin_ppo_adam: the weight image is built for in_dim 56");
     if (!params || !grad || !adam_m || !adam_v || !hp || n_params <= 0 || step < 1) return kin_fail(KIN_ERR_INVALID_ARG, "kin_ppo_adam: bad arguments");
     const float bc1 = 1.0f - powf(hp->adam_beta1, (float)step), bc2 = 1.0f - powf(hp->adam_beta2, (float)step);
-    kin_ppo_adam_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(params, grad, adam_m, adam_v, n_params, *hp, bc1, bc2, stats, stats_accum);
+    kin_ppo_adam_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(params, grad, adam_m, adam_v, n_params, *hp, bc1, bc2, stats, stats_accum,
+                                                              static_cast<unsigned short*>(weight_image), in_dim);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? KIN_OK : kin_fail_cuda(e, "kin_ppo_adam");
 }

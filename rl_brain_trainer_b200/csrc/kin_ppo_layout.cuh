@@ -28,6 +28,29 @@ __host__ __device__ inline PpoOffsets ppo_offsets(int in_dim) {
     return o;
 }
 
+// ---- bf16 operand image of the weights (the B operands of the tensor-core kernels), 36 KB:
+//   [W0 actor 8 KB][W0 critic 8 KB][W1 actor 8 KB][W1 critic 8 KB][WO actor 2 KB][WO critic 2 KB]
+// every block a [rows][64 bf16] SWIZZLE_128B tile (kin_umma.cuh): W0 rows = hidden unit, col 56 = its bias, cols 57.. zero;
+// WO actor rows 0..6 = act_w, WO critic row 7 = val_w, other rows zero.  b1 / act_b / val_b / log_std stay fp32 in `params`.
+constexpr int KIN_WIMG_BYTES = 36864;
+constexpr int KIN_WIMG_W0 = 0, KIN_WIMG_W1 = 16384, KIN_WIMG_WO = 32768;
+__host__ __device__ inline int wimg_elem(int row, int col) { return row * 128 + ((((col >> 3) ^ (row & 7)) << 4) | ((col & 7) << 1)); }
+// byte offset of flat parameter p inside the image, or -1 when the parameter is not part of it
+__host__ __device__ inline int wimg_offset(const PpoOffsets& o, int in_dim, int p) {
+    if (p < o.pi_b0) return KIN_WIMG_W0 + wimg_elem((p - o.pi_w0) / in_dim, (p - o.pi_w0) % in_dim);
+    if (p < o.pi_w1) return KIN_WIMG_W0 + wimg_elem(p - o.pi_b0, in_dim);
+    if (p < o.pi_b1) return KIN_WIMG_W1 + wimg_elem((p - o.pi_w1) >> 6, (p - o.pi_w1) & 63);
+    if (p < o.act_w) return -1;
+    if (p < o.act_b) return KIN_WIMG_WO + wimg_elem((p - o.act_w) >> 6, (p - o.act_w) & 63);
+    if (p < o.vf_w0) return -1;
+    if (p < o.vf_b0) return KIN_WIMG_W0 + 8192 + wimg_elem((p - o.vf_w0) / in_dim, (p - o.vf_w0) % in_dim);
+    if (p < o.vf_w1) return KIN_WIMG_W0 + 8192 + wimg_elem(p - o.vf_b0, in_dim);
+    if (p < o.vf_b1) return KIN_WIMG_W1 + 8192 + wimg_elem((p - o.vf_w1) >> 6, (p - o.vf_w1) & 63);
+    if (p < o.val_w) return -1;
+    if (p < o.val_b) return KIN_WIMG_WO + 2048 + wimg_elem(7, p - o.val_w);
+    return -1;
+}
+
 // grad[p] = sum over CTAs of partials[c][p] (rows of P + KIN_PPO_STATS + 8 floats); stats (nullable) likewise, scaled
 int kin_ppo_reduce_launch(const float* partials, int n_cta, int P, float* grad, float* stats, float inv_global_batch, cudaStream_t st);
 

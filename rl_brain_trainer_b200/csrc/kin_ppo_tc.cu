@@ -64,7 +64,7 @@ struct __align__(1024) TcGradSmem {
     float ls[8];
     float inv_sig[8];
     float scal[32];                      // 0 adv mean, 1 1/(std+eps), 2..5 statistics, 8..14 d log_std
-    unsigned long long mbar[4];          // 0 forward/backward chain, 1 trailing weight-gradient batch, 2/3 X image buffers
+    unsigned long long mbar[5];          // 0 forward/backward chain, 1 trailing weight-gradient batch, 2/3 X image buffers, 4 weights
     unsigned tmem_base;
 };
 
@@ -119,7 +119,7 @@ kin_ppo_grad_tc_kernel(const float* __restrict__ params, KinPpoHyper hp, const f
                        const float* __restrict__ old_logp, const float* __restrict__ advantage, const float* __restrict__ returns,
                        const double* __restrict__ tile_sums, const int* __restrict__ tile_ids, int n_pairs, float inv_global_batch,
                        float* __restrict__ partials, float* __restrict__ logp_out, float* __restrict__ value_out, int forward_only, int net_base,
-                       const float* __restrict__ adv_stats) {
+                       const float* __restrict__ adv_stats, const unsigned char* __restrict__ wimg) {
     constexpr int IN = 56;
     extern __shared__ unsigned char smem_raw[];
     TcGradSmem& S = *reinterpret_cast<TcGradSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -128,26 +128,29 @@ kin_ppo_grad_tc_kernel(const float* __restrict__ params, KinPpoHyper hp, const f
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row = tid;
     const int net = net_base + (int)blockIdx.y;    // 0 actor, 1 critic
-    const int dbg = hp.pad0;
     const int o_w0 = net ? O.vf_w0 : O.pi_w0, o_b0 = net ? O.vf_b0 : O.pi_b0, o_w1 = net ? O.vf_w1 : O.pi_w1, o_b1 = net ? O.vf_b1 : O.pi_b1;
 
     // ---- prologue: this net's weights -> bf16 operand tiles -------------------------------------------------------------
     {
         uint4* z = reinterpret_cast<uint4*>(S.DO);
         for (int i = tid; i < TILE_BYTES / 16; i += TCG_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
-        if (tid < 16 * 128 / 16) reinterpret_cast<uint4*>(S.WO)[tid] = make_uint4(0u, 0u, 0u, 0u);
+        if (!wimg && tid < 16 * 128 / 16) reinterpret_cast<uint4*>(S.WO)[tid] = make_uint4(0u, 0u, 0u, 0u);   // the image carries its own zero rows
     }
-    for (int i = tid; i < 64 * 64; i += TCG_THREADS) {
-        const int u = i >> 6, k = i & 63;
-        const float v = k < IN ? __ldg(params + o_w0 + u * IN + k) : (k == IN ? __ldg(params + o_b0 + u) : 0.0f);
-        st_bf16(S.W0, u, k, v);
-        st_bf16(S.W1, u, k, __ldg(params + o_w1 + i));
+    if (!wimg) {       // no prebuilt operand image: convert this net's weights here (latency-bound; the trainer passes the image)
+        for (int i = tid; i < 64 * 64; i += TCG_THREADS) {
+            const int u = i >> 6, k = i & 63;
+            const float v = k < IN ? __ldg(params + o_w0 + u * IN + k) : (k == IN ? __ldg(params + o_b0 + u) : 0.0f);
+            st_bf16(S.W0, u, k, v);
+            st_bf16(S.W1, u, k, __ldg(params + o_w1 + i));
+        }
     }
     __syncthreads();   // WO / DO zero fill is complete before the real rows go in
-    if (net == 0) {
-        for (int i = tid; i < 7 * 64; i += TCG_THREADS) st_bf16(S.WO, i >> 6, i & 63, __ldg(params + O.act_w + i));
-    } else if (tid < 64) {
-        st_bf16(S.WO, 7, tid, __ldg(params + O.val_w + tid));
+    if (!wimg) {
+        if (net == 0) {
+            for (int i = tid; i < 7 * 64; i += TCG_THREADS) st_bf16(S.WO, i >> 6, i & 63, __ldg(params + O.act_w + i));
+        } else if (tid < 64) {
+            st_bf16(S.WO, 7, tid, __ldg(params + O.val_w + tid));
+        }
     }
     if (tid < 64) S.b1[tid] = __ldg(params + o_b1 + tid);
     *reinterpret_cast<uint4*>(S.DO + sw_chunk(tid, 1)) = make_uint4(0x00003F80u, 0u, 0u, 0u);   // col 8 = 1.0 (bf16)
@@ -184,13 +187,24 @@ kin_ppo_grad_tc_kernel(const float* __restrict__ params, KinPpoHyper hp, const f
     if (warp == 0) tmem_alloc(smem_u32(&S.tmem_base), TMEM_COLS_G);
     if (tid == 0) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&S.mbar[i]), 1);
+        for (int i = 0; i < 5; ++i) mbar_init(smem_u32(&S.mbar[i]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (wimg) {    // this net's W0 | W1 | WO blocks of the prebuilt image: three bulk copies (TMA engine) on one mbarrier
+            const unsigned mbw = smem_u32(&S.mbar[4]);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbw), "r"(8192 + 8192 + 2048) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_u32(S.W0)), "l"(wimg + KIN_WIMG_W0 + net * 8192), "r"(8192), "r"(mbw) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_u32(S.W1)), "l"(wimg + KIN_WIMG_W1 + net * 8192), "r"(8192), "r"(mbw) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_u32(S.WO)), "l"(wimg + KIN_WIMG_WO + net * 2048), "r"(2048), "r"(mbw) : "memory");
+        }
     }
     fence_async_smem();
     fence_before();
     __syncthreads();
     fence_after();
+    if (wimg) mbar_wait(smem_u32(&S.mbar[4]), 0u);
 
     const unsigned tb = S.tmem_base;
     const unsigned tlane = tb + ((unsigned)(warp * 32) << 16);     // this warp's lane quadrant, column 0
@@ -264,7 +278,7 @@ kin_ppo_grad_tc_kernel(const float* __restrict__ params, KinPpoHyper hp, const f
         mbar_wait(mb_main, par_main);
         par_main ^= 1u;
         fence_after();
-        if (!(dbg & 2)) epilogue64<0>(tz, S.H1, row, nullptr, h1p);
+        epilogue64<0>(tz, S.H1, row, nullptr, h1p);
         fence_async_smem();
         fence_before();
         __syncthreads();
@@ -279,7 +293,7 @@ kin_ppo_grad_tc_kernel(const float* __restrict__ params, KinPpoHyper hp, const f
         mbar_wait(mb_main, par_main);
         par_main ^= 1u;
         fence_after();
-        if (!(dbg & 2)) epilogue64<1>(tz, S.H2, row, S.b1, h2p);
+        epilogue64<1>(tz, S.H2, row, S.b1, h2p);
         fence_async_smem();
         fence_before();
         __syncthreads();
@@ -295,7 +309,7 @@ kin_ppo_grad_tc_kernel(const float* __restrict__ params, KinPpoHyper hp, const f
         par_main ^= 1u;
         fence_after();
         // ---- loss and d(loss)/d(outputs), one thread per sample ------------------------------------------------------------
-        if (!(dbg & 4)) {
+        {
             float o[16];
             tmem_ld16(tlane + COL_Z, o);
             if (net == 0) {
@@ -351,7 +365,6 @@ kin_ppo_grad_tc_kernel(const float* __restrict__ params, KinPpoHyper hp, const f
             fence_after();
             constexpr unsigned id = idesc_bf16(128, 64, false, true), id16 = idesc_bf16(64, 16, true, true);
             mma_bf16(tb + COL_Z, desc_k(aDO), desc_mn(aWO), id, 0u);
-            if (!(dbg & 1))
 #pragma unroll
             for (int k = 0; k < 8; ++k) mma_bf16(tb + COL_WO, desc_mn(aH2 + k * 2048), desc_mn(aDO + k * 2048), id16, acc0 | (k > 0));
             commit(mb_main);
@@ -359,7 +372,7 @@ kin_ppo_grad_tc_kernel(const float* __restrict__ params, KinPpoHyper hp, const f
         mbar_wait(mb_main, par_main);
         par_main ^= 1u;
         fence_after();
-        if (!(dbg & 2)) epilogue64<2>(tz, S.H2, row, nullptr, h2p);          // G2 replaces H2
+        epilogue64<2>(tz, S.H2, row, nullptr, h2p);          // G2 replaces H2
         fence_async_smem();
         fence_before();
         __syncthreads();
@@ -369,18 +382,16 @@ kin_ppo_grad_tc_kernel(const float* __restrict__ params, KinPpoHyper hp, const f
             constexpr unsigned id = idesc_bf16(128, 64, false, true), id16 = idesc_bf16(64, 16, true, true), id64 = idesc_bf16(64, 64, true, true);
 #pragma unroll
             for (int k = 0; k < 4; ++k) mma_bf16(tb + COL_Z, desc_k(aH2 + k * 32), desc_mn(aW1 + k * 2048), id, k > 0);
-            if (!(dbg & 1)) {
 #pragma unroll
             for (int k = 0; k < 8; ++k) mma_bf16(tb + COL_W1, desc_mn(aH2 + k * 2048), desc_mn(aH1 + k * 2048), id64, acc0 | (k > 0));
 #pragma unroll
             for (int k = 0; k < 8; ++k) mma_bf16(tb + COL_B1, desc_mn(aH2 + k * 2048), desc_mn(aDO + k * 2048), id16, acc0 | (k > 0));
-            }
             commit(mb_main);
         }
         mbar_wait(mb_main, par_main);
         par_main ^= 1u;
         fence_after();
-        if (!(dbg & 2)) epilogue64<2>(tz, S.H1, row, nullptr, h1p);          // G1 replaces H1
+        epilogue64<2>(tz, S.H1, row, nullptr, h1p);          // G1 replaces H1
         fence_async_smem();
         fence_before();
         __syncthreads();
@@ -388,12 +399,10 @@ kin_ppo_grad_tc_kernel(const float* __restrict__ params, KinPpoHyper hp, const f
         if (tid == 0) {
             fence_after();
             constexpr unsigned id16 = idesc_bf16(64, 16, true, true), id64 = idesc_bf16(64, 64, true, true);
-            if (!(dbg & 1)) {
 #pragma unroll
             for (int k = 0; k < 8; ++k) mma_bf16(tb + COL_W0, desc_mn(aH1 + k * 2048), desc_mn(aX + k * 2048), id64, acc0 | (k > 0));
 #pragma unroll
             for (int k = 0; k < 8; ++k) mma_bf16(tb + COL_BO, desc_mn(aX + k * 2048), desc_mn(aDO + k * 2048), id16, acc0 | (k > 0));
-            }
             commit(mb_wg);
         }
     }
@@ -490,7 +499,7 @@ using namespace kin;
 extern "C" int kin_ppo_grad_tc(const float* params, int in_dim, const KinPpoHyper* hp, const void* obs_any, const float* action, const float* old_logp,
                                const float* advantage, const float* returns, const double* tile_sums, const int* tile_ids, int n_tiles,
                                long long global_batch, float* partials, int grid, float* grad, float* stats, float* logp_out, float* value_out,
-                               int forward_only, int obs_is_image, const float* adv_stats, void* stream) {
+                               int forward_only, int obs_is_image, const float* adv_stats, const void* weight_image, void* stream) {
     const float* obs = static_cast<const float*>(obs_any);
     if (!params || !hp || !obs || !action || !tile_ids || n_tiles <= 0 || grid <= 0)
         return kin_fail(KIN_ERR_INVALID_ARG, "kin_ppo_grad_tc: bad arguments");
@@ -522,10 +531,12 @@ extern "C" int kin_ppo_grad_tc(const float* params, int in_dim, const KinPpoHype
     }
     if (obs_is_image)
         kin_ppo_grad_tc_kernel<true><<<dg, TCG_THREADS, smem, st>>>(params, *hp, obs, action, old_logp, advantage, returns, tile_sums, tile_ids, n_pairs,
-                                                                    inv, partials, logp_out, value_out, forward_only, net_base, adv_stats);
+                                                                    inv, partials, logp_out, value_out, forward_only, net_base, adv_stats,
+                                                                    static_cast<const unsigned char*>(weight_image));
     else
         kin_ppo_grad_tc_kernel<false><<<dg, TCG_THREADS, smem, st>>>(params, *hp, obs, action, old_logp, advantage, returns, tile_sums, tile_ids, n_pairs,
-                                                                     inv, partials, logp_out, value_out, forward_only, net_base, adv_stats);
+                                                                     inv, partials, logp_out, value_out, forward_only, net_base, adv_stats,
+                                                                    static_cast<const unsigned char*>(weight_image));
     if (!forward_only) kin_ppo_reduce_launch(partials, g, P, grad, stats, inv, st);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? KIN_OK : kin_fail_cuda(e, "kin_ppo_grad_tc");

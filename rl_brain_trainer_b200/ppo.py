@@ -143,6 +143,8 @@ class PPOTrainer:
             self.adam_v = torch.zeros_like(self.params)
             self.grad = torch.zeros_like(self.params)
             self.stats = torch.zeros(_D("KIN_PPO_STATS"), dtype=torch.float32, device=self.device)
+            self.weight_image = torch.zeros(36864, dtype=torch.uint8, device=self.device)   # bf16 operand image of `params`
+            self.pack_weights()
             self.stats_accum = torch.zeros(_D("KIN_PPO_STATS"), dtype=torch.float32, device=self.device)
             self._adv_stats = torch.zeros((max(self.S // self.local_batch, 1), 2), dtype=torch.float32, device=self.device)
             props = torch.cuda.get_device_properties(self.device)
@@ -185,6 +187,11 @@ class PPOTrainer:
                                             stage_index) if cur.enabled else None
         self.last_rollout: dict[str, float] = {}
 
+    def pack_weights(self) -> None:
+        """Rebuild the bf16 operand image from ``self.params`` (needed after the parameters were written from outside the trainer)."""
+        _lib.check(self._L.kin_ppo_pack_weights(self.params.data_ptr(), 56, self.weight_image.data_ptr(),
+                                                torch.cuda.current_stream(self.device).cuda_stream))
+
     # ------------------------------------------------------------------ rollout
     def collect(self) -> dict[str, float]:
         """``collect_rollouts``: T steps of (sample action, env step with auto-reset, TimeLimit bootstrap), then GAE."""
@@ -226,7 +233,8 @@ class PPOTrainer:
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream(self.device).cuda_stream
             mode = _D("KIN_MODE_APPROACH") if env._mode_all is None else env._mode_all
-            _lib.check(L.kin_ppo_collect(env._params.handle, env.state.data_ptr(), env.stride, self.N, mode, self.params.data_ptr(), 56, self.T,
+            _lib.check(L.kin_ppo_collect(env._params.handle, env.state.data_ptr(), env.stride, self.N, mode, self.params.data_ptr(), self.weight_image.data_ptr(), 56,
+                                         self.T,
                                          self.seed, self.global_step, env._seed, self.obs_img.data_ptr(), self.act_buf.data_ptr(),
                                          self.logp_buf.data_ptr(), self.val_buf.data_ptr(), self.rew_buf.data_ptr(), self.done_buf.data_ptr(),
                                          self.start_buf.data_ptr(), self._next_start.data_ptr(), self.last_val.data_ptr(), self.boot_count.data_ptr(),
@@ -264,7 +272,8 @@ class PPOTrainer:
             _lib.check(self._L.kin_ppo_grad_tc(self.params.data_ptr(), 56, ctypes.byref(hp), (self.obs_img if img else self.obs_buf).data_ptr(),
                                                self.act_buf.data_ptr(), self.logp_buf.data_ptr(), self.adv_buf.data_ptr(), self.ret_buf.data_ptr(),
                                                self.tile_sums.data_ptr(), tile_ptr, n_tiles, global_batch, self.partials.data_ptr(),
-                                               self.grad_ctas, self.grad.data_ptr(), self.stats.data_ptr(), None, None, 0, int(img), adv_ptr, stream))
+                                               self.grad_ctas, self.grad.data_ptr(), self.stats.data_ptr(), None, None, 0, int(img), adv_ptr,
+                                               self.weight_image.data_ptr(), stream))
             return
         _lib.check(self._L.kin_ppo_grad(self.params.data_ptr(), 56, ctypes.byref(hp), self.obs_buf.data_ptr(), self.act_buf.data_ptr(),
                                         self.logp_buf.data_ptr(), self.adv_buf.data_ptr(), self.ret_buf.data_ptr(), self.tile_sums.data_ptr(),
@@ -284,7 +293,8 @@ class PPOTrainer:
         hp = self.hp.c()
         _lib.check(self._L.kin_ppo_grad_tc(self.params.data_ptr(), 56, ctypes.byref(hp), self.obs_buf.data_ptr(), self.act_buf.data_ptr(), None, None,
                                            None, None, self._all_tiles.data_ptr(), int(self._all_tiles.numel()), 0, None, self.grad_ctas, None, None,
-                                           self.logp_buf.data_ptr(), None, 1, 0, None, torch.cuda.current_stream(self.device).cuda_stream))
+                                           self.logp_buf.data_ptr(), None, 1, 0, None, self.weight_image.data_ptr(),
+                                           torch.cuda.current_stream(self.device).cuda_stream))
 
     def apply_update(self) -> None:
         """All-reduce the gradient (sum over ranks), clip by global norm, Adam step -- identical on every rank."""
@@ -295,7 +305,7 @@ class PPOTrainer:
         hp = getattr(self, "_c_hyper", None) or self.hp.c()
         _lib.check(self._L.kin_ppo_adam(self.params.data_ptr(), self.grad.data_ptr(), self.adam_m.data_ptr(), self.adam_v.data_ptr(), self.P,
                                         ctypes.byref(hp), self.update_count, self.stats.data_ptr(), self.stats_accum.data_ptr(),
-                                        torch.cuda.current_stream(self.device).cuda_stream))
+                                        self.weight_image.data_ptr(), 56, torch.cuda.current_stream(self.device).cuda_stream))
 
     def update(self) -> dict[str, float]:
         """``PPO.train``: n_epochs passes over the rollout in random minibatches; no host synchronisation until the statistics are read."""

@@ -172,7 +172,7 @@ def test_minibatch_gradient_tc_matches_autograd():
     # forward only: log-prob and value of the visited samples
     lp_out, v_out = torch.full((S,), 123.0, device="cuda"), torch.full((S,), 123.0, device="cuda")
     _lib.check(L.kin_ppo_grad_tc(flat.data_ptr(), 56, ctypes.byref(c_hp), obs.data_ptr(), act.data_ptr(), None, None, None, None,
-                                 tile_ids.data_ptr(), tile_ids.numel(), 0, None, 3, None, None, lp_out.data_ptr(), v_out.data_ptr(), 1, 0, None, stream))
+                                 tile_ids.data_ptr(), tile_ids.numel(), 0, None, 3, None, None, lp_out.data_ptr(), v_out.data_ptr(), 1, 0, None, None, stream))
     torch.cuda.synchronize()
     assert float((v_out[idx] - value[idx]).abs().max()) < 0.03 and float((lp_out[idx] - exact_logp[idx]).abs().max()) < 0.06
     assert float((lp_out[idx] - exact_logp[idx]).abs().mean()) < 0.008
@@ -196,7 +196,7 @@ def test_minibatch_gradient_tc_matches_autograd():
             grad, stats = torch.zeros(P, device="cuda"), torch.zeros(8, device="cuda")
             _lib.check(L.kin_ppo_grad_tc(flat.data_ptr(), 56, ctypes.byref(c_hp), obs.data_ptr(), act.data_ptr(), old_logp.data_ptr(), adv.data_ptr(),
                                          ret.data_ptr(), sums.data_ptr(), tile_ids.data_ptr(), tile_ids.numel(), tile_ids.numel() * 64,
-                                         partials.data_ptr(), ctas, grad.data_ptr(), stats.data_ptr(), None, None, 0, 0, None, stream))
+                                         partials.data_ptr(), ctas, grad.data_ptr(), stats.data_ptr(), None, None, 0, 0, None, None, stream))
             torch.cuda.synchronize()
             off = 0
             for k, gk in zip(ppo.PARAM_ORDER, grads):
@@ -213,7 +213,7 @@ def test_minibatch_gradient_tc_matches_autograd():
     # odd tile counts are refused (two 64-sample tiles per GEMM tile)
     rc = L.kin_ppo_grad_tc(flat.data_ptr(), 56, ctypes.byref(c_hp), obs.data_ptr(), act.data_ptr(), old_logp.data_ptr(), adv.data_ptr(),
                            ret.data_ptr(), sums.data_ptr(), tile_ids.data_ptr(), 3, 192, partials.data_ptr(), 2, grad.data_ptr(), stats.data_ptr(),
-                           None, None, 0, 0, None, stream)
+                           None, None, 0, 0, None, None, stream)
     assert rc != 0
 
 
@@ -233,7 +233,7 @@ def test_adam_matches_torch():
         ref_p.grad = grad.clone()
         norm = torch.nn.utils.clip_grad_norm_([ref_p], 0.5)
         opt.step()
-        _lib.check(_lib.lib().kin_ppo_adam(params.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(), P, ctypes.byref(c_hp), step, stats.data_ptr(), None,
+        _lib.check(_lib.lib().kin_ppo_adam(params.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(), P, ctypes.byref(c_hp), step, stats.data_ptr(), None, None, 56,
                                            torch.cuda.current_stream().cuda_stream))
         assert abs(float(stats[5]) - float(norm)) < 1e-4 * float(norm)
         assert float((params - ref_p.detach()).abs().max()) < 2e-6
@@ -275,6 +275,10 @@ def test_trainer_runs_and_improves_value_fit(variant):
     assert log[0]["minibatches"] == 4 * (1024 * 32 // 2048)
     sd = tr.state_dict()
     assert "mlp_extractor.policy_net.0.weight" in sd and sd["log_std"].shape == (7,)
+    # the bf16 operand image Adam maintains equals a fresh pack of the final parameters
+    kept = tr.weight_image.clone()
+    tr.pack_weights()
+    assert torch.equal(kept, tr.weight_image) and int(kept.count_nonzero()) > 30000
     # lr = 0 leaves the parameters untouched
     tr2 = ppo.PPOTrainer(cfg, ppo.random_policy(56, seed=1, device="cuda"), num_envs=256, hyper=ppo.PPOHyper(learning_rate=0.0, n_steps=8, batch_size=512, n_epochs=1),
                          update_variant=variant)

@@ -588,7 +588,8 @@ kin_ppo_adv_stats_kernel(const double* __restrict__ tile_sums, const int* __rest
     }
 }
 
-// clip_grad_norm_ + Adam, one CTA
+// clip_grad_norm_ + Adam.  Every CTA computes the global gradient norm itself (64 KB of L2-resident data, identical summation
+// order -> bitwise-identical clip coefficient in every CTA), then updates its own 1024 parameters.
 __global__ void __launch_bounds__(1024)
 kin_ppo_adam_kernel(float* __restrict__ params, const float* __restrict__ grad, float* __restrict__ m, float* __restrict__ v, int P,
                     KinPpoHyper hp, float bc1, float bc2, float* __restrict__ stats, float* __restrict__ stats_accum,
@@ -609,8 +610,8 @@ kin_ppo_adam_kernel(float* __restrict__ params, const float* __restrict__ grad, 
             const float norm = sqrtf(t);
             const float c = hp.max_grad_norm > 0.0f ? hp.max_grad_norm / (norm + 1e-6f) : 1.0f;
             coef = c < 1.0f ? c : 1.0f;
-            if (stats) stats[KIN_PPO_STAT_GRAD_NORM] = norm;
-            if (stats && stats_accum) {          // running sums over the minibatches of an update (slot 7 counts them)
+            if (stats && blockIdx.x == 0) stats[KIN_PPO_STAT_GRAD_NORM] = norm;
+            if (stats && stats_accum && blockIdx.x == 0) {          // running sums over the minibatches of an update (slot 7 counts them)
 #pragma unroll
                 for (int q = 0; q < 5; ++q) stats_accum[q] += stats[q];
                 stats_accum[KIN_PPO_STAT_GRAD_NORM] += norm;
@@ -620,7 +621,7 @@ kin_ppo_adam_kernel(float* __restrict__ params, const float* __restrict__ grad, 
     }
     __syncthreads();
     const float cf = coef;
-    for (int p = threadIdx.x; p < P; p += blockDim.x) {
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x) {
         const float g = grad[p] * cf;
         const float mm = fmaf(hp.adam_beta1, m[p], (1.0f - hp.adam_beta1) * g);
         const float vv = fmaf(hp.adam_beta2, v[p], (1.0f - hp.adam_beta2) * g * g);
@@ -756,7 +757,7 @@ extern "C" int kin_ppo_adam(float* params, const float* grad, float* adam_m, flo
     if (weight_image && in_dim != 56) return kin_fail(KIN_ERR_UNSUPPORTED, "kin_ppo_adam: the weight image is built for in_dim 56");
     if (!params || !grad || !adam_m || !adam_v || !hp || n_params <= 0 || step < 1) return kin_fail(KIN_ERR_INVALID_ARG, "kin_ppo_adam: bad arguments");
     const float bc1 = 1.0f - powf(hp->adam_beta1, (float)step), bc2 = 1.0f - powf(hp->adam_beta2, (float)step);
-    kin_ppo_adam_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(params, grad, adam_m, adam_v, n_params, *hp, bc1, bc2, stats, stats_accum,
+    kin_ppo_adam_kernel<<<(n_params + 1023) / 1024, 1024, 0, (cudaStream_t)stream>>>(params, grad, adam_m, adam_v, n_params, *hp, bc1, bc2, stats, stats_accum,
                                                               static_cast<unsigned short*>(weight_image), in_dim);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? KIN_OK : kin_fail_cuda(e, "kin_ppo_adam");

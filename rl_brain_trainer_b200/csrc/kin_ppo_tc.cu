@@ -81,34 +81,31 @@ __device__ __forceinline__ void st_bf16(unsigned char* tile, int row, int col, f
 // this row's 64 accumulator columns -> f -> bf16 row of `tile`.  MODE 0: tanh; 1: tanh(x + b1); 2: x * (1 - h^2), h = keep[]
 template <int MODE>
 __device__ __forceinline__ void epilogue64(unsigned tz, unsigned char* tile, int row, const float* bias, unsigned* keep) {
+    float v[64];
+    tmem_ld32x2(tz, v);          // both halves in flight, one wait
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-        float v[32];
-        tmem_ld32(tz + half * 32, v);
+    for (int j = 0; j < 8; ++j) {
+        unsigned p[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            unsigned p[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int c = 8 * j + 2 * e;
-                float a = v[c], b = v[c + 1];
-                if (MODE == 0) {
-                    a = tanh_fast(a);
-                    b = tanh_fast(b);
-                } else if (MODE == 1) {
-                    a = tanh_fast(a + bias[half * 32 + c]);
-                    b = tanh_fast(b + bias[half * 32 + c + 1]);
-                } else {
-                    const unsigned h = keep[half * 16 + 4 * j + e];
-                    const float hl = bf16_lo(h), hh = bf16_hi(h);
-                    a *= fmaf(-hl, hl, 1.0f);
-                    b *= fmaf(-hh, hh, 1.0f);
-                }
-                p[e] = pack_bf16(a, b);
-                if (MODE != 2) keep[half * 16 + 4 * j + e] = p[e];
+        for (int e = 0; e < 4; ++e) {
+            const int c = 8 * j + 2 * e;
+            float a = v[c], b = v[c + 1];
+            if (MODE == 0) {
+                a = tanh_fast(a);
+                b = tanh_fast(b);
+            } else if (MODE == 1) {
+                a = tanh_fast(a + bias[c]);
+                b = tanh_fast(b + bias[c + 1]);
+            } else {
+                const unsigned h = keep[4 * j + e];
+                const float hl = bf16_lo(h), hh = bf16_hi(h);
+                a *= fmaf(-hl, hl, 1.0f);
+                b *= fmaf(-hh, hh, 1.0f);
             }
-            *reinterpret_cast<uint4*>(tile + sw_chunk(row, half * 4 + j)) = make_uint4(p[0], p[1], p[2], p[3]);
+            p[e] = pack_bf16(a, b);
+            if (MODE != 2) keep[4 * j + e] = p[e];
         }
+        *reinterpret_cast<uint4*>(tile + sw_chunk(row, j)) = make_uint4(p[0], p[1], p[2], p[3]);
     }
 }
 

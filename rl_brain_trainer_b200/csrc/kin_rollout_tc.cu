@@ -22,14 +22,16 @@
 // (tests/test_gpu_rollout.py::test_fused_rollout_tc_*).  The FFMA variant stays the strict-parity path.
 //
 // Replaces the same reference loops as kin_rollout.cu (eval_workspace_expansion.py:126-147 etc.).
+#include <cstdlib>
+
 #include "kin_internal.h"
 #include "kin_state.cuh"
 
 namespace kin {
 
 constexpr int TC_TILE = 128;               // episodes per tile == UMMA M == TMEM lanes
-constexpr int TC_TILES = 2;                // tiles per CTA
-constexpr int TC_THREADS = TC_TILE * TC_TILES;
+constexpr int TC_TILES = 4;                // tiles per CTA (the last one may be partial: 1..4 warps)
+constexpr int TC_MAX_THREADS = TC_TILE * TC_TILES;
 constexpr int TC_K = 64;                   // padded reduction width of every layer
 constexpr int TC_HID = 64;
 constexpr int CHUNK_FLOATS_A = TC_TILE * 32;   // one 128-byte-wide K chunk of an A tile: 128 rows x 32 floats
@@ -38,10 +40,8 @@ constexpr int CHUNK_FLOATS_W = TC_HID * 32;    // 64 rows x 32 floats
 constexpr int W_FLOATS = 2 * CHUNK_FLOATS_W;
 constexpr int CHUNK_FLOATS_WO = 8 * 32;        // output layer: 8 rows (7 actions + zero row)
 constexpr int WO_FLOATS = 2 * CHUNK_FLOATS_WO;
-constexpr int TMEM_COLS = 128;                 // 64 accumulator columns per tile
 
 struct TcSmem {
-    float A[TC_TILES][A_TILE_FLOATS];   // 2 x 32 KB, each tile 1024-byte aligned
     float W0[W_FLOATS];                 // 16 KB  [64][64]: 56 inputs | bias column | zero pad
     float W1[W_FLOATS];                 // 16 KB
     float WO[WO_FLOATS];                // 2 KB   [8][64]
@@ -50,6 +50,7 @@ struct TcSmem {
     unsigned long long mbar[TC_TILES];
     unsigned tmem_base;
     int run_flags[2][TC_TILES][4];   // double-buffered by step parity: written before, read after the layer-1 barrier
+    alignas(1024) float A[1][A_TILE_FLOATS];   // one 32 KB A tile per tile of the CTA (1..4, sized at launch), 1024-byte aligned
 };
 
 struct DevPolicyTc {
@@ -103,7 +104,7 @@ __device__ __forceinline__ void mbar_wait(unsigned saddr, unsigned parity) {
         "@P1 bra DONE;\n\tbra WAIT_LOOP;\n\tDONE:\n\t}"
         ::"r"(saddr), "r"(parity) : "memory");
 }
-__device__ __forceinline__ void tile_barrier(int tile) { asm volatile("bar.sync %0, %1;" ::"r"(tile + 1), "r"(TC_TILE) : "memory"); }
+__device__ __forceinline__ void tile_barrier(int tile, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(tile + 1), "r"(threads) : "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -133,19 +134,19 @@ __device__ __forceinline__ void tmem_ld8(unsigned taddr, float* v) {
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// stage one policy's actor into the swizzled B-operand images (all 256 threads)
-__device__ void load_weights_tc(TcSmem& S, const DevPolicyTc& p, int tid) {
-    for (int i = tid; i < TC_HID * TC_K; i += TC_THREADS) {
+// stage one policy's actor into the swizzled B-operand images (all threads of the CTA)
+__device__ void load_weights_tc(TcSmem& S, const DevPolicyTc& p, int tid, int nthreads) {
+    for (int i = tid; i < TC_HID * TC_K; i += nthreads) {
         const int n = i >> 6, k = i & 63;
         float v0 = k < KIN_OBS_DIM ? __ldg(p.w0 + n * KIN_OBS_DIM + k) : (k == KIN_OBS_DIM ? __ldg(p.b0 + n) : 0.0f);
         S.W0[sw128_offset(n, k, CHUNK_FLOATS_W)] = to_tf32(v0);
         S.W1[sw128_offset(n, k, CHUNK_FLOATS_W)] = to_tf32(__ldg(p.w1 + n * TC_HID + k));
     }
-    for (int i = tid; i < 8 * TC_K; i += TC_THREADS) {
+    for (int i = tid; i < 8 * TC_K; i += nthreads) {
         const int n = i >> 6, k = i & 63;
         S.WO[sw128_offset(n, k, CHUNK_FLOATS_WO)] = n < KIN_NJ ? to_tf32(__ldg(p.wo + n * TC_HID + k)) : 0.0f;
     }
-    if (tid < TC_HID) S.b1[tid] = __ldg(p.b1 + tid);
+    for (int i = tid; i < TC_HID; i += nthreads) S.b1[i] = __ldg(p.b1 + i);     // a CTA may be a single warp
     if (tid < 8) S.bo[tid] = tid < KIN_NJ ? __ldg(p.bo + tid) : 0.0f;
 }
 
@@ -171,7 +172,7 @@ __device__ __forceinline__ void issue_layer(unsigned a_saddr, unsigned w_saddr, 
 struct TileCtx {
     float* A;
     unsigned a_saddr, w0_saddr, w1_saddr, wo_saddr, mbar_saddr, tmem_d, tmem_row;
-    int tile, row, flag_buf;
+    int tile, row, flag_buf, tile_threads;
     unsigned parity;
     bool issuer;
 };
@@ -190,7 +191,7 @@ __device__ __forceinline__ bool mlp_tc(TcSmem& S, TileCtx& c, const float* o, fl
     a_store4(c.A, c.row, 15, 0.0f, 0.0f, 0.0f, 0.0f);
     fence_async_smem();
     tc_fence_before();
-    tile_barrier(c.tile);
+    tile_barrier(c.tile, c.tile_threads);
     if (!(S.run_flags[fb][c.tile][0] | S.run_flags[fb][c.tile][1] | S.run_flags[fb][c.tile][2] | S.run_flags[fb][c.tile][3])) return false;
     if (c.issuer) issue_layer(c.a_saddr, c.w0_saddr, CHUNK_FLOATS_W * 4, c.tmem_d, umma_idesc(TC_TILE, TC_HID), c.mbar_saddr);
     mbar_wait(c.mbar_saddr, c.parity);
@@ -208,7 +209,7 @@ __device__ __forceinline__ bool mlp_tc(TcSmem& S, TileCtx& c, const float* o, fl
     // ---- layer 2
     fence_async_smem();
     tc_fence_before();
-    tile_barrier(c.tile);
+    tile_barrier(c.tile, c.tile_threads);
     if (c.issuer) issue_layer(c.a_saddr, c.w1_saddr, CHUNK_FLOATS_W * 4, c.tmem_d, umma_idesc(TC_TILE, TC_HID), c.mbar_saddr);
     mbar_wait(c.mbar_saddr, c.parity);
     c.parity ^= 1u;
@@ -226,7 +227,7 @@ __device__ __forceinline__ bool mlp_tc(TcSmem& S, TileCtx& c, const float* o, fl
     // ---- layer 3 (N = 8)
     fence_async_smem();
     tc_fence_before();
-    tile_barrier(c.tile);
+    tile_barrier(c.tile, c.tile_threads);
     if (c.issuer) issue_layer(c.a_saddr, c.wo_saddr, CHUNK_FLOATS_WO * 4, c.tmem_d, umma_idesc(TC_TILE, 8), c.mbar_saddr);
     mbar_wait(c.mbar_saddr, c.parity);
     c.parity ^= 1u;
@@ -243,7 +244,11 @@ __device__ __forceinline__ bool ready_pred_tc(float pos_thr, float ori_thr, floa
     return pos_thr > 0.0f && ori_thr > 0.0f && pos <= pos_thr && ori <= ori_thr && (a_thr <= 0.0f || an <= a_thr) && (dq_thr <= 0.0f || dqn <= dq_thr);
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 2)
+// Launch shape: blockDim.x = 32 * W threads, W = 1..16 warps = up to 4 tiles of 4 warps (the last tile may have fewer warps: its
+// GEMMs are still M = 128, the rows of the missing warps are simply nobody's); shared memory and TMEM are sized by the tile count.
+// A batch that fits one wave gets ONE CTA per SM with W = ceil(warps / SMs), so every SM carries the same number of episodes
+// (65 536 episodes -> 148 CTAs x 14 warps); larger batches run 8-warp CTAs, two per SM, wave after wave.
+__global__ void __launch_bounds__(TC_MAX_THREADS, 1)
 kin_rollout_tc_kernel(const __grid_constant__ KinEnvParams PA, const __grid_constant__ KinEnvParams PF, DevPolicyTc pol_a, DevPolicyTc pol_f,
                       int has_finisher, const float* __restrict__ iq, const float* __restrict__ idq, const float* __restrict__ ipa,
                       const float* __restrict__ gq, const float* __restrict__ gpose, int n, int stride, int confirm,
@@ -255,21 +260,25 @@ kin_rollout_tc_kernel(const __grid_constant__ KinEnvParams PA, const __grid_cons
     TileCtx c;
     c.tile = tid >> 7;
     c.row = tid & (TC_TILE - 1);
-    c.A = S.A[c.tile];
+    c.tile_threads = min(TC_TILE, (int)blockDim.x - c.tile * TC_TILE);
+    c.A = &S.A[0][0] + (size_t)c.tile * A_TILE_FLOATS;
     c.issuer = c.row == 0;
     c.parity = 0u;
     c.flag_buf = 0;
 
+    const int n_tiles_cta = ((int)blockDim.x + TC_TILE - 1) / TC_TILE;
+    const unsigned tmem_cols = n_tiles_cta == 1 ? 64u : (n_tiles_cta == 2 ? 128u : 256u);   // 64 accumulator columns per tile, power of two
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)), "r"(tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 0) {
-        mbar_init(smem_u32(&S.mbar[0]), 1);
-        mbar_init(smem_u32(&S.mbar[1]), 1);
+#pragma unroll
+        for (int i = 0; i < TC_TILES; ++i) mbar_init(smem_u32(&S.mbar[i]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    load_weights_tc(S, pol_a, tid);
+    if (tid < 2 * TC_TILES * 4) (&S.run_flags[0][0][0])[tid] = 0;   // warps a partial tile does not have never vote
+    load_weights_tc(S, pol_a, tid, (int)blockDim.x);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -283,7 +292,7 @@ kin_rollout_tc_kernel(const __grid_constant__ KinEnvParams PA, const __grid_cons
     c.tmem_d = tmem_base + c.tile * TC_HID;                                   // lane 0, this tile's 64 columns
     c.tmem_row = c.tmem_d + ((unsigned)((warp & 3) * 32) << 16);              // this warp's 32-lane slice
 
-    const int ep = blockIdx.x * TC_THREADS + tid;
+    const int ep = blockIdx.x * (int)blockDim.x + tid;
     const bool active = ep < n;
     const int epc = active ? ep : n - 1;
 
@@ -366,7 +375,7 @@ kin_rollout_tc_kernel(const __grid_constant__ KinEnvParams PA, const __grid_cons
     // ---- finisher phase ------------------------------------------------------------------------------
     __syncthreads();   // both tiles are out of the approach loop: nobody reads the approach weights any more
     if (has_finisher) {
-        load_weights_tc(S, pol_f, tid);
+        load_weights_tc(S, pol_f, tid, (int)blockDim.x);
         fence_async_smem();
         __syncthreads();
         running = active && handoff_kind != 0;
@@ -432,7 +441,7 @@ kin_rollout_tc_kernel(const __grid_constant__ KinEnvParams PA, const __grid_cons
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
 }
 
 }  // namespace kin
@@ -443,17 +452,29 @@ int kin_rollout_tc_launch(const KinHandle* ha, const KinHandle* hf, const KinPol
                           const float* iq, const float* idq, const float* ipa, const float* gq, const float* gpose, int n, int stride,
                           int confirm, int variant, uint32_t* result, unsigned long long* env_steps, cudaStream_t st) {
     (void)variant;
-    const size_t smem = sizeof(TcSmem) + 1024;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kin_rollout_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        const size_t smem_max = sizeof(TcSmem) + (TC_TILES - 1) * A_TILE_FLOATS * sizeof(float) + 1024;
+        cudaError_t e = cudaFuncSetAttribute(kin_rollout_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
         if (e != cudaSuccess) return kin_fail_cuda(e, "kin_rollout_approach_finisher(tc): smem attribute");
         attr_set = true;
     }
     DevPolicyTc da{pa->pi_w0, pa->pi_b0, pa->pi_w1, pa->pi_b1, pa->act_w, pa->act_b};
     DevPolicyTc df = pf ? DevPolicyTc{pf->pi_w0, pf->pi_b0, pf->pi_w1, pf->pi_b1, pf->act_w, pf->act_b} : da;
     const KinEnvParams& PF = hf ? hf->params : ha->params;
-    kin_rollout_tc_kernel<<<(n + TC_THREADS - 1) / TC_THREADS, TC_THREADS, smem, st>>>(ha->params, PF, da, df, (hf && pf) ? 1 : 0, iq, idq, ipa, gq,
+    static int n_sm = 0;
+    if (n_sm == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
+    }
+    // one wave: spread the warps evenly over the SMs; several waves: 8-warp CTAs, two resident per SM (98 KB each)
+    const int warps = (n + 31) / 32;
+    int w_per_cta = (warps + n_sm - 1) / n_sm;
+    if (w_per_cta > 16) w_per_cta = 8;
+    if (const char* v = getenv("KIN_TC_WARPS")) { const int f = atoi(v); if (f >= 1 && f <= 16) w_per_cta = f; }
+    const int threads = 32 * w_per_cta;
+    const size_t smem = sizeof(TcSmem) + ((threads + TC_TILE - 1) / TC_TILE - 1) * A_TILE_FLOATS * sizeof(float) + 1024;
+    kin_rollout_tc_kernel<<<(n + threads - 1) / threads, threads, smem, st>>>(ha->params, PF, da, df, (hf && pf) ? 1 : 0, iq, idq, ipa, gq,
                                                                                        gpose, n, stride, confirm, result, env_steps);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? KIN_OK : kin_fail_cuda(e, "kin_rollout_approach_finisher(tc)");

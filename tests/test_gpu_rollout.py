@@ -217,7 +217,7 @@ def test_fused_rollout_tc_close_to_strict_fp32():
         b = _rollout(VARIANT_TC).evaluate_suite(suite).to_numpy()
         flips = int((a["success"] != b["success"]).sum())
         assert flips <= max(1, 0.005 * n), f"{flips} of {n} success flags differ between tf32 and fp32 MLP"
-        assert abs(a["success"].mean() - b["success"].mean()) <= max(0.005, 1.0 / n)
+        assert abs(a["success"].mean() - b["success"].mean()) <= max(0.005, 1.0 / n) + 1e-9
         assert np.array_equal(a["approach_steps"], b["approach_steps"])
         assert float(np.abs(a["final_q"] - b["final_q"]).mean()) < 5e-4      # TF32 operands: O(1e-3) action differences
         assert abs(a["final_position_error"].mean() - b["final_position_error"].mean()) < 2e-5

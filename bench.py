@@ -41,6 +41,9 @@ STAGE = 5
 SUITE_SEED = 700001 + STAGE * 1009
 # algorithmic work per env-step (DESIGN.md / SURVEY 8d)
 STEP_BYTES_APPROACH = 532
+# measured DRAM traffic per launch (ncu --set full captures committed under profiles/): read + write bytes
+NCU_TRAFFIC_STEP_KERNEL = 369_145_856 + 682_055_168     # kin_step_kernel<approach>, 2 097 152 envs: 1 051 MB vs 1 116 MB algorithmic
+NCU_TRAFFIC_ROLLOUT_TC = 4_632_832 + 432_384            # kin_rollout_tc_kernel, 65 536 episodes: inputs + result rows only
 ACTOR_FLOPS = 2 * (56 * 64 + 64 * 64 + 64 * 7)   # 16256
 ENV_FLOPS = 1800
 
@@ -203,7 +206,9 @@ def measure_step_kernel(torch, device, pk, n_envs: int = 1 << 21, launches: int 
     gbs = STEP_BYTES_APPROACH * n_envs / t / 1e9
     del env
     return {"kernel": "kin_step_kernel<approach>", "bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
-            "frac": gbs / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"], "n_envs": n_envs, "launches": launches,
+            "frac": gbs / pk["hbm_gbs"], "traffic": NCU_TRAFFIC_STEP_KERNEL if n_envs == 2_097_152 else None,
+            "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r1_step_optimised_raw.csv (ncu --set full, same size)",
+            "peak_source": pk["source"], "n_envs": n_envs, "launches": launches,
             "us_per_launch": t * 1e6, "env_steps_per_sec": n_envs / t, "bytes_per_env_step": STEP_BYTES_APPROACH,
             "note": "working set %.0f MB per launch (> L2), CUDA events on the launching stream" % (STEP_BYTES_APPROACH * n_envs / 1e6)}
 
@@ -362,7 +367,9 @@ def main() -> None:
         if tc:
             peak_tf = pk["bf16_tflops_sustained"] / 2.0   # kind::tf32 runs at half the bf16 rate
             roof = {"kernel": "kin_rollout_tc_kernel", "bound": "tensor", "achieved": flops / t_launch / 1e12, "peak": peak_tf,
-                    "unit": "TFLOP/s", "frac": flops / t_launch / 1e12 / peak_tf, "traffic": None, "peak_source": pk["source"],
+                    "unit": "TFLOP/s", "frac": flops / t_launch / 1e12 / peak_tf,
+                    "traffic": NCU_TRAFFIC_ROLLOUT_TC if n == EPISODES_PER_GPU else None,
+                    "traffic_source": "dram bytes per launch, profiles/r1_rollout_tc_raw.csv (ncu --set full, 65 536 episodes)", "peak_source": pk["source"],
                     "note": "actor MLP 16,256 FLOP/env-step on tcgen05 kind::tf32; peak = measured sustained bf16 / 2"}
         else:
             fp32_peak = 148 * 128 * 2 * pk["sm_max_mhz"] * 1e6 / 1e12

@@ -177,8 +177,10 @@ kin_collect_kernel(const __grid_constant__ KinEnvParams P, const KinSamplerParam
                    const float* __restrict__ params, const unsigned char* __restrict__ wimg, int T, uint64_t noise_seed, uint32_t step0,
                    uint64_t reset_seed, CollectOut out) {
     constexpr int IN = 56;
-    extern __shared__ unsigned char smem_raw[];
-    CollectSmem<TILES>& S = *reinterpret_cast<CollectSmem<TILES>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    // round up to 1024 bytes WITHOUT leaving the shared address space (pointer + offset, not an integer round trip), so every
+    // access below compiles to LDS / STS rather than generic LD / ST with 64-bit address arithmetic
+    CollectSmem<TILES>& S = *reinterpret_cast<CollectSmem<TILES>*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
     const PpoOffsets O = ppo_offsets(IN);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     constexpr int NT = TILES * CT_ROWS;

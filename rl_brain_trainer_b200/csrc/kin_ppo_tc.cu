@@ -118,8 +118,10 @@ kin_ppo_grad_tc_kernel(const float* __restrict__ params, KinPpoHyper hp, const f
                        float* __restrict__ partials, float* __restrict__ logp_out, float* __restrict__ value_out, int forward_only, int net_base,
                        const float* __restrict__ adv_stats, const unsigned char* __restrict__ wimg) {
     constexpr int IN = 56;
-    extern __shared__ unsigned char smem_raw[];
-    TcGradSmem& S = *reinterpret_cast<TcGradSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    // round up to 1024 bytes WITHOUT leaving the shared address space (pointer + offset, not an integer round trip), so every
+    // access below compiles to LDS / STS rather than generic LD / ST with 64-bit address arithmetic
+    TcGradSmem& S = *reinterpret_cast<TcGradSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
     const PpoOffsets O = ppo_offsets(IN);
     const int P = O.total;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;

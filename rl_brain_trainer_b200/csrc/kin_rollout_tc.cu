@@ -59,11 +59,10 @@ struct DevPolicyTc {
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ float to_tf32(float x) {
-    unsigned r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
+// Round-to-nearest (ties away) TF32: cvt.rna.tf32 is "add half an ulp of the 10-bit mantissa, clear the low 13 bits"; the
+// tensor core ignores those 13 bits of a kind::tf32 operand, so the add alone feeds it the same operand (values here are finite
+// and far from overflow: observations in [-1, 1], tanh outputs, trained weights).
+__device__ __forceinline__ float to_tf32(float x) { return __uint_as_float(__float_as_uint(x) + 0x1000u); }
 __device__ __forceinline__ float tanh_approx(float x) {
     float y;
     asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -253,8 +252,10 @@ kin_rollout_tc_kernel(const __grid_constant__ KinEnvParams PA, const __grid_cons
                       int has_finisher, const float* __restrict__ iq, const float* __restrict__ idq, const float* __restrict__ ipa,
                       const float* __restrict__ gq, const float* __restrict__ gpose, int n, int stride, int confirm,
                       uint32_t* __restrict__ result, unsigned long long* __restrict__ env_steps) {
-    extern __shared__ unsigned char smem_raw[];
-    TcSmem& S = *reinterpret_cast<TcSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    // round up to 1024 bytes WITHOUT leaving the shared address space (pointer + offset, not an integer round trip), so every
+    // access below compiles to LDS / STS rather than generic LD / ST with 64-bit address arithmetic
+    TcSmem& S = *reinterpret_cast<TcSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
     TileCtx c;

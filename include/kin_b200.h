@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define KIN_ABI_VERSION 1
+#define KIN_ABI_VERSION 2
 #define KIN_NJ 7
 #define KIN_OBS_DIM 56
 #define KIN_ROUTE_OBS_DIM 80
@@ -361,7 +361,23 @@ typedef struct KinSamplerParams {
     float dock_goal_q[7];
     float dock_goal_noise[7];
     float dock_init_q_noise[7];
+    /* close-bucket branch (reset_samplers.py:452-515): rejection-sample a start whose pose error lies in the bucket */
+    float dock_close_bucket_probability;
+    float dock_close_init_q_noise[7];
+    float dock_close_bucket_min_pos_error_m;
+    float dock_close_bucket_max_pos_error_m;
+    float dock_close_bucket_min_ori_error_rad;
+    float dock_close_bucket_max_ori_error_rad;
+    int dock_close_bucket_max_attempts;
+    /* handoff-state replay (reset_samplers.py:434-446): with this probability a reset copies one state of the buffer
+     * (built by the Approach rollouts, training/build_finisher_handoff_state_buffer.py).  dock_handoff_states is a DEVICE
+     * pointer to [count][KIN_HANDOFF_STATE_FLOATS] floats owned by the caller:
+     * initial_q 7 | initial_dq 7 | initial_prev_action 7 | goal_q 7 | goal_pose6 6.                                       */
+    float dock_handoff_state_probability;
+    int dock_handoff_state_count;
+    const float *dock_handoff_states;
 } KinSamplerParams;
+#define KIN_HANDOFF_STATE_FLOATS 34
 
 /* SB3 MultiInputPolicy weights, fp32, row-major [out][in] exactly as in policy.pth:
  * x[in_dim] -> tanh(W0 x + b0)[64] -> tanh(W1 h + b1)[64] -> Wa h + ba [7]; value head likewise -> [1]. */
@@ -468,6 +484,21 @@ int kin_env_step(void *handle, float *state, int stride, int n_envs, int mode_hi
 /* Replaces: ArmKinematicEnv.current_observation() (AKE:381) -> obs [n,56].                        */
 int kin_env_observe(void *handle, const float *state, int stride, int n_envs, float *obs, void *stream);
 
+/* rows of the handoff-state output of kin_rollout_handoff_states: [KIN_HO_ROWS][stride] floats */
+#define KIN_HO_FINAL_Q 0              /* approach end state: q, dq, prev_action (7 each) */
+#define KIN_HO_FINAL_DQ 7
+#define KIN_HO_FINAL_PA 14
+#define KIN_HO_SNAP_Q 21              /* first-confirmed snapshot (zeros when there was none) */
+#define KIN_HO_SNAP_DQ 28
+#define KIN_HO_SNAP_PA 35
+#define KIN_HO_GOAL_Q 42
+#define KIN_HO_GOAL_POSE 49           /* 6 */
+#define KIN_HO_FINAL_METRICS 55       /* position error, orientation error, action magnitude, dq norm */
+#define KIN_HO_SNAP_METRICS 59
+#define KIN_HO_FINAL_STEP 63          /* step counts as floats; KIN_HO_SNAP_STEP = -1 when no snapshot */
+#define KIN_HO_SNAP_STEP 64
+#define KIN_HO_ROWS 65
+
 /* Replaces: `model.predict(obs, deterministic=True)` of the SB3 MultiInputPolicy
  * (eval/eval_three_stage.py:25-27) for a batch: obs [n,in_dim] -> action [n,7] (clipped to +-1),
  * value [n] (nullable).                                                                           */
@@ -486,6 +517,14 @@ int kin_rollout_approach_finisher(void *approach_handle, void *finisher_handle,
                                   const float *goal_q, const float *goal_pose6, int n, int stride,
                                   int handoff_confirm_steps, int variant, uint32_t *result,
                                   unsigned long long *env_steps, void *stream);
+
+/* Replaces: training/build_finisher_handoff_state_buffer.py:73-112 -- the Approach policy alone over n episodes with the handoff
+ * bookkeeping of _run_approach_with_handoff; besides the usual result rows it writes, per episode, the approach end state and the
+ * first-confirmed snapshot (q, dq, prev_action, their error / action / dq metrics and step), the goal pose and goal_q
+ * (KIN_HO_* rows) from which the three handoff modes (final_settled, first_confirmed, final_always) are assembled.  Strict fp32. */
+int kin_rollout_handoff_states(void *approach_handle, const KinPolicyWeights *host_approach, const float *initial_q, const float *initial_dq,
+                               const float *initial_prev_action, const float *goal_q, const float *goal_pose6, int n, int stride,
+                               int handoff_confirm_steps, uint32_t *result, float *handoff_out, unsigned long long *env_steps, void *stream);
 
 /* Replaces: RouteKinematicEnv.reset(options={route_index, start_route_index}) / RouteSequenceKinematicEnv.reset and
  * the evaluator's state override (route/route_env.py:49-97, route/route_sequence_env.py:96-137,

@@ -314,7 +314,7 @@ kin_collect_kernel(const __grid_constant__ KinEnvParams P, const KinSamplerParam
                 ResetDraw d;
                 sample_reset(P, *SP, rng, MODE, d);
                 float gq[NJ];
-                reset_core(P, s, MODE, d.iq, d.idq, d.ipa, d.gq, nullptr, gq);
+                reset_core(P, s, MODE, d.iq, d.idq, d.ipa, d.gq, d.has_gpose ? d.gpose : nullptr, gq);
                 s.flags = (s.flags & ~(0xfu << KIN_FLAG_STAGE_SHIFT)) | ((unsigned)d.stage << KIN_FLAG_STAGE_SHIFT);
                 store_env_reset(state, stride, env, s, gq);
                 st_row_u(state, stride, KIN_ROW_EPISODE, env, episode);

@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(RO_THREADS)
 kin_rollout_ffma_kernel(const __grid_constant__ KinEnvParams PA, const __grid_constant__ KinEnvParams PF, DevPolicy pol_a, DevPolicy pol_f,
                         int has_finisher, const float* __restrict__ iq, const float* __restrict__ idq, const float* __restrict__ ipa,
                         const float* __restrict__ gq, const float* __restrict__ gpose, int n, int stride, int confirm,
-                        uint32_t* __restrict__ result, unsigned long long* __restrict__ env_steps) {
+                        uint32_t* __restrict__ result, unsigned long long* __restrict__ env_steps, float* __restrict__ handoff_out) {
     extern __shared__ __align__(16) float smem[];
     float* sw = smem;                                   // weights of the policy currently in the loop
     float* scratch_all = smem + MlpSmem<OBS>::FLOATS;   // [64][RO_THREADS]
@@ -69,6 +69,7 @@ kin_rollout_ffma_kernel(const __grid_constant__ KinEnvParams PA, const __grid_co
     int steps = 0, streak = 0, max_streak = 0, first_ready = -1;
     bool ready_hit = false, have_snap = false;
     float snap[3 * NJ];   // q, dq, prev_action at the first confirmed handoff
+    float snap_m[4] = {0.0f, 0.0f, 0.0f, 0.0f};   // its position / orientation error, action magnitude, dq norm
     int snap_step = -1;
     float last_an = 0.0f, last_dqn = 0.0f;
     StepOut so;
@@ -104,6 +105,7 @@ kin_rollout_ffma_kernel(const __grid_constant__ KinEnvParams PA, const __grid_co
                 snap_step = steps;
 #pragma unroll
                 for (int i = 0; i < NJ; ++i) { snap[i] = s.q[i]; snap[NJ + i] = s.dq[i]; snap[2 * NJ + i] = s.pa[i]; }
+                snap_m[0] = so.pos; snap_m[1] = so.ori; snap_m[2] = an; snap_m[3] = so.dq_l2;
             }
             last_an = an;
             last_dqn = so.dq_l2;
@@ -120,6 +122,26 @@ kin_rollout_ffma_kernel(const __grid_constant__ KinEnvParams PA, const __grid_co
     bool success = approach_success;
     float final_pos = so.pos, final_ori = so.ori, final_an = last_an, final_dqn = last_dqn;
     int finisher_steps = 0;
+
+    // ---- handoff states for the Finisher's reset buffer (training/build_finisher_handoff_state_buffer.py:73-112) -----
+    if (handoff_out && active) {
+        auto put = [&](int row, float v) { handoff_out[(size_t)row * stride + ep] = v; };
+#pragma unroll
+        for (int i = 0; i < NJ; ++i) {
+            put(KIN_HO_FINAL_Q + i, s.q[i]); put(KIN_HO_FINAL_DQ + i, s.dq[i]); put(KIN_HO_FINAL_PA + i, s.pa[i]);
+            put(KIN_HO_SNAP_Q + i, have_snap ? snap[i] : 0.0f); put(KIN_HO_SNAP_DQ + i, have_snap ? snap[NJ + i] : 0.0f);
+            put(KIN_HO_SNAP_PA + i, have_snap ? snap[2 * NJ + i] : 0.0f);
+            put(KIN_HO_GOAL_Q + i, goal_q[i]);
+        }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) put(KIN_HO_GOAL_POSE + k, s.goal[k]);
+        put(KIN_HO_FINAL_METRICS + 0, so.pos); put(KIN_HO_FINAL_METRICS + 1, so.ori);
+        put(KIN_HO_FINAL_METRICS + 2, last_an); put(KIN_HO_FINAL_METRICS + 3, last_dqn);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) put(KIN_HO_SNAP_METRICS + k, snap_m[k]);
+        put(KIN_HO_FINAL_STEP, (float)steps);
+        put(KIN_HO_SNAP_STEP, (float)snap_step);
+    }
 
     // ---- finisher phase: _run_policy(dock) from the handed-over state ----------------------------------
     __syncthreads();  // everyone is done reading the approach weights
@@ -266,9 +288,28 @@ extern "C" int kin_rollout_approach_finisher(void* approach_handle, void* finish
     DevPolicy da = actor_of(host_approach), df = has_f ? actor_of(host_finisher) : actor_of(host_approach);
     kin_rollout_ffma_kernel<<<(n + RO_THREADS - 1) / RO_THREADS, RO_THREADS, smem, st>>>(ha->params, PF, da, df, has_f ? 1 : 0, initial_q, initial_dq,
                                                                                            initial_prev_action, goal_q, goal_pose6, n, stride,
-                                                                                           handoff_confirm_steps, result, env_steps);
+                                                                                           handoff_confirm_steps, result, env_steps, nullptr);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? KIN_OK : kin_fail_cuda(e, "kin_rollout_approach_finisher");
+}
+
+extern "C" int kin_rollout_handoff_states(void* approach_handle, const KinPolicyWeights* host_approach, const float* initial_q, const float* initial_dq,
+                                          const float* initial_prev_action, const float* goal_q, const float* goal_pose6, int n, int stride,
+                                          int handoff_confirm_steps, uint32_t* result, float* handoff_out, unsigned long long* env_steps, void* stream) {
+    KinHandle* ha = kin_handle(approach_handle);
+    if (!ha) return kin_fail(KIN_ERR_INVALID_ARG, "kin_rollout_handoff_states: bad handle");
+    if (!actor_ok(host_approach) || host_approach->in_dim != OBS) return kin_fail(KIN_ERR_INVALID_ARG, "kin_rollout_handoff_states: approach policy must be a 56-input actor");
+    if (!initial_q || (!goal_q && !goal_pose6) || !result || !handoff_out || n <= 0 || stride < n) return kin_fail(KIN_ERR_INVALID_ARG, "kin_rollout_handoff_states: bad buffers / sizes");
+    if (handoff_confirm_steps < 1) return kin_fail(KIN_ERR_INVALID_ARG, "kin_rollout_handoff_states: handoff_confirm_steps >= 1");
+    const size_t smem = (size_t)(MlpSmem<OBS>::FLOATS + HID * RO_THREADS) * sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(kin_rollout_ffma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return kin_fail_cuda(e, "kin_rollout_handoff_states: smem attribute");
+    DevPolicy da = actor_of(host_approach);
+    kin_rollout_ffma_kernel<<<(n + RO_THREADS - 1) / RO_THREADS, RO_THREADS, smem, (cudaStream_t)stream>>>(
+        ha->params, ha->params, da, da, 0, initial_q, initial_dq, initial_prev_action, goal_q, goal_pose6, n, stride, handoff_confirm_steps, result, env_steps,
+        handoff_out);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? KIN_OK : kin_fail_cuda(e, "kin_rollout_handoff_states");
 }
 
 extern "C" int kin_policy_forward(const KinPolicyWeights* w, const float* obs, float* action, float* value, int n, void* stream) {

@@ -255,6 +255,8 @@ __device__ __forceinline__ int sample_target_stage(const KinSamplerParams& S, Ph
 
 struct ResetDraw {
     float iq[NJ], gq[NJ], idq[NJ], ipa[NJ];
+    float gpose[6];      // explicit goal pose (handoff-state replay); otherwise the reset computes FK(goal_q)
+    bool has_gpose;
     int stage;
 };
 
@@ -323,12 +325,63 @@ __device__ __forceinline__ void sample_random_start_pair(const KinEnvParams& P, 
 __device__ __forceinline__ void sample_reset(const KinEnvParams& P, const KinSamplerParams& S, Philox& rng, int mode, ResetDraw& d) {
 #pragma unroll
     for (int i = 0; i < NJ; ++i) { d.idq[i] = 0.0f; d.ipa[i] = 0.0f; }
+    d.has_gpose = false;
     d.stage = clampi(S.current_stage, 0, max(S.n_stages - 1, 0));
     if (mode == KIN_MODE_DOCK) {
+        // handoff-state replay (reset_samplers.py:434-446)
+        if (S.dock_handoff_state_probability > 0.0f && S.dock_handoff_state_count > 0 && S.dock_handoff_states &&
+            rng.uniform() < S.dock_handoff_state_probability) {
+            const float* st = S.dock_handoff_states + (size_t)rng.integers(0, S.dock_handoff_state_count - 1) * KIN_HANDOFF_STATE_FLOATS;
+#pragma unroll
+            for (int i = 0; i < NJ; ++i) { d.iq[i] = st[i]; d.idq[i] = st[7 + i]; d.ipa[i] = st[14 + i]; d.gq[i] = st[21 + i]; }
+#pragma unroll
+            for (int k = 0; k < 6; ++k) d.gpose[k] = st[28 + k];
+            d.has_gpose = true;
+            return;
+        }
         if (S.dock_use_stage_goal && S.curriculum_enabled && S.n_stages > 0)
             sample_shell(P, rng, S.goal_q + d.stage * NJ, S.goal_noise + d.stage * NJ, d.gq);
         else
             sample_shell(P, rng, S.dock_goal_q, S.dock_goal_noise, d.gq);
+        // close bucket (reset_samplers.py:452-515): near-success but not-yet-success starts, best miss kept as the fallback
+        if (S.dock_close_bucket_probability > 0.0f && rng.uniform() < S.dock_close_bucket_probability) {
+            float goal_pose[6], best[NJ];
+            fk_pose6(P, d.gq, goal_pose);
+            float best_dist = CUDART_INF_F;
+            bool have_best = false, found = false;
+            const int attempts = max(S.dock_close_bucket_max_attempts, 1);
+            for (int a = 0; a < attempts && !found; ++a) {
+                float cand[NJ], pose[6], pe[3], oe[3];
+#pragma unroll
+                for (int i = 0; i < NJ; ++i)
+                    cand[i] = clampf(d.gq[i] + rng.uniform(-S.dock_close_init_q_noise[i], S.dock_close_init_q_noise[i]), P.joint_lower[i], P.joint_upper[i]);
+                fk_pose6(P, cand, pose);
+                pose_error(pose, goal_pose, pe, oe);
+                const float pos = norm3(pe[0], pe[1], pe[2]), ori = norm3(oe[0], oe[1], oe[2]);
+                if (pos >= S.dock_close_bucket_min_pos_error_m && pos <= S.dock_close_bucket_max_pos_error_m &&
+                    ori >= S.dock_close_bucket_min_ori_error_rad && ori <= S.dock_close_bucket_max_ori_error_rad) {
+#pragma unroll
+                    for (int i = 0; i < NJ; ++i) d.iq[i] = cand[i];
+                    found = true;
+                } else {
+                    float dist;
+                    if (pos < S.dock_close_bucket_min_pos_error_m) dist = S.dock_close_bucket_min_pos_error_m - pos;
+                    else if (pos > S.dock_close_bucket_max_pos_error_m) dist = pos - S.dock_close_bucket_max_pos_error_m;
+                    else dist = fmaxf(fmaxf(S.dock_close_bucket_min_ori_error_rad - ori, ori - S.dock_close_bucket_max_ori_error_rad), 0.0f);
+                    if (dist < best_dist) {
+                        best_dist = dist;
+                        have_best = true;
+#pragma unroll
+                        for (int i = 0; i < NJ; ++i) best[i] = cand[i];
+                    }
+                }
+            }
+            if (!found) {
+#pragma unroll
+                for (int i = 0; i < NJ; ++i) d.iq[i] = have_best ? best[i] : clampf(d.gq[i], P.joint_lower[i], P.joint_upper[i]);
+            }
+            return;
+        }
 #pragma unroll
         for (int i = 0; i < NJ; ++i)
             d.iq[i] = clampf(d.gq[i] + rng.uniform(-S.dock_init_q_noise[i], S.dock_init_q_noise[i]), P.joint_lower[i], P.joint_upper[i]);

@@ -90,7 +90,7 @@ kin_step_kernel(const __grid_constant__ KinEnvParams P, const KinSamplerParams* 
                 ResetDraw d;
                 sample_reset(P, *S, rng, mode, d);
                 float gq[NJ];
-                reset_core(P, s, mode, d.iq, d.idq, d.ipa, d.gq, nullptr, gq);
+                reset_core(P, s, mode, d.iq, d.idq, d.ipa, d.gq, d.has_gpose ? d.gpose : nullptr, gq);
                 s.flags = (s.flags & ~(0xfu << KIN_FLAG_STAGE_SHIFT)) | ((unsigned)d.stage << KIN_FLAG_STAGE_SHIFT);
                 store_env_reset(state, stride, env, s, gq);
                 st_row_u(state, stride, KIN_ROW_EPISODE, env, episode);
@@ -164,7 +164,7 @@ kin_reset_sampled_kernel(const __grid_constant__ KinEnvParams P, const KinSample
     EnvRegs s;
     s.flags = 0u;
     float gq[NJ];
-    reset_core(P, s, mode, d.iq, d.idq, d.ipa, d.gq, nullptr, gq);
+    reset_core(P, s, mode, d.iq, d.idq, d.ipa, d.gq, d.has_gpose ? d.gpose : nullptr, gq);
     s.flags |= (unsigned)d.stage << KIN_FLAG_STAGE_SHIFT;
     store_env_reset(state, stride, env, s, gq);
     st_row_u(state, stride, KIN_ROW_EPISODE, env, episode);

@@ -103,8 +103,18 @@ class ParamsHandle:
     def handle(self) -> ctypes.c_void_p:
         return self._h
 
-    def set_sampler(self, stage_index: int) -> None:
+    def set_sampler(self, stage_index: int, handoff_states: torch.Tensor | None = None) -> None:
+        """Upload the reset sampler tables; ``handoff_states`` ([M, 34] float32 on the device, ``handoff.HandoffBuffer.device_rows``)
+        arms the dock reset's handoff-state replay with ``dock_reset_config.handoff_state_probability``."""
         self._sampler = _params.sampler_params(self.config, stage_index)
+        self._handoff_states = handoff_states          # keep the device buffer alive as long as the sampler points at it
+        if handoff_states is not None and handoff_states.numel() > 0:
+            if handoff_states.dtype != torch.float32 or handoff_states.dim() != 2 or handoff_states.shape[1] != _D("KIN_HANDOFF_STATE_FLOATS") \
+                    or not handoff_states.is_cuda or not handoff_states.is_contiguous():
+                raise ValueError("handoff_states must be a contiguous CUDA float32 [M, 34] tensor")
+            self._sampler.dock_handoff_state_probability = float(self.config.dock_reset_config.handoff_state_probability)
+            self._sampler.dock_handoff_state_count = int(handoff_states.shape[0])
+            self._sampler.dock_handoff_states = handoff_states.data_ptr()
         _lib.check(_lib.lib().kin_params_set_sampler(self._h, ctypes.byref(self._sampler)))
 
     def __del__(self) -> None:  # pragma: no cover - interpreter teardown order
@@ -195,8 +205,14 @@ class BatchedArmKinematicEnv:
 
     def _ensure_sampler(self) -> None:
         if self._sampler_stage != self._stage:
-            self._params.set_sampler(self._stage)
+            self._params.set_sampler(self._stage, getattr(self, "_handoff_rows", None))
             self._sampler_stage = self._stage
+
+    def set_handoff_states(self, rows: torch.Tensor | None) -> None:
+        """Arm (or clear) the dock reset's handoff-state replay (reset_samplers.py:434-446): ``rows`` is ``[M, 34]`` float32
+        (initial_q | initial_dq | initial_prev_action | goal_q | goal_pose6), e.g. ``HandoffBuffer.device_rows(device)``."""
+        self._handoff_rows = None if rows is None else rows.to(self.device, torch.float32).contiguous()
+        self._sampler_stage = None
 
     # ------------------------------------------------------------------ reset
     def _as_dev(self, x: Any, cols: int, m: int) -> torch.Tensor | None:

@@ -122,4 +122,14 @@ def sampler_params(cfg: Phase1EnvConfig, stage_index: int = 0):
         s.dock_goal_q[i] = d.goal_q[i]
         s.dock_goal_noise[i] = d.goal_noise[i]
         s.dock_init_q_noise[i] = d.init_q_noise[i]
+        s.dock_close_init_q_noise[i] = d.close_init_q_noise[i]
+    s.dock_close_bucket_probability = float(d.close_bucket_probability)
+    s.dock_close_bucket_min_pos_error_m = float(d.close_bucket_min_pos_error_m)
+    s.dock_close_bucket_max_pos_error_m = float(d.close_bucket_max_pos_error_m)
+    s.dock_close_bucket_min_ori_error_rad = float(d.close_bucket_min_ori_error_rad)
+    s.dock_close_bucket_max_ori_error_rad = float(d.close_bucket_max_ori_error_rad)
+    s.dock_close_bucket_max_attempts = int(d.close_bucket_max_attempts)
+    s.dock_handoff_state_probability = 0.0      # set together with the device buffer (ParamsHandle.set_sampler(handoff_states=...))
+    s.dock_handoff_state_count = 0
+    s.dock_handoff_states = None
     return s

@@ -105,7 +105,7 @@ class PPOTrainer:
 
     def __init__(self, config: Phase1EnvConfig, policy: PolicyWeights, *, num_envs: int, hyper: PPOHyper, device: str | torch.device = "cuda",
                  seed: int = 0, stage_index: int = 0, process_group: Any = None, grad_ctas: int | None = None,
-                 update_variant: str = "tc", collect_variant: str | None = None) -> None:
+                 update_variant: str = "tc", collect_variant: str | None = None, handoff_states: torch.Tensor | None = None) -> None:
         if not torch.cuda.is_available():
             raise _lib.KinError("PPOTrainer needs a CUDA device; there is no CPU fallback")
         if policy.in_dim != 56:
@@ -152,6 +152,8 @@ class PPOTrainer:
             self.partials = torch.zeros((self.grad_ctas, self.P + _D("KIN_PPO_STATS") + 8), dtype=torch.float32, device=self.device)
             self.env = BatchedArmKinematicEnv(config, self.N, self.device, auto_reset=True, seed=self.seed, host_sampler=False, with_aux=False)
             self.env.set_curriculum_stage(stage_index)
+            if handoff_states is not None:       # Finisher training: dock resets replay Approach handoff states (handoff.py)
+                self.env.set_handoff_states(handoff_states)
             f32 = dict(dtype=torch.float32, device=self.device)
             fused = self.collect_variant == "fused"
             self.obs_buf = None if fused else torch.zeros((self.T + 1, self.N, 56), **f32)

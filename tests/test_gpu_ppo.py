@@ -287,7 +287,7 @@ def test_trainer_runs_and_improves_value_fit(variant):
     assert torch.equal(tr2.params, q0)
 
 
-@pytest.mark.parametrize("tiles_per_cta,num_envs,trained", [(1, 256, False), (2, 512, False), (4, 640, True)])
+@pytest.mark.parametrize("tiles_per_cta,num_envs,trained", [(1, 256, False), (2, 512, False), (4, 640, True), (2, 384, "dock")])
 def test_fused_collection_replays_through_the_step_kernel(tiles_per_cta, num_envs, trained):
     """kin_ppo_collect (one launch per rollout, tensor-core policy) against the per-step kernels: replaying its recorded actions
     through kin_env_step from the same start state reproduces rewards, done flags, observations (as bf16 images) and the
@@ -297,10 +297,23 @@ def test_fused_collection_replays_through_the_step_kernel(tiles_per_cta, num_env
     from rl_brain_trainer_b200 import _lib, ppo
     from rl_brain_trainer_b200.env import BatchedArmKinematicEnv
 
-    cfg = env_config("approach_dynamic_scale_big")      # short episodes: several time-limit truncations per rollout
+    cfg = env_config("finisher_noop_ft" if trained == "dock" else "approach_dynamic_scale_big")
+    # short episodes: several time-limit truncations per rollout
     cfg = dataclasses.replace(cfg, episode_length=24, termination_config=dataclasses.replace(cfg.termination_config, max_episode_steps=24))
     T = 60
-    if trained:       # the bundled approach checkpoint on the easiest shell: success / near-goal flags and dwell counters are exercised
+    handoff_rows = None
+    if trained == "dock":   # Finisher training set-up: dock mode, dock reward, resets replay Approach handoff states / close buckets
+        from rl_brain_trainer_b200 import handoff
+        from rl_brain_trainer_b200.policy import PolicyWeights
+        from rl_brain_trainer_b200.samplers import build_curriculum_local_eval_suite
+
+        acfg = env_config("approach_dynamic_scale_big")
+        buf, _ = handoff.build_finisher_handoff_state_buffer(acfg, PolicyWeights.preset("approach_stage8_11", "cuda"), stage_index=5,
+                                                             suite=build_curriculum_local_eval_suite(acfg, seed=3, stage_index=5, n_episodes=256))
+        handoff_rows = buf.device_rows("cuda")
+        assert len(buf) > 100 and cfg.dock_reset_config.handoff_state_probability > 0.5
+        pol, stage = PolicyWeights.preset("finisher", "cuda"), 5
+    elif trained:     # the bundled approach checkpoint on the easiest shell: success / near-goal flags and dwell counters are exercised
         from rl_brain_trainer_b200.policy import PolicyWeights
 
         pol, stage = PolicyWeights.preset("approach_stage8_11", "cuda"), 0
@@ -309,10 +322,13 @@ def test_fused_collection_replays_through_the_step_kernel(tiles_per_cta, num_env
         pol.tensors["act_w"].mul_(40.0)
         pol.tensors["vf_b1"].normal_(0, 0.2)
     hp = ppo.PPOHyper(n_steps=T, batch_size=num_envs * T // 4, n_epochs=1, gamma=0.97, learning_rate=0.0)
-    tr = ppo.PPOTrainer(cfg, pol, num_envs=num_envs, hyper=hp, seed=11, stage_index=stage, update_variant="tc", collect_variant="fused")
+    tr = ppo.PPOTrainer(cfg, pol, num_envs=num_envs, hyper=hp, seed=11, stage_index=stage, update_variant="tc", collect_variant="fused",
+                        handoff_states=handoff_rows)
     tr.tiles_per_cta = tiles_per_cta
     replay = BatchedArmKinematicEnv(cfg, num_envs, "cuda", auto_reset=True, seed=tr.env._seed, host_sampler=False, with_aux=False)
     replay.set_curriculum_stage(stage)
+    if handoff_rows is not None:
+        replay.set_handoff_states(handoff_rows)
     replay._ensure_sampler()
     for rollout in range(2):                 # the second rollout starts mid-episode from the state the first one left
         replay.state.copy_(tr.env.state)
@@ -353,6 +369,8 @@ def test_fused_collection_replays_through_the_step_kernel(tiles_per_cta, num_env
             obs_t = replay.obs.clone()
         assert n_trunc == int(tr.boot_count) and n_trunc > 0
         assert not trained or bool(((tr.done_buf & 4) != 0).any())           # the trained policy reaches the success zone
+        if trained == "dock":
+            assert int(tr.env._mode_all) == 1 and bool(((tr.done_buf & 0x80) != 0).any())
         assert torch.equal(replay.state[:, :num_envs], tr.env.state[:, :num_envs])
         _, v_last = _torch_forward(pol, obs_t)
         assert float((tr.last_val - v_last).abs().max()) < 0.05 * max(1.0, float(v_last.abs().max()))

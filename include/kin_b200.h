@@ -415,6 +415,8 @@ typedef struct KinPolicyWeights {
 #define KIN_RES_FINAL_ACTION 12       /* f32 final_action_magnitude */
 #define KIN_RES_FINAL_DQ 13           /* f32 final_dq_norm */
 #define KIN_RES_FINAL_Q 14            /* 7 x f32 */
+#define KIN_RES_APPROACH_ACTION 21    /* f32 action magnitude / dq norm at the END OF THE APPROACH phase (what _failure_reason reads) */
+#define KIN_RES_APPROACH_DQ 22
 #define KIN_RES_ROWS 24
 
 /* Dense q-goal route (route/route_dataset.py:16-99): device arrays, one row per waypoint. */

@@ -362,6 +362,10 @@ kin_rollout_tc_kernel(const __grid_constant__ KinEnvParams PA, const __grid_cons
             running = !(so.done & (KIN_DONE_TERMINATED | KIN_DONE_TRUNCATED));
         }
     }
+    if (active) {   // approach-phase motion metrics (eval_workspace_expansion.py:47-66 classifies failures with them)
+        result[(size_t)KIN_RES_APPROACH_ACTION * stride + ep] = __float_as_uint(last_an);
+        result[(size_t)KIN_RES_APPROACH_DQ * stride + ep] = __float_as_uint(last_dqn);
+    }
     const int approach_steps = steps;
     const bool approach_success = (so.done & KIN_DONE_SUCCESS) != 0;
     const float approach_pos = so.pos, approach_ori = so.ori;

@@ -68,6 +68,8 @@ class RolloutResult:
     approach_final_orientation_error = property(lambda self: self._f("KIN_RES_APPROACH_ORI"))
     min_position_error = property(lambda self: self._f("KIN_RES_MIN_POS"))
     min_orientation_error = property(lambda self: self._f("KIN_RES_MIN_ORI"))
+    approach_final_action_magnitude = property(lambda self: self._f("KIN_RES_APPROACH_ACTION"))
+    approach_final_dq_norm = property(lambda self: self._f("KIN_RES_APPROACH_DQ"))
     final_action_magnitude = property(lambda self: self._f("KIN_RES_FINAL_ACTION"))
     final_dq_norm = property(lambda self: self._f("KIN_RES_FINAL_DQ"))
 
@@ -194,18 +196,24 @@ class ApproachFinisherRollout:
 FAILURE_REASONS = ("success", "position", "orientation", "motion_action", "motion_dq", "dwell", "timeout_or_regression")
 
 
-def summarize(result: RolloutResult, approach_config: Phase1EnvConfig) -> dict[str, Any]:
-    """``_summarize_stage`` + ``_failure_reason`` (eval_workspace_expansion.py:47-83) from device reductions."""
+def failure_reason_codes(result: RolloutResult, approach_config: Phase1EnvConfig, handoff_confirm_steps: int = 2) -> torch.Tensor:
+    """``_failure_reason`` / ``_reason`` (eval_workspace_expansion.py:47-66, eval_full_workspace_coverage.py:38-52) per episode, as an
+    index into ``FAILURE_REASONS``: the checks read the APPROACH result in the reference's order (position, orientation, action, dq,
+    dock-coarse-ready dwell)."""
     rc = approach_config.reward_config
+    reason = torch.full((result.n,), 6, dtype=torch.int64, device=result.raw.device)
+    reason = torch.where(result.max_ready_streak < int(handoff_confirm_steps), torch.full_like(reason, 5), reason)
+    reason = torch.where(result.approach_final_dq_norm > rc.finisher_ready_dq_threshold, torch.full_like(reason, 4), reason)
+    reason = torch.where(result.approach_final_action_magnitude > rc.finisher_ready_action_threshold, torch.full_like(reason, 3), reason)
+    reason = torch.where(result.approach_final_orientation_error > rc.finisher_ready_ori_threshold_rad, torch.full_like(reason, 2), reason)
+    reason = torch.where(result.approach_final_position_error > rc.finisher_ready_pos_threshold_m, torch.full_like(reason, 1), reason)
+    return torch.where(result.success, torch.zeros_like(reason), reason)
+
+
+def summarize(result: RolloutResult, approach_config: Phase1EnvConfig, handoff_confirm_steps: int = 2) -> dict[str, Any]:
+    """``_summarize_stage`` + ``_failure_reason`` (eval_workspace_expansion.py:47-83) from device reductions."""
     ok = result.success
-    # _failure_reason looks at the APPROACH result (final pos/ori/action/dq of the approach phase).  The fused kernel keeps the
-    # approach pos/ori; action/dq are those of the last executed phase, so the motion_* split is exact only without a finisher.
-    pos, ori = result.approach_final_position_error, result.approach_final_orientation_error
-    reason = torch.full((result.n,), 6, dtype=torch.int64, device=ok.device)
-    reason = torch.where(~result.ready_dwell, torch.full_like(reason, 5), reason)
-    reason = torch.where(ori > rc.finisher_ready_ori_threshold_rad, torch.full_like(reason, 2), reason)
-    reason = torch.where(pos > rc.finisher_ready_pos_threshold_m, torch.full_like(reason, 1), reason)
-    reason = torch.where(ok, torch.zeros_like(reason), reason)
+    reason = failure_reason_codes(result, approach_config, handoff_confirm_steps)
     counts = torch.bincount(reason, minlength=len(FAILURE_REASONS)).cpu().numpy()
     regress = (result.approach_final_position_error > result.min_position_error + 0.002) | \
               (result.approach_final_orientation_error > result.min_orientation_error + 0.01)

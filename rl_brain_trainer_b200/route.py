@@ -152,10 +152,26 @@ class BatchedRouteKinematicEnv:
             self.raux = torch.zeros((_D("KIN_RAUX_ROWS"), self.stride), dtype=torch.float32, device=self.device)
             self.rcomp = torch.zeros((17, self.stride), dtype=torch.float32, device=self.device) if with_components else None
 
-    def reset(self, *, route_index: Any, start_route_index: Any = None, initial_q: Any = None, initial_dq: Any = None,
-              initial_prev_action: Any = None, env_ids: Any = None) -> torch.Tensor:
+    def set_route_window(self, *, max_route_index: int, min_route_index: int = 1) -> None:
+        """``RouteKinematicEnv.set_route_window`` (route_env.py:99-121): the waypoint range sampled resets draw from."""
+        import dataclasses
+
+        self.config = dataclasses.replace(self.config, reset_config=dataclasses.replace(self.config.reset_config, min_route_index=int(min_route_index),
+                                                                                         max_route_index=int(max_route_index)))
+
+    def reset(self, *, route_index: Any = None, start_route_index: Any = None, initial_q: Any = None, initial_dq: Any = None,
+              initial_prev_action: Any = None, env_ids: Any = None, seed: int | None = None) -> torch.Tensor:
         ids = None if env_ids is None else torch.as_tensor(env_ids, dtype=torch.int32, device=self.device).contiguous()
         m = self.num_envs if ids is None else int(ids.numel())
+        self.last_reset: dict[str, torch.Tensor] | None = None
+        if route_index is None:      # route_env.py:60-73: no explicit waypoint -> sample_route_reset
+            if seed is not None or not hasattr(self, "_gen"):
+                self._gen = torch.Generator(device=self.device)
+                self._gen.manual_seed(0 if seed is None else int(seed))
+            smp = sample_route_reset_batch(self.table, self.config.base_env_config.joint_specs, self.config.reset_config, m, self._gen)
+            route_index, start_route_index = smp["route_index"], smp["start_route_index"]
+            initial_q, initial_dq, initial_prev_action = smp["initial_q"], smp["initial_dq"], smp["initial_prev_action"]
+            self.last_reset = smp
         ri = torch.as_tensor(route_index, dtype=torch.int32, device=self.device).reshape(-1)
         if ri.numel() == 1 and m > 1:
             ri = ri.expand(m)
@@ -202,6 +218,135 @@ class BatchedRouteKinematicEnv:
         if self.rcomp is not None:
             info["reward_components"] = self.rcomp[:, :n]
         return self.obs, self.reward, (d & _D("KIN_DONE_TERMINATED")) != 0, (d & _D("KIN_DONE_TRUNCATED")) != 0, info
+
+
+ROUTE_RESET_MODES = ("prefix_start", "random_prefix", "segment", "replay", "recovery")
+_FORCED_MODE = {"prefix_start_reset": 0, "random_prefix_reset": 1, "segment_reset": 2, "replay_reset": 3, "recovery_reset": 4}
+
+
+def _reset_mode_ratios(config: Any) -> np.ndarray:
+    r = np.asarray([max(config.prefix_start_reset_ratio, 0.0), max(config.random_prefix_reset_ratio, 0.0), max(config.segment_reset_ratio, 0.0),
+                    max(config.replay_reset_ratio, 0.0), max(config.recovery_reset_ratio, 0.0)], dtype=float)
+    return r / r.sum() if r.sum() > 0.0 else np.array([0.0, 1.0, 0.0, 0.0, 0.0])
+
+
+def _reset_index_ranges(config: Any, max_index: int) -> np.ndarray:
+    """[5, 2] inclusive (low, high) of the target waypoint per reset mode (route_reset_samplers.py:48-95)."""
+    lo = int(np.clip(config.min_route_index, 1, max_index))
+    hi = int(np.clip(config.max_route_index, lo, max_index))
+    seg_lo = int(np.clip(config.segment_start_index, 1, max_index))
+    seg_hi = int(np.clip(config.segment_end_index, seg_lo, max_index))
+    rep_lo = int(np.clip(config.replay_start_index, 1, max_index))
+    rep_hi = int(np.clip(config.replay_end_index, rep_lo, max_index))
+    return np.array([[lo, hi], [lo, hi], [seg_lo, min(seg_hi, hi)], [rep_lo, min(rep_hi, hi)], [lo, hi]], dtype=np.int64)
+
+
+def sample_route_reset(rng: np.random.Generator, route: RouteDataset, joint_specs: Sequence[Any], config: Any) -> dict[str, Any]:
+    """Host port of ``sample_route_reset`` (route_reset_samplers.py:43-117), consuming the numpy stream in the reference's order
+    (``rng.choice`` for the mode, ``rng.integers`` for the waypoint, three ``rng.normal`` noise vectors)."""
+    max_index = len(route) - 1
+    mode = int(rng.choice(5, p=_reset_mode_ratios(config)))          # rng.choice(list_of_5, p=...) draws the same index
+    mode = _FORCED_MODE.get(config.mode, mode)
+    lo, hi = _reset_index_ranges(config, max_index)[mode]
+    route_index = int(rng.integers(lo, hi + 1))
+    start_index = 0 if mode == 0 else max(route_index - 1, 0)
+    src = route_index if mode == 4 else start_index
+    noise = lambda std: rng.normal(0.0, float(std), size=(7,)) if std > 0.0 else np.zeros(7)  # noqa: E731
+    lower = np.array([sp.lower for sp in joint_specs]); upper = np.array([sp.upper for sp in joint_specs])
+    initial_q = np.clip(route.q_goal[src] + noise(config.q_noise_std), lower, upper)
+    initial_dq = noise(config.dq_noise_std)
+    initial_prev_action = np.clip(noise(config.prev_action_noise_std), -1.0, 1.0)
+    return {"initial_q": initial_q, "initial_dq": initial_dq, "initial_prev_action": initial_prev_action, "goal_q": route.q_goal[route_index].copy(),
+            "route_index": route_index, "start_route_index": start_index, "reset_mode": ROUTE_RESET_MODES[mode]}
+
+
+def sample_route_reset_batch(table: "DeviceRoute", joint_specs: Sequence[Any], config: Any, n: int, generator: torch.Generator) -> dict[str, torch.Tensor]:
+    """The same sampler for ``n`` resets at once on the device (torch Philox stream: distributionally, not bitwise, the reference's)."""
+    dev = table.device
+    max_index = len(table.route) - 1
+    if config.mode in _FORCED_MODE:
+        mode = torch.full((n,), _FORCED_MODE[config.mode], dtype=torch.int64, device=dev)
+    else:
+        p = torch.as_tensor(_reset_mode_ratios(config), dtype=torch.float32, device=dev)
+        mode = torch.multinomial(p, n, replacement=True, generator=generator)
+    rng_tab = torch.as_tensor(_reset_index_ranges(config, max_index), device=dev)
+    lo, hi = rng_tab[mode, 0], rng_tab[mode, 1]
+    u = torch.rand(n, device=dev, generator=generator)
+    route_index = (lo + torch.floor(u * (hi - lo + 1).float()).long()).clamp(max=hi)
+    start_index = torch.where(mode == 0, torch.zeros_like(route_index), (route_index - 1).clamp_min(0))
+    src = torch.where(mode == 4, route_index, start_index)
+    g = lambda std: torch.randn((n, 7), device=dev, generator=generator) * float(std) if std > 0.0 else torch.zeros((n, 7), device=dev)  # noqa: E731
+    lower = torch.tensor([sp.lower for sp in joint_specs], dtype=torch.float32, device=dev)
+    upper = torch.tensor([sp.upper for sp in joint_specs], dtype=torch.float32, device=dev)
+    initial_q = torch.minimum(torch.maximum(table.q[src] + g(config.q_noise_std), lower), upper)
+    return {"initial_q": initial_q, "initial_dq": g(config.dq_noise_std), "initial_prev_action": g(config.prev_action_noise_std).clamp(-1.0, 1.0),
+            "route_index": route_index.to(torch.int32), "start_route_index": start_index.to(torch.int32), "reset_mode": mode}
+
+
+@dataclass(frozen=True)
+class RouteCurriculumStage:
+    name: str
+    prefix_end_index: int
+
+
+class RoutePrefixCurriculum:
+    """``RoutePrefixCurriculumCallback`` (route/route_curriculum.py:23-132) without SB3: feed the finished episodes' flags in env
+    order, get the prefix window to apply.  Promotion needs all four windowed rates (success, route-ready hit, orientation hit,
+    regression) over ``window_episodes`` and at least ``min_episodes_per_stage`` episodes in the stage."""
+
+    def __init__(self, stages: Sequence[RouteCurriculumStage], *, promotion_success_rate: float, promotion_route_ready_hit_rate: float,
+                 promotion_orientation_hit_rate: float, promotion_max_regression_rate: float, window_episodes: int, min_episodes_per_stage: int = 128) -> None:
+        if not stages:
+            raise ValueError("RoutePrefixCurriculumCallback requires at least one stage")
+        from collections import deque
+
+        self.stages = list(stages)
+        self.thresholds = (float(promotion_success_rate), float(promotion_route_ready_hit_rate), float(promotion_orientation_hit_rate),
+                           float(promotion_max_regression_rate))
+        self.window_episodes = max(int(window_episodes), 1)
+        self.min_episodes_per_stage = max(int(min_episodes_per_stage), 1)
+        self.current_stage_index = 0
+        self.stage_episode_count = 0
+        self._win = [deque(maxlen=self.window_episodes) for _ in range(4)]
+        self.history: list[dict[str, Any]] = []
+
+    @property
+    def prefix_end_index(self) -> int:
+        return int(self.stages[self.current_stage_index].prefix_end_index)
+
+    def metrics(self) -> dict[str, float]:
+        m = lambda d: float(sum(d)) / float(len(d)) if d else 0.0  # noqa: E731
+        return {"recent_success_rate": m(self._win[0]), "recent_route_ready_hit_rate": m(self._win[1]),
+                "recent_orientation_hit_rate": m(self._win[2]), "recent_regression_rate": m(self._win[3])}
+
+    def record(self, success: Any, route_ready: Any, orientation_hit: Any, regression: Any, *, total_timesteps: int = 0) -> bool:
+        """One ``_on_step``: the flags of the episodes that finished at this step (env order).  True when a promotion happened."""
+        promoted = False
+        for flags in zip(np.atleast_1d(success), np.atleast_1d(route_ready), np.atleast_1d(orientation_hit), np.atleast_1d(regression)):
+            self.stage_episode_count += 1
+            for d, f in zip(self._win, flags):
+                d.append(1 if bool(f) else 0)
+            if self.stage_episode_count < self.min_episodes_per_stage or len(self._win[0]) < self.window_episodes:
+                continue
+            m = self.metrics()
+            if (m["recent_success_rate"] >= self.thresholds[0] and m["recent_route_ready_hit_rate"] >= self.thresholds[1]
+                    and m["recent_orientation_hit_rate"] >= self.thresholds[2] and m["recent_regression_rate"] <= self.thresholds[3]
+                    and self.current_stage_index < len(self.stages) - 1):
+                prev = self.stages[self.current_stage_index]
+                self.current_stage_index += 1
+                nxt = self.stages[self.current_stage_index]
+                self.history.append({"from_stage": prev.name, "to_stage": nxt.name, "from_prefix_end_index": int(prev.prefix_end_index),
+                                     "to_prefix_end_index": int(nxt.prefix_end_index), "total_timesteps": int(total_timesteps), **m})
+                self.stage_episode_count = 0
+                for d in self._win:
+                    d.clear()
+                promoted = True
+        return promoted
+
+    def summary(self) -> dict[str, Any]:
+        st = self.stages[self.current_stage_index]
+        return {"stage_index": int(self.current_stage_index), "stage_name": st.name, "prefix_end_index": int(st.prefix_end_index),
+                "stage_episode_count": int(self.stage_episode_count), **self.metrics(), "history": list(self.history)}
 
 
 def evaluate_sequential_route(route: RouteDataset, config: RouteEnvConfig, policy: PolicyWeights, *, n_replicas: int = 1, start_index: int = 1,

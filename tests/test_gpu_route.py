@@ -141,3 +141,42 @@ def test_route_sequential_probe_matches_oracle():
     big = synthetic_route(483, seed=7)
     res = evaluate_sequential_route(big, renv, pol, n_replicas=256, start_index=1, end_index=170, start_q_noise_std=0.0008)
     assert int(res["env_steps"].item()) >= 170 * 256 and res["longest_success_prefix"].shape == (256,)
+
+
+def test_sampled_route_reset_and_route_window():
+    """reset() without an explicit waypoint draws from the batched device port of sample_route_reset; set_route_window narrows it."""
+    from rl_brain_trainer_b200.route import BatchedRouteKinematicEnv, _reset_mode_ratios
+
+    g, renv, _, route, _ = _setup()
+    n = 16384
+    env = BatchedRouteKinematicEnv(route, renv, n)
+    env.set_route_window(max_route_index=30, min_route_index=4)
+    obs = env.reset(seed=3)
+    torch.cuda.synchronize()
+    smp = env.last_reset
+    cfg = env.config.reset_config
+    assert obs.shape == (n, 80) and bool(torch.isfinite(obs).all())
+    frac = torch.bincount(smp["reset_mode"], minlength=5).double().cpu().numpy() / n
+    assert np.abs(frac - _reset_mode_ratios(cfg)).max() < 0.015
+    ri, si, mode = smp["route_index"].long(), smp["start_route_index"].long(), smp["reset_mode"]
+    assert int(ri.min()) >= 1 and int(ri.max()) <= 30
+    plain = (mode == 1) | (mode == 4) | (mode == 0)
+    assert int(ri[plain].min()) == 4 and int(ri[plain].max()) == 30           # uniform over the window, both ends reached
+    assert bool((si[mode == 0] == 0).all()) and bool((si[mode != 0] == ri[mode != 0] - 1).all())
+    # starts: the waypoint before the target (the target itself in recovery mode) + N(0, q_noise_std), clipped
+    src = torch.where(mode == 4, ri, si)
+    dq0 = smp["initial_q"] - env.table.q[src]
+    assert abs(float(dq0.std()) - cfg.q_noise_std) < 0.1 * cfg.q_noise_std and float(dq0.abs().max()) < 6 * cfg.q_noise_std
+    assert abs(float(smp["initial_dq"].std()) - cfg.dq_noise_std) < 0.1 * cfg.dq_noise_std
+    assert float(smp["initial_prev_action"].abs().max()) <= 1.0
+    info_idx = env.state  # the reset landed in the env state: q row equals the sampled start
+    assert torch.allclose(info_idx[0:7, :n].t(), smp["initial_q"], atol=1e-6)
+    # same seed -> same draws; the window can be moved between resets (RoutePrefixCurriculum promotion)
+    env.reset(seed=3)
+    assert torch.equal(env.last_reset["route_index"], smp["route_index"])
+    env.set_route_window(max_route_index=8)
+    env.reset()
+    assert int(env.last_reset["route_index"].max()) <= 8 and int(env.last_reset["route_index"].min()) >= 1
+    # explicit waypoints still bypass the sampler
+    env.reset(route_index=[5])
+    assert env.last_reset is None

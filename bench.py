@@ -213,6 +213,43 @@ def measure_step_kernel(torch, device, pk, n_envs: int = 1 << 21, launches: int 
             "note": "working set %.0f MB per launch (> L2), CUDA events on the launching stream" % (STEP_BYTES_APPROACH * n_envs / 1e6)}
 
 
+def measure_training(torch, dist, device, world: int, envs: int = 65536, n_steps: int = 128, iters: int = 2) -> dict:
+    """BASELINE config 5: Stage-10 stress-shell PPO (fused collection K4 + tensor-core update K3-TC, 8 epochs x 16 minibatches,
+    NCCL gradient all-reduce per minibatch when world > 1).  CUDA events, max over ranks; whole-job env-steps/s."""
+    from rl_brain_trainer_b200 import config as kcfg, ppo
+
+    cfg = kcfg.load_preset("approach_dynamic_scale_big")
+    pol = ppo.random_policy(56, seed=0, log_std_init=-1.0, device=device)
+    S = envs * n_steps
+    hp = ppo.PPOHyper(learning_rate=4e-6, n_steps=n_steps, batch_size=S // 16, n_epochs=8, gamma=0.995, gae_lambda=0.95, clip_range=0.1, ent_coef=0.0003)
+    tr = ppo.PPOTrainer(cfg, pol, num_envs=envs, hyper=hp, device=device, seed=1, stage_index=10,
+                        process_group=dist.group.WORLD if world > 1 else None)
+    tr.collect()
+    tr.update()
+    torch.cuda.synchronize(device)
+    if world > 1:
+        dist.barrier()
+    t_roll = t_upd = 0.0
+    for _ in range(iters):
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record()
+        tr.collect()
+        e1.record()
+        stats = tr.update()
+        e2.record()
+        torch.cuda.synchronize(device)
+        t_roll += e0.elapsed_time(e1) * 1e-3
+        t_upd += e1.elapsed_time(e2) * 1e-3
+    t = torch.tensor([t_roll, t_upd], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    steps = S * iters * world
+    return {"workload": "stage10_ppo_train", "envs_per_gpu": envs, "n_steps": n_steps, "epochs": 8, "minibatches_per_epoch": 16, "iters": iters,
+            "rollout_env_steps_per_s": steps / float(t[0]), "update_env_steps_per_s": steps / float(t[1]),
+            "e2e_env_steps_per_s": steps / float(t[0] + t[1]), "collect": "kin_ppo_collect (fused, tcgen05 bf16)", "update": "kin_ppo_grad_tc (tcgen05 bf16)",
+            "approx_kl": stats["approx_kl"], "value_loss": stats["value_loss"]}
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -223,6 +260,7 @@ def main() -> None:
     ap.add_argument("--variant", default=os.environ.get("KIN_ROLLOUT_VARIANT", "auto"), choices=["auto", "ffma", "tc"])
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-step-kernel", action="store_true")
+    ap.add_argument("--skip-train", action="store_true", help="skip the BASELINE config-5 leg (Stage-10 PPO training, extra key `train`)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -337,6 +375,13 @@ def main() -> None:
     e2e_value = float(sums[1]) / e2e_s_max
     success_all = float(sums[2] / sums[3])
 
+    # ---- BASELINE config 5 (extra key, every rank takes part: NCCL gradient all-reduce per minibatch) ------------------
+    train = None
+    if not args.skip_train:
+        del flush
+        torch.cuda.empty_cache()
+        train = measure_training(torch, dist, device, world)
+
     step_roof = None
     cpu_base = None
     parity = None
@@ -387,7 +432,7 @@ def main() -> None:
             "env_steps_per_step": env_steps / max(args.steps, 1), "success_rate": success_all, "wall_s_timed_region": t_wall,
             "roofline": roof, "step_kernel_roofline": step_roof, "cpu_baseline": cpu_base, "parity": parity,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "success_rate": e2e_success},
-            "clocks": clocks.summary(), "gpu_launches": launches,
+            "clocks": clocks.summary(), "gpu_launches": launches, "train": train,
         }
         print(json.dumps(line))
     if world > 1:

@@ -170,8 +170,11 @@ def run_reference_arm(args) -> None:
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * total_s / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": "stage5_approach_finisher_eval", "episodes_per_step": n_ep, "env_steps_per_episode": 164,
-                   "note": "bounded sample of the 65,536-episode suite; CPU port (C, fp64) of the reference's pure-Python env + fp32 MLP"},
+        "config": {"workload": "stage5_approach_finisher_eval_65536env", "episodes_per_gpu": EPISODES_PER_GPU, "env_steps_per_episode": 164,
+                   "approach_config": "workspace_expansion_dynamic_scale_big", "finisher_config": "dock_workspace_handoff_noop_ft_12env",
+                   "policies": "bundled approach stage8-11 + finisher checkpoints", "episodes_per_step_sampled": n_ep,
+                   "note": "each step is a bounded sample of the same 65,536-episode suite; CPU port (C, fp64) of the reference's pure-Python "
+                           "env + fp32 MLP on all host threads (the Python reference itself runs ~1,000 env-steps/s per core)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{args.steps} x {n_ep} episodes x 164 env-steps, {threads} host threads"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

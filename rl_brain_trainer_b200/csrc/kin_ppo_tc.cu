@@ -3,7 +3,8 @@
 //
 // Same contract as kin_ppo_grad (kin_ppo.cu; SB3 2.8.0 ppo.py train()), different arithmetic engine:
 //   * the actor and the critic are independent networks with independent parameter gradients, so each CTA works on ONE
-//     of them (blockIdx.y): 128 threads, thread r <-> sample row r of a 128-sample GEMM tile <-> TMEM lane r.  A CTA needs
+//     of them (blockIdx.y): 256 threads, threads r and r + 128 <-> sample row r of a 128-sample GEMM tile <-> TMEM lane r (each
+//     owns 32 of the row's 64 accumulator columns, halving every epilogue on the per-tile dependency chain).  A CTA needs
 //     98 KB of shared memory and 256 TMEM columns, so an actor CTA and a critic CTA (or two of a kind) share every SM and
 //     one's epilogue arithmetic overlaps the other's GEMMs and barrier round trips.
 //   * every operand lives in shared memory as a [rows][64 bf16] SWIZZLE_128B tile (kin_umma.cuh).  The tiles written for
@@ -37,7 +38,7 @@ namespace kin {
 
 using namespace umma;
 
-constexpr int TCG_THREADS = 128;
+constexpr int TCG_THREADS = 256;   // 128 sample rows x 2 column halves (32 accumulator columns per thread and epilogue)
 constexpr int TCG_ROWS = 128;
 constexpr int TILE_BYTES = TCG_ROWS * 128;        // [128][64 bf16]
 constexpr float kHalfLog2PiTc = 0.91893853320467274178f;
@@ -50,6 +51,19 @@ constexpr unsigned COL_B1 = 96;       // 16 (column 8 = db1)
 constexpr unsigned COL_W1 = 128;      // 64
 constexpr unsigned COL_W0 = 192;      // 64 (column 56 = db0)
 constexpr unsigned TMEM_COLS_G = 256;
+
+#ifdef KIN_PPO_TRACE
+// phase profiler (debug builds only, tools/ppo_trace.py): cycles per phase of the per-tile chain, summed over the tiles of a CTA,
+// for threads 0 (the MMA issuer) and 32 of CTAs (0, 0) and (1, 1)
+__device__ unsigned long long kin_ppo_trace_buf[4][16];
+#define TRACE_DECL unsigned long long tr_acc[13] = {}; long long tr_t = clock64(); const bool tr_on = (tid == 0 || tid == 32) && blockIdx.x == blockIdx.y && blockIdx.x < 2;
+#define TRACE_MARK(i) do { if (tr_on) { const long long t_ = clock64(); tr_acc[i] += (unsigned long long)(t_ - tr_t); tr_t = t_; } } while (0)
+#define TRACE_FLUSH(ntiles) do { if (tr_on) { unsigned long long* o_ = kin_ppo_trace_buf[blockIdx.x * 2 + (tid == 32)]; for (int i_ = 0; i_ < 13; ++i_) o_[i_] = tr_acc[i_]; o_[15] = (unsigned long long)(ntiles); } } while (0)
+#else
+#define TRACE_DECL
+#define TRACE_MARK(i)
+#define TRACE_FLUSH(n)
+#endif
 
 struct __align__(1024) TcGradSmem {
     unsigned char X[2][TILE_BYTES];      // double-buffered in image mode (the next tile's image is prefetched by the TMA engine)
@@ -78,13 +92,14 @@ __device__ __forceinline__ void st_bf16(unsigned char* tile, int row, int col, f
     *reinterpret_cast<unsigned short*>(tile + sw_elem(row, col)) = (unsigned short)(pack_bf16(v, 0.0f) & 0xffffu);
 }
 
-// this row's 64 accumulator columns -> f -> bf16 row of `tile`.  MODE 0: tanh; 1: tanh(x + b1); 2: x * (1 - h^2), h = keep[]
+// this thread's 32 accumulator columns [32 * half, 32 * half + 32) of its row -> f -> bf16 into `tile`.
+// MODE 0: tanh; 1: tanh(x + b1); 2: x * (1 - h^2), h = keep[] (the packed copy of the same columns from the forward pass)
 template <int MODE>
-__device__ __forceinline__ void epilogue64(unsigned tz, unsigned char* tile, int row, const float* bias, unsigned* keep) {
-    float v[64];
-    tmem_ld32x2(tz, v);          // both halves in flight, one wait
+__device__ __forceinline__ void epilogue32(unsigned tz, unsigned char* tile, int row, int half, const float* bias, unsigned* keep) {
+    float v[32];
+    tmem_ld32(tz + half * 32, v);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < 4; ++j) {
         unsigned p[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -94,8 +109,8 @@ __device__ __forceinline__ void epilogue64(unsigned tz, unsigned char* tile, int
                 a = tanh_fast(a);
                 b = tanh_fast(b);
             } else if (MODE == 1) {
-                a = tanh_fast(a + bias[c]);
-                b = tanh_fast(b + bias[c + 1]);
+                a = tanh_fast(a + bias[half * 32 + c]);
+                b = tanh_fast(b + bias[half * 32 + c + 1]);
             } else {
                 const unsigned h = keep[4 * j + e];
                 const float hl = bf16_lo(h), hh = bf16_hi(h);
@@ -105,7 +120,7 @@ __device__ __forceinline__ void epilogue64(unsigned tz, unsigned char* tile, int
             p[e] = pack_bf16(a, b);
             if (MODE != 2) keep[4 * j + e] = p[e];
         }
-        *reinterpret_cast<uint4*>(tile + sw_chunk(row, j)) = make_uint4(p[0], p[1], p[2], p[3]);
+        *reinterpret_cast<uint4*>(tile + sw_chunk(row, half * 4 + j)) = make_uint4(p[0], p[1], p[2], p[3]);
     }
 }
 
@@ -125,7 +140,7 @@ kin_ppo_grad_tc_kernel(const float* __restrict__ params, KinPpoHyper hp, const f
     const PpoOffsets O = ppo_offsets(IN);
     const int P = O.total;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int row = tid;
+    const int row = tid & 127, half = tid >> 7;    // two threads per sample row: columns 0..31 / 32..63 of every activation
     const int net = net_base + (int)blockIdx.y;    // 0 actor, 1 critic
     const int o_w0 = net ? O.vf_w0 : O.pi_w0, o_b0 = net ? O.vf_b0 : O.pi_b0, o_w1 = net ? O.vf_w1 : O.pi_w1, o_b1 = net ? O.vf_b1 : O.pi_b1;
 
@@ -152,7 +167,7 @@ kin_ppo_grad_tc_kernel(const float* __restrict__ params, KinPpoHyper hp, const f
         }
     }
     if (tid < 64) S.b1[tid] = __ldg(params + o_b1 + tid);
-    *reinterpret_cast<uint4*>(S.DO + sw_chunk(tid, 1)) = make_uint4(0x00003F80u, 0u, 0u, 0u);   // col 8 = 1.0 (bf16)
+    if (tid < 128) *reinterpret_cast<uint4*>(S.DO + sw_chunk(tid, 1)) = make_uint4(0x00003F80u, 0u, 0u, 0u);   // col 8 = 1.0 (bf16)
     if (tid < 8) {
         const float ls = tid < 7 ? __ldg(params + O.log_std + tid) : 0.0f;
         S.bo[tid] = tid < 7 ? __ldg(params + O.act_b + tid) : __ldg(params + O.val_b);
@@ -206,7 +221,7 @@ kin_ppo_grad_tc_kernel(const float* __restrict__ params, KinPpoHyper hp, const f
     if (wimg) mbar_wait(smem_u32(&S.mbar[4]), 0u);
 
     const unsigned tb = S.tmem_base;
-    const unsigned tlane = tb + ((unsigned)(warp * 32) << 16);     // this warp's lane quadrant, column 0
+    const unsigned tlane = tb + ((unsigned)((warp & 3) * 32) << 16);     // this warp's lane quadrant, column 0
     const unsigned tz = tlane + COL_Z;
     const unsigned mb_main = smem_u32(&S.mbar[0]), mb_wg = smem_u32(&S.mbar[1]);
     const unsigned aXb[2] = {smem_u32(S.X[0]), smem_u32(S.X[1])}, aDO = smem_u32(S.DO), aW0 = smem_u32(S.W0);
@@ -217,18 +232,22 @@ kin_ppo_grad_tc_kernel(const float* __restrict__ params, KinPpoHyper hp, const f
         bulk_load_tile(aXb[0], img + (size_t)(tile_ids[2 * blockIdx.x] >> 1) * TILE_BYTES, mb_x[0]);
     const unsigned aH1 = smem_u32(S.H1), aH2 = smem_u32(S.H2), aW1 = smem_u32(S.W1), aWO = smem_u32(S.WO);
     unsigned par_main = 0u, par_wg = 0u;
-    unsigned h1p[32] = {}, h2p[32] = {};
+    unsigned h1p[16] = {}, h2p[16] = {};
     float dls[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, st[4] = {0.f, 0.f, 0.f, 0.f};   // per-thread partial sums
 
     int it = 0;
+    TRACE_DECL
     for (int j = blockIdx.x; j < n_pairs; j += gridDim.x, ++it) {
+        TRACE_MARK(12);
         const int t0 = tile_ids[2 * j], t1 = tile_ids[2 * j + 1];
         const int xb = IMG ? (it & 1) : 0;
         const unsigned aX = aXb[xb];
         // loss inputs of this thread's sample: issue the loads now, consume them after layer 3
         const size_t g = (size_t)(row < 64 ? t0 : t1) * 64 + (row & 63);
         float act_r[7], adv_r = 0.0f, olp_r = 0.0f, ret_r = 0.0f;
-        if (net == 0) {
+        if (half != 0) {
+            // the second column half has no per-sample loss work
+        } else if (net == 0) {
 #pragma unroll
             for (int d = 0; d < 7; ++d) act_r[d] = __ldg(action + g * 7 + d);
             if (!forward_only) {
@@ -242,6 +261,7 @@ kin_ppo_grad_tc_kernel(const float* __restrict__ params, KinPpoHyper hp, const f
             mbar_wait(mb_wg, par_wg);
             par_wg ^= 1u;
         }
+        TRACE_MARK(0);
         if (IMG) {
             // the other buffer is free (its last readers were the previous tile's GEMMs): prefetch the next tile's image into it
             const int jn = j + gridDim.x;
@@ -254,18 +274,19 @@ kin_ppo_grad_tc_kernel(const float* __restrict__ params, KinPpoHyper hp, const f
             // ---- X tile: obs fp32 -> bf16, coalesced float4 reads; column 56 = 1 carries the layer-1 bias --------------
             unsigned char* X = S.X[0];
 #pragma unroll
-            for (int i = 0; i < 14; ++i) {
+            for (int i = 0; i < 7; ++i) {
                 const int idx = tid + TCG_THREADS * i;           // 0 .. 1791
                 const int half = idx >= 896, rem = idx - half * 896;
                 const int r = half * 64 + rem / 14, q = rem % 14;
                 const float4 v = __ldg(reinterpret_cast<const float4*>(obs + (size_t)(half ? t1 : t0) * 64 * IN) + rem);
                 *reinterpret_cast<uint2*>(X + sw_chunk(r, q >> 1) + ((q & 1) << 3)) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
             }
-            *reinterpret_cast<uint4*>(X + sw_chunk(tid, 7)) = make_uint4(0x00003F80u, 0u, 0u, 0u);
+            if (tid < 128) *reinterpret_cast<uint4*>(X + sw_chunk(tid, 7)) = make_uint4(0x00003F80u, 0u, 0u, 0u);
             fence_async_smem();
             fence_before();
             __syncthreads();
         }
+        TRACE_MARK(1);
         // ---- layer 1 ----------------------------------------------------------------------------------------------------
         if (tid == 0) {
             fence_after();
@@ -277,10 +298,12 @@ kin_ppo_grad_tc_kernel(const float* __restrict__ params, KinPpoHyper hp, const f
         mbar_wait(mb_main, par_main);
         par_main ^= 1u;
         fence_after();
-        epilogue64<0>(tz, S.H1, row, nullptr, h1p);
+        TRACE_MARK(2);
+        epilogue32<0>(tz, S.H1, row, half, nullptr, h1p);
         fence_async_smem();
         fence_before();
         __syncthreads();
+        TRACE_MARK(3);
         // ---- layer 2 ----------------------------------------------------------------------------------------------------
         if (tid == 0) {
             fence_after();
@@ -292,10 +315,12 @@ kin_ppo_grad_tc_kernel(const float* __restrict__ params, KinPpoHyper hp, const f
         mbar_wait(mb_main, par_main);
         par_main ^= 1u;
         fence_after();
-        epilogue64<1>(tz, S.H2, row, S.b1, h2p);
+        TRACE_MARK(4);
+        epilogue32<1>(tz, S.H2, row, half, S.b1, h2p);
         fence_async_smem();
         fence_before();
         __syncthreads();
+        TRACE_MARK(5);
         // ---- layer 3: action means (cols 0..6) or value (col 7) -------------------------------------------------------------
         if (tid == 0) {
             fence_after();
@@ -307,8 +332,9 @@ kin_ppo_grad_tc_kernel(const float* __restrict__ params, KinPpoHyper hp, const f
         mbar_wait(mb_main, par_main);
         par_main ^= 1u;
         fence_after();
+        TRACE_MARK(6);
         // ---- loss and d(loss)/d(outputs), one thread per sample ------------------------------------------------------------
-        {
+        if (half == 0) {
             float o[16];
             tmem_ld16(tlane + COL_Z, o);
             if (net == 0) {
@@ -358,6 +384,7 @@ kin_ppo_grad_tc_kernel(const float* __restrict__ params, KinPpoHyper hp, const f
         fence_async_smem();
         fence_before();
         __syncthreads();
+        TRACE_MARK(7);
         const unsigned acc0 = it > 0;
         // ---- dZ2 = (dO WO) * (1 - H2^2); dWO += H2^T dO rides along (H2's last reader) ----------------------------------------
         if (tid == 0) {
@@ -371,10 +398,12 @@ kin_ppo_grad_tc_kernel(const float* __restrict__ params, KinPpoHyper hp, const f
         mbar_wait(mb_main, par_main);
         par_main ^= 1u;
         fence_after();
-        epilogue64<2>(tz, S.H2, row, nullptr, h2p);          // G2 replaces H2
+        TRACE_MARK(8);
+        epilogue32<2>(tz, S.H2, row, half, nullptr, h2p);          // G2 replaces H2
         fence_async_smem();
         fence_before();
         __syncthreads();
+        TRACE_MARK(9);
         // ---- dZ1 = (G2 W1) * (1 - H1^2); dW1 += G2^T H1 and db1 += G2^T dO(ones) ride along (H1's last readers) ---------------
         if (tid == 0) {
             fence_after();
@@ -390,10 +419,12 @@ kin_ppo_grad_tc_kernel(const float* __restrict__ params, KinPpoHyper hp, const f
         mbar_wait(mb_main, par_main);
         par_main ^= 1u;
         fence_after();
-        epilogue64<2>(tz, S.H1, row, nullptr, h1p);          // G1 replaces H1
+        TRACE_MARK(10);
+        epilogue32<2>(tz, S.H1, row, half, nullptr, h1p);          // G1 replaces H1
         fence_async_smem();
         fence_before();
         __syncthreads();
+        TRACE_MARK(11);
         // ---- dW0 | db0 += G1^T X, dbo += X(ones row)^T dO -- drain before the next tile touches H1 / X / dO -------------------------
         if (tid == 0) {
             fence_after();
@@ -406,6 +437,7 @@ kin_ppo_grad_tc_kernel(const float* __restrict__ params, KinPpoHyper hp, const f
         }
     }
 
+    TRACE_FLUSH(it);
     if (!forward_only) {
         if (it > 0) mbar_wait(mb_wg, par_wg);
         fence_after();
@@ -433,10 +465,9 @@ kin_ppo_grad_tc_kernel(const float* __restrict__ params, KinPpoHyper hp, const f
         __syncthreads();
         // ---- accumulators (M = 64: row m lives in lane m % 16 + 32 * (m / 16)) -> this CTA's slice of the partial gradient ----------
         float* out = partials + (size_t)blockIdx.x * (P + KIN_PPO_STATS + 8);
-        const int u = warp * 16 + lane;             // valid for lane < 16
+        const int u = (warp & 3) * 16 + lane;       // valid for lane < 16
         const bool rowok = lane < 16;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
+        {   // warps 0..3 store columns 0..31 of dW1 / dW0, warps 4..7 columns 32..63
             float v[32];
             tmem_ld32(tlane + COL_W1 + half * 32, v);
             if (rowok) {
@@ -453,7 +484,7 @@ kin_ppo_grad_tc_kernel(const float* __restrict__ params, KinPpoHyper hp, const f
                 }
             }
         }
-        {
+        if (half == 0) {
             float o[16];
             tmem_ld16(tlane + COL_WO, o);
             if (rowok) {
@@ -494,6 +525,12 @@ kin_ppo_grad_tc_kernel(const float* __restrict__ params, KinPpoHyper hp, const f
 }  // namespace kin
 
 using namespace kin;
+
+#ifdef KIN_PPO_TRACE
+extern "C" int kin_debug_ppo_trace(unsigned long long* out) {      // 4 x 16 counters, see TRACE_DECL
+    return cudaMemcpyFromSymbol(out, kin_ppo_trace_buf, sizeof(kin_ppo_trace_buf)) == cudaSuccess ? KIN_OK : KIN_ERR_INVALID_ARG;
+}
+#endif
 
 extern "C" int kin_ppo_grad_tc(const float* params, int in_dim, const KinPpoHyper* hp, const void* obs_any, const float* action, const float* old_logp,
                                const float* advantage, const float* returns, const double* tile_sums, const int* tile_ids, int n_tiles,

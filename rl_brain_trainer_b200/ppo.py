@@ -141,8 +141,10 @@ class PPOTrainer:
             self.P = self.params.numel()
             self.adam_m = torch.zeros_like(self.params)
             self.adam_v = torch.zeros_like(self.params)
-            self.grad = torch.zeros_like(self.params)
-            self.stats = torch.zeros(_D("KIN_PPO_STATS"), dtype=torch.float32, device=self.device)
+            # gradient and per-minibatch statistics share one buffer so that several ranks need ONE all-reduce per minibatch
+            self._gradstats = torch.zeros(self.P + _D("KIN_PPO_STATS"), dtype=torch.float32, device=self.device)
+            self.grad = self._gradstats[: self.P]
+            self.stats = self._gradstats[self.P:]
             self.weight_image = torch.zeros(36864, dtype=torch.uint8, device=self.device)   # bf16 operand image of `params`
             self.pack_weights()
             self.stats_accum = torch.zeros(_D("KIN_PPO_STATS"), dtype=torch.float32, device=self.device)
@@ -301,8 +303,7 @@ class PPOTrainer:
     def apply_update(self) -> None:
         """All-reduce the gradient (sum over ranks), clip by global norm, Adam step -- identical on every rank."""
         if self.world > 1:
-            allreduce_sum_(self.grad, self.group)
-            allreduce_sum_(self.stats[:5], self.group)
+            allreduce_sum_(self._gradstats[: self.P + 5], self.group)      # gradient + the five loss statistics
         self.update_count += 1
         hp = getattr(self, "_c_hyper", None) or self.hp.c()
         _lib.check(self._L.kin_ppo_adam(self.params.data_ptr(), self.grad.data_ptr(), self.adam_m.data_ptr(), self.adam_v.data_ptr(), self.P,

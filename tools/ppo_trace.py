@@ -1,0 +1,59 @@
+"""Diagnostic: where the cycles of one 128-sample tile of kin_ppo_grad_tc go (debug build with -DKIN_PPO_TRACE).
+
+  python tools/ppo_trace.py --build        # here (nvcc, no GPU needed): tools/_bin/libkin_b200_trace.so
+  python tools/ppo_trace.py [--envs 65536] # on a B200: one PPO update, then the per-phase cycle table
+
+The trace build is a separate library; the product library never carries the counters.
+"""
+import argparse, ctypes, os, subprocess, sys
+from pathlib import Path
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+OUT = ROOT / "tools" / "_bin"
+TRACE_LIB = OUT / "libkin_b200_trace.so"
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--build", action="store_true")
+ap.add_argument("--envs", type=int, default=65536)
+ap.add_argument("--n-steps", type=int, default=128)
+a = ap.parse_args()
+
+if a.build:
+    from rl_brain_trainer_b200 import build as kb
+    OUT.mkdir(exist_ok=True)
+    env = dict(os.environ); env.pop("CC", None); env.pop("CXX", None)
+    objs = []
+    for src in sorted(kb.CSRC.glob("*.cu")):
+        obj = OUT / f"trace_{src.stem}.o"
+        subprocess.run([kb._nvcc(), *kb.NVCC_FLAGS, "-DKIN_PPO_TRACE", "-c", str(src), "-o", str(obj)], check=True, env=env)
+        objs.append(str(obj))
+    subprocess.run([kb._nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(TRACE_LIB), *objs, "-lcudart"], check=True, env=env)
+    print(TRACE_LIB)
+    sys.exit(0)
+
+import torch
+from rl_brain_trainer_b200 import _lib
+_lib.LIB_PATH = TRACE_LIB
+from rl_brain_trainer_b200 import config as kcfg, ppo
+
+dev = torch.device("cuda", 0)
+cfg = kcfg.load_preset("approach_dynamic_scale_big")
+pol = ppo.random_policy(56, seed=0, log_std_init=-1.0, device=dev)
+S = a.envs * a.n_steps
+hp = ppo.PPOHyper(learning_rate=4e-6, n_steps=a.n_steps, batch_size=S // 16, n_epochs=1, gamma=0.995, gae_lambda=0.95, clip_range=0.1, ent_coef=0.0003)
+tr = ppo.PPOTrainer(cfg, pol, num_envs=a.envs, hyper=hp, device=dev, seed=1, stage_index=10, update_variant="tc")
+tr.collect(); tr.update(); tr.collect(); tr.update()
+torch.cuda.synchronize()
+buf = (ctypes.c_ulonglong * 64)()
+L = _lib.lib()
+L.kin_debug_ppo_trace.argtypes = [ctypes.c_void_p]
+assert L.kin_debug_ppo_trace(buf) == 0
+names = ["wg wait", "X wait+sync", "L1 mma wait", "epi1+sync", "L2 mma wait", "epi2+sync", "L3 mma wait", "loss+sync", "bwd1 mma wait", "epiG2+sync",
+         "bwd2 mma wait", "epiG1+sync", "loop top (issuer: trailing MMA issue)"]
+who = ["cta(0,0) tid0", "cta(0,0) tid32", "cta(1,1) tid0", "cta(1,1) tid32"]
+for w in range(4):
+    row = [buf[w * 16 + i] for i in range(16)]
+    n = max(row[15], 1)
+    print(f"{who[w]}: {n} tiles, {sum(row[:13]) / n:.0f} cycles/tile")
+    for i in range(13):
+        print(f"   {names[i]:40s} {row[i] / n:8.0f}")

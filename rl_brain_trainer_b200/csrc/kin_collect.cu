@@ -46,6 +46,11 @@ struct __align__(1024) CollectSmem {
     unsigned tmem_base;
 };
 
+__device__ __forceinline__ bool elect_lane() {
+    unsigned pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0u;
+}
 __device__ __forceinline__ void tile_bar(int tile) { asm volatile("bar.sync %0, %1;" ::"r"(tile + 1), "r"(CT_ROWS) : "memory"); }
 __device__ __forceinline__ void mbar_arrive(unsigned saddr) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(saddr) : "memory");
@@ -89,7 +94,7 @@ __device__ __forceinline__ void policy_forward_tc(CollectSmem<TILES>& S, TileSta
     fence_async_smem();
     fence_before();
     tile_bar(c.tile);
-    if (c.issuer) {
+    if (c.row < 32 && elect_lane()) {      // one lane of the tile's first (converged) warp: uniform-register descriptors
         fence_after();
         constexpr unsigned id = idesc_bf16(128, 128, false, false);
 #pragma unroll
@@ -122,7 +127,7 @@ __device__ __forceinline__ void policy_forward_tc(CollectSmem<TILES>& S, TileSta
     fence_async_smem();
     fence_before();
     tile_bar(c.tile);
-    if (c.issuer) {
+    if (c.row < 32 && elect_lane()) {      // one lane of the tile's first (converged) warp: uniform-register descriptors
         fence_after();
         constexpr unsigned id = idesc_bf16(128, 64, false, false);
 #pragma unroll
@@ -152,7 +157,7 @@ __device__ __forceinline__ void policy_forward_tc(CollectSmem<TILES>& S, TileSta
     fence_async_smem();
     fence_before();
     tile_bar(c.tile);
-    if (c.issuer) {
+    if (c.row < 32 && elect_lane()) {      // one lane of the tile's first (converged) warp: uniform-register descriptors
         fence_after();
         constexpr unsigned id = idesc_bf16(128, 16, false, false);
 #pragma unroll

@@ -16,12 +16,21 @@
 //                 Z  = H1 W1^T     128 x 64 x 64
 //                 O  = H2 WO^T     128 x 16 x 64   (actor: cols 0-6 action means; critic: col 7 value)
 //       backward  Z  = dO WO       128 x 64 x 16   + dWO += H2^T dO          (H2's last readers: G2 then replaces H2 in place)
-//                 Z  = G2 W1       128 x 64 x 64   + dW1 += G2^T H1, db1 += G2^T dO(ones col)   (G1 then replaces H1 in place)
-//       weights   dW0|db0 += G1^T X, dbo += X(ones row)^T dO      M = 64, K = 128 samples
-//     The weight-gradient accumulators (and the bias gradients, which fall out of the constant-one columns) stay in TMEM
-//     across all tiles of the CTA: 256 columns = Z/O 64 | dbo 16 | dWO 16 | db1 16 | - | dW1 64 | dW0 64.
-//   * one thread issues the MMAs; completion is tracked with mbarriers (the forward/backward chain, the trailing
-//     weight-gradient batch that must drain before the next tile overwrites the operand tiles, and the X image buffers).
+//                 Z  = G2 W1       128 x 64 x 64   + dW1|db1 += G2^T [H1 | dO(ones col)]   64 x 80 x 128: ONE GEMM, the B operand
+//                                                    spans the adjacent H1 and dO tiles     (G1 then replaces H1 in place)
+//       weights   dW0|db0 += G1^T X                  M = 64, K = 128 samples
+//     The weight-gradient accumulators (and the bias gradients b0 / b1, which fall out of the constant-one columns) stay in TMEM
+//     across all tiles of the CTA: 224 of 256 columns = Z/O 64 | dWO 16 | dW1 64 + db1 16 | dW0 64.  The output-bias gradient is
+//     a per-thread fp32 sum of dO, reduced once per CTA.
+//   * a dedicated ninth warp issues the MMAs from warp-uniform control flow (one elected lane executes the tcgen05 instructions,
+//     descriptors stay in uniform registers); the 256 epilogue threads never issue and never block on a CTA-wide barrier: they
+//     `bar.arrive` on a named barrier when an operand tile is written and go on to wait for the next accumulator, the issuer
+//     `bar.sync`s on it.  Issuing from `if (tid == 0)` inside an epilogue warp cost ~70 cycles per MMA (R2UR round trips in a
+//     divergent branch) on the critical path of every tile -- 4 000 of 11 000 cycles per tile (tools/ppo_trace.py).
+//   * completion is tracked with mbarriers: `main` (the forward/backward chain GEMM the epilogue threads wait for), `ride` (the
+//     weight-gradient GEMMs that ride behind a chain GEMM and read a tile the next epilogue overwrites in place: the epilogue
+//     does its arithmetic first and waits for `ride` only before its stores), `wg` (the trailing dW0 batch, which must drain
+//     before the X buffer it reads is refilled) and the X image buffers.
 //   * image mode (the rollout buffer kin_ppo_collect wrote): the X operand is one 16 KB bulk copy (TMA engine) per tile,
 //     double-buffered so the next tile's image lands while this one is processed.
 //   * the elementwise work (tanh, 1 - h^2, the loss and its derivative, log_std gradient, statistics) is fp32 in registers;
@@ -38,25 +47,25 @@ namespace kin {
 
 using namespace umma;
 
-constexpr int TCG_THREADS = 256;   // 128 sample rows x 2 column halves (32 accumulator columns per thread and epilogue)
+constexpr int TCG_EPI_THREADS = 256;   // 128 sample rows x 2 column halves (32 accumulator columns per thread and epilogue)
+constexpr int TCG_THREADS = TCG_EPI_THREADS + 32;   // + the MMA issuer warp
+constexpr int TCG_ISSUER_WARP = TCG_EPI_THREADS / 32;
 constexpr int TCG_ROWS = 128;
 constexpr int TILE_BYTES = TCG_ROWS * 128;        // [128][64 bf16]
 constexpr float kHalfLog2PiTc = 0.91893853320467274178f;
 
 // TMEM column map (fp32 columns)
 constexpr unsigned COL_Z = 0;         // 64 (layer 3's O aliases columns 0..15)
-constexpr unsigned COL_BO = 64;       // 16   (M = 64 rows = X columns; row 56 = sum over samples of dO)
-constexpr unsigned COL_WO = 80;       // 16
-constexpr unsigned COL_B1 = 96;       // 16 (column 8 = db1)
-constexpr unsigned COL_W1 = 128;      // 64
-constexpr unsigned COL_W0 = 192;      // 64 (column 56 = db0)
+constexpr unsigned COL_WO = 64;       // 16
+constexpr unsigned COL_W1 = 80;       // 64 + 16: the N = 80 GEMM's columns 64..79 come from the dO tile, column 64 + 8 = db1
+constexpr unsigned COL_W0 = 160;      // 64 (column 56 = db0)
 constexpr unsigned TMEM_COLS_G = 256;
 
 #ifdef KIN_PPO_TRACE
 // phase profiler (debug builds only, tools/ppo_trace.py): cycles per phase of the per-tile chain, summed over the tiles of a CTA,
-// for threads 0 (the MMA issuer) and 32 of CTAs (0, 0) and (1, 1)
+// for thread 256 (the MMA issuer warp) and thread 32 (an epilogue thread) of CTAs (0, 0) and (1, 1)
 __device__ unsigned long long kin_ppo_trace_buf[4][16];
-#define TRACE_DECL unsigned long long tr_acc[13] = {}; long long tr_t = clock64(); const bool tr_on = (tid == 0 || tid == 32) && blockIdx.x == blockIdx.y && blockIdx.x < 2;
+#define TRACE_DECL unsigned long long tr_acc[13] = {}; long long tr_t = clock64(); const bool tr_on = (tid == TCG_EPI_THREADS || tid == 32) && blockIdx.x == blockIdx.y && blockIdx.x < 2;
 #define TRACE_MARK(i) do { if (tr_on) { const long long t_ = clock64(); tr_acc[i] += (unsigned long long)(t_ - tr_t); tr_t = t_; } } while (0)
 #define TRACE_FLUSH(ntiles) do { if (tr_on) { unsigned long long* o_ = kin_ppo_trace_buf[blockIdx.x * 2 + (tid == 32)]; for (int i_ = 0; i_ < 13; ++i_) o_[i_] = tr_acc[i_]; o_[15] = (unsigned long long)(ntiles); } } while (0)
 #else
@@ -67,9 +76,9 @@ __device__ unsigned long long kin_ppo_trace_buf[4][16];
 
 struct __align__(1024) TcGradSmem {
     unsigned char X[2][TILE_BYTES];      // double-buffered in image mode (the next tile's image is prefetched by the TMA engine)
-    unsigned char H1[TILE_BYTES];        // H1, later G1 = dL/dZ1
     unsigned char H2[TILE_BYTES];        // H2, later G2 = dL/dZ2
-    unsigned char DO[TILE_BYTES];        // cols 0..7 dL/d(mean, value), col 8 = 1, rest 0
+    unsigned char H1[TILE_BYTES];        // H1, later G1 = dL/dZ1
+    unsigned char DO[TILE_BYTES];        // cols 0..7 dL/d(mean, value), col 8 = 1, rest 0.  MUST follow H1: [H1 | DO] is one MN-major operand
     unsigned char W0[64 * 128];          // col 56 = b0
     unsigned char W1[64 * 128];
     unsigned char WO[16 * 128];          // actor: rows 0..6 = act_w; critic: row 7 = val_w
@@ -77,8 +86,8 @@ struct __align__(1024) TcGradSmem {
     float bo[8];
     float ls[8];
     float inv_sig[8];
-    float scal[32];                      // 0 adv mean, 1 1/(std+eps), 2..5 statistics, 8..14 d log_std
-    unsigned long long mbar[5];          // 0 forward/backward chain, 1 trailing weight-gradient batch, 2/3 X image buffers, 4 weights
+    float scal[32];                      // 0 adv mean, 1 1/(std+eps), 2..5 statistics, 8..14 d log_std, 16..23 d output bias
+    unsigned long long mbar[6];          // 0 main (chain GEMMs), 1 wg (trailing dW0 batch), 2/3 X image buffers, 4 weights, 5 ride
     unsigned tmem_base;
 };
 
@@ -92,36 +101,40 @@ __device__ __forceinline__ void st_bf16(unsigned char* tile, int row, int col, f
     *reinterpret_cast<unsigned short*>(tile + sw_elem(row, col)) = (unsigned short)(pack_bf16(v, 0.0f) & 0xffffu);
 }
 
-// this thread's 32 accumulator columns [32 * half, 32 * half + 32) of its row -> f -> bf16 into `tile`.
+__device__ __forceinline__ bool elect_one() {
+    unsigned pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0u;
+}
+// named barrier 1: the epilogue threads arrive when an operand tile (or a TMEM read) is complete, the issuer warp waits for it
+__device__ __forceinline__ void ready_arrive() { asm volatile("bar.arrive 1, %0;" ::"n"(TCG_THREADS) : "memory"); }
+__device__ __forceinline__ void ready_sync() { asm volatile("bar.sync 1, %0;" ::"n"(TCG_THREADS) : "memory"); }
+
+// this thread's 32 accumulator columns [32 * half, 32 * half + 32) of its row -> f -> packed bf16 in p[16].
 // MODE 0: tanh; 1: tanh(x + b1); 2: x * (1 - h^2), h = keep[] (the packed copy of the same columns from the forward pass)
 template <int MODE>
-__device__ __forceinline__ void epilogue32(unsigned tz, unsigned char* tile, int row, int half, const float* bias, unsigned* keep) {
+__device__ __forceinline__ void epilogue_math(unsigned tz, int half, const float* bias, unsigned* keep, unsigned* p) {
     float v[32];
     tmem_ld32(tz + half * 32, v);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        unsigned p[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int c = 8 * j + 2 * e;
-            float a = v[c], b = v[c + 1];
-            if (MODE == 0) {
-                a = tanh_fast(a);
-                b = tanh_fast(b);
-            } else if (MODE == 1) {
-                a = tanh_fast(a + bias[half * 32 + c]);
-                b = tanh_fast(b + bias[half * 32 + c + 1]);
-            } else {
-                const unsigned h = keep[4 * j + e];
-                const float hl = bf16_lo(h), hh = bf16_hi(h);
-                a *= fmaf(-hl, hl, 1.0f);
-                b *= fmaf(-hh, hh, 1.0f);
-            }
-            p[e] = pack_bf16(a, b);
-            if (MODE != 2) keep[4 * j + e] = p[e];
+    for (int i = 0; i < 16; ++i) {
+        float a = v[2 * i], b = v[2 * i + 1];
+        if (MODE == 0) {
+            p[i] = pack_bf16(tanh_fast(a), tanh_fast(b));
+        } else if (MODE == 1) {
+            p[i] = pack_bf16(tanh_fast(a + bias[half * 32 + 2 * i]), tanh_fast(b + bias[half * 32 + 2 * i + 1]));
+        } else {
+            const unsigned h = keep[i];
+            const float hl = bf16_lo(h), hh = bf16_hi(h);
+            p[i] = pack_bf16(a * fmaf(-hl, hl, 1.0f), b * fmaf(-hh, hh, 1.0f));
         }
-        *reinterpret_cast<uint4*>(tile + sw_chunk(row, half * 4 + j)) = make_uint4(p[0], p[1], p[2], p[3]);
+        if (MODE != 2) keep[i] = p[i];
     }
+}
+__device__ __forceinline__ void epilogue_store(unsigned char* tile, int row, int half, const unsigned* p) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<uint4*>(tile + sw_chunk(row, half * 4 + j)) = make_uint4(p[4 * j], p[4 * j + 1], p[4 * j + 2], p[4 * j + 3]);
 }
 
 // IMG: obs is the rollout buffer of bf16 operand images written by kin_ppo_collect (one 16 KB image per 128 consecutive samples)
@@ -140,7 +153,8 @@ kin_ppo_grad_tc_kernel(const float* __restrict__ params, KinPpoHyper hp, const f
     const PpoOffsets O = ppo_offsets(IN);
     const int P = O.total;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int row = tid & 127, half = tid >> 7;    // two threads per sample row: columns 0..31 / 32..63 of every activation
+    const int row = tid & 127, half = (tid >> 7) & 1;    // two threads per sample row: columns 0..31 / 32..63 of every activation
+    const bool issuer = warp == TCG_ISSUER_WARP;         // warp-uniform
     const int net = net_base + (int)blockIdx.y;    // 0 actor, 1 critic
     const int o_w0 = net ? O.vf_w0 : O.pi_w0, o_b0 = net ? O.vf_b0 : O.pi_b0, o_w1 = net ? O.vf_w1 : O.pi_w1, o_b1 = net ? O.vf_b1 : O.pi_b1;
 
@@ -201,7 +215,7 @@ kin_ppo_grad_tc_kernel(const float* __restrict__ params, KinPpoHyper hp, const f
     if (warp == 0) tmem_alloc(smem_u32(&S.tmem_base), TMEM_COLS_G);
     if (tid == 0) {
 #pragma unroll
-        for (int i = 0; i < 5; ++i) mbar_init(smem_u32(&S.mbar[i]), 1);
+        for (int i = 0; i < 6; ++i) mbar_init(smem_u32(&S.mbar[i]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         if (wimg) {    // this net's W0 | W1 | WO blocks of the prebuilt image: three bulk copies (TMA engine) on one mbarrier
             const unsigned mbw = smem_u32(&S.mbar[4]);
@@ -223,251 +237,292 @@ kin_ppo_grad_tc_kernel(const float* __restrict__ params, KinPpoHyper hp, const f
     const unsigned tb = S.tmem_base;
     const unsigned tlane = tb + ((unsigned)((warp & 3) * 32) << 16);     // this warp's lane quadrant, column 0
     const unsigned tz = tlane + COL_Z;
-    const unsigned mb_main = smem_u32(&S.mbar[0]), mb_wg = smem_u32(&S.mbar[1]);
-    const unsigned aXb[2] = {smem_u32(S.X[0]), smem_u32(S.X[1])}, aDO = smem_u32(S.DO), aW0 = smem_u32(S.W0);
-    const unsigned mb_x[2] = {smem_u32(&S.mbar[2]), smem_u32(&S.mbar[3])};
-    unsigned par_x[2] = {0u, 0u};
+    const unsigned mb_main = smem_u32(&S.mbar[0]), mb_wg = smem_u32(&S.mbar[1]), mb_ride = smem_u32(&S.mbar[5]);
     const unsigned char* img = reinterpret_cast<const unsigned char*>(obs);
-    if (IMG && tid == 0 && (int)blockIdx.x < n_pairs)
-        bulk_load_tile(aXb[0], img + (size_t)(tile_ids[2 * blockIdx.x] >> 1) * TILE_BYTES, mb_x[0]);
-    const unsigned aH1 = smem_u32(S.H1), aH2 = smem_u32(S.H2), aW1 = smem_u32(S.W1), aWO = smem_u32(S.WO);
-    unsigned par_main = 0u, par_wg = 0u;
-    unsigned h1p[16] = {}, h2p[16] = {};
-    float dls[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, st[4] = {0.f, 0.f, 0.f, 0.f};   // per-thread partial sums
-
     int it = 0;
     TRACE_DECL
-    for (int j = blockIdx.x; j < n_pairs; j += gridDim.x, ++it) {
-        TRACE_MARK(12);
-        const int t0 = tile_ids[2 * j], t1 = tile_ids[2 * j + 1];
-        const int xb = IMG ? (it & 1) : 0;
-        const unsigned aX = aXb[xb];
-        // loss inputs of this thread's sample: issue the loads now, consume them after layer 3
-        const size_t g = (size_t)(row < 64 ? t0 : t1) * 64 + (row & 63);
-        float act_r[7], adv_r = 0.0f, olp_r = 0.0f, ret_r = 0.0f;
-        if (half != 0) {
-            // the second column half has no per-sample loss work
-        } else if (net == 0) {
-#pragma unroll
-            for (int d = 0; d < 7; ++d) act_r[d] = __ldg(action + g * 7 + d);
-            if (!forward_only) {
-                adv_r = __ldg(advantage + g);
-                olp_r = __ldg(old_logp + g);
-            }
-        } else if (!forward_only) {
-            ret_r = __ldg(returns + g);
-        }
-        if (it > 0 && !forward_only) {      // the previous tile's trailing weight-gradient GEMMs still read X / G1 / dO
-            mbar_wait(mb_wg, par_wg);
-            par_wg ^= 1u;
-        }
-        TRACE_MARK(0);
-        if (IMG) {
-            // the other buffer is free (its last readers were the previous tile's GEMMs): prefetch the next tile's image into it
+
+    if (issuer) {
+        // ================= MMA issuer warp: warp-uniform control flow, one elected lane executes the tcgen05 / TMA instructions =========
+        const bool lead = elect_one();
+        const unsigned aX0 = smem_u32(S.X[0]), aH1 = smem_u32(S.H1), aH2 = smem_u32(S.H2), aDO = smem_u32(S.DO);
+        const unsigned aW0 = smem_u32(S.W0), aW1 = smem_u32(S.W1), aWO = smem_u32(S.WO);
+        const unsigned mb_x0 = smem_u32(&S.mbar[2]);
+        constexpr unsigned id_fwd = idesc_bf16(128, 64, false, false), id_out = idesc_bf16(128, 16, false, false);
+        constexpr unsigned id_bwd = idesc_bf16(128, 64, false, true);
+        constexpr unsigned id_w16 = idesc_bf16(64, 16, true, true), id_w64 = idesc_bf16(64, 64, true, true), id_w80 = idesc_bf16(64, 80, true, true);
+        if (IMG && lead && (int)blockIdx.x < n_pairs)
+            bulk_load_tile(aX0, img + (size_t)(__ldg(tile_ids + 2 * blockIdx.x) >> 1) * TILE_BYTES, mb_x0);
+        for (int j = blockIdx.x; j < n_pairs; j += gridDim.x, ++it) {
+            TRACE_MARK(12);
+            const int xb = IMG ? (it & 1) : 0;
+            const unsigned aX = aX0 + xb * TILE_BYTES;
             const int jn = j + gridDim.x;
-            if (tid == 0 && jn < n_pairs) bulk_load_tile(aXb[xb ^ 1], img + (size_t)(tile_ids[2 * jn] >> 1) * TILE_BYTES, mb_x[xb ^ 1]);
-            mbar_wait(mb_x[xb], par_x[xb]);
-            par_x[xb] ^= 1u;
-            fence_before();
-            __syncthreads();
-        } else {
-            // ---- X tile: obs fp32 -> bf16, coalesced float4 reads; column 56 = 1 carries the layer-1 bias --------------
-            unsigned char* X = S.X[0];
-#pragma unroll
-            for (int i = 0; i < 7; ++i) {
-                const int idx = tid + TCG_THREADS * i;           // 0 .. 1791
-                const int half = idx >= 896, rem = idx - half * 896;
-                const int r = half * 64 + rem / 14, q = rem % 14;
-                const float4 v = __ldg(reinterpret_cast<const float4*>(obs + (size_t)(half ? t1 : t0) * 64 * IN) + rem);
-                *reinterpret_cast<uint2*>(X + sw_chunk(r, q >> 1) + ((q & 1) << 3)) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+            int next_img = 0;
+            if (IMG && jn < n_pairs) next_img = __ldg(tile_ids + 2 * jn) >> 1;      // issued early, consumed after layer 1 is in flight
+            if (IMG) {
+                mbar_wait(mb_x0 + 8 * xb, (unsigned)(it >> 1) & 1u);                // this tile's image has landed
+                if (forward_only && it > 0) ready_sync();                           // the previous tile's outputs have left TMEM
+            } else {
+                ready_sync();                                                       // the threads have written X (after reading O)
             }
-            if (tid < 128) *reinterpret_cast<uint4*>(X + sw_chunk(tid, 7)) = make_uint4(0x00003F80u, 0u, 0u, 0u);
+            TRACE_MARK(0);
+            fence_after();
+            if (lead) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) mma_bf16(tb + COL_Z, desc_k(aX + k * 32), desc_k(aW0 + k * 32), id_fwd, k > 0);
+                commit(mb_main);
+            }
+            TRACE_MARK(1);
+            if (IMG && jn < n_pairs) {
+                // the other X buffer's last reader was the previous tile's trailing dW0 batch (gradient pass) / layer 1 (forward only,
+                // complete: its epilogue arrived long ago): refill it with the next tile's image
+                if (!forward_only && it > 0) mbar_wait(mb_wg, (unsigned)(it - 1) & 1u);
+                if (lead) bulk_load_tile(aX0 + (xb ^ 1) * TILE_BYTES, img + (size_t)next_img * TILE_BYTES, mb_x0 + 8 * (xb ^ 1));
+            }
+            TRACE_MARK(2);
+            // ---- layer 2 -------------------------------------------------------------------------------------------------
+            ready_sync();                       // H1 written
+            TRACE_MARK(3);
+            fence_after();
+            if (lead) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) mma_bf16(tb + COL_Z, desc_k(aH1 + k * 32), desc_k(aW1 + k * 32), id_fwd, k > 0);
+                commit(mb_main);
+            }
+            // ---- layer 3: action means (cols 0..6) or value (col 7) ----------------------------------------------------------
+            ready_sync();                       // H2 written
+            TRACE_MARK(4);
+            fence_after();
+            if (lead) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) mma_bf16(tb + COL_Z, desc_k(aH2 + k * 32), desc_k(aWO + k * 32), id_out, k > 0);
+                commit(mb_main);
+            }
+            if (forward_only) continue;
+            const unsigned acc0 = it > 0;
+            // ---- Z = dO WO; dWO += H2^T dO rides behind it (H2's last reader) ----------------------------------------------------
+            ready_sync();                       // dO written
+            TRACE_MARK(5);
+            fence_after();
+            if (lead) {
+                mma_bf16(tb + COL_Z, desc_k(aDO), desc_mn(aWO), id_bwd, 0u);
+                commit(mb_main);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) mma_bf16(tb + COL_WO, desc_mn(aH2 + k * 2048), desc_mn(aDO + k * 2048), id_w16, acc0 | (k > 0));
+                commit(mb_ride);
+            }
+            // ---- Z = G2 W1; dW1|db1 += G2^T [H1 | dO] rides behind it (H1's last reader) ------------------------------------------
+            ready_sync();                       // G2 written (over H2)
+            TRACE_MARK(6);
+            fence_after();
+            if (lead) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) mma_bf16(tb + COL_Z, desc_k(aH2 + k * 32), desc_mn(aW1 + k * 2048), id_bwd, k > 0);
+                commit(mb_main);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) mma_bf16(tb + COL_W1, desc_mn(aH2 + k * 2048), desc_mn(aH1 + k * 2048), id_w80, acc0 | (k > 0));
+                commit(mb_ride);
+            }
+            // ---- dW0|db0 += G1^T X: must drain before this X buffer is refilled ----------------------------------------------------
+            ready_sync();                       // G1 written (over H1)
+            TRACE_MARK(7);
+            fence_after();
+            if (lead) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) mma_bf16(tb + COL_W0, desc_mn(aH1 + k * 2048), desc_mn(aX + k * 2048), id_w64, acc0 | (k > 0));
+                commit(mb_wg);
+            }
+            TRACE_MARK(8);
+        }
+        if (IMG && forward_only && it > 0) ready_sync();      // pairs with the last tile's output arrive
+    } else {
+        // ================= epilogue threads ==============================================================================================
+        unsigned par_main = 0u;
+        unsigned h1p[16] = {}, h2p[16] = {};
+        float dls[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, dbo[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, st[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int j = blockIdx.x; j < n_pairs; j += gridDim.x, ++it) {
+            TRACE_MARK(12);
+            const int t0 = tile_ids[2 * j], t1 = tile_ids[2 * j + 1];
+            // loss inputs of this thread's sample: issue the loads now, consume them after layer 3
+            const size_t g = (size_t)(row < 64 ? t0 : t1) * 64 + (row & 63);
+            float act_r[7], adv_r = 0.0f, olp_r = 0.0f, ret_r = 0.0f;
+            if (half != 0) {
+                // the second column half has no per-sample loss work
+            } else if (net == 0) {
+#pragma unroll
+                for (int d = 0; d < 7; ++d) act_r[d] = __ldg(action + g * 7 + d);
+                if (!forward_only) {
+                    adv_r = __ldg(advantage + g);
+                    olp_r = __ldg(old_logp + g);
+                }
+            } else if (!forward_only) {
+                ret_r = __ldg(returns + g);
+            }
+            if (!IMG) {
+                // ---- X tile: obs fp32 -> bf16, coalesced float4 reads; column 56 = 1 carries the layer-1 bias ---------------
+                if (it > 0 && !forward_only) mbar_wait(mb_wg, (unsigned)(it - 1) & 1u);    // the previous tile's dW0 batch still reads X
+                unsigned char* X = S.X[0];
+#pragma unroll
+                for (int i = 0; i < 7; ++i) {
+                    const int idx = tid + TCG_EPI_THREADS * i;           // 0 .. 1791
+                    const int hh = idx >= 896, rem = idx - hh * 896;
+                    const int r = hh * 64 + rem / 14, q = rem % 14;
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(obs + (size_t)(hh ? t1 : t0) * 64 * IN) + rem);
+                    *reinterpret_cast<uint2*>(X + sw_chunk(r, q >> 1) + ((q & 1) << 3)) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+                }
+                if (tid < 128) *reinterpret_cast<uint4*>(X + sw_chunk(tid, 7)) = make_uint4(0x00003F80u, 0u, 0u, 0u);
+                fence_async_smem();
+                fence_before();
+                ready_arrive();
+            }
+            TRACE_MARK(0);
+            unsigned p[16];
+            // ---- layer 1 -------------------------------------------------------------------------------------------------
+            mbar_wait(mb_main, par_main);
+            par_main ^= 1u;
+            fence_after();
+            TRACE_MARK(1);
+            epilogue_math<0>(tz, half, nullptr, h1p, p);
+            epilogue_store(S.H1, row, half, p);
             fence_async_smem();
             fence_before();
-            __syncthreads();
-        }
-        TRACE_MARK(1);
-        // ---- layer 1 ----------------------------------------------------------------------------------------------------
-        if (tid == 0) {
+            ready_arrive();
+            TRACE_MARK(2);
+            // ---- layer 2 -------------------------------------------------------------------------------------------------
+            mbar_wait(mb_main, par_main);
+            par_main ^= 1u;
             fence_after();
-            constexpr unsigned id = idesc_bf16(128, 64, false, false);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) mma_bf16(tb + COL_Z, desc_k(aX + k * 32), desc_k(aW0 + k * 32), id, k > 0);
-            commit(mb_main);
-        }
-        mbar_wait(mb_main, par_main);
-        par_main ^= 1u;
-        fence_after();
-        TRACE_MARK(2);
-        epilogue32<0>(tz, S.H1, row, half, nullptr, h1p);
-        fence_async_smem();
-        fence_before();
-        __syncthreads();
-        TRACE_MARK(3);
-        // ---- layer 2 ----------------------------------------------------------------------------------------------------
-        if (tid == 0) {
+            TRACE_MARK(3);
+            epilogue_math<1>(tz, half, S.b1, h2p, p);
+            epilogue_store(S.H2, row, half, p);
+            fence_async_smem();
+            fence_before();
+            ready_arrive();
+            TRACE_MARK(4);
+            // ---- layer 3 -> loss and d(loss)/d(outputs), one thread per sample -------------------------------------------------
+            mbar_wait(mb_main, par_main);
+            par_main ^= 1u;
             fence_after();
-            constexpr unsigned id = idesc_bf16(128, 64, false, false);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) mma_bf16(tb + COL_Z, desc_k(aH1 + k * 32), desc_k(aW1 + k * 32), id, k > 0);
-            commit(mb_main);
-        }
-        mbar_wait(mb_main, par_main);
-        par_main ^= 1u;
-        fence_after();
-        TRACE_MARK(4);
-        epilogue32<1>(tz, S.H2, row, half, S.b1, h2p);
-        fence_async_smem();
-        fence_before();
-        __syncthreads();
-        TRACE_MARK(5);
-        // ---- layer 3: action means (cols 0..6) or value (col 7) -------------------------------------------------------------
-        if (tid == 0) {
-            fence_after();
-            constexpr unsigned id = idesc_bf16(128, 16, false, false);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) mma_bf16(tb + COL_Z, desc_k(aH2 + k * 32), desc_k(aWO + k * 32), id, k > 0);
-            commit(mb_main);
-        }
-        mbar_wait(mb_main, par_main);
-        par_main ^= 1u;
-        fence_after();
-        TRACE_MARK(6);
-        // ---- loss and d(loss)/d(outputs), one thread per sample ------------------------------------------------------------
-        if (half == 0) {
-            float o[16];
-            tmem_ld16(tlane + COL_Z, o);
-            if (net == 0) {
-                float lp = 0.0f, z[7];
-#pragma unroll
-                for (int d = 0; d < 7; ++d) {
-                    z[d] = (act_r[d] - (o[d] + S.bo[d])) * S.inv_sig[d];
-                    lp += -0.5f * z[d] * z[d] - S.ls[d] - kHalfLog2PiTc;
-                }
-                if (logp_out) logp_out[g] = lp;
-                if (!forward_only) {
-                    const float adv_n = (adv_r - S.scal[0]) * S.scal[1];
-                    const float log_ratio = lp - olp_r;
-                    const float ratio = expf(log_ratio);
-                    const float pl1 = adv_n * ratio, pl2 = adv_n * fminf(fmaxf(ratio, 1.0f - hp.clip_range), 1.0f + hp.clip_range);
-                    const float dpl_dlp = (pl1 <= pl2) ? -adv_n * ratio : 0.0f;
-                    float dm[7];
-                    float ent = 0.0f;
+            TRACE_MARK(5);
+            if (half == 0) {
+                float o[16];
+                tmem_ld16(tlane + COL_Z, o);
+                if (net == 0) {
+                    float lp = 0.0f, z[7];
 #pragma unroll
                     for (int d = 0; d < 7; ++d) {
-                        dm[d] = inv_global_batch * dpl_dlp * z[d] * S.inv_sig[d];
-                        dls[d] += inv_global_batch * dpl_dlp * (z[d] * z[d] - 1.0f) - inv_global_batch * hp.ent_coef;
-                        ent += 0.5f + kHalfLog2PiTc + S.ls[d];
+                        z[d] = (act_r[d] - (o[d] + S.bo[d])) * S.inv_sig[d];
+                        lp += -0.5f * z[d] * z[d] - S.ls[d] - kHalfLog2PiTc;
                     }
-                    *reinterpret_cast<uint4*>(S.DO + sw_chunk(row, 0)) =
-                        make_uint4(pack_bf16(dm[0], dm[1]), pack_bf16(dm[2], dm[3]), pack_bf16(dm[4], dm[5]), pack_bf16(dm[6], 0.0f));
-                    st[0] += -fminf(pl1, pl2);
-                    st[1] += ent;
-                    st[2] += (ratio - 1.0f) - log_ratio;
-                    st[3] += fabsf(ratio - 1.0f) > hp.clip_range ? 1.0f : 0.0f;
-                }
-            } else {
-                const float v = o[7] + S.bo[7];
-                if (value_out) value_out[g] = v;
-                if (!forward_only) {
-                    *reinterpret_cast<uint4*>(S.DO + sw_chunk(row, 0)) =
-                        make_uint4(0u, 0u, 0u, pack_bf16(0.0f, inv_global_batch * hp.vf_coef * 2.0f * (v - ret_r)));
-                    st[0] += (ret_r - v) * (ret_r - v);
+                    if (logp_out) logp_out[g] = lp;
+                    if (!forward_only) {
+                        const float adv_n = (adv_r - S.scal[0]) * S.scal[1];
+                        const float log_ratio = lp - olp_r;
+                        const float ratio = expf(log_ratio);
+                        const float pl1 = adv_n * ratio, pl2 = adv_n * fminf(fmaxf(ratio, 1.0f - hp.clip_range), 1.0f + hp.clip_range);
+                        const float dpl_dlp = (pl1 <= pl2) ? -adv_n * ratio : 0.0f;
+                        float dm[7];
+                        float ent = 0.0f;
+#pragma unroll
+                        for (int d = 0; d < 7; ++d) {
+                            dm[d] = inv_global_batch * dpl_dlp * z[d] * S.inv_sig[d];
+                            dbo[d] += dm[d];
+                            dls[d] += inv_global_batch * dpl_dlp * (z[d] * z[d] - 1.0f) - inv_global_batch * hp.ent_coef;
+                            ent += 0.5f + kHalfLog2PiTc + S.ls[d];
+                        }
+                        *reinterpret_cast<uint4*>(S.DO + sw_chunk(row, 0)) =
+                            make_uint4(pack_bf16(dm[0], dm[1]), pack_bf16(dm[2], dm[3]), pack_bf16(dm[4], dm[5]), pack_bf16(dm[6], 0.0f));
+                        st[0] += -fminf(pl1, pl2);
+                        st[1] += ent;
+                        st[2] += (ratio - 1.0f) - log_ratio;
+                        st[3] += fabsf(ratio - 1.0f) > hp.clip_range ? 1.0f : 0.0f;
+                    }
+                } else {
+                    const float v = o[7] + S.bo[7];
+                    if (value_out) value_out[g] = v;
+                    if (!forward_only) {
+                        const float dv = inv_global_batch * hp.vf_coef * 2.0f * (v - ret_r);
+                        dbo[0] += dv;
+                        *reinterpret_cast<uint4*>(S.DO + sw_chunk(row, 0)) = make_uint4(0u, 0u, 0u, pack_bf16(0.0f, dv));
+                        st[0] += (ret_r - v) * (ret_r - v);
+                    }
                 }
             }
-        }
-        if (forward_only) {
+            if (forward_only) {
+                if (IMG) {           // Z / O is re-written by the next tile's layer 1 only after everyone has read it
+                    fence_before();
+                    ready_arrive();
+                }
+                continue;
+            }
+            fence_async_smem();
             fence_before();
-            __syncthreads();     // Z / O is re-written by the next tile's layer 1 only after everyone has read it
-            continue;
-        }
-        fence_async_smem();
-        fence_before();
-        __syncthreads();
-        TRACE_MARK(7);
-        const unsigned acc0 = it > 0;
-        // ---- dZ2 = (dO WO) * (1 - H2^2); dWO += H2^T dO rides along (H2's last reader) ----------------------------------------
-        if (tid == 0) {
+            ready_arrive();
+            TRACE_MARK(6);
+            // ---- dZ2 = (dO WO) * (1 - H2^2): G2 replaces H2 once dWO += H2^T dO has read it ---------------------------------------
+            mbar_wait(mb_main, par_main);
+            par_main ^= 1u;
             fence_after();
-            constexpr unsigned id = idesc_bf16(128, 64, false, true), id16 = idesc_bf16(64, 16, true, true);
-            mma_bf16(tb + COL_Z, desc_k(aDO), desc_mn(aWO), id, 0u);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) mma_bf16(tb + COL_WO, desc_mn(aH2 + k * 2048), desc_mn(aDO + k * 2048), id16, acc0 | (k > 0));
-            commit(mb_main);
-        }
-        mbar_wait(mb_main, par_main);
-        par_main ^= 1u;
-        fence_after();
-        TRACE_MARK(8);
-        epilogue32<2>(tz, S.H2, row, half, nullptr, h2p);          // G2 replaces H2
-        fence_async_smem();
-        fence_before();
-        __syncthreads();
-        TRACE_MARK(9);
-        // ---- dZ1 = (G2 W1) * (1 - H1^2); dW1 += G2^T H1 and db1 += G2^T dO(ones) ride along (H1's last readers) ---------------
-        if (tid == 0) {
+            TRACE_MARK(7);
+            epilogue_math<2>(tz, half, nullptr, h2p, p);
+            mbar_wait(mb_ride, 0u);
+            TRACE_MARK(8);
+            epilogue_store(S.H2, row, half, p);
+            fence_async_smem();
+            fence_before();
+            ready_arrive();
+            // ---- dZ1 = (G2 W1) * (1 - H1^2): G1 replaces H1 once dW1|db1 += G2^T [H1 | dO] has read it ---------------------------
+            mbar_wait(mb_main, par_main);
+            par_main ^= 1u;
             fence_after();
-            constexpr unsigned id = idesc_bf16(128, 64, false, true), id16 = idesc_bf16(64, 16, true, true), id64 = idesc_bf16(64, 64, true, true);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) mma_bf16(tb + COL_Z, desc_k(aH2 + k * 32), desc_mn(aW1 + k * 2048), id, k > 0);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) mma_bf16(tb + COL_W1, desc_mn(aH2 + k * 2048), desc_mn(aH1 + k * 2048), id64, acc0 | (k > 0));
-#pragma unroll
-            for (int k = 0; k < 8; ++k) mma_bf16(tb + COL_B1, desc_mn(aH2 + k * 2048), desc_mn(aDO + k * 2048), id16, acc0 | (k > 0));
-            commit(mb_main);
+            TRACE_MARK(9);
+            epilogue_math<2>(tz, half, nullptr, h1p, p);
+            mbar_wait(mb_ride, 1u);
+            TRACE_MARK(10);
+            epilogue_store(S.H1, row, half, p);
+            fence_async_smem();
+            fence_before();
+            ready_arrive();
+            TRACE_MARK(11);
         }
-        mbar_wait(mb_main, par_main);
-        par_main ^= 1u;
-        fence_after();
-        TRACE_MARK(10);
-        epilogue32<2>(tz, S.H1, row, half, nullptr, h1p);          // G1 replaces H1
-        fence_async_smem();
-        fence_before();
-        __syncthreads();
-        TRACE_MARK(11);
-        // ---- dW0 | db0 += G1^T X, dbo += X(ones row)^T dO -- drain before the next tile touches H1 / X / dO -------------------------
-        if (tid == 0) {
-            fence_after();
-            constexpr unsigned id16 = idesc_bf16(64, 16, true, true), id64 = idesc_bf16(64, 64, true, true);
+        if (!forward_only) {
+            // log_std / output-bias gradients and statistics: warp shuffle, then shared atomics
 #pragma unroll
-            for (int k = 0; k < 8; ++k) mma_bf16(tb + COL_W0, desc_mn(aH1 + k * 2048), desc_mn(aX + k * 2048), id64, acc0 | (k > 0));
+            for (int d = 0; d < 7; ++d) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) mma_bf16(tb + COL_BO, desc_mn(aX + k * 2048), desc_mn(aDO + k * 2048), id16, acc0 | (k > 0));
-            commit(mb_wg);
+                for (int off = 16; off > 0; off >>= 1) {
+                    dls[d] += __shfl_xor_sync(0xffffffffu, dls[d], off);
+                    dbo[d] += __shfl_xor_sync(0xffffffffu, dbo[d], off);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) st[q] += __shfl_xor_sync(0xffffffffu, st[q], off);
+            }
+            if (lane == 0 && half == 0) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) atomicAdd(&S.scal[2 + q], st[q]);
+#pragma unroll
+                for (int d = 0; d < 7; ++d) {
+                    atomicAdd(&S.scal[8 + d], dls[d]);
+                    atomicAdd(&S.scal[16 + d], dbo[d]);
+                }
+            }
         }
     }
 
     TRACE_FLUSH(it);
     if (!forward_only) {
-        if (it > 0) mbar_wait(mb_wg, par_wg);
+        if (it > 0) mbar_wait(mb_wg, (unsigned)(it - 1) & 1u);
         fence_after();
-        // log_std gradient and statistics: warp shuffle, then shared atomics (4 warps)
-        if (net == 0) {
-#pragma unroll
-            for (int d = 0; d < 7; ++d) {
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) dls[d] += __shfl_xor_sync(0xffffffffu, dls[d], off);
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) st[q] += __shfl_xor_sync(0xffffffffu, st[q], off);
-        }
-        if (lane == 0) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) atomicAdd(&S.scal[2 + q], st[q]);
-            if (net == 0) {
-#pragma unroll
-                for (int d = 0; d < 7; ++d) atomicAdd(&S.scal[8 + d], dls[d]);
-            }
-        }
         __syncthreads();
         // ---- accumulators (M = 64: row m lives in lane m % 16 + 32 * (m / 16)) -> this CTA's slice of the partial gradient ----------
         float* out = partials + (size_t)blockIdx.x * (P + KIN_PPO_STATS + 8);
         const int u = (warp & 3) * 16 + lane;       // valid for lane < 16
         const bool rowok = lane < 16;
-        {   // warps 0..3 store columns 0..31 of dW1 / dW0, warps 4..7 columns 32..63
+        if (!issuer) {   // warps 0..3 store columns 0..31 of dW1 / dW0, warps 4..7 columns 32..63
             float v[32];
             tmem_ld32(tlane + COL_W1 + half * 32, v);
             if (rowok) {
@@ -484,7 +539,7 @@ kin_ppo_grad_tc_kernel(const float* __restrict__ params, KinPpoHyper hp, const f
                 }
             }
         }
-        if (half == 0) {
+        if (half == 0 && !issuer) {
             float o[16];
             tmem_ld16(tlane + COL_WO, o);
             if (rowok) {
@@ -495,26 +550,19 @@ kin_ppo_grad_tc_kernel(const float* __restrict__ params, KinPpoHyper hp, const f
                     out[O.val_w + u] = o[7];
                 }
             }
-            tmem_ld16(tlane + COL_B1, o);
+            tmem_ld16(tlane + COL_W1 + 64, o);
             if (rowok) out[o_b1 + u] = o[8];
-            if (warp == 3) {                        // X column 56 (the ones column) = row 56 -> lane 96 + 8
-                tmem_ld16(tlane + COL_BO, o);
-                if (lane == 8) {
-                    if (net == 0) {
-#pragma unroll
-                        for (int d = 0; d < 7; ++d) out[O.act_b + d] = o[d];
-                    } else {
-                        out[O.val_b] = o[7];
-                    }
-                }
-            }
         }
         if (net == 0) {
-            if (tid < 7) out[O.log_std + tid] = S.scal[8 + tid];
+            if (tid < 7) {
+                out[O.log_std + tid] = S.scal[8 + tid];
+                out[O.act_b + tid] = S.scal[16 + tid];
+            }
             // statistics slots: 0 policy loss, 2 entropy, 3 approx_kl, 4 clip fraction (actor CTAs); 1 value loss (critic CTAs)
             if (tid == 0) { out[P + 0] = S.scal[2]; out[P + 2] = S.scal[3]; out[P + 3] = S.scal[4]; out[P + 4] = S.scal[5]; }
         } else if (tid == 0) {
             out[P + 1] = S.scal[2];
+            out[O.val_b] = S.scal[16];
         }
     }
     fence_before();

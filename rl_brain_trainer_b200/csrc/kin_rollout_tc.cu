@@ -103,6 +103,12 @@ __device__ __forceinline__ void mbar_wait(unsigned saddr, unsigned parity) {
         "@P1 bra DONE;\n\tbra WAIT_LOOP;\n\tDONE:\n\t}"
         ::"r"(saddr), "r"(parity) : "memory");
 }
+// one lane of a converged warp (the MMA issue is then compiled with uniform-register descriptors instead of per-MMA R2UR chains)
+__device__ __forceinline__ bool elect_one_tc() {
+    unsigned pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0u;
+}
 __device__ __forceinline__ void tile_barrier(int tile, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(tile + 1), "r"(threads) : "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -192,7 +198,7 @@ __device__ __forceinline__ bool mlp_tc(TcSmem& S, TileCtx& c, const float* o, fl
     tc_fence_before();
     tile_barrier(c.tile, c.tile_threads);
     if (!(S.run_flags[fb][c.tile][0] | S.run_flags[fb][c.tile][1] | S.run_flags[fb][c.tile][2] | S.run_flags[fb][c.tile][3])) return false;
-    if (c.issuer) issue_layer(c.a_saddr, c.w0_saddr, CHUNK_FLOATS_W * 4, c.tmem_d, umma_idesc(TC_TILE, TC_HID), c.mbar_saddr);
+    if (c.row < 32 && elect_one_tc()) issue_layer(c.a_saddr, c.w0_saddr, CHUNK_FLOATS_W * 4, c.tmem_d, umma_idesc(TC_TILE, TC_HID), c.mbar_saddr);
     mbar_wait(c.mbar_saddr, c.parity);
     c.parity ^= 1u;
     tc_fence_after();
@@ -209,7 +215,7 @@ __device__ __forceinline__ bool mlp_tc(TcSmem& S, TileCtx& c, const float* o, fl
     fence_async_smem();
     tc_fence_before();
     tile_barrier(c.tile, c.tile_threads);
-    if (c.issuer) issue_layer(c.a_saddr, c.w1_saddr, CHUNK_FLOATS_W * 4, c.tmem_d, umma_idesc(TC_TILE, TC_HID), c.mbar_saddr);
+    if (c.row < 32 && elect_one_tc()) issue_layer(c.a_saddr, c.w1_saddr, CHUNK_FLOATS_W * 4, c.tmem_d, umma_idesc(TC_TILE, TC_HID), c.mbar_saddr);
     mbar_wait(c.mbar_saddr, c.parity);
     c.parity ^= 1u;
     tc_fence_after();
@@ -227,7 +233,7 @@ __device__ __forceinline__ bool mlp_tc(TcSmem& S, TileCtx& c, const float* o, fl
     fence_async_smem();
     tc_fence_before();
     tile_barrier(c.tile, c.tile_threads);
-    if (c.issuer) issue_layer(c.a_saddr, c.wo_saddr, CHUNK_FLOATS_WO * 4, c.tmem_d, umma_idesc(TC_TILE, 8), c.mbar_saddr);
+    if (c.row < 32 && elect_one_tc()) issue_layer(c.a_saddr, c.wo_saddr, CHUNK_FLOATS_WO * 4, c.tmem_d, umma_idesc(TC_TILE, 8), c.mbar_saddr);
     mbar_wait(c.mbar_saddr, c.parity);
     c.parity ^= 1u;
     tc_fence_after();

@@ -48,12 +48,14 @@ buf = (ctypes.c_ulonglong * 64)()
 L = _lib.lib()
 L.kin_debug_ppo_trace.argtypes = [ctypes.c_void_p]
 assert L.kin_debug_ppo_trace(buf) == 0
-names = ["wg wait", "X wait+sync", "L1 mma wait", "epi1+sync", "L2 mma wait", "epi2+sync", "L3 mma wait", "loss+sync", "bwd1 mma wait", "epiG2+sync",
-         "bwd2 mma wait", "epiG1+sync", "loop top (issuer: trailing MMA issue)"]
-who = ["cta(0,0) tid0", "cta(0,0) tid32", "cta(1,1) tid0", "cta(1,1) tid32"]
+epi_names = ["loss-input loads (+ X conversion)", "L1 wait", "epi1 + arrive", "L2 wait", "epi2 + arrive", "L3 wait", "loss + arrive", "bwd1 wait",
+             "G2 math + ride wait", "G2 store + arrive, bwd2 wait", "G1 math + ride wait", "G1 store + arrive", "loop top"]
+iss_names = ["X wait", "L1 issue", "wg wait + prefetch", "wait H1", "wait H2 (+ L2 issue)", "wait dO (+ L3 issue)", "wait G2 (+ bwd1 issue)",
+             "wait G1 (+ bwd2 issue)", "trailing issue", "-", "-", "-", "loop top"]
+who = ["cta(0,0) issuer", "cta(0,0) tid32", "cta(1,1) issuer", "cta(1,1) tid32"]
 for w in range(4):
     row = [buf[w * 16 + i] for i in range(16)]
     n = max(row[15], 1)
     print(f"{who[w]}: {n} tiles, {sum(row[:13]) / n:.0f} cycles/tile")
     for i in range(13):
-        print(f"   {names[i]:40s} {row[i] / n:8.0f}")
+        print(f"   {(epi_names if w & 1 else iss_names)[i]:40s} {row[i] / n:8.0f}")

@@ -32,7 +32,9 @@
 //     does its arithmetic first and waits for `ride` only before its stores), `wg` (the trailing dW0 batch, which must drain
 //     before the X buffer it reads is refilled) and the X image buffers.
 //   * image mode (the rollout buffer kin_ppo_collect wrote): the X operand is one 16 KB bulk copy (TMA engine) per tile,
-//     double-buffered so the next tile's image lands while this one is processed.
+//     double-buffered so the next tile's image lands while this one is processed.  The loss inputs of the tile (actions,
+//     advantages, old log-probs / returns) ride on the same mbarrier into small shared-memory buffers, so the epilogue threads
+//     hold no global loads in flight (their registers and latency were on the per-tile chain before).
 //   * the elementwise work (tanh, 1 - h^2, the loss and its derivative, log_std gradient, statistics) is fp32 in registers;
 //     each thread keeps packed bf16 copies of its H1 / H2 rows in registers for the backward pass.
 //
@@ -82,21 +84,23 @@ struct __align__(1024) TcGradSmem {
     unsigned char W0[64 * 128];          // col 56 = b0
     unsigned char W1[64 * 128];
     unsigned char WO[16 * 128];          // actor: rows 0..6 = act_w; critic: row 7 = val_w
+    float act[2][TCG_ROWS * 7];         // loss inputs of the tile, staged by the TMA engine next to the X image (double-buffered)
+    float adv[2][TCG_ROWS];
+    float olp[2][TCG_ROWS];
+    float ret[2][TCG_ROWS];
     float b1[64];
     float bo[8];
     float ls[8];
     float inv_sig[8];
     float scal[32];                      // 0 adv mean, 1 1/(std+eps), 2..5 statistics, 8..14 d log_std, 16..23 d output bias
-    unsigned long long mbar[6];          // 0 main (chain GEMMs), 1 wg (trailing dW0 batch), 2/3 X image buffers, 4 weights, 5 ride
+    unsigned long long mbar[6];          // 0 main (chain GEMMs), 1 wg (trailing dW0 batch), 2/3 staged inputs (X image + loss inputs), 4 weights, 5 ride
     unsigned tmem_base;
 };
 
-__device__ __forceinline__ void bulk_load_tile(unsigned dst_saddr, const void* src, unsigned mbar_saddr) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_saddr), "r"(TILE_BYTES) : "memory");
+__device__ __forceinline__ void bulk_load(unsigned dst_saddr, const void* src, unsigned bytes, unsigned mbar_saddr) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst_saddr), "l"(src), "r"(TILE_BYTES), "r"(mbar_saddr) : "memory");
+                 ::"r"(dst_saddr), "l"(src), "r"(bytes), "r"(mbar_saddr) : "memory");
 }
-
 __device__ __forceinline__ void st_bf16(unsigned char* tile, int row, int col, float v) {
     *reinterpret_cast<unsigned short*>(tile + sw_elem(row, col)) = (unsigned short)(pack_bf16(v, 0.0f) & 0xffffu);
 }
@@ -251,17 +255,37 @@ kin_ppo_grad_tc_kernel(const float* __restrict__ params, KinPpoHyper hp, const f
         constexpr unsigned id_fwd = idesc_bf16(128, 64, false, false), id_out = idesc_bf16(128, 16, false, false);
         constexpr unsigned id_bwd = idesc_bf16(128, 64, false, true);
         constexpr unsigned id_w16 = idesc_bf16(64, 16, true, true), id_w64 = idesc_bf16(64, 64, true, true), id_w80 = idesc_bf16(64, 80, true, true);
-        if (IMG && lead && (int)blockIdx.x < n_pairs)
-            bulk_load_tile(aX0, img + (size_t)(__ldg(tile_ids + 2 * blockIdx.x) >> 1) * TILE_BYTES, mb_x0);
+        // staged inputs of one tile -> buffer b: the X image (image mode) and the loss inputs of its two 64-sample halves, all on mb_x[b]
+        const unsigned loss_bytes = net == 0 ? 2u * 1792u + (forward_only ? 0u : 4u * 256u) : (forward_only ? 0u : 2u * 256u);
+        const unsigned stage_bytes = (IMG ? (unsigned)TILE_BYTES : 0u) + loss_bytes;
+        const unsigned aAct = smem_u32(S.act[0]), aAdv = smem_u32(S.adv[0]), aOlp = smem_u32(S.olp[0]), aRet = smem_u32(S.ret[0]);
+        auto stage = [&](int jj, int b) {       // called by the elected lane only
+            const int t0 = __ldg(tile_ids + 2 * jj), t1 = __ldg(tile_ids + 2 * jj + 1);
+            const unsigned mb = mb_x0 + 8 * b;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(stage_bytes) : "memory");
+            if (IMG) bulk_load(aX0 + b * TILE_BYTES, img + (size_t)(t0 >> 1) * TILE_BYTES, TILE_BYTES, mb);
+            if (net == 0) {
+                bulk_load(aAct + b * 3584, action + (size_t)t0 * 448, 1792u, mb);
+                bulk_load(aAct + b * 3584 + 1792, action + (size_t)t1 * 448, 1792u, mb);
+                if (!forward_only) {
+                    bulk_load(aAdv + b * 512, advantage + (size_t)t0 * 64, 256u, mb);
+                    bulk_load(aAdv + b * 512 + 256, advantage + (size_t)t1 * 64, 256u, mb);
+                    bulk_load(aOlp + b * 512, old_logp + (size_t)t0 * 64, 256u, mb);
+                    bulk_load(aOlp + b * 512 + 256, old_logp + (size_t)t1 * 64, 256u, mb);
+                }
+            } else if (!forward_only) {
+                bulk_load(aRet + b * 512, returns + (size_t)t0 * 64, 256u, mb);
+                bulk_load(aRet + b * 512 + 256, returns + (size_t)t1 * 64, 256u, mb);
+            }
+        };
+        if (stage_bytes && lead && (int)blockIdx.x < n_pairs) stage(blockIdx.x, 0);
         for (int j = blockIdx.x; j < n_pairs; j += gridDim.x, ++it) {
             TRACE_MARK(12);
-            const int xb = IMG ? (it & 1) : 0;
+            const int lb = it & 1, xb = IMG ? lb : 0;
             const unsigned aX = aX0 + xb * TILE_BYTES;
             const int jn = j + gridDim.x;
-            int next_img = 0;
-            if (IMG && jn < n_pairs) next_img = __ldg(tile_ids + 2 * jn) >> 1;      // issued early, consumed after layer 1 is in flight
             if (IMG) {
-                mbar_wait(mb_x0 + 8 * xb, (unsigned)(it >> 1) & 1u);                // this tile's image has landed
+                mbar_wait(mb_x0 + 8 * lb, (unsigned)(it >> 1) & 1u);                // this tile's image has landed
                 if (forward_only && it > 0) ready_sync();                           // the previous tile's outputs have left TMEM
             } else {
                 ready_sync();                                                       // the threads have written X (after reading O)
@@ -274,11 +298,11 @@ kin_ppo_grad_tc_kernel(const float* __restrict__ params, KinPpoHyper hp, const f
                 commit(mb_main);
             }
             TRACE_MARK(1);
-            if (IMG && jn < n_pairs) {
-                // the other X buffer's last reader was the previous tile's trailing dW0 batch (gradient pass) / layer 1 (forward only,
-                // complete: its epilogue arrived long ago): refill it with the next tile's image
-                if (!forward_only && it > 0) mbar_wait(mb_wg, (unsigned)(it - 1) & 1u);
-                if (lead) bulk_load_tile(aX0 + (xb ^ 1) * TILE_BYTES, img + (size_t)next_img * TILE_BYTES, mb_x0 + 8 * (xb ^ 1));
+            if (stage_bytes && jn < n_pairs) {
+                // the other buffer's last readers were the previous tile's trailing dW0 batch (gradient pass, image mode) / its layer 1
+                // (forward only) / its loss threads (all done: they arrived on `ready` since): refill it with the next tile's inputs
+                if (IMG && !forward_only && it > 0) mbar_wait(mb_wg, (unsigned)(it - 1) & 1u);
+                if (lead) stage(jn, lb ^ 1);
             }
             TRACE_MARK(2);
             // ---- layer 2 -------------------------------------------------------------------------------------------------
@@ -343,22 +367,10 @@ kin_ppo_grad_tc_kernel(const float* __restrict__ params, KinPpoHyper hp, const f
         float dls[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, dbo[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, st[4] = {0.f, 0.f, 0.f, 0.f};
         for (int j = blockIdx.x; j < n_pairs; j += gridDim.x, ++it) {
             TRACE_MARK(12);
-            const int t0 = tile_ids[2 * j], t1 = tile_ids[2 * j + 1];
-            // loss inputs of this thread's sample: issue the loads now, consume them after layer 3
-            const size_t g = (size_t)(row < 64 ? t0 : t1) * 64 + (row & 63);
-            float act_r[7], adv_r = 0.0f, olp_r = 0.0f, ret_r = 0.0f;
-            if (half != 0) {
-                // the second column half has no per-sample loss work
-            } else if (net == 0) {
-#pragma unroll
-                for (int d = 0; d < 7; ++d) act_r[d] = __ldg(action + g * 7 + d);
-                if (!forward_only) {
-                    adv_r = __ldg(advantage + g);
-                    olp_r = __ldg(old_logp + g);
-                }
-            } else if (!forward_only) {
-                ret_r = __ldg(returns + g);
-            }
+            const int lb = it & 1;
+            int t0 = 0, t1 = 0;
+            if (!IMG || logp_out || value_out) { t0 = __ldg(tile_ids + 2 * j); t1 = __ldg(tile_ids + 2 * j + 1); }
+            const size_t g = (size_t)(row < 64 ? t0 : t1) * 64 + (row & 63);      // only used by the X conversion / the forward outputs
             if (!IMG) {
                 // ---- X tile: obs fp32 -> bf16, coalesced float4 reads; column 56 = 1 carries the layer-1 bias ---------------
                 if (it > 0 && !forward_only) mbar_wait(mb_wg, (unsigned)(it - 1) & 1u);    // the previous tile's dW0 batch still reads X
@@ -408,7 +420,10 @@ kin_ppo_grad_tc_kernel(const float* __restrict__ params, KinPpoHyper hp, const f
             if (half == 0) {
                 float o[16];
                 tmem_ld16(tlane + COL_Z, o);
+                if (net == 0 || !forward_only) mbar_wait(smem_u32(&S.mbar[2 + lb]), (unsigned)(it >> 1) & 1u);     // staged loss inputs (landed long ago)
                 if (net == 0) {
+                    const float* act_r = S.act[lb] + row * 7;
+                    const float adv_r = S.adv[lb][row], olp_r = S.olp[lb][row];
                     float lp = 0.0f, z[7];
 #pragma unroll
                     for (int d = 0; d < 7; ++d) {
@@ -442,6 +457,7 @@ kin_ppo_grad_tc_kernel(const float* __restrict__ params, KinPpoHyper hp, const f
                     const float v = o[7] + S.bo[7];
                     if (value_out) value_out[g] = v;
                     if (!forward_only) {
+                        const float ret_r = S.ret[lb][row];
                         const float dv = inv_global_batch * hp.vf_coef * 2.0f * (v - ret_r);
                         dbo[0] += dv;
                         *reinterpret_cast<uint4*>(S.DO + sw_chunk(row, 0)) = make_uint4(0u, 0u, 0u, pack_bf16(0.0f, dv));
@@ -593,6 +609,8 @@ extern "C" int kin_ppo_grad_tc(const float* params, int in_dim, const KinPpoHype
     if (in_dim != 56) return kin_fail(KIN_ERR_UNSUPPORTED, "kin_ppo_grad_tc: in_dim must be 56");
     if (n_tiles & 1) return kin_fail(KIN_ERR_INVALID_ARG, "kin_ppo_grad_tc: n_tiles must be even (two 64-sample tiles per 128-row GEMM tile)");
     if (((uintptr_t)obs & 15u)) return kin_fail(KIN_ERR_INVALID_ARG, "kin_ppo_grad_tc: obs must be 16-byte aligned");
+    if (((uintptr_t)action | (uintptr_t)old_logp | (uintptr_t)advantage | (uintptr_t)returns) & 15u)      // staged by the TMA engine
+        return kin_fail(KIN_ERR_INVALID_ARG, "kin_ppo_grad_tc: action / old_logp / advantage / returns must be 16-byte aligned");
     const int P = ppo_offsets(in_dim).total;
     const size_t smem = sizeof(TcGradSmem) + 1024;
     static bool attr_set = false;

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define KIN_ABI_VERSION 2
+#define KIN_ABI_VERSION 3
 #define KIN_NJ 7
 #define KIN_OBS_DIM 56
 #define KIN_ROUTE_OBS_DIM 80
@@ -609,6 +609,7 @@ int kin_ppo_gae(const float *reward, const float *value, const uint8_t *episode_
  * row tile_ids[j]*64 + s of obs [S,56] / action [S,7] / old_logp / advantage / returns.  global_batch = samples in the
  * whole (all-rank) minibatch.  grad [P] receives the SUM over local samples of d(loss*global_batch)/dparam / global_batch,
  * i.e. ranks all-reduce (sum) grad and stats afterwards.  partials: scratch [grid][P + KIN_PPO_STATS + 8] floats.
+ * grad == NULL (both variants): the per-CTA rows stay unreduced in partials[0 .. min(grid, tiles)) for kin_peer_grad_push.
  * adv_stats (nullable): this minibatch's (mean, 1/(std+eps)) from kin_ppo_adv_stats; NULL -> computed from tile_sums.     */
 int kin_ppo_grad(const float *params, int in_dim, const KinPpoHyper *host_hyper, const float *obs, const float *action, const float *old_logp,
                  const float *advantage, const float *returns, const double *tile_sums, const int *tile_ids, int n_tiles,
@@ -663,6 +664,25 @@ int kin_ppo_adam(float *params, const float *grad, float *adam_m, float *adam_v,
 /* Build the 36 KB bf16 operand image of the flat parameters (the B operands of the tensor-core kernels: W0 | W1 | WO of both
  * nets as SWIZZLE_128B tiles, layer-1 bias folded in as column 56).  kin_ppo_adam(weight_image != NULL) keeps it current.   */
 int kin_ppo_pack_weights(const float *params, int in_dim, void *weight_image, void *stream);
+
+/* ---- gradient exchange over NVLink peer memory (the training path's one collective) ------------------------------
+ * Replaces: the per-minibatch all-reduce (sum) of the flat gradient + 5 loss statistics between the gradient kernel and Adam.
+ * Every rank (one per GPU of ONE node, world <= 8) owns a receive buffer; peers open it through CUDA IPC.  Per exchange:
+ * kin_peer_grad_push reduces this rank's per-CTA partial rows and stores the result into slot[epoch & 1][rank] of EVERY rank's
+ * buffer (posted NVLink stores) followed by a release-store of `epoch` into the peer's arrival counter; kin_peer_grad_gather
+ * waits (on the device) until all `world` counters reached `epoch` and writes grad / stats = the sum of the slots in rank
+ * order, bitwise identical on every rank.  epoch = 1, 2, 3, ... must advance by one per exchange on all ranks.  A dead peer is
+ * reported through *timed_out (device int, zero it once) after ~10 s instead of hanging the GPU.                              */
+#define KIN_PEER_HANDLE_BYTES 64
+int kin_peer_buffer_bytes(int n_params, int world);
+int kin_peer_buffer_create(int n_params, int world, void **buffer, unsigned char *ipc_handle /* [KIN_PEER_HANDLE_BYTES] */);
+int kin_peer_buffer_open(const unsigned char *ipc_handle, void **buffer);
+int kin_peer_buffer_close(void *buffer);
+int kin_peer_buffer_destroy(void *buffer);
+/* peer_buffers: HOST array of `world` device pointers (own buffer at index rank, the others from kin_peer_buffer_open). */
+int kin_peer_grad_push(const float *partials, int n_cta, int n_params, long long global_batch, void *const *peer_buffers, int rank, int world,
+                       unsigned epoch, void *stream);
+int kin_peer_grad_gather(const void *local_buffer, int n_params, int world, unsigned epoch, float *grad, float *stats, int *timed_out, void *stream);
 
 #ifdef __cplusplus
 }

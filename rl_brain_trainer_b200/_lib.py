@@ -110,6 +110,13 @@ def lib() -> ctypes.CDLL:
     L.kin_ppo_adv_stats.argtypes = [vp, vp, i32, i32, i32, vp, vp]
     L.kin_ppo_collect.argtypes = [vp, vp, i32, i32, i32, vp, vp, i32, i32, u64, u32, u64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp]
     L.kin_ppo_bootstrap_list.argtypes = [vp, i32, vp, vp, vp, i32, vp, f32, vp]
+    L.kin_peer_buffer_bytes.argtypes = [i32, i32]
+    L.kin_peer_buffer_create.argtypes = [i32, i32, ctypes.POINTER(vp), ctypes.c_char_p]
+    L.kin_peer_buffer_open.argtypes = [ctypes.c_char_p, ctypes.POINTER(vp)]
+    L.kin_peer_buffer_close.argtypes = [vp]
+    L.kin_peer_buffer_destroy.argtypes = [vp]
+    L.kin_peer_grad_push.argtypes = [vp, i32, i32, i64, ctypes.POINTER(vp), i32, i32, u32, vp]
+    L.kin_peer_grad_gather.argtypes = [vp, i32, i32, u32, vp, vp, vp, vp]
     for name in declared_functions():
         fn = getattr(L, name)  # raises AttributeError if the .so lacks a declared symbol
         if name not in ("kin_last_error_string",):

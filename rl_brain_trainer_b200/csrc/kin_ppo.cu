@@ -714,7 +714,7 @@ extern "C" int kin_ppo_gae(const float* reward, const float* value, const uint8_
 extern "C" int kin_ppo_grad(const float* params, int in_dim, const KinPpoHyper* hp, const float* obs, const float* action, const float* old_logp,
                             const float* advantage, const float* returns, const double* tile_sums, const int* tile_ids, int n_tiles,
                             long long global_batch, float* partials, int grid, float* grad, float* stats, const float* adv_stats, void* stream) {
-    if (!params || !hp || !obs || !action || !old_logp || !advantage || !returns || (!tile_sums && !adv_stats) || !tile_ids || !partials || !grad || n_tiles <= 0 ||
+    if (!params || !hp || !obs || !action || !old_logp || !advantage || !returns || (!tile_sums && !adv_stats) || !tile_ids || !partials || n_tiles <= 0 ||
         grid <= 0 || global_batch <= 0)
         return kin_fail(KIN_ERR_INVALID_ARG, "kin_ppo_grad: bad arguments");
     if (in_dim != 56) return kin_fail(KIN_ERR_UNSUPPORTED, "kin_ppo_grad: in_dim must be 56 (the route policy's 80-input update is not built yet)");
@@ -726,7 +726,7 @@ extern "C" int kin_ppo_grad(const float* params, int in_dim, const KinPpoHyper* 
     const int g = grid < n_tiles ? grid : n_tiles;
     const float inv = 1.0f / (float)global_batch;
     kin_ppo_grad_kernel<56><<<g, PPO_THREADS, smem, st>>>(params, *hp, obs, action, old_logp, advantage, returns, tile_sums, tile_ids, n_tiles, inv, partials, adv_stats);
-    kin_ppo_reduce_launch(partials, g, P, grad, stats, inv, st);
+    if (grad) kin_ppo_reduce_launch(partials, g, P, grad, stats, inv, st);      // grad == NULL: the caller reduces `partials` (kin_peer_grad_push)
     e = cudaGetLastError();
     return e == cudaSuccess ? KIN_OK : kin_fail_cuda(e, "kin_ppo_grad");
 }

@@ -93,6 +93,7 @@ struct __align__(1024) TcGradSmem {
     float ls[8];
     float inv_sig[8];
     float scal[32];                      // 0 adv mean, 1 1/(std+eps), 2..5 statistics, 8..14 d log_std, 16..23 d output bias
+    float red[4][20];                    // per-warp partial sums of the loss-side reductions (folded in a fixed order: deterministic)
     unsigned long long mbar[6];          // 0 main (chain GEMMs), 1 wg (trailing dW0 batch), 2/3 staged inputs (X image + loss inputs), 4 weights, 5 ride
     unsigned tmem_base;
 };
@@ -503,7 +504,7 @@ kin_ppo_grad_tc_kernel(const float* __restrict__ params, KinPpoHyper hp, const f
             TRACE_MARK(11);
         }
         if (!forward_only) {
-            // log_std / output-bias gradients and statistics: warp shuffle, then shared atomics
+            // log_std / output-bias gradients and statistics: warp shuffle, then one partial row per warp
 #pragma unroll
             for (int d = 0; d < 7; ++d) {
 #pragma unroll
@@ -517,13 +518,14 @@ kin_ppo_grad_tc_kernel(const float* __restrict__ params, KinPpoHyper hp, const f
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) st[q] += __shfl_xor_sync(0xffffffffu, st[q], off);
             }
-            if (lane == 0 && half == 0) {
+            if (lane == 0 && half == 0) {       // warps 0..3 own the loss threads
+                float* r = S.red[warp];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) atomicAdd(&S.scal[2 + q], st[q]);
+                for (int q = 0; q < 4; ++q) r[q] = st[q];
 #pragma unroll
                 for (int d = 0; d < 7; ++d) {
-                    atomicAdd(&S.scal[8 + d], dls[d]);
-                    atomicAdd(&S.scal[16 + d], dbo[d]);
+                    r[4 + d] = dls[d];
+                    r[11 + d] = dbo[d];
                 }
             }
         }
@@ -533,6 +535,11 @@ kin_ppo_grad_tc_kernel(const float* __restrict__ params, KinPpoHyper hp, const f
     if (!forward_only) {
         if (it > 0) mbar_wait(mb_wg, (unsigned)(it - 1) & 1u);
         fence_after();
+        __syncthreads();
+        if (tid < 18) {      // statistics -> scal[2..5], d log_std -> scal[8..14], d output bias -> scal[16..22]
+            const float a = ((S.red[0][tid] + S.red[1][tid]) + S.red[2][tid]) + S.red[3][tid];
+            S.scal[tid < 4 ? 2 + tid : (tid < 11 ? 8 + tid - 4 : 16 + tid - 11)] = a;
+        }
         __syncthreads();
         // ---- accumulators (M = 64: row m lives in lane m % 16 + 32 * (m / 16)) -> this CTA's slice of the partial gradient ----------
         float* out = partials + (size_t)blockIdx.x * (P + KIN_PPO_STATS + 8);
@@ -603,7 +610,7 @@ extern "C" int kin_ppo_grad_tc(const float* params, int in_dim, const KinPpoHype
     const float* obs = static_cast<const float*>(obs_any);
     if (!params || !hp || !obs || !action || !tile_ids || n_tiles <= 0 || grid <= 0)
         return kin_fail(KIN_ERR_INVALID_ARG, "kin_ppo_grad_tc: bad arguments");
-    if (!forward_only && (!old_logp || !advantage || !returns || (!tile_sums && !adv_stats) || !partials || !grad || global_batch <= 0))
+    if (!forward_only && (!old_logp || !advantage || !returns || (!tile_sums && !adv_stats) || !partials || global_batch <= 0))
         return kin_fail(KIN_ERR_INVALID_ARG, "kin_ppo_grad_tc: the gradient pass needs old_logp, advantage, returns, tile_sums, partials and grad");
     if (forward_only && !logp_out && !value_out) return kin_fail(KIN_ERR_INVALID_ARG, "kin_ppo_grad_tc: forward_only without an output");
     if (in_dim != 56) return kin_fail(KIN_ERR_UNSUPPORTED, "kin_ppo_grad_tc: in_dim must be 56");
@@ -639,7 +646,7 @@ extern "C" int kin_ppo_grad_tc(const float* params, int in_dim, const KinPpoHype
         kin_ppo_grad_tc_kernel<false><<<dg, TCG_THREADS, smem, st>>>(params, *hp, obs, action, old_logp, advantage, returns, tile_sums, tile_ids, n_pairs,
                                                                      inv, partials, logp_out, value_out, forward_only, net_base, adv_stats,
                                                                     static_cast<const unsigned char*>(weight_image));
-    if (!forward_only) kin_ppo_reduce_launch(partials, g, P, grad, stats, inv, st);
+    if (!forward_only && grad) kin_ppo_reduce_launch(partials, g, P, grad, stats, inv, st);      // grad == NULL: the caller reduces `partials` (kin_peer_grad_push)
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? KIN_OK : kin_fail_cuda(e, "kin_ppo_grad_tc");
 }

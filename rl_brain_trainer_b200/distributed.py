@@ -6,6 +6,10 @@
 
 All helpers take plain tensors and an optional process group, so they run under NCCL (one rank per GPU) and under gloo on
 CPU tensors (tests/test_distributed_gloo.py, world_size 2).
+
+``PeerGradExchange`` is the NVLink peer-memory form of the training all-reduce (``csrc/kin_peer.cu``): the reduction kernel pushes
+the rank's gradient straight into every peer's receive buffer and a gather kernel sums the slots in rank order -- two small
+kernels per minibatch instead of a latency-bound NCCL call; ``torch.distributed`` only carries the one-off IPC handle exchange.
 """
 
 from __future__ import annotations
@@ -56,6 +60,74 @@ def reduce_eval_stats(success: torch.Tensor, final_pos: torch.Tensor, final_ori:
     n = max(float(v[1]), 1.0)
     return {"episodes": float(v[1]), "success_rate": float(v[0]) / n, "mean_final_position_error": float(v[2]) / n,
             "mean_final_orientation_error": float(v[3]) / n, "env_steps": float(v[4])}
+
+
+class PeerGradExchange:
+    """Per-minibatch gradient all-reduce (sum) over CUDA-IPC peer buffers of the GPUs of one node (``kin_peer_*`` in the C ABI).
+
+    ``push(partials, n_cta, global_batch)`` reduces this rank's per-CTA rows and stores them into every rank's buffer;
+    ``gather(grad, stats)`` waits on the device for all ranks and writes the rank-ordered sum (bitwise identical everywhere).
+    Both only enqueue kernels on the current stream.  ``check()`` raises if a peer never arrived (device-side timeout).
+    """
+
+    def __init__(self, n_params: int, device: torch.device, group: Any = None) -> None:
+        import ctypes
+
+        from . import _lib
+
+        self._L, self._check = _lib.lib(), _lib.check
+        self.rank, self.world = world(group)
+        if self.world > 8:
+            raise _lib.KinError("PeerGradExchange: at most 8 ranks (the GPUs of one NVSwitch node)")
+        self.P, self.device = int(n_params), torch.device(device)
+        self.epoch = 0
+        with torch.cuda.device(self.device):
+            own = ctypes.c_void_p()
+            handle = ctypes.create_string_buffer(_lib.define("KIN_PEER_HANDLE_BYTES"))
+            self._check(self._L.kin_peer_buffer_create(self.P, self.world, ctypes.byref(own), handle))
+            self._own = own.value
+            handles: list[Any] = [None] * self.world
+            if self.world > 1:
+                dist.all_gather_object(handles, bytes(handle.raw), group=group)
+            self._bufs = (ctypes.c_void_p * self.world)()
+            self._opened: list[int] = []
+            for r in range(self.world):
+                if r == self.rank:
+                    self._bufs[r] = self._own
+                else:
+                    ptr = ctypes.c_void_p()
+                    self._check(self._L.kin_peer_buffer_open(handles[r], ctypes.byref(ptr)))
+                    self._bufs[r] = ptr.value
+                    self._opened.append(ptr.value)
+            self.timed_out = torch.zeros(1, dtype=torch.int32, device=self.device)
+            torch.cuda.synchronize(self.device)
+        if self.world > 1:
+            dist.barrier(group=group)        # every buffer exists and is zeroed before the first push can reach it
+
+    def push(self, partials: torch.Tensor, n_cta: int, global_batch: int) -> None:
+        self.epoch += 1
+        self._check(self._L.kin_peer_grad_push(partials.data_ptr(), int(n_cta), self.P, int(global_batch), self._bufs, self.rank, self.world,
+                                               self.epoch, torch.cuda.current_stream(self.device).cuda_stream))
+
+    def gather(self, grad: torch.Tensor, stats: torch.Tensor | None) -> None:
+        self._check(self._L.kin_peer_grad_gather(self._own, self.P, self.world, self.epoch, grad.data_ptr(),
+                                                 None if stats is None else stats.data_ptr(), self.timed_out.data_ptr(),
+                                                 torch.cuda.current_stream(self.device).cuda_stream))
+
+    def check(self) -> None:
+        if int(self.timed_out.item()):
+            from . import _lib
+
+            raise _lib.KinError("PeerGradExchange: a peer rank never delivered its gradient (device-side wait timed out)")
+
+    def close(self) -> None:
+        if getattr(self, "_own", None) is None:
+            return
+        torch.cuda.synchronize(self.device)
+        for ptr in self._opened:
+            self._L.kin_peer_buffer_close(ptr)
+        self._L.kin_peer_buffer_destroy(self._own)
+        self._own, self._opened = None, []
 
 
 class CurriculumTracker:

@@ -18,7 +18,7 @@ import torch
 
 from . import _lib
 from .config import Phase1EnvConfig
-from .distributed import CurriculumTracker, allreduce_sum_, world
+from .distributed import CurriculumTracker, PeerGradExchange, allreduce_sum_, world
 from .env import BatchedArmKinematicEnv, _D
 from .policy import KEYS, PolicyWeights
 
@@ -105,7 +105,8 @@ class PPOTrainer:
 
     def __init__(self, config: Phase1EnvConfig, policy: PolicyWeights, *, num_envs: int, hyper: PPOHyper, device: str | torch.device = "cuda",
                  seed: int = 0, stage_index: int = 0, process_group: Any = None, grad_ctas: int | None = None,
-                 update_variant: str = "tc", collect_variant: str | None = None, handoff_states: torch.Tensor | None = None) -> None:
+                 update_variant: str = "tc", collect_variant: str | None = None, handoff_states: torch.Tensor | None = None,
+                 grad_exchange: str = "nccl") -> None:
         if not torch.cuda.is_available():
             raise _lib.KinError("PPOTrainer needs a CUDA device; there is no CPU fallback")
         if policy.in_dim != 56:
@@ -115,6 +116,8 @@ class PPOTrainer:
             raise ValueError(f"num_envs must be a multiple of {tile}")
         if update_variant not in ("tc", "fp32"):
             raise ValueError("update_variant must be 'tc' (tcgen05 bf16 GEMMs, fp32 accumulate) or 'fp32' (strict FP32-pipe kernel)")
+        if grad_exchange not in ("nccl", "peer"):
+            raise ValueError("grad_exchange must be 'nccl' (torch.distributed all-reduce) or 'peer' (NVLink peer-memory push, one node)")
         self.update_variant = update_variant
         # "fused": one kin_ppo_collect launch per rollout (tensor-core policy, bf16 observation images, needs the tc update);
         # "steps": one policy / env-step / bootstrap launch per time step (strict fp32, fp32 observation buffer)
@@ -152,6 +155,8 @@ class PPOTrainer:
             props = torch.cuda.get_device_properties(self.device)
             self.grad_ctas = int(grad_ctas or props.multi_processor_count)
             self.partials = torch.zeros((self.grad_ctas, self.P + _D("KIN_PPO_STATS") + 8), dtype=torch.float32, device=self.device)
+            # several ranks: the per-minibatch gradient sum goes through NCCL or through NVLink peer buffers (distributed.PeerGradExchange)
+            self.peer = PeerGradExchange(self.P, self.device, process_group) if grad_exchange == "peer" else None
             self.env = BatchedArmKinematicEnv(config, self.N, self.device, auto_reset=True, seed=self.seed, host_sampler=False, with_aux=False)
             self.env.set_curriculum_stage(stage_index)
             if handoff_states is not None:       # Finisher training: dock resets replay Approach handoff states (handoff.py)
@@ -276,13 +281,17 @@ class PPOTrainer:
             _lib.check(self._L.kin_ppo_grad_tc(self.params.data_ptr(), 56, ctypes.byref(hp), (self.obs_img if img else self.obs_buf).data_ptr(),
                                                self.act_buf.data_ptr(), self.logp_buf.data_ptr(), self.adv_buf.data_ptr(), self.ret_buf.data_ptr(),
                                                self.tile_sums.data_ptr(), tile_ptr, n_tiles, global_batch, self.partials.data_ptr(),
-                                               self.grad_ctas, self.grad.data_ptr(), self.stats.data_ptr(), None, None, 0, int(img), adv_ptr,
-                                               self.weight_image.data_ptr(), stream))
+                                               self.grad_ctas, None if self.peer else self.grad.data_ptr(), self.stats.data_ptr(), None, None, 0,
+                                               int(img), adv_ptr, self.weight_image.data_ptr(), stream))
+            if self.peer:
+                self.peer.push(self.partials, min(self.grad_ctas, n_tiles // 2), global_batch)
             return
         _lib.check(self._L.kin_ppo_grad(self.params.data_ptr(), 56, ctypes.byref(hp), self.obs_buf.data_ptr(), self.act_buf.data_ptr(),
                                         self.logp_buf.data_ptr(), self.adv_buf.data_ptr(), self.ret_buf.data_ptr(), self.tile_sums.data_ptr(),
                                         tile_ptr, n_tiles, global_batch, self.partials.data_ptr(), self.grad_ctas,
-                                        self.grad.data_ptr(), self.stats.data_ptr(), adv_ptr, stream))
+                                        None if self.peer else self.grad.data_ptr(), self.stats.data_ptr(), adv_ptr, stream))
+        if self.peer:
+            self.peer.push(self.partials, min(self.grad_ctas, n_tiles), global_batch)
 
     def minibatch_grad(self, tile_ids: torch.Tensor) -> None:
         """Gradient of one minibatch (sum over local samples, already divided by the GLOBAL minibatch size) into ``self.grad``."""
@@ -302,7 +311,9 @@ class PPOTrainer:
 
     def apply_update(self) -> None:
         """All-reduce the gradient (sum over ranks), clip by global norm, Adam step -- identical on every rank."""
-        if self.world > 1:
+        if self.peer:
+            self.peer.gather(self.grad, self.stats)                        # waits for every rank's push, rank-ordered sum
+        elif self.world > 1:
             allreduce_sum_(self._gradstats[: self.P + 5], self.group)      # gradient + the five loss statistics
         self.update_count += 1
         hp = getattr(self, "_c_hyper", None) or self.hp.c()
@@ -337,6 +348,8 @@ class PPOTrainer:
                     self._grad_launch(perm.data_ptr() + 4 * m * tiles_per_mb, tiles_per_mb, adv.data_ptr() + 8 * m)
                     self.apply_update()
             a = self.stats_accum.cpu().numpy().astype(np.float64)
+            if self.peer:
+                self.peer.check()
         n_mb = max(int(round(a[7])), 1)
         a = a / n_mb
         return {"policy_loss": float(a[0]), "value_loss": float(a[1]), "entropy": float(a[2]), "approx_kl": float(a[3]),

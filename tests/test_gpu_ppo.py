@@ -287,6 +287,27 @@ def test_trainer_runs_and_improves_value_fit(variant):
     assert torch.equal(tr2.params, q0)
 
 
+@pytest.mark.parametrize("variant", ["tc", "fp32"])
+def test_peer_gradient_exchange_single_rank_is_the_plain_reduction(variant):
+    """The NVLink peer-memory exchange (kin_peer_grad_push / kin_peer_grad_gather, csrc/kin_peer.cu) with one rank pushes into its own
+    buffer: the update must be bitwise the one of the in-kernel reduction (the N-rank sum is checked by tools/peer_check.py)."""
+    from rl_brain_trainer_b200 import ppo
+
+    cfg = env_config("approach_dynamic_scale_big")
+    hp = ppo.PPOHyper(learning_rate=1e-3, n_steps=16, batch_size=2048, n_epochs=2, gamma=0.98, clip_range=0.2)
+    params = {}
+    for ex in ("nccl", "peer"):
+        tr = ppo.PPOTrainer(cfg, ppo.random_policy(56, seed=1, log_std_init=-1.0, device="cuda"), num_envs=512, hyper=hp, seed=3, update_variant=variant,
+                            grad_exchange=ex)
+        assert (tr.peer is not None) == (ex == "peer")
+        tr.learn(2)
+        params[ex] = tr.params.clone()
+        if tr.peer:
+            assert tr.peer.epoch == 2 * 2 * (512 * 16 // 2048)
+            tr.peer.close()
+    assert torch.equal(params["nccl"], params["peer"])
+
+
 @pytest.mark.parametrize("tiles_per_cta,num_envs,trained", [(1, 256, False), (2, 512, False), (4, 640, True), (2, 384, "dock")])
 def test_fused_collection_replays_through_the_step_kernel(tiles_per_cta, num_envs, trained):
     """kin_ppo_collect (one launch per rollout, tensor-core policy) against the per-step kernels: replaying its recorded actions

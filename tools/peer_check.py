@@ -1,0 +1,45 @@
+"""Multi-GPU check of the NVLink peer-memory gradient exchange against the NCCL all-reduce.
+
+  torchrun --nproc-per-node 2 tools/peer_check.py
+
+Two trainers per rank from the same seeds, one per exchange; after two collect + update iterations the parameters must agree to
+float rounding (the two exchanges add the ranks in different orders) and the peer path's parameters must be bitwise identical
+on every rank.  Prints one JSON line on rank 0.
+"""
+import json, os, sys
+from pathlib import Path
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+import torch
+import torch.distributed as dist
+
+from rl_brain_trainer_b200 import config as kcfg, ppo
+
+rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+os.environ["NCCL_DEBUG"] = "WARN"
+dist.init_process_group("nccl", device_id=dev)
+cfg = kcfg.load_preset("approach_dynamic_scale_big")
+N, T = 4096, 32
+hp = ppo.PPOHyper(learning_rate=3e-4, n_steps=T, batch_size=N * T // 4, n_epochs=2, gamma=0.995, gae_lambda=0.95, clip_range=0.1, ent_coef=0.0003)
+out = {}
+params = {}
+for ex in ("nccl", "peer"):
+    pol = ppo.random_policy(56, seed=0, log_std_init=-1.0, device=dev)
+    tr = ppo.PPOTrainer(cfg, pol, num_envs=N, hyper=hp, device=dev, seed=1, stage_index=10, update_variant="tc", grad_exchange=ex)
+    for _ in range(2):
+        tr.collect()
+        u = tr.update()
+    torch.cuda.synchronize(dev)
+    params[ex] = tr.params.clone()
+    out[ex] = {"approx_kl": u["approx_kl"], "grad_norm": u["grad_norm"], "value_loss": u["value_loss"]}
+    if tr.peer:
+        tr.peer.close()
+rel = float((params["peer"] - params["nccl"]).norm() / params["nccl"].norm())
+gathered = [torch.zeros_like(params["peer"]) for _ in range(world)]
+dist.all_gather(gathered, params["peer"])
+identical = all(bool(torch.equal(gathered[0], g)) for g in gathered)
+if rank == 0:
+    print(json.dumps({"world": world, "peer_vs_nccl_rel_diff": rel, "peer_params_bitwise_identical_across_ranks": identical, **out}))
+dist.destroy_process_group()
+assert rel < 1e-5 and identical

@@ -216,9 +216,10 @@ def measure_step_kernel(torch, device, pk, n_envs: int = 1 << 21, launches: int 
             "note": "working set %.0f MB per launch (> L2), CUDA events on the launching stream" % (STEP_BYTES_APPROACH * n_envs / 1e6)}
 
 
-def measure_training(torch, dist, device, world: int, envs: int = 65536, n_steps: int = 128, iters: int = 2) -> dict:
+def measure_training(torch, dist, device, world: int, envs: int = 65536, n_steps: int = 128, iters: int = 2, grad_exchange: str = "peer") -> dict:
     """BASELINE config 5: Stage-10 stress-shell PPO (fused collection K4 + tensor-core update K3-TC, 8 epochs x 16 minibatches,
-    NCCL gradient all-reduce per minibatch when world > 1).  CUDA events, max over ranks; whole-job env-steps/s."""
+    one gradient sum over ranks per minibatch when world > 1: NVLink peer-memory push (csrc/kin_peer.cu) or NCCL all-reduce).
+    CUDA events, max over ranks; whole-job env-steps/s."""
     from rl_brain_trainer_b200 import config as kcfg, ppo
 
     cfg = kcfg.load_preset("approach_dynamic_scale_big")
@@ -226,7 +227,7 @@ def measure_training(torch, dist, device, world: int, envs: int = 65536, n_steps
     S = envs * n_steps
     hp = ppo.PPOHyper(learning_rate=4e-6, n_steps=n_steps, batch_size=S // 16, n_epochs=8, gamma=0.995, gae_lambda=0.95, clip_range=0.1, ent_coef=0.0003)
     tr = ppo.PPOTrainer(cfg, pol, num_envs=envs, hyper=hp, device=device, seed=1, stage_index=10,
-                        process_group=dist.group.WORLD if world > 1 else None)
+                        process_group=dist.group.WORLD if world > 1 else None, grad_exchange=grad_exchange if world > 1 else "nccl")
     tr.collect()
     tr.update()
     torch.cuda.synchronize(device)
@@ -250,7 +251,7 @@ def measure_training(torch, dist, device, world: int, envs: int = 65536, n_steps
     return {"workload": "stage10_ppo_train", "envs_per_gpu": envs, "n_steps": n_steps, "epochs": 8, "minibatches_per_epoch": 16, "iters": iters,
             "rollout_env_steps_per_s": steps / float(t[0]), "update_env_steps_per_s": steps / float(t[1]),
             "e2e_env_steps_per_s": steps / float(t[0] + t[1]), "collect": "kin_ppo_collect (fused, tcgen05 bf16)", "update": "kin_ppo_grad_tc (tcgen05 bf16)",
-            "approx_kl": stats["approx_kl"], "value_loss": stats["value_loss"]}
+            "grad_exchange": (grad_exchange if world > 1 else "none"), "approx_kl": stats["approx_kl"], "value_loss": stats["value_loss"]}
 
 
 def main() -> None:
@@ -263,6 +264,7 @@ def main() -> None:
     ap.add_argument("--variant", default=os.environ.get("KIN_ROLLOUT_VARIANT", "auto"), choices=["auto", "ffma", "tc"])
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-step-kernel", action="store_true")
+    ap.add_argument("--grad-exchange", default="peer", choices=["peer", "nccl"], help="training leg, N > 1: gradient sum over NVLink peer buffers or NCCL")
     ap.add_argument("--skip-train", action="store_true", help="skip the BASELINE config-5 leg (Stage-10 PPO training, extra key `train`)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -383,7 +385,7 @@ def main() -> None:
     if not args.skip_train:
         del flush
         torch.cuda.empty_cache()
-        train = measure_training(torch, dist, device, world)
+        train = measure_training(torch, dist, device, world, grad_exchange=args.grad_exchange)
 
     step_roof = None
     cpu_base = None

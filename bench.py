@@ -43,7 +43,7 @@ SUITE_SEED = 700001 + STAGE * 1009
 STEP_BYTES_APPROACH = 532
 # measured DRAM traffic per launch (ncu --set full captures committed under profiles/): read + write bytes
 NCU_TRAFFIC_STEP_KERNEL = 369_145_856 + 682_055_168     # kin_step_kernel<approach>, 2 097 152 envs: 1 051 MB vs 1 116 MB algorithmic
-NCU_TRAFFIC_ROLLOUT_TC = 4_632_832 + 432_384            # kin_rollout_tc_kernel, 65 536 episodes: inputs + result rows only
+NCU_TRAFFIC_ROLLOUT_TC = 4_509_696 + 158_464            # kin_rollout_tc_kernel, 65 536 episodes: inputs + result rows only
 ACTOR_FLOPS = 2 * (56 * 64 + 64 * 64 + 64 * 7)   # 16256
 ENV_FLOPS = 1800
 
@@ -419,7 +419,7 @@ def main() -> None:
             roof = {"kernel": "kin_rollout_tc_kernel", "bound": "tensor", "achieved": flops / t_launch / 1e12, "peak": peak_tf,
                     "unit": "TFLOP/s", "frac": flops / t_launch / 1e12 / peak_tf,
                     "traffic": NCU_TRAFFIC_ROLLOUT_TC if n == EPISODES_PER_GPU else None,
-                    "traffic_source": "dram bytes per launch, profiles/r1_rollout_tc_raw.csv (ncu --set full, 65 536 episodes)", "peak_source": pk["source"],
+                    "traffic_source": "dram bytes per launch, profiles/r1_rollout_tc_v2_raw.csv (ncu --set full, 65 536 episodes)", "peak_source": pk["source"],
                     "note": "actor MLP 16,256 FLOP/env-step on tcgen05 kind::tf32; peak = measured sustained bf16 / 2"}
         else:
             fp32_peak = 148 * 128 * 2 * pk["sm_max_mhz"] * 1e6 / 1e12

@@ -596,8 +596,23 @@ kin_ppo_adam_kernel(float* __restrict__ params, const float* __restrict__ grad, 
                     unsigned short* __restrict__ wimg, int in_dim) {
     __shared__ float red[32];
     __shared__ float coef;
+    // this thread's own parameter: fetch its optimiser state now, so the loads fly while the norm is being reduced
+    const int own = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool has_own = own < P && gridDim.x * blockDim.x >= P;      // the usual launch: one parameter per thread
+    float own_m = 0.0f, own_v = 0.0f, own_p = 0.0f;
+    if (has_own) { own_m = m[own]; own_v = v[own]; own_p = params[own]; }
+    // sum of squares in a fixed order; batches of 8 independent loads (the trip count is a runtime value: unroll by hand)
     float ss = 0.0f;
-    for (int p = threadIdx.x; p < P; p += blockDim.x) ss = fmaf(grad[p], grad[p], ss);
+    for (int p0 = threadIdx.x; p0 < P; p0 += 8 * blockDim.x) {
+        float g[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int p = p0 + k * blockDim.x;
+            g[k] = p < P ? __ldcg(grad + p) : 0.0f;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) ss = fmaf(g[k], g[k], ss);
+    }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
@@ -622,13 +637,14 @@ kin_ppo_adam_kernel(float* __restrict__ params, const float* __restrict__ grad, 
     __syncthreads();
     const float cf = coef;
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x) {
-        const float g = grad[p] * cf;
-        const float mm = fmaf(hp.adam_beta1, m[p], (1.0f - hp.adam_beta1) * g);
-        const float vv = fmaf(hp.adam_beta2, v[p], (1.0f - hp.adam_beta2) * g * g);
+        const float g = __ldcg(grad + p) * cf;
+        const float m0 = has_own ? own_m : m[p], v0 = has_own ? own_v : v[p];
+        const float mm = fmaf(hp.adam_beta1, m0, (1.0f - hp.adam_beta1) * g);
+        const float vv = fmaf(hp.adam_beta2, v0, (1.0f - hp.adam_beta2) * g * g);
         m[p] = mm;
         v[p] = vv;
         const float denom = sqrtf(vv) / sqrtf(bc2) + hp.adam_eps;
-        const float np = params[p] - (hp.learning_rate / bc1) * (mm / denom);
+        const float np = (has_own ? own_p : params[p]) - (hp.learning_rate / bc1) * (mm / denom);
         params[p] = np;
         if (wimg) {      // keep the bf16 operand image of the weights in step with the parameters
             const int off = wimg_offset(ppo_offsets(in_dim), in_dim, p);

@@ -11,206 +11,10 @@
 // route/route_observation.py:31-61, eval/eval_route_curriculum.py:55-136,188-218 (paths under kinematic_phase1/).
 #include "kin_internal.h"
 #include "kin_mlp.cuh"
+#include "kin_route_core.cuh"
 #include "kin_state.cuh"
 
 namespace kin {
-
-constexpr int ROBS = KIN_ROUTE_OBS_DIM;
-constexpr int ROBS_TILE_FLOATS = WARP * ROBS;   // 2560 floats = 10 240 B per warp
-constexpr int RT_THREADS = 128;
-constexpr int RT_WARPS = RT_THREADS / WARP;
-constexpr int ROUTE_MAX_SMEM_WP = 1024;         // waypoint joint vectors staged in smem for the nearest-waypoint scan
-
-struct RouteView {
-    int n;
-    const float* q;      // [n][7]
-    const float* pose;   // [n][6]
-    const float* tan;    // [n][7] next_q_delta
-    const float* prog;   // [n]
-};
-
-struct RouteRegs {
-    int index, streak, last, completed;
-};
-
-struct RouteOut {
-    float reward, q_err, nearest;
-    unsigned flags;      // bit0 ready, bit1 regression, bit2 orientation hit, bit3 waypoint success
-    unsigned done;       // KIN_DONE_* with route semantics
-};
-
-__device__ __forceinline__ int wp_clamp(const RouteView& R, int i) { return min(max(i, 0), R.n - 1); }
-
-__device__ __forceinline__ float dist7(const float* a, const float* b) {
-    float acc = 0.0f;
-#pragma unroll
-    for (int i = 0; i < NJ; ++i) acc = fmaf(a[i] - b[i], a[i] - b[i], acc);
-    return sqrtf(acc);
-}
-
-// route/route_observation.py:31-61 spliced into the alphabetical 80-vector
-__device__ __forceinline__ void build_route_obs(const KinEnvParams& P, const RouteView& R, const EnvRegs& s, int route_index, const float* base56, float* o) {
-#pragma unroll
-    for (int k = 0; k < 47; ++k) o[k] = base56[k];
-    const float* goal = R.q + (size_t)wp_clamp(R, route_index) * NJ;
-    const float* tan = R.tan + (size_t)wp_clamp(R, max(route_index - 1, 0)) * NJ;
-#pragma unroll
-    for (int i = 0; i < NJ; ++i) {
-        const float g = __ldg(goal + i);
-        o[47 + i] = clampf((g - s.q[i]) * P.k_inv_delta_limit[i], -1.0f, 1.0f);
-        o[54 + i] = clampf(fmaf(2.0f * P.k_inv_span[i], g - P.joint_lower[i], -1.0f), -1.0f, 1.0f);
-        o[64 + i] = clampf(__ldg(tan + i) * P.k_inv_delta_limit[i], -1.0f, 1.0f);
-    }
-    const int max_idx = R.n - 1;
-    o[61] = clampf((float)route_index / (float)max(max_idx, 1), 0.0f, 1.0f);
-    o[62] = clampf(__ldg(R.prog + wp_clamp(R, route_index)) / fmaxf(__ldg(R.prog + max_idx), 1e-9f), 0.0f, 1.0f);
-    o[63] = 0.0f;
-    o[71] = base56[47]; o[72] = base56[48]; o[73] = base56[49];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) o[74 + k] = base56[50 + k];
-}
-
-__device__ __forceinline__ bool route_ready(const KinEnvParams& P, float qe, float pos, float ori, float an, float dqn) {
-    return qe <= P.rr_route_ready_q_threshold && pos <= P.rr_route_ready_pos_threshold_m && ori <= P.rr_route_ready_ori_threshold_rad &&
-           an <= P.rr_route_ready_action_threshold && dqn <= P.rr_route_ready_dq_threshold;
-}
-
-// One wrapper step.  q_table: waypoint joint vectors for the nearest scan (smem or global), nullptr -> scan skipped.
-template <bool SEQ, bool COMP>
-__device__ __forceinline__ void route_step_core(const KinEnvParams& P, const RouteView& R, const float* q_table, EnvRegs& s, RouteRegs& rr,
-                                                const float* action, bool reset_streak_on_advance, StepOut& so, RouteOut& ro, float* rc) {
-    float prev_q[NJ], prev_pa[NJ], prev_ee[6];
-#pragma unroll
-    for (int i = 0; i < NJ; ++i) { prev_q[i] = s.q[i]; prev_pa[i] = s.pa[i]; }
-#pragma unroll
-    for (int k = 0; k < 6; ++k) prev_ee[k] = s.ee[k];
-    const int target = rr.index;
-    float goal_q[NJ], goal_pose[6], tangent[NJ];
-    {
-        const float* gq = R.q + (size_t)wp_clamp(R, target) * NJ;
-        const float* gp = R.pose + (size_t)wp_clamp(R, target) * 6;
-        const float* tn = R.tan + (size_t)wp_clamp(R, max(target - 1, 0)) * NJ;
-#pragma unroll
-        for (int i = 0; i < NJ; ++i) { goal_q[i] = __ldg(gq + i); tangent[i] = __ldg(tn + i); }
-#pragma unroll
-        for (int k = 0; k < 6; ++k) goal_pose[k] = __ldg(gp + k);
-    }
-    step_core<KIN_MODE_APPROACH, false>(P, s, action, so, nullptr);
-
-    const float q_err = dist7(goal_q, s.q), prev_q_err = dist7(goal_q, prev_q);
-    // the wrapper norms the RAW action (route_env.py:140); a policy's action is already inside [-1, 1]
-    float an2 = 0.0f, msq = 0.0f, dmsq = 0.0f, dot = 0.0f, tn2 = 0.0f;
-#pragma unroll
-    for (int i = 0; i < NJ; ++i) {
-        an2 = fmaf(action[i], action[i], an2);
-        const float da = action[i] - prev_pa[i];
-        dmsq = fmaf(da, da, dmsq);
-        dot = fmaf(s.q[i] - prev_q[i], tangent[i], dot);
-        tn2 = fmaf(tangent[i], tangent[i], tn2);
-    }
-    msq = an2 * (1.0f / NJ);
-    dmsq *= (1.0f / NJ);
-    const float an = sqrtf(an2), dqn = so.dq_l2, tn = sqrtf(tn2);
-    float nearest = 0.0f;
-    if (q_table) {
-        nearest = CUDART_INF_F;
-        for (int w = 0; w < R.n; ++w) {
-            const float* qw = q_table + w * NJ;
-            float acc = 0.0f;
-#pragma unroll
-            for (int i = 0; i < NJ; ++i) acc = fmaf(qw[i] - s.q[i], qw[i] - s.q[i], acc);
-            nearest = fminf(nearest, acc);
-        }
-        nearest = sqrtf(nearest);
-    }
-    const bool ready = route_ready(P, q_err, so.pos, so.ori, an, dqn);
-    rr.streak = ready ? rr.streak + 1 : 0;
-
-    // route reward (reward_route.py:54-143): pose errors against the waypoint's FK pose, prev pose = cached FK(prev_q)
-    float pe[3], oe[3];
-    pose_error(prev_ee, goal_pose, pe, oe);
-    const float prev_pos = norm3(pe[0], pe[1], pe[2]), prev_ori = norm3(oe[0], oe[1], oe[2]);
-    pose_error(s.ee, goal_pose, pe, oe);
-    const float curr_pos = norm3(pe[0], pe[1], pe[2]), curr_ori = norm3(oe[0], oe[1], oe[2]);
-    const float tangent_progress = tn > 0.0f ? dot / fmaxf(tn, 1e-9f) : 0.0f;
-    const bool ready_r = route_ready(P, q_err, curr_pos, curr_ori, an, dqn);
-    float low_motion = 0.0f;
-    if (curr_pos <= 2.0f * P.rr_route_ready_pos_threshold_m && curr_ori <= 2.0f * P.rr_route_ready_ori_threshold_rad) {
-        const float a_clean = fmaxf(1.0f - an / fmaxf(P.rr_route_ready_action_threshold, 1e-9f), 0.0f);
-        const float d_clean = fmaxf(1.0f - dqn / fmaxf(P.rr_route_ready_dq_threshold, 1e-9f), 0.0f);
-        low_motion = P.rr_low_motion_near_waypoint_bonus * 0.5f * (a_clean + d_clean);
-    }
-    float c[13];
-    c[0] = P.rr_q_goal_progress_weight * (prev_q_err - q_err);
-    c[1] = P.rr_ee_position_progress_weight * (prev_pos - curr_pos);
-    c[2] = P.rr_ee_orientation_progress_weight * (prev_ori - curr_ori);
-    c[3] = P.rr_route_tangent_progress_weight * fmaxf(tangent_progress, 0.0f);
-    c[4] = ready_r ? P.rr_same_step_route_ready_bonus : 0.0f;
-    c[5] = (ready_r && rr.streak >= 1) ? P.rr_route_ready_dwell_bonus : 0.0f;
-    c[6] = low_motion;
-    c[7] = -P.rr_orientation_regression_penalty_weight * fmaxf(curr_ori - prev_ori, 0.0f);
-    c[8] = -P.rr_q_route_regression_penalty_weight * fmaxf(q_err - prev_q_err, 0.0f);
-    c[9] = -P.rr_off_route_penalty_weight * fmaxf(nearest, 0.0f);
-    float smooth = -P.rr_action_magnitude_weight * msq;
-    smooth += -P.rr_action_delta_weight * dmsq;
-    c[10] = smooth;
-    c[11] = -P.rr_dq_penalty_weight * dqn;
-    c[12] = (q_err >= prev_q_err && curr_pos >= prev_pos && curr_ori >= prev_ori) ? -P.rr_no_progress_penalty : 0.0f;
-    float reward = 0.0f;
-#pragma unroll
-    for (int k = 0; k < 13; ++k) reward += c[k];
-    if (COMP) {
-#pragma unroll
-        for (int k = 0; k < 13; ++k) rc[k] = c[k];
-        rc[13] = q_err; rc[14] = curr_pos; rc[15] = curr_ori; rc[16] = ready_r ? 1.0f : 0.0f;
-    }
-
-    const bool wp_success = ready && rr.streak >= P.term_success_dwell_steps;
-    const bool base_term = (so.done & KIN_DONE_TERMINATED) != 0;
-    const unsigned base_reason = (so.done >> KIN_DONE_REASON_SHIFT) & 3u;
-    bool success, terminated;
-    if (!SEQ) {
-        success = wp_success;
-        terminated = base_term;
-        if (base_term && base_reason == 1u && !success) terminated = false;
-        if (success && P.term_terminate_on_success) terminated = true;
-    } else {
-        success = false;
-        terminated = false;
-        if (wp_success) {
-            rr.completed += 1;
-            if (target >= rr.last) {
-                success = true;
-                terminated = true;
-            } else {   // _advance_target (route_sequence_env.py:253-257): swap the goal in place, re-capture entry metrics
-                rr.index = target + 1;
-                const float* gp = R.pose + (size_t)wp_clamp(R, rr.index) * 6;
-#pragma unroll
-                for (int k = 0; k < 6; ++k) s.goal[k] = __ldg(gp + k);
-                capture_entry_metrics(s);
-                if (reset_streak_on_advance) rr.streak = 0;
-            }
-        }
-        if (base_term && !terminated && base_reason != 1u) terminated = true;
-    }
-    ro.reward = reward;
-    ro.q_err = q_err;
-    ro.nearest = nearest;
-    ro.flags = (ready ? 1u : 0u) | (q_err > prev_q_err ? 2u : 0u) | (so.ori <= P.rr_route_ready_ori_threshold_rad ? 4u : 0u) | (wp_success ? 8u : 0u);
-    ro.done = (terminated ? KIN_DONE_TERMINATED : 0u) | (so.done & KIN_DONE_TRUNCATED) | (success ? KIN_DONE_SUCCESS : 0u) |
-              (so.done & (KIN_DONE_PRE_NEAR | KIN_DONE_NEAR)) | (base_reason << KIN_DONE_REASON_SHIFT);
-}
-
-__device__ __forceinline__ void stage_route_obs_row(float* tile, int lane, const float* o) {
-    float4* dst = reinterpret_cast<float4*>(tile + lane * ROBS);
-#pragma unroll
-    for (int k = 0; k < ROBS / 4; ++k) dst[k] = make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
-}
-
-__device__ __forceinline__ void load_q_table(float* dst, const RouteView& R, int tid, int nthreads) {
-    const int n = min(R.n, ROUTE_MAX_SMEM_WP) * NJ;
-    for (int i = tid; i < n; i += nthreads) dst[i] = __ldg(R.q + i);
-}
 
 template <bool SEQ, bool COMP>
 __global__ void __launch_bounds__(RT_THREADS)
@@ -393,8 +197,6 @@ kin_route_probe_kernel(const __grid_constant__ KinEnvParams P, RouteView R, DevP
     }
 }
 
-static bool route_ok(const KinRouteTable* r) { return r && r->n_waypoints >= 2 && r->n_waypoints <= 65535 && r->q_goal && r->pose6 && r->next_q_delta && r->progress_m; }
-static RouteView view_of(const KinRouteTable* r) { return RouteView{r->n_waypoints, r->q_goal, r->pose6, r->next_q_delta, r->progress_m}; }
 
 }  // namespace kin
 

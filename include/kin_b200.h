@@ -553,6 +553,12 @@ int kin_route_probe(void *handle, const KinRouteTable *host_route, const KinPoli
                     int start_index, int end_index, int n, int *prefix, uint32_t *success_bits, unsigned long long *env_steps,
                     void *stream);
 
+/* The same probe with the 80-input actor on tcgen05 (kind::tf32 operands, fp32 accumulation; csrc/kin_route_tc.cu): actions move by
+ * O(1e-3) against the strict-fp32 probe, which stays the parity path.  Same arguments and outputs.                              */
+int kin_route_probe_tc(void *handle, const KinRouteTable *host_route, const KinPolicyWeights *host_policy, const float *start_q,
+                    int start_index, int end_index, int n, int *prefix, uint32_t *success_bits, unsigned long long *env_steps,
+                    void *stream);
+
 /* ---------------------------------------------------------------------------------------------
  * PPO agent update (third-party arithmetic: stable-baselines3 2.8.0 PPO, call sites
  * kinematic_phase1/train_workspace_expansion.py:189-232; restated in DESIGN.md section 3 "K3").

@@ -119,7 +119,7 @@ __device__ __forceinline__ void tmem_ld8(unsigned taddr, float* v) {
 }
 
 // stage one policy's actor into the swizzled B-operand images (all threads of the CTA)
-__device__ void load_weights_tc(TcSmem& S, const DevPolicyTc& p, int tid, int nthreads) {
+__device__ __forceinline__ void load_weights_tc(TcSmem& S, const DevPolicyTc& p, int tid, int nthreads) {
     for (int i = tid; i < TC_HID * TC_K; i += nthreads) {
         const int n = i >> 6, k = i & 63;
         float v0 = k < KIN_OBS_DIM ? __ldg(p.w0 + n * KIN_OBS_DIM + k) : (k == KIN_OBS_DIM ? __ldg(p.b0 + n) : 0.0f);

@@ -351,14 +351,18 @@ class RoutePrefixCurriculum:
 
 def evaluate_sequential_route(route: RouteDataset, config: RouteEnvConfig, policy: PolicyWeights, *, n_replicas: int = 1, start_index: int = 1,
                               end_index: int | None = None, start_q_noise_std: float = 0.0, seed: int = 0,
-                              device: str | torch.device = "cuda") -> dict[str, Any]:
+                              device: str | torch.device = "cuda", variant: str = "fp32") -> dict[str, Any]:
     """``evaluate_sequential_route`` (eval_route_curriculum.py:188-246) for ``n_replicas`` independent chains in one launch.
+
+    ``variant``: "fp32" = strict-fp32 policy in the loop (the parity path), "tc" = the actor on tcgen05 tensor cores (TF32 operands).
 
     Replica 0 starts exactly at waypoint ``start_index - 1`` like the reference; the others add N(0, std) joint noise.
     Returns per-replica ``longest_success_prefix``, the success bitmask, the prefix histogram and env-step count.
     """
     if not torch.cuda.is_available():
         raise _lib.KinError("evaluate_sequential_route needs a CUDA device; there is no CPU fallback")
+    if variant not in ("fp32", "tc"):
+        raise ValueError("variant must be 'fp32' or 'tc'")
     device = torch.device(device)
     end = min(len(route) - 1, len(route) - 1 if end_index is None else int(end_index))
     m = end - start_index + 1
@@ -376,13 +380,14 @@ def evaluate_sequential_route(route: RouteDataset, config: RouteEnvConfig, polic
         prefix = torch.zeros(n_replicas, dtype=torch.int32, device=device)
         bits = torch.zeros((n_replicas, words), dtype=torch.int32, device=device)
         steps = torch.zeros(1, dtype=torch.int64, device=device)
-        _lib.check(_lib.lib().kin_route_probe(params.handle, ctypes.byref(table.c), ctypes.byref(policy.c), base.data_ptr(), int(start_index), end,
-                                              n_replicas, prefix.data_ptr(), bits.data_ptr(), steps.data_ptr(), _stream()))
+        probe = _lib.lib().kin_route_probe_tc if variant == "tc" else _lib.lib().kin_route_probe
+        _lib.check(probe(params.handle, ctypes.byref(table.c), ctypes.byref(policy.c), base.data_ptr(), int(start_index), end,
+                         n_replicas, prefix.data_ptr(), bits.data_ptr(), steps.data_ptr(), _stream()))
     hist = torch.bincount(prefix.long(), minlength=m + 1)
     p0 = int(prefix[0].item())
     return {
         "longest_success_prefix": prefix, "success_bits": bits, "prefix_histogram": hist, "env_steps": steps,
         "replica0_longest_success_prefix": p0,
         "replica0_cumulative_successful_route_distance_m": float(route.progress_m[min(p0, len(route) - 1)] - route.progress_m[0]),
-        "start_index": int(start_index), "end_index": int(end),
+        "start_index": int(start_index), "end_index": int(end), "variant": variant,
     }

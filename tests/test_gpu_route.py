@@ -143,6 +143,33 @@ def test_route_sequential_probe_matches_oracle():
     assert int(res["env_steps"].item()) >= 170 * 256 and res["longest_success_prefix"].shape == (256,)
 
 
+def test_route_probe_tensor_core_variant_tracks_the_strict_probe():
+    """kin_route_probe_tc (80-input actor on tcgen05, TF32 operands) against the strict-fp32 probe on the same replicas: the waypoint
+    success flags agree up to the O(1e-3) action differences of TF32 + tanh.approx, for full and partial tiles / several CTAs."""
+    from rl_brain_trainer_b200.policy import PolicyWeights
+    from rl_brain_trainer_b200.route import evaluate_sequential_route, synthetic_route
+
+    _, renv, _, _, _ = _setup()
+    pol = PolicyWeights.preset("route_prefix120", "cuda")
+    route = synthetic_route(483, seed=7)
+    for n in (1, 200, 20000):       # one partial tile; two tiles in one CTA; one CTA per SM with one tile each
+        kw = dict(n_replicas=n, start_index=1, end_index=40, start_q_noise_std=0.0008, seed=3)
+        a = evaluate_sequential_route(route, renv, pol, variant="fp32", **kw)
+        b = evaluate_sequential_route(route, renv, pol, variant="tc", **kw)
+        ba, bb = a["success_bits"].cpu().numpy().view(np.uint32), b["success_bits"].cpu().numpy().view(np.uint32)
+        flips = sum(bin(int(x)).count("1") for x in (ba ^ bb).reshape(-1))
+        assert flips <= 0.02 * n * 40 + 2, (n, flips)
+        pa, pb = a["longest_success_prefix"].float(), b["longest_success_prefix"].float()
+        assert abs(float(pa.mean()) - float(pb.mean())) <= 0.05 * 40 + 1
+        sa, sb = int(a["env_steps"].item()), int(b["env_steps"].item())
+        assert abs(sa - sb) <= 0.03 * sa
+        assert int(b["prefix_histogram"].sum()) == n
+    # results depend on the replica alone, not on the launch shape: replica 0 (no start noise) gives the same bits in every batch
+    one = evaluate_sequential_route(route, renv, pol, variant="tc", n_replicas=1, start_index=1, end_index=40)
+    many = evaluate_sequential_route(route, renv, pol, variant="tc", n_replicas=777, start_index=1, end_index=40, start_q_noise_std=0.0008, seed=9)
+    assert torch.equal(one["success_bits"][0], many["success_bits"][0])
+
+
 def test_sampled_route_reset_and_route_window():
     """reset() without an explicit waypoint draws from the batched device port of sample_route_reset; set_route_window narrows it."""
     from rl_brain_trainer_b200.route import BatchedRouteKinematicEnv, _reset_mode_ratios

@@ -106,7 +106,7 @@ else:
     pol = PolicyWeights.preset("route_prefix120", dev)
     n = a.replicas // world
     out, secs = timed(lambda: evaluate_sequential_route(route, renv, pol, n_replicas=n, start_index=1, end_index=a.end, start_q_noise_std=0.0008,
-                                                        seed=11 + rank, device=dev), a.iters)
+                                                        seed=11 + rank, device=dev, variant="tc" if a.variant == "tc" else "fp32"), a.iters)
     hist = out["prefix_histogram"].double()
     steps = out["env_steps"].double()
     allreduce_sum_(hist, group)
@@ -116,7 +116,8 @@ else:
             "waypoints_probed": a.end, "env_steps_per_s": float(steps) / secs, "s_per_pass": secs, "env_steps": float(steps),
             "mean_longest_success_prefix": float((hist * torch.arange(hist.numel(), device=dev)).sum() / hist.sum()),
             "full_prefix_fraction": float(hist[-1] / hist.sum()), "replica0_prefix": int(out["replica0_longest_success_prefix"]),
-            "rank0_prefix_min_max": [float(prefix.min()), float(prefix.max())], "route": "synthetic 483 waypoints (seed 7)"}
+            "rank0_prefix_min_max": [float(prefix.min()), float(prefix.max())], "route": "synthetic 483 waypoints (seed 7)",
+            "probe_variant": "tc" if a.variant == "tc" else "fp32"}
     if rank == 0 and a.oracle_sample > 0:
         from oracle import kin_oracle as ko
         w = {k: v for k, v in np.load(kcfg.PRESET_DIR / "policies" / "route_prefix120.npz").items()}

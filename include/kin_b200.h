@@ -635,7 +635,9 @@ int kin_ppo_adv_stats(const double *tile_sums, const int *tile_ids, int n_tiles_
  * obs_is_image != 0: obs is the rollout buffer kin_ppo_collect wrote -- one 16 KB bf16 operand image per 128 consecutive
  * samples -- and every pair (tile_ids[2j], tile_ids[2j+1]) must be (2m, 2m+1), i.e. one whole image.
  * weight_image (nullable): the bf16 operand image of params (kin_ppo_pack_weights / kin_ppo_adam keep it current); each CTA then
- * fetches its weights with bulk copies instead of converting them from fp32.                                               */
+ * fetches its weights with bulk copies instead of converting them from fp32.
+ * in_dim: 56 (Approach / Finisher policies) or 80 (the route policy of train_route_curriculum.py: obs [S,80] fp32 only, layer 1 runs
+ * over two K tiles and dW0 is an N = 96 GEMM; obs_is_image and weight_image must be 0 / NULL).                                  */
 int kin_ppo_grad_tc(const float *params, int in_dim, const KinPpoHyper *host_hyper, const void *obs, const float *action, const float *old_logp,
                     const float *advantage, const float *returns, const double *tile_sums, const int *tile_ids, int n_tiles,
                     long long global_batch, float *partials, int grid, float *grad, float *stats, float *logp_out, float *value_out,

@@ -706,11 +706,19 @@ extern "C" int kin_policy_act(const KinPolicyWeights* w, const float* obs, float
 extern "C" int kin_ppo_bootstrap(const KinPolicyWeights* w, const float* terminal_obs, const uint8_t* done, float* reward, float gamma, int n,
                                  void* stream) {
     if (!w || !w->vf_w0 || !terminal_obs || !done || !reward || n <= 0) return kin_fail(KIN_ERR_INVALID_ARG, "kin_ppo_bootstrap: bad arguments");
-    if (w->in_dim != 56) return kin_fail(KIN_ERR_UNSUPPORTED, "kin_ppo_bootstrap: in_dim must be 56");
-    const size_t smem = (size_t)(MlpSmem<56>::FLOATS + HID * 128) * sizeof(float);
-    cudaError_t e = cudaFuncSetAttribute(kin_ppo_bootstrap_kernel<56>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return kin_fail_cuda(e, "kin_ppo_bootstrap: smem attribute");
-    kin_ppo_bootstrap_kernel<56><<<(n + 127) / 128, 128, smem, (cudaStream_t)stream>>>(critic_w(w), terminal_obs, done, reward, gamma, n);
+    if (w->in_dim != 56 && w->in_dim != 80) return kin_fail(KIN_ERR_UNSUPPORTED, "kin_ppo_bootstrap: in_dim must be 56 or 80");
+    cudaError_t e;
+    if (w->in_dim == 56) {
+        const size_t smem = (size_t)(MlpSmem<56>::FLOATS + HID * 128) * sizeof(float);
+        e = cudaFuncSetAttribute(kin_ppo_bootstrap_kernel<56>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return kin_fail_cuda(e, "kin_ppo_bootstrap: smem attribute");
+        kin_ppo_bootstrap_kernel<56><<<(n + 127) / 128, 128, smem, (cudaStream_t)stream>>>(critic_w(w), terminal_obs, done, reward, gamma, n);
+    } else {       // the 80-input route policy
+        const size_t smem = (size_t)(MlpSmem<80>::FLOATS + HID * 128) * sizeof(float);
+        e = cudaFuncSetAttribute(kin_ppo_bootstrap_kernel<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return kin_fail_cuda(e, "kin_ppo_bootstrap: smem attribute");
+        kin_ppo_bootstrap_kernel<80><<<(n + 127) / 128, 128, smem, (cudaStream_t)stream>>>(critic_w(w), terminal_obs, done, reward, gamma, n);
+    }
     e = cudaGetLastError();
     return e == cudaSuccess ? KIN_OK : kin_fail_cuda(e, "kin_ppo_bootstrap");
 }

@@ -76,12 +76,15 @@ __device__ unsigned long long kin_ppo_trace_buf[4][16];
 #define TRACE_FLUSH(n)
 #endif
 
+// KT = K tiles of layer 1: 1 for the 56-input policies (K = 64), 2 for the 80-input route policy (K = 96: X[0] | X[1] are then the
+// two K tiles of ONE X operand, fp32 observations only -- there is no image / double buffering for that policy)
+template <int KT>
 struct __align__(1024) TcGradSmem {
     unsigned char X[2][TILE_BYTES];      // double-buffered in image mode (the next tile's image is prefetched by the TMA engine)
     unsigned char H2[TILE_BYTES];        // H2, later G2 = dL/dZ2
     unsigned char H1[TILE_BYTES];        // H1, later G1 = dL/dZ1
     unsigned char DO[TILE_BYTES];        // cols 0..7 dL/d(mean, value), col 8 = 1, rest 0.  MUST follow H1: [H1 | DO] is one MN-major operand
-    unsigned char W0[64 * 128];          // col 56 = b0
+    unsigned char W0[KT][64 * 128];      // col IN = b0
     unsigned char W1[64 * 128];
     unsigned char WO[16 * 128];          // actor: rows 0..6 = act_w; critic: row 7 = val_w
     float act[2][TCG_ROWS * 7];         // loss inputs of the tile, staged by the TMA engine next to the X image (double-buffered)
@@ -143,18 +146,20 @@ __device__ __forceinline__ void epilogue_store(unsigned char* tile, int row, int
 }
 
 // IMG: obs is the rollout buffer of bf16 operand images written by kin_ppo_collect (one 16 KB image per 128 consecutive samples)
-template <bool IMG>
-__global__ void __launch_bounds__(TCG_THREADS, 2)
+template <bool IMG, int IN>
+__global__ void __launch_bounds__(TCG_THREADS, IN == 56 ? 2 : 1)
 kin_ppo_grad_tc_kernel(const float* __restrict__ params, KinPpoHyper hp, const float* __restrict__ obs, const float* __restrict__ action,
                        const float* __restrict__ old_logp, const float* __restrict__ advantage, const float* __restrict__ returns,
                        const double* __restrict__ tile_sums, const int* __restrict__ tile_ids, int n_pairs, float inv_global_batch,
                        float* __restrict__ partials, float* __restrict__ logp_out, float* __restrict__ value_out, int forward_only, int net_base,
                        const float* __restrict__ adv_stats, const unsigned char* __restrict__ wimg) {
-    constexpr int IN = 56;
+    static_assert(IN == 56 || (IN == 80 && !IMG), "56-input policies (fp32 observations or images) or the 80-input route policy (fp32 observations)");
+    constexpr int KT = IN > 63 ? 2 : 1;              // K tiles of layer 1
+    constexpr int K1 = IN == 56 ? 64 : 96;           // padded reduction width of layer 1 (IN inputs | 1 | zeros)
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // round up to 1024 bytes WITHOUT leaving the shared address space (pointer + offset, not an integer round trip), so every
     // access below compiles to LDS / STS rather than generic LD / ST with 64-bit address arithmetic
-    TcGradSmem& S = *reinterpret_cast<TcGradSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+    TcGradSmem<KT>& S = *reinterpret_cast<TcGradSmem<KT>*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
     const PpoOffsets O = ppo_offsets(IN);
     const int P = O.total;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -170,12 +175,12 @@ kin_ppo_grad_tc_kernel(const float* __restrict__ params, KinPpoHyper hp, const f
         if (!wimg && tid < 16 * 128 / 16) reinterpret_cast<uint4*>(S.WO)[tid] = make_uint4(0u, 0u, 0u, 0u);   // the image carries its own zero rows
     }
     if (!wimg) {       // no prebuilt operand image: convert this net's weights here (latency-bound; the trainer passes the image)
-        for (int i = tid; i < 64 * 64; i += TCG_THREADS) {
-            const int u = i >> 6, k = i & 63;
+        for (int i = tid; i < 64 * KT * 64; i += TCG_THREADS) {
+            const int u = i / (KT * 64), k = i - u * (KT * 64);
             const float v = k < IN ? __ldg(params + o_w0 + u * IN + k) : (k == IN ? __ldg(params + o_b0 + u) : 0.0f);
-            st_bf16(S.W0, u, k, v);
-            st_bf16(S.W1, u, k, __ldg(params + o_w1 + i));
+            st_bf16(S.W0[k >> 6], u, k & 63, v);
         }
+        for (int i = tid; i < 64 * 64; i += TCG_THREADS) st_bf16(S.W1, i >> 6, i & 63, __ldg(params + o_w1 + i));
     }
     __syncthreads();   // WO / DO zero fill is complete before the real rows go in
     if (!wimg) {
@@ -226,7 +231,7 @@ kin_ppo_grad_tc_kernel(const float* __restrict__ params, KinPpoHyper hp, const f
             const unsigned mbw = smem_u32(&S.mbar[4]);
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbw), "r"(8192 + 8192 + 2048) : "memory");
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(smem_u32(S.W0)), "l"(wimg + KIN_WIMG_W0 + net * 8192), "r"(8192), "r"(mbw) : "memory");
+                         ::"r"(smem_u32(S.W0[0])), "l"(wimg + KIN_WIMG_W0 + net * 8192), "r"(8192), "r"(mbw) : "memory");
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                          ::"r"(smem_u32(S.W1)), "l"(wimg + KIN_WIMG_W1 + net * 8192), "r"(8192), "r"(mbw) : "memory");
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -251,11 +256,11 @@ kin_ppo_grad_tc_kernel(const float* __restrict__ params, KinPpoHyper hp, const f
         // ================= MMA issuer warp: warp-uniform control flow, one elected lane executes the tcgen05 / TMA instructions =========
         const bool lead = elect_one();
         const unsigned aX0 = smem_u32(S.X[0]), aH1 = smem_u32(S.H1), aH2 = smem_u32(S.H2), aDO = smem_u32(S.DO);
-        const unsigned aW0 = smem_u32(S.W0), aW1 = smem_u32(S.W1), aWO = smem_u32(S.WO);
+        const unsigned aW0 = smem_u32(S.W0[0]), aW1 = smem_u32(S.W1), aWO = smem_u32(S.WO);
         const unsigned mb_x0 = smem_u32(&S.mbar[2]);
         constexpr unsigned id_fwd = idesc_bf16(128, 64, false, false), id_out = idesc_bf16(128, 16, false, false);
         constexpr unsigned id_bwd = idesc_bf16(128, 64, false, true);
-        constexpr unsigned id_w16 = idesc_bf16(64, 16, true, true), id_w64 = idesc_bf16(64, 64, true, true), id_w80 = idesc_bf16(64, 80, true, true);
+        constexpr unsigned id_w16 = idesc_bf16(64, 16, true, true), id_w0 = idesc_bf16(64, K1, true, true), id_w80 = idesc_bf16(64, 80, true, true);
         // staged inputs of one tile -> buffer b: the X image (image mode) and the loss inputs of its two 64-sample halves, all on mb_x[b]
         const unsigned loss_bytes = net == 0 ? 2u * 1792u + (forward_only ? 0u : 4u * 256u) : (forward_only ? 0u : 2u * 256u);
         const unsigned stage_bytes = (IMG ? (unsigned)TILE_BYTES : 0u) + loss_bytes;
@@ -295,7 +300,8 @@ kin_ppo_grad_tc_kernel(const float* __restrict__ params, KinPpoHyper hp, const f
             fence_after();
             if (lead) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) mma_bf16(tb + COL_Z, desc_k(aX + k * 32), desc_k(aW0 + k * 32), id_fwd, k > 0);
+                for (int k = 0; k < K1 / 16; ++k)      // K tile k / 4 of X and W0, 32 bytes (16 bf16) per step inside it
+                    mma_bf16(tb + COL_Z, desc_k(aX + (k >> 2) * TILE_BYTES + (k & 3) * 32), desc_k(aW0 + (k >> 2) * 8192 + (k & 3) * 32), id_fwd, k > 0);
                 commit(mb_main);
             }
             TRACE_MARK(1);
@@ -355,7 +361,8 @@ kin_ppo_grad_tc_kernel(const float* __restrict__ params, KinPpoHyper hp, const f
             fence_after();
             if (lead) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) mma_bf16(tb + COL_W0, desc_mn(aH1 + k * 2048), desc_mn(aX + k * 2048), id_w64, acc0 | (k > 0));
+                for (int k = 0; k < 8; ++k)            // N = K1: the MN-major B operand spans the adjacent X K tiles
+                    mma_bf16(tb + COL_W0, desc_mn(aH1 + k * 2048), desc_mn(aX + k * 2048), id_w0, acc0 | (k > 0));
                 commit(mb_wg);
             }
             TRACE_MARK(8);
@@ -375,16 +382,19 @@ kin_ppo_grad_tc_kernel(const float* __restrict__ params, KinPpoHyper hp, const f
             if (!IMG) {
                 // ---- X tile: obs fp32 -> bf16, coalesced float4 reads; column 56 = 1 carries the layer-1 bias ---------------
                 if (it > 0 && !forward_only) mbar_wait(mb_wg, (unsigned)(it - 1) & 1u);    // the previous tile's dW0 batch still reads X
-                unsigned char* X = S.X[0];
+                constexpr int Q = IN / 4;                                    // float4 per observation row
 #pragma unroll
-                for (int i = 0; i < 7; ++i) {
-                    const int idx = tid + TCG_EPI_THREADS * i;           // 0 .. 1791
-                    const int hh = idx >= 896, rem = idx - hh * 896;
-                    const int r = hh * 64 + rem / 14, q = rem % 14;
+                for (int i = 0; i < IN / 8; ++i) {
+                    const int idx = tid + TCG_EPI_THREADS * i;           // 0 .. 2 * 64 * Q - 1
+                    const int hh = idx >= 64 * Q, rem = idx - hh * 64 * Q;
+                    const int r = hh * 64 + rem / Q, c4 = (rem % Q) * 4;    // row, first of its four columns
                     const float4 v = __ldg(reinterpret_cast<const float4*>(obs + (size_t)(hh ? t1 : t0) * 64 * IN) + rem);
-                    *reinterpret_cast<uint2*>(X + sw_chunk(r, q >> 1) + ((q & 1) << 3)) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+                    *reinterpret_cast<uint2*>(S.X[c4 >> 6] + sw_chunk(r, (c4 & 63) >> 3) + (c4 & 4) * 2) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
                 }
-                if (tid < 128) *reinterpret_cast<uint4*>(X + sw_chunk(tid, 7)) = make_uint4(0x00003F80u, 0u, 0u, 0u);
+                if (tid < 128) {      // column IN = 1 (carries the bias), zero up to K1
+                    *reinterpret_cast<uint4*>(S.X[IN >> 6] + sw_chunk(tid, (IN & 63) >> 3)) = make_uint4(0x00003F80u, 0u, 0u, 0u);
+                    if (IN == 80) *reinterpret_cast<uint4*>(S.X[1] + sw_chunk(tid, 3)) = make_uint4(0u, 0u, 0u, 0u);
+                }
                 fence_async_smem();
                 fence_before();
                 ready_arrive();
@@ -552,13 +562,16 @@ kin_ppo_grad_tc_kernel(const float* __restrict__ params, KinPpoHyper hp, const f
 #pragma unroll
                 for (int c = 0; c < 32; ++c) out[o_w1 + u * 64 + half * 32 + c] = v[c];   // flat offsets are not 16-byte aligned
             }
-            tmem_ld32(tlane + COL_W0 + half * 32, v);
-            if (rowok) {
 #pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                    const int k = half * 32 + c;
-                    if (k < IN) out[o_w0 + u * IN + k] = v[c];
-                    else if (k == IN) out[o_b0 + u] = v[c];
+            for (int cb = half; cb < K1 / 32; cb += 2) {      // 32-column blocks of dW0 | db0: this half's, plus block 2 for K1 = 96
+                tmem_ld32(tlane + COL_W0 + cb * 32, v);
+                if (rowok) {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        const int k = cb * 32 + c;
+                        if (k < IN) out[o_w0 + u * IN + k] = v[c];
+                        else if (k == IN) out[o_b0 + u] = v[c];
+                    }
                 }
             }
         }
@@ -613,17 +626,20 @@ extern "C" int kin_ppo_grad_tc(const float* params, int in_dim, const KinPpoHype
     if (!forward_only && (!old_logp || !advantage || !returns || (!tile_sums && !adv_stats) || !partials || global_batch <= 0))
         return kin_fail(KIN_ERR_INVALID_ARG, "kin_ppo_grad_tc: the gradient pass needs old_logp, advantage, returns, tile_sums, partials and grad");
     if (forward_only && !logp_out && !value_out) return kin_fail(KIN_ERR_INVALID_ARG, "kin_ppo_grad_tc: forward_only without an output");
-    if (in_dim != 56) return kin_fail(KIN_ERR_UNSUPPORTED, "kin_ppo_grad_tc: in_dim must be 56");
+    if (in_dim != 56 && in_dim != 80) return kin_fail(KIN_ERR_UNSUPPORTED, "kin_ppo_grad_tc: in_dim must be 56 or 80");
+    if (in_dim == 80 && (obs_is_image || weight_image))
+        return kin_fail(KIN_ERR_UNSUPPORTED, "kin_ppo_grad_tc: the 80-input route policy takes fp32 observations and converts its weights itself");
     if (n_tiles & 1) return kin_fail(KIN_ERR_INVALID_ARG, "kin_ppo_grad_tc: n_tiles must be even (two 64-sample tiles per 128-row GEMM tile)");
     if (((uintptr_t)obs & 15u)) return kin_fail(KIN_ERR_INVALID_ARG, "kin_ppo_grad_tc: obs must be 16-byte aligned");
     if (((uintptr_t)action | (uintptr_t)old_logp | (uintptr_t)advantage | (uintptr_t)returns) & 15u)      // staged by the TMA engine
         return kin_fail(KIN_ERR_INVALID_ARG, "kin_ppo_grad_tc: action / old_logp / advantage / returns must be 16-byte aligned");
     const int P = ppo_offsets(in_dim).total;
-    const size_t smem = sizeof(TcGradSmem) + 1024;
+    const size_t smem = (in_dim == 56 ? sizeof(TcGradSmem<1>) : sizeof(TcGradSmem<2>)) + 1024;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kin_ppo_grad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(kin_ppo_grad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(kin_ppo_grad_tc_kernel<false, 56>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(TcGradSmem<1>) + 1024));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(kin_ppo_grad_tc_kernel<true, 56>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(TcGradSmem<1>) + 1024));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(kin_ppo_grad_tc_kernel<false, 80>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(TcGradSmem<2>) + 1024));
         if (e != cudaSuccess) return kin_fail_cuda(e, "kin_ppo_grad_tc: smem attribute");
         attr_set = true;
     }
@@ -638,14 +654,14 @@ extern "C" int kin_ppo_grad_tc(const float* params, int in_dim, const KinPpoHype
         dg.y = 1u;
         net_base = logp_out ? 0 : 1;
     }
-    if (obs_is_image)
-        kin_ppo_grad_tc_kernel<true><<<dg, TCG_THREADS, smem, st>>>(params, *hp, obs, action, old_logp, advantage, returns, tile_sums, tile_ids, n_pairs,
-                                                                    inv, partials, logp_out, value_out, forward_only, net_base, adv_stats,
-                                                                    static_cast<const unsigned char*>(weight_image));
-    else
-        kin_ppo_grad_tc_kernel<false><<<dg, TCG_THREADS, smem, st>>>(params, *hp, obs, action, old_logp, advantage, returns, tile_sums, tile_ids, n_pairs,
-                                                                     inv, partials, logp_out, value_out, forward_only, net_base, adv_stats,
-                                                                    static_cast<const unsigned char*>(weight_image));
+    const unsigned char* wimg = static_cast<const unsigned char*>(weight_image);
+#define KIN_GRAD_TC_LAUNCH(IMG, IN)                                                                                                              \
+    kin_ppo_grad_tc_kernel<IMG, IN><<<dg, TCG_THREADS, smem, st>>>(params, *hp, obs, action, old_logp, advantage, returns, tile_sums, tile_ids, n_pairs, inv, \
+                                                                   partials, logp_out, value_out, forward_only, net_base, adv_stats, wimg)
+    if (in_dim == 80) KIN_GRAD_TC_LAUNCH(false, 80);
+    else if (obs_is_image) KIN_GRAD_TC_LAUNCH(true, 56);
+    else KIN_GRAD_TC_LAUNCH(false, 56);
+#undef KIN_GRAD_TC_LAUNCH
     if (!forward_only && grad) kin_ppo_reduce_launch(partials, g, P, grad, stats, inv, st);      // grad == NULL: the caller reduces `partials` (kin_peer_grad_push)
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? KIN_OK : kin_fail_cuda(e, "kin_ppo_grad_tc");

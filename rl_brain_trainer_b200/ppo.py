@@ -101,16 +101,28 @@ def random_policy(in_dim: int = 56, *, seed: int = 0, log_std_init: float = 0.0,
 
 
 class PPOTrainer:
-    """Batched on-device PPO: ``collect()`` fills the rollout buffer, ``update()`` runs the epochs, ``learn()`` loops."""
+    """Batched on-device PPO: ``collect()`` fills the rollout buffer, ``update()`` runs the epochs, ``learn()`` loops.
 
-    def __init__(self, config: Phase1EnvConfig, policy: PolicyWeights, *, num_envs: int, hyper: PPOHyper, device: str | torch.device = "cuda",
+    Two env families: the 56-input Approach / Finisher policies on ``BatchedArmKinematicEnv`` (``config`` = ``Phase1EnvConfig``;
+    ``train_workspace_expansion.py:144-270``), and -- with ``route=`` -- the 80-input route policy on ``BatchedRouteKinematicEnv``
+    (``config`` = ``RouteEnvConfig``; ``train_route_curriculum.py``), which collects step by step (policy, route step, TimeLimit
+    bootstrap, sampled route resets of the finished slots) and updates with the tensor-core kernel's fp32-observation path.
+    """
+
+    def __init__(self, config: Any, policy: PolicyWeights, *, num_envs: int, hyper: PPOHyper, device: str | torch.device = "cuda",
                  seed: int = 0, stage_index: int = 0, process_group: Any = None, grad_ctas: int | None = None,
                  update_variant: str = "tc", collect_variant: str | None = None, handoff_states: torch.Tensor | None = None,
-                 grad_exchange: str = "nccl") -> None:
+                 grad_exchange: str = "nccl", route: Any = None, route_sequence_config: Any = None, route_curriculum: Any = None) -> None:
         if not torch.cuda.is_available():
             raise _lib.KinError("PPOTrainer needs a CUDA device; there is no CPU fallback")
-        if policy.in_dim != 56:
-            raise _lib.KinError("the on-device PPO update is built for the 56-input policies (the 80-input route policy is next)")
+        self.in_dim = int(policy.in_dim)
+        self.is_route = route is not None
+        if self.in_dim != (80 if self.is_route else 56):
+            raise _lib.KinError("PPOTrainer: 56-input policies train on the arm env, the 80-input route policy needs route=<RouteDataset>")
+        if self.is_route:
+            if update_variant != "tc" or collect_variant not in (None, "steps"):
+                raise ValueError("route training uses update_variant='tc' and the per-step collection")
+            collect_variant = "steps"
         tile = _D("KIN_PPO_TILE")
         if num_envs % tile:
             raise ValueError(f"num_envs must be a multiple of {tile}")
@@ -148,7 +160,8 @@ class PPOTrainer:
             self._gradstats = torch.zeros(self.P + _D("KIN_PPO_STATS"), dtype=torch.float32, device=self.device)
             self.grad = self._gradstats[: self.P]
             self.stats = self._gradstats[self.P:]
-            self.weight_image = torch.zeros(36864, dtype=torch.uint8, device=self.device)   # bf16 operand image of `params`
+            # bf16 operand image of `params` (56-input policies; the route policy's kernel converts its weights itself)
+            self.weight_image = None if self.is_route else torch.zeros(36864, dtype=torch.uint8, device=self.device)
             self.pack_weights()
             self.stats_accum = torch.zeros(_D("KIN_PPO_STATS"), dtype=torch.float32, device=self.device)
             self._adv_stats = torch.zeros((max(self.S // self.local_batch, 1), 2), dtype=torch.float32, device=self.device)
@@ -157,13 +170,24 @@ class PPOTrainer:
             self.partials = torch.zeros((self.grad_ctas, self.P + _D("KIN_PPO_STATS") + 8), dtype=torch.float32, device=self.device)
             # several ranks: the per-minibatch gradient sum goes through NCCL or through NVLink peer buffers (distributed.PeerGradExchange)
             self.peer = PeerGradExchange(self.P, self.device, process_group) if grad_exchange == "peer" else None
-            self.env = BatchedArmKinematicEnv(config, self.N, self.device, auto_reset=True, seed=self.seed, host_sampler=False, with_aux=False)
-            self.env.set_curriculum_stage(stage_index)
-            if handoff_states is not None:       # Finisher training: dock resets replay Approach handoff states (handoff.py)
-                self.env.set_handoff_states(handoff_states)
+            self.route_curriculum = None
+            if self.is_route:
+                from .route import BatchedRouteKinematicEnv
+
+                self.env = BatchedRouteKinematicEnv(route, config, self.N, self.device, sequence_config=route_sequence_config)
+                self.route_curriculum = route_curriculum
+                if route_curriculum is not None:
+                    if self.world > 1:
+                        raise _lib.KinError("route prefix curriculum promotion is per process; run route training on one rank or without it")
+                    self.env.set_route_window(max_route_index=route_curriculum.prefix_end_index)
+            else:
+                self.env = BatchedArmKinematicEnv(config, self.N, self.device, auto_reset=True, seed=self.seed, host_sampler=False, with_aux=False)
+                self.env.set_curriculum_stage(stage_index)
+                if handoff_states is not None:       # Finisher training: dock resets replay Approach handoff states (handoff.py)
+                    self.env.set_handoff_states(handoff_states)
             f32 = dict(dtype=torch.float32, device=self.device)
             fused = self.collect_variant == "fused"
-            self.obs_buf = None if fused else torch.zeros((self.T + 1, self.N, 56), **f32)
+            self.obs_buf = None if fused else torch.zeros((self.T + 1, self.N, self.in_dim), **f32)
             if fused:
                 self.obs_img = torch.zeros((self.T, self.N // 128, 128 * 128), dtype=torch.uint8, device=self.device)
                 limit = max(int(getattr(config.termination_config, "max_episode_steps", config.episode_length)), 1)
@@ -183,7 +207,10 @@ class PPOTrainer:
             self.tile_sums = torch.zeros((self.S // tile, 2), dtype=torch.float64, device=self.device)
             self._gen = torch.Generator(device=self.device)
             self._gen.manual_seed(self.seed)
-            self.env.reset()
+            if self.is_route:
+                self.env.reset(seed=self.seed)
+            else:
+                self.env.reset()
             if not fused:
                 self.obs_buf[0].copy_(self.env.obs)
         self._next_start = torch.ones(self.N, dtype=torch.uint8, device=self.device)
@@ -191,19 +218,23 @@ class PPOTrainer:
         self.num_timesteps = 0
         self.update_count = 0
         self.global_step = 0
-        cur = config.curriculum_config
+        cur = None if self.is_route else config.curriculum_config
         self.curriculum = CurriculumTracker(len(cur.stages), cur.success_rate_threshold, cur.window_episodes, cur.min_episodes_per_stage,
-                                            stage_index) if cur.enabled else None
+                                            stage_index) if (cur is not None and cur.enabled) else None
         self.last_rollout: dict[str, float] = {}
 
     def pack_weights(self) -> None:
         """Rebuild the bf16 operand image from ``self.params`` (needed after the parameters were written from outside the trainer)."""
+        if self.weight_image is None:
+            return
         _lib.check(self._L.kin_ppo_pack_weights(self.params.data_ptr(), 56, self.weight_image.data_ptr(),
                                                 torch.cuda.current_stream(self.device).cuda_stream))
 
     # ------------------------------------------------------------------ rollout
     def collect(self) -> dict[str, float]:
         """``collect_rollouts``: T steps of (sample action, env step with auto-reset, TimeLimit bootstrap), then GAE."""
+        if self.is_route:
+            return self._collect_route()
         self.env._ensure_sampler()          # a curriculum promotion since the last rollout re-uploads the device sampler
         if self.collect_variant == "fused":
             return self._collect_fused()
@@ -234,6 +265,48 @@ class PPOTrainer:
         finished = (self.done_buf & done_bits) != 0
         succ = ((self.done_buf & _D("KIN_DONE_SUCCESS")) != 0) & finished
         self.last_rollout = {"episodes": float(finished.sum()), "successes": float(succ.sum()), "mean_reward": float(self.rew_buf.mean())}
+        return self.last_rollout
+
+    def _collect_route(self) -> dict[str, float]:
+        """Route env rollout: per step policy sample -> ``kin_route_step`` -> TimeLimit bootstrap from the terminal observation ->
+        sampled route resets (``sample_route_reset``) of the finished slots; the finished episodes feed the prefix curriculum."""
+        L, env, hp = self._L, self.env, self.hp
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        w = ctypes.byref(self.policy.c)
+        done_bits = _D("KIN_DONE_TERMINATED") | _D("KIN_DONE_TRUNCATED")
+        episodes = successes = 0.0
+        with torch.cuda.device(self.device):
+            for t in range(self.T):
+                self.start_buf[t].copy_(self._next_start)
+                _lib.check(L.kin_policy_act(w, self.obs_buf[t].data_ptr(), self.act_buf[t].data_ptr(), self.logp_buf[t].data_ptr(),
+                                            self.val_buf[t].data_ptr(), self.N, self.seed, self.global_step, 0, stream))
+                _, reward, _, _, info = env.step(self.act_buf[t])
+                self.rew_buf[t].copy_(reward)
+                self.done_buf[t].copy_(env.done)
+                # env.obs is the terminal observation of the slots that just finished (no auto-reset inside the route kernels)
+                _lib.check(L.kin_ppo_bootstrap(w, env.obs.data_ptr(), self.done_buf[t].data_ptr(), self.rew_buf[t].data_ptr(), float(hp.gamma), self.N, stream))
+                finished = (env.done & done_bits) != 0
+                self._next_start = finished.to(torch.uint8)
+                ids = torch.nonzero(finished).reshape(-1)
+                if ids.numel():
+                    episodes += float(ids.numel())
+                    flags = torch.stack([info["success"][ids], info["route_ready"][ids], info["route_orientation_hit"][ids],
+                                         info["route_regression"][ids]]).cpu().numpy()
+                    successes += float(flags[0].sum())
+                    if self.route_curriculum is not None and self.route_curriculum.record(
+                            flags[0], flags[1], flags[2], flags[3], total_timesteps=self.num_timesteps + (t + 1) * self.N):
+                        env.set_route_window(max_route_index=self.route_curriculum.prefix_end_index)
+                    env.reset(env_ids=ids.to(torch.int32))
+                self.obs_buf[t + 1].copy_(env.obs)
+                self.global_step += 1
+            _lib.check(L.kin_policy_act(w, self.obs_buf[self.T].data_ptr(), self._scratch_act().data_ptr(),
+                                        self._scratch_logp().data_ptr(), self.last_val.data_ptr(), self.N, self.seed, self.global_step, 1, stream))
+            _lib.check(L.kin_ppo_gae(self.rew_buf.data_ptr(), self.val_buf.data_ptr(), self.start_buf.data_ptr(), self.last_val.data_ptr(),
+                                     self.done_buf[self.T - 1].data_ptr(), float(hp.gamma), float(hp.gae_lambda), self.T, self.N,
+                                     self.adv_buf.data_ptr(), self.ret_buf.data_ptr(), self.tile_sums.data_ptr(), stream))
+            self.obs_buf[0].copy_(self.obs_buf[self.T])
+        self.num_timesteps += self.S * self.world
+        self.last_rollout = {"episodes": episodes, "successes": successes, "mean_reward": float(self.rew_buf.mean())}
         return self.last_rollout
 
     def _collect_fused(self) -> dict[str, float]:
@@ -278,11 +351,11 @@ class PPOTrainer:
         global_batch = n_tiles * _D("KIN_PPO_TILE") * self.world
         if self.update_variant == "tc":
             img = self.collect_variant == "fused"
-            _lib.check(self._L.kin_ppo_grad_tc(self.params.data_ptr(), 56, ctypes.byref(hp), (self.obs_img if img else self.obs_buf).data_ptr(),
+            _lib.check(self._L.kin_ppo_grad_tc(self.params.data_ptr(), self.in_dim, ctypes.byref(hp), (self.obs_img if img else self.obs_buf).data_ptr(),
                                                self.act_buf.data_ptr(), self.logp_buf.data_ptr(), self.adv_buf.data_ptr(), self.ret_buf.data_ptr(),
                                                self.tile_sums.data_ptr(), tile_ptr, n_tiles, global_batch, self.partials.data_ptr(),
                                                self.grad_ctas, None if self.peer else self.grad.data_ptr(), self.stats.data_ptr(), None, None, 0,
-                                               int(img), adv_ptr, self.weight_image.data_ptr(), stream))
+                                               int(img), adv_ptr, None if self.weight_image is None else self.weight_image.data_ptr(), stream))
             if self.peer:
                 self.peer.push(self.partials, min(self.grad_ctas, n_tiles // 2), global_batch)
             return
@@ -304,9 +377,9 @@ class PPOTrainer:
         if not hasattr(self, "_all_tiles"):
             self._all_tiles = torch.arange(self.S // _D("KIN_PPO_TILE"), dtype=torch.int32, device=self.device)
         hp = self.hp.c()
-        _lib.check(self._L.kin_ppo_grad_tc(self.params.data_ptr(), 56, ctypes.byref(hp), self.obs_buf.data_ptr(), self.act_buf.data_ptr(), None, None,
+        _lib.check(self._L.kin_ppo_grad_tc(self.params.data_ptr(), self.in_dim, ctypes.byref(hp), self.obs_buf.data_ptr(), self.act_buf.data_ptr(), None, None,
                                            None, None, self._all_tiles.data_ptr(), int(self._all_tiles.numel()), 0, None, self.grad_ctas, None, None,
-                                           self.logp_buf.data_ptr(), None, 1, 0, None, self.weight_image.data_ptr(),
+                                           self.logp_buf.data_ptr(), None, 1, 0, None, None if self.weight_image is None else self.weight_image.data_ptr(),
                                            torch.cuda.current_stream(self.device).cuda_stream))
 
     def apply_update(self) -> None:
@@ -319,7 +392,8 @@ class PPOTrainer:
         hp = getattr(self, "_c_hyper", None) or self.hp.c()
         _lib.check(self._L.kin_ppo_adam(self.params.data_ptr(), self.grad.data_ptr(), self.adam_m.data_ptr(), self.adam_v.data_ptr(), self.P,
                                         ctypes.byref(hp), self.update_count, self.stats.data_ptr(), self.stats_accum.data_ptr(),
-                                        self.weight_image.data_ptr(), 56, torch.cuda.current_stream(self.device).cuda_stream))
+                                        None if self.weight_image is None else self.weight_image.data_ptr(), self.in_dim,
+                                        torch.cuda.current_stream(self.device).cuda_stream))
 
     def update(self) -> dict[str, float]:
         """``PPO.train``: n_epochs passes over the rollout in random minibatches; no host synchronisation until the statistics are read."""
@@ -363,7 +437,9 @@ class PPOTrainer:
             u = self.update()
             if self.curriculum is not None and self.curriculum.record(r["successes"], r["episodes"], self.group):
                 self.env.set_curriculum_stage(self.curriculum.stage_index)
-            row = {**r, **u, "stage": float(self.env.get_curriculum_stage()), "timesteps": float(self.num_timesteps)}
+            stage = float(self.route_curriculum.current_stage_index) if (self.is_route and self.route_curriculum is not None) else (
+                0.0 if self.is_route else float(self.env.get_curriculum_stage()))
+            row = {**r, **u, "stage": stage, "timesteps": float(self.num_timesteps)}
             if gate is not None:
                 rec = gate.maybe_eval(self.num_timesteps, self.policy)
                 if rec is not None:

@@ -13,10 +13,10 @@ from ._util import env_config
 pytestmark = pytest.mark.gpu
 
 
-def _setup(seed=0, log_std=-0.5):
+def _setup(seed=0, log_std=-0.5, in_dim=56):
     from rl_brain_trainer_b200 import ppo
 
-    pol = ppo.random_policy(56, seed=seed, log_std_init=log_std, device="cuda")
+    pol = ppo.random_policy(in_dim, seed=seed, log_std_init=log_std, device="cuda")
     # make the action head non-trivial (SB3's 0.01 gain would hide errors in the actor gradient)
     pol.tensors["act_w"].mul_(30.0)
     pol.tensors["pi_b0"].normal_(0, 0.1)
@@ -143,17 +143,19 @@ def test_minibatch_gradient_matches_autograd():
         t.requires_grad_(False)
 
 
-def test_minibatch_gradient_tc_matches_autograd():
+@pytest.mark.parametrize("in_dim", [56, 80])
+def test_minibatch_gradient_tc_matches_autograd(in_dim):
     """Tensor-core (bf16 operand, fp32 accumulate) variant of the minibatch gradient vs fp32 autograd: bf16-level agreement per
-    tensor, near-perfect direction overall; the forward-only pass reproduces log-prob / value to bf16 accuracy."""
+    tensor, near-perfect direction overall; the forward-only pass reproduces log-prob / value to bf16 accuracy.  in_dim 80 is the
+    route policy (two K tiles in layer 1, N = 96 weight-gradient GEMM)."""
     from rl_brain_trainer_b200 import _lib
 
-    ppo, pol, flat = _setup(seed=4)
+    ppo, pol, flat = _setup(seed=4, in_dim=in_dim)
     hp = ppo.PPOHyper(clip_range=0.15, ent_coef=0.01, vf_coef=0.5, normalize_advantage=True)
     c_hp = hp.c()
     S = 64 * 48
     g = torch.Generator(device="cuda").manual_seed(2)
-    obs = (torch.rand((S, 56), device="cuda", generator=g) * 2 - 1).contiguous()
+    obs = (torch.rand((S, in_dim), device="cuda", generator=g) * 2 - 1).contiguous()
     with torch.no_grad():
         mean, value = _torch_forward(pol, obs)
     sigma = pol.tensors["log_std"].exp()
@@ -171,7 +173,7 @@ def test_minibatch_gradient_tc_matches_autograd():
     stream = torch.cuda.current_stream().cuda_stream
     # forward only: log-prob and value of the visited samples
     lp_out, v_out = torch.full((S,), 123.0, device="cuda"), torch.full((S,), 123.0, device="cuda")
-    _lib.check(L.kin_ppo_grad_tc(flat.data_ptr(), 56, ctypes.byref(c_hp), obs.data_ptr(), act.data_ptr(), None, None, None, None,
+    _lib.check(L.kin_ppo_grad_tc(flat.data_ptr(), in_dim, ctypes.byref(c_hp), obs.data_ptr(), act.data_ptr(), None, None, None, None,
                                  tile_ids.data_ptr(), tile_ids.numel(), 0, None, 3, None, None, lp_out.data_ptr(), v_out.data_ptr(), 1, 0, None, None, stream))
     torch.cuda.synchronize()
     assert float((v_out[idx] - value[idx]).abs().max()) < 0.03 and float((lp_out[idx] - exact_logp[idx]).abs().max()) < 0.06
@@ -194,7 +196,7 @@ def test_minibatch_gradient_tc_matches_autograd():
         for ctas in (2, 7, 148):      # several GEMM tiles per CTA (TMEM accumulation across tiles), one per CTA, more CTAs than tiles
             partials = torch.zeros((ctas, P + 16), device="cuda")
             grad, stats = torch.zeros(P, device="cuda"), torch.zeros(8, device="cuda")
-            _lib.check(L.kin_ppo_grad_tc(flat.data_ptr(), 56, ctypes.byref(c_hp), obs.data_ptr(), act.data_ptr(), old_logp.data_ptr(), adv.data_ptr(),
+            _lib.check(L.kin_ppo_grad_tc(flat.data_ptr(), in_dim, ctypes.byref(c_hp), obs.data_ptr(), act.data_ptr(), old_logp.data_ptr(), adv.data_ptr(),
                                          ret.data_ptr(), sums.data_ptr(), tile_ids.data_ptr(), tile_ids.numel(), tile_ids.numel() * 64,
                                          partials.data_ptr(), ctas, grad.data_ptr(), stats.data_ptr(), None, None, 0, 0, None, None, stream))
             torch.cuda.synchronize()
@@ -211,7 +213,7 @@ def test_minibatch_gradient_tc_matches_autograd():
             for i, key in enumerate(("policy_loss", "value_loss", "entropy", "approx_kl", "clip_fraction")):
                 assert abs(got_stats[i] - ref_stats[key]) < 3e-2 * max(1.0, abs(ref_stats[key])), (key, got_stats[i], ref_stats[key])
     # odd tile counts are refused (two 64-sample tiles per GEMM tile)
-    rc = L.kin_ppo_grad_tc(flat.data_ptr(), 56, ctypes.byref(c_hp), obs.data_ptr(), act.data_ptr(), old_logp.data_ptr(), adv.data_ptr(),
+    rc = L.kin_ppo_grad_tc(flat.data_ptr(), in_dim, ctypes.byref(c_hp), obs.data_ptr(), act.data_ptr(), old_logp.data_ptr(), adv.data_ptr(),
                            ret.data_ptr(), sums.data_ptr(), tile_ids.data_ptr(), 3, 192, partials.data_ptr(), 2, grad.data_ptr(), stats.data_ptr(),
                            None, None, 0, 0, None, None, stream)
     assert rc != 0
@@ -285,6 +287,44 @@ def test_trainer_runs_and_improves_value_fit(variant):
     q0 = tr2.params.clone()
     tr2.learn(1)
     assert torch.equal(tr2.params, q0)
+
+
+def test_route_policy_training_runs_end_to_end():
+    """train_route_curriculum.py on the device: the 80-input route policy on the batched RouteSequence env -- rollout with sampled
+    route resets, TimeLimit bootstrap, tensor-core update (fp32 route observations), prefix curriculum promotion."""
+    from rl_brain_trainer_b200 import config as kcfg, ppo
+    from rl_brain_trainer_b200.policy import PolicyWeights
+    from rl_brain_trainer_b200.route import RouteCurriculumStage, RoutePrefixCurriculum, evaluate_sequential_route, synthetic_route
+
+    route = synthetic_route(160, seed=7)
+    renv, seq = kcfg.to_route_env_config(kcfg.preset_dict("route_prefix120"), max_route_index=len(route) - 1)
+    # (1) a fresh policy: finite statistics, parameters move, the critic's fit improves
+    pol = ppo.random_policy(80, seed=2, log_std_init=-1.0, device="cuda")
+    hp = ppo.PPOHyper(learning_rate=1e-3, n_steps=32, batch_size=4096, n_epochs=4, gamma=0.98, clip_range=0.2)
+    tr = ppo.PPOTrainer(renv, pol, num_envs=512, hyper=hp, seed=3, route=route, route_sequence_config=seq)
+    assert tr.is_route and tr.in_dim == 80 and tr.obs_buf.shape == (33, 512, 80) and tr.weight_image is None
+    p0 = tr.params.clone()
+    log = tr.learn(4)
+    assert all(np.isfinite(list(row.values())).all() for row in log)
+    assert float((tr.params - p0).abs().max()) > 1e-4
+    assert log[-1]["value_loss"] < log[0]["value_loss"]
+    assert log[0]["episodes"] > 0 and log[0]["minibatches"] == 4 * (512 * 32 // 4096)
+    assert tr.state_dict()["mlp_extractor.policy_net.0.weight"].shape == (64, 80)
+    # (2) the bundled route checkpoint under a two-stage prefix curriculum: it already passes the promotion thresholds on the short
+    # prefix, so the window opens; a few updates at the reference's learning rate keep the probe's prefix
+    pol = PolicyWeights.preset("route_prefix120", "cuda")
+    before = evaluate_sequential_route(route, renv, pol, n_replicas=64, start_index=1, end_index=60, start_q_noise_std=0.0008)
+    cur = RoutePrefixCurriculum([RouteCurriculumStage("prefix20", 20), RouteCurriculumStage("prefix60", 60)], promotion_success_rate=0.5,
+                                promotion_route_ready_hit_rate=0.5, promotion_orientation_hit_rate=0.5, promotion_max_regression_rate=0.6,
+                                window_episodes=128, min_episodes_per_stage=128)
+    hp = ppo.PPOHyper(learning_rate=4e-6, n_steps=64, batch_size=8192, n_epochs=2, gamma=0.98, clip_range=0.1)
+    tr = ppo.PPOTrainer(renv, pol, num_envs=512, hyper=hp, seed=5, route=route, route_sequence_config=seq, route_curriculum=cur)
+    assert tr.env.config.reset_config.max_route_index == 20
+    log = tr.learn(3)
+    assert cur.current_stage_index == 1 and tr.env.config.reset_config.max_route_index == 60 and cur.history[0]["to_prefix_end_index"] == 60
+    assert log[-1]["stage"] == 1.0 and log[-1]["approx_kl"] < 0.05
+    after = evaluate_sequential_route(route, renv, pol, n_replicas=64, start_index=1, end_index=60, start_q_noise_std=0.0008)
+    assert float(after["longest_success_prefix"].float().mean()) >= float(before["longest_success_prefix"].float().mean()) - 6.0
 
 
 @pytest.mark.parametrize("variant", ["tc", "fp32"])

@@ -22,6 +22,7 @@ ap.add_argument("--iters", type=int, default=3)
 ap.add_argument("--stage", type=int, default=10)
 ap.add_argument("--update", default="tc", choices=("tc", "fp32"))
 ap.add_argument("--grad-exchange", default="peer", choices=("peer", "nccl"), help="per-minibatch gradient sum over ranks: NVLink peer buffers or NCCL")
+ap.add_argument("--route", action="store_true", help="train the 80-input route policy on the batched RouteSequence env (train_route_curriculum.py)")
 ap.add_argument("--from-checkpoint", action="store_true", help="fine-tune the bundled approach checkpoint instead of a random init")
 a = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -30,12 +31,20 @@ dev = torch.device("cuda", local)
 if world > 1:
     os.environ["NCCL_DEBUG"] = "WARN"
     dist.init_process_group("nccl", device_id=dev)
-cfg = kcfg.load_preset("approach_dynamic_scale_big")
-pol = PolicyWeights.preset("approach_stage8_11", dev) if a.from_checkpoint else ppo.random_policy(56, seed=0, log_std_init=-1.0, device=dev)
+route_kw = {}
+if a.route:
+    from rl_brain_trainer_b200.route import synthetic_route
+    route = synthetic_route(483, seed=7)
+    cfg, seq = kcfg.to_route_env_config(kcfg.preset_dict("route_prefix120"), max_route_index=len(route) - 1)
+    route_kw = dict(route=route, route_sequence_config=seq)
+    pol = PolicyWeights.preset("route_prefix120", dev) if a.from_checkpoint else ppo.random_policy(80, seed=0, log_std_init=-1.0, device=dev)
+else:
+    cfg = kcfg.load_preset("approach_dynamic_scale_big")
+    pol = PolicyWeights.preset("approach_stage8_11", dev) if a.from_checkpoint else ppo.random_policy(56, seed=0, log_std_init=-1.0, device=dev)
 S = a.envs * a.n_steps
 hp = ppo.PPOHyper(learning_rate=4e-6, n_steps=a.n_steps, batch_size=S // 16, n_epochs=a.epochs, gamma=0.995, gae_lambda=0.95, clip_range=0.1, ent_coef=0.0003)
 tr = ppo.PPOTrainer(cfg, pol, num_envs=a.envs, hyper=hp, device=dev, seed=1, stage_index=a.stage, update_variant=a.update,
-                    grad_exchange=a.grad_exchange if world > 1 else "nccl")
+                    grad_exchange=a.grad_exchange if world > 1 else "nccl", **route_kw)
 tr.collect(); tr.update()          # warm-up
 torch.cuda.synchronize(dev)
 ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
@@ -55,7 +64,7 @@ if world > 1:
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
 steps = S * a.iters * world
 if rank == 0:
-    print(json.dumps({"workload": f"stage{a.stage}_ppo_train", "n_gpus": world, "envs_per_gpu": a.envs, "n_steps": a.n_steps, "epochs": a.epochs, "update_variant": a.update, "grad_exchange": a.grad_exchange if world > 1 else "none",
+    print(json.dumps({"workload": "route_prefix120_ppo_train" if a.route else f"stage{a.stage}_ppo_train", "n_gpus": world, "envs_per_gpu": a.envs, "n_steps": a.n_steps, "epochs": a.epochs, "update_variant": a.update, "grad_exchange": a.grad_exchange if world > 1 else "none",
                       "minibatches_per_epoch": 16, "iters": a.iters, "rollout_env_steps_per_s": steps / float(t[0]),
                       "update_env_steps_per_s": steps / float(t[1]), "e2e_env_steps_per_s": steps / float(t[0] + t[1]),
                       "wall_env_steps_per_s": steps / float(t[2]), "rollout_s": float(t[0]) / a.iters, "update_s": float(t[1]) / a.iters,

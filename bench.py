@@ -287,9 +287,14 @@ def main() -> None:
         raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    # stdout carries exactly ONE JSON line: native libraries that write to fd 1 (NCCL prints its version banner there when the
+    # first communicator comes up) are pointed at stderr; the line itself goes to the saved descriptor
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = os.environ.get("KIN_NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout (one JSON line only)
+        os.environ["NCCL_DEBUG"] = os.environ.get("KIN_NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=device)
     pk = peaks()
 
@@ -439,7 +444,8 @@ def main() -> None:
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "success_rate": e2e_success},
             "clocks": clocks.summary(), "gpu_launches": launches, "train": train,
         }
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

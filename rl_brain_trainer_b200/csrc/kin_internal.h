@@ -23,6 +23,14 @@ inline KinHandle* kin_handle(void* p) {
     return (h && h->magic == KIN_HANDLE_MAGIC) ? h : nullptr;
 }
 
+// cudaFuncSetAttribute is per device: one-time guards are indexed by the current device (a process may drive several GPUs)
+constexpr int KIN_MAX_DEVICES = 64;
+inline int kin_device_slot() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return (d >= 0 && d < KIN_MAX_DEVICES) ? d : 0;
+}
+
 int kin_fail(int code, const char* msg);
 int kin_fail_cuda(cudaError_t e, const char* where);
 bool kin_env_flag(const char* name);

@@ -635,13 +635,14 @@ extern "C" int kin_ppo_grad_tc(const float* params, int in_dim, const KinPpoHype
         return kin_fail(KIN_ERR_INVALID_ARG, "kin_ppo_grad_tc: action / old_logp / advantage / returns must be 16-byte aligned");
     const int P = ppo_offsets(in_dim).total;
     const size_t smem = (in_dim == 56 ? sizeof(TcGradSmem<1>) : sizeof(TcGradSmem<2>)) + 1024;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[KIN_MAX_DEVICES] = {};
+    const int dev_slot = kin_device_slot();
+    if (!attr_set[dev_slot]) {
         cudaError_t e = cudaFuncSetAttribute(kin_ppo_grad_tc_kernel<false, 56>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(TcGradSmem<1>) + 1024));
         if (e == cudaSuccess) e = cudaFuncSetAttribute(kin_ppo_grad_tc_kernel<true, 56>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(TcGradSmem<1>) + 1024));
         if (e == cudaSuccess) e = cudaFuncSetAttribute(kin_ppo_grad_tc_kernel<false, 80>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(TcGradSmem<2>) + 1024));
         if (e != cudaSuccess) return kin_fail_cuda(e, "kin_ppo_grad_tc: smem attribute");
-        attr_set = true;
+        attr_set[dev_slot] = true;
     }
     cudaStream_t st = (cudaStream_t)stream;
     const int n_pairs = n_tiles / 2;

@@ -282,11 +282,12 @@ extern "C" int kin_rollout_approach_finisher(void* approach_handle, void* finish
         return kin_rollout_tc_launch(ha, has_f ? hf : nullptr, host_approach, has_f ? host_finisher : nullptr, initial_q, initial_dq,
                                      initial_prev_action, goal_q, goal_pose6, n, stride, handoff_confirm_steps, variant, result, env_steps, st);
     const size_t smem = (size_t)(MlpSmem<OBS>::FLOATS + HID * RO_THREADS) * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[KIN_MAX_DEVICES] = {};
+    const int dev_slot = kin_device_slot();
+    if (!attr_set[dev_slot]) {
         cudaError_t e = cudaFuncSetAttribute(kin_rollout_ffma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return kin_fail_cuda(e, "kin_rollout_approach_finisher: smem attribute");
-        attr_set = true;
+        attr_set[dev_slot] = true;
     }
     const KinEnvParams& PF = has_f ? hf->params : ha->params;
     DevPolicy da = actor_of(host_approach), df = has_f ? actor_of(host_finisher) : actor_of(host_approach);

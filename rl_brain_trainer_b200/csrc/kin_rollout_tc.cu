@@ -317,12 +317,13 @@ int kin_rollout_tc_launch(const KinHandle* ha, const KinHandle* hf, const KinPol
                           const float* iq, const float* idq, const float* ipa, const float* gq, const float* gpose, int n, int stride,
                           int confirm, int variant, uint32_t* result, unsigned long long* env_steps, cudaStream_t st) {
     (void)variant;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[KIN_MAX_DEVICES] = {};
+    const int dev_slot = kin_device_slot();
+    if (!attr_set[dev_slot]) {
         const size_t smem_max = sizeof(TcSmem) + (TC_TILES - 1) * A_TILE_FLOATS * sizeof(float) + 1024;
         cudaError_t e = cudaFuncSetAttribute(kin_rollout_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
         if (e != cudaSuccess) return kin_fail_cuda(e, "kin_rollout_approach_finisher(tc): smem attribute");
-        attr_set = true;
+        attr_set[dev_slot] = true;
     }
     DevPolicyTc da{pa->pi_w0, pa->pi_b0, pa->pi_w1, pa->pi_b1, pa->act_w, pa->act_b};
     DevPolicyTc df = pf ? DevPolicyTc{pf->pi_w0, pf->pi_b0, pf->pi_w1, pf->pi_b1, pf->act_w, pf->act_b} : da;

@@ -17,9 +17,14 @@ namespace kin {
 
 constexpr int STEP_THREADS = 128;
 constexpr int STEP_WARPS = STEP_THREADS / WARP;
+// resident CTAs per SM the plain step is compiled for (registers <= 65536 / (128 * n)): the kernel is HBM-bound, more warps in
+// flight hide more of the load latency; the info-heavy variants (components / aux rows) keep the compiler's own choice
+#ifndef KIN_STEP_MIN_BLOCKS
+#define KIN_STEP_MIN_BLOCKS 5
+#endif
 
 template <int MODE, bool COMP, bool AUX, bool AUTORESET, bool BULK>
-__global__ void __launch_bounds__(STEP_THREADS)
+__global__ void __launch_bounds__(STEP_THREADS, (COMP || AUX) ? 1 : KIN_STEP_MIN_BLOCKS)
 kin_step_kernel(const __grid_constant__ KinEnvParams P, const KinSamplerParams* __restrict__ S, float* __restrict__ state,
                 int stride, int n, const float* __restrict__ action, float* __restrict__ obs, float* __restrict__ reward,
                 uint8_t* __restrict__ done, float* __restrict__ aux, float* __restrict__ comps, uint64_t seed,

@@ -14,7 +14,10 @@ from typing import Any
 PKG_DIR = Path(__file__).resolve().parent
 REPO_ROOT = PKG_DIR.parent
 HEADER = REPO_ROOT / "include" / "kin_b200.h"
-LIB_PATH = PKG_DIR / "libkin_b200.so"
+import os
+
+# KIN_B200_LIB: load another build of the same C ABI (experiment / trace builds under tools/_bin); default = the in-tree library
+LIB_PATH = Path(os.environ["KIN_B200_LIB"]).resolve() if os.environ.get("KIN_B200_LIB") else PKG_DIR / "libkin_b200.so"
 
 _SCALARS = {"float": ctypes.c_float, "int": ctypes.c_int, "double": ctypes.c_double}
 _structs: dict[str, type] = {}

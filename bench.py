@@ -42,7 +42,7 @@ SUITE_SEED = 700001 + STAGE * 1009
 # algorithmic work per env-step (DESIGN.md / SURVEY 8d)
 STEP_BYTES_APPROACH = 532
 # measured DRAM traffic per launch (ncu --set full captures committed under profiles/): read + write bytes
-NCU_TRAFFIC_STEP_KERNEL = 369_145_856 + 682_055_168     # kin_step_kernel<approach>, 2 097 152 envs: 1 051 MB vs 1 116 MB algorithmic
+NCU_TRAFFIC_STEP_KERNEL = 369_136_896 + 690_771_968     # kin_step_kernel<approach>, 2 097 152 envs: 1 060 MB vs 1 116 MB algorithmic
 NCU_TRAFFIC_ROLLOUT_TC = 4_509_696 + 158_464            # kin_rollout_tc_kernel, 65 536 episodes: inputs + result rows only
 ACTOR_FLOPS = 2 * (56 * 64 + 64 * 64 + 64 * 7)   # 16256
 ENV_FLOPS = 1800
@@ -210,7 +210,7 @@ def measure_step_kernel(torch, device, pk, n_envs: int = 1 << 21, launches: int 
     del env
     return {"kernel": "kin_step_kernel<approach>", "bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
             "frac": gbs / pk["hbm_gbs"], "traffic": NCU_TRAFFIC_STEP_KERNEL if n_envs == 2_097_152 else None,
-            "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r1_step_optimised_raw.csv (ncu --set full, same size)",
+            "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r1_step_v3_raw.csv (ncu --set full, same size)",
             "peak_source": pk["source"], "n_envs": n_envs, "launches": launches,
             "us_per_launch": t * 1e6, "env_steps_per_sec": n_envs / t, "bytes_per_env_step": STEP_BYTES_APPROACH,
             "note": "working set %.0f MB per launch (> L2), CUDA events on the launching stream" % (STEP_BYTES_APPROACH * n_envs / 1e6)}

@@ -532,7 +532,8 @@ int kin_rollout_handoff_states(void *approach_handle, const KinPolicyWeights *ho
  * the evaluator's state override (route/route_env.py:49-97, route/route_sequence_env.py:96-137,
  * eval/eval_route_curriculum.py:67-87).  route_index [n_reset] int32; last_route_index (nullable, sequence mode);
  * initial_q (nullable -> waypoint(start_route_index[i]) with start_route_index nullable -> route_index-1);
- * obs [n_reset,80] nullable.                                                                                     */
+ * obs [n_reset,80] nullable.  route_index[i] < 0 skips entry i (masked reset: pass every slot, -1 for the ones that keep
+ * running -- no host-side compaction of the finished slots).                                                        */
 int kin_route_reset(void *handle, const KinRouteTable *host_route, float *state, int stride, int n_envs, const int *env_ids,
                     int n_reset, const int *route_index, const int *start_route_index, const int *last_route_index,
                     const float *initial_q, const float *initial_dq, const float *initial_prev_action, float *obs, void *stream);

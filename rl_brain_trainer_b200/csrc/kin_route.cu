@@ -95,6 +95,7 @@ kin_route_reset_kernel(const __grid_constant__ KinEnvParams P, RouteView R, floa
     const int env = env_ids ? env_ids[i] : i;
     if (env < 0 || env >= n_envs) return;
     const int ri = route_index[i];
+    if (ri < 0) return;           // masked reset: a negative waypoint leaves this slot (state and observation row) untouched
     const int st = start_index ? start_index[i] : max(ri - 1, 0);
     float r_iq[NJ], r_idq[NJ], r_ipa[NJ], r_gq[NJ], gq_out[NJ];
     const float* sq = R.q + (size_t)wp_clamp(R, st) * NJ;

@@ -269,12 +269,15 @@ class PPOTrainer:
 
     def _collect_route(self) -> dict[str, float]:
         """Route env rollout: per step policy sample -> ``kin_route_step`` -> TimeLimit bootstrap from the terminal observation ->
-        sampled route resets (``sample_route_reset``) of the finished slots; the finished episodes feed the prefix curriculum."""
+        masked sampled route reset (``sample_route_reset``) of the finished slots, all on the device with no host round trip.
+        The finished episodes' flags are kept per step and fed to the prefix curriculum in time order after the rollout, so a
+        promotion widens the reset window from the next rollout on (the reference's callback widens it at the very step)."""
         L, env, hp = self._L, self.env, self.hp
         stream = torch.cuda.current_stream(self.device).cuda_stream
         w = ctypes.byref(self.policy.c)
         done_bits = _D("KIN_DONE_TERMINATED") | _D("KIN_DONE_TRUNCATED")
-        episodes = successes = 0.0
+        if not hasattr(self, "_route_flags"):
+            self._route_flags = torch.zeros((self.T, 5, self.N), dtype=torch.bool, device=self.device)
         with torch.cuda.device(self.device):
             for t in range(self.T):
                 self.start_buf[t].copy_(self._next_start)
@@ -287,16 +290,10 @@ class PPOTrainer:
                 _lib.check(L.kin_ppo_bootstrap(w, env.obs.data_ptr(), self.done_buf[t].data_ptr(), self.rew_buf[t].data_ptr(), float(hp.gamma), self.N, stream))
                 finished = (env.done & done_bits) != 0
                 self._next_start = finished.to(torch.uint8)
-                ids = torch.nonzero(finished).reshape(-1)
-                if ids.numel():
-                    episodes += float(ids.numel())
-                    flags = torch.stack([info["success"][ids], info["route_ready"][ids], info["route_orientation_hit"][ids],
-                                         info["route_regression"][ids]]).cpu().numpy()
-                    successes += float(flags[0].sum())
-                    if self.route_curriculum is not None and self.route_curriculum.record(
-                            flags[0], flags[1], flags[2], flags[3], total_timesteps=self.num_timesteps + (t + 1) * self.N):
-                        env.set_route_window(max_route_index=self.route_curriculum.prefix_end_index)
-                    env.reset(env_ids=ids.to(torch.int32))
+                fl = self._route_flags[t]
+                fl[0] = finished
+                fl[1], fl[2], fl[3], fl[4] = info["success"], info["route_ready"], info["route_orientation_hit"], info["route_regression"]
+                env.reset_where(finished)
                 self.obs_buf[t + 1].copy_(env.obs)
                 self.global_step += 1
             _lib.check(L.kin_policy_act(w, self.obs_buf[self.T].data_ptr(), self._scratch_act().data_ptr(),
@@ -305,6 +302,18 @@ class PPOTrainer:
                                      self.done_buf[self.T - 1].data_ptr(), float(hp.gamma), float(hp.gae_lambda), self.T, self.N,
                                      self.adv_buf.data_ptr(), self.ret_buf.data_ptr(), self.tile_sums.data_ptr(), stream))
             self.obs_buf[0].copy_(self.obs_buf[self.T])
+            flags = self._route_flags.cpu().numpy()          # the rollout's one device -> host transfer
+        fin = flags[:, 0]
+        episodes, successes = float(fin.sum()), float((flags[:, 1] & fin).sum())
+        if self.route_curriculum is not None:
+            promoted = False
+            for t in range(self.T):
+                ids = np.nonzero(fin[t])[0]
+                if ids.size:
+                    promoted |= self.route_curriculum.record(flags[t, 1, ids], flags[t, 2, ids], flags[t, 3, ids], flags[t, 4, ids],
+                                                            total_timesteps=self.num_timesteps + (t + 1) * self.N * self.world)
+            if promoted:
+                env.set_route_window(max_route_index=self.route_curriculum.prefix_end_index)
         self.num_timesteps += self.S * self.world
         self.last_rollout = {"episodes": episodes, "successes": successes, "mean_reward": float(self.rew_buf.mean())}
         return self.last_rollout

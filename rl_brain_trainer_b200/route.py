@@ -192,6 +192,27 @@ class BatchedRouteKinematicEnv:
             self.obs[ids.long()] = out
         return self.obs
 
+    def reset_where(self, mask: torch.Tensor) -> torch.Tensor:
+        """Sampled reset (``sample_route_reset``) of the slots where ``mask`` is set, without a host round trip: every slot gets a
+        draw, the ones that keep running pass waypoint -1 and the reset kernel skips them (state and observation row untouched)."""
+        if not hasattr(self, "_gen"):
+            self._gen = torch.Generator(device=self.device)
+            self._gen.manual_seed(0)
+        n = self.num_envs
+        smp = sample_route_reset_batch(self.table, self.config.base_env_config.joint_specs, self.config.reset_config, n, self._gen)
+        ri = smp["route_index"]
+        last = None
+        if self.sequence is not None:  # route_sequence_env.py:120-124
+            max_index = min(self.config.reset_config.max_route_index, len(self.route) - 1)
+            ri = ri.clamp(1, max_index)
+            last = torch.clamp(ri + max(int(self.sequence.sequence_length), 1) - 1, max=max_index).to(torch.int32).contiguous()
+        ri = torch.where(mask.to(torch.bool), ri, torch.full_like(ri, -1)).to(torch.int32).contiguous()
+        st, iq, idq, ipa = (smp[k].contiguous() for k in ("start_route_index", "initial_q", "initial_dq", "initial_prev_action"))
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.kin_route_reset(self._params.handle, ctypes.byref(self.table.c), _ptr(self.state), self.stride, n, None, n,
+                                               _ptr(ri), _ptr(st), _ptr(last), _ptr(iq), _ptr(idq), _ptr(ipa), _ptr(self.obs), _stream()))
+        return self.obs
+
     def step(self, actions: torch.Tensor):
         a = torch.as_tensor(actions, dtype=torch.float32, device=self.device)
         if a.shape != (self.num_envs, 7):

@@ -538,6 +538,29 @@ int kin_route_reset(void *handle, const KinRouteTable *host_route, float *state,
                     int n_reset, const int *route_index, const int *start_route_index, const int *last_route_index,
                     const float *initial_q, const float *initial_dq, const float *initial_prev_action, float *obs, void *stream);
 
+/* sample_route_reset (route/route_reset_samplers.py:43-117) as a table: reset-mode probabilities in the reference's order
+ * (prefix_start, random_prefix, segment, replay, recovery), the inclusive target-waypoint range of every mode, the three noise
+ * scales; forced_mode >= 0 pins the mode (config.mode = "<name>_reset").  sequence_length > 0: RouteSequenceKinematicEnv.reset
+ * (route/route_sequence_env.py:120-124) clamps the target to [1, max_route_index] and sets last = min(target + length - 1, max). */
+typedef struct KinRouteResetParams {
+    float mode_cdf[5];
+    int forced_mode;
+    int index_lo[5];
+    int index_hi[5];
+    float q_noise_std;
+    float dq_noise_std;
+    float prev_action_noise_std;
+    int sequence_length;
+    int max_route_index;
+} KinRouteResetParams;
+
+/* Replaces: RouteKinematicEnv.reset() without options (route/route_env.py:60-73 -> sample_route_reset) for every slot whose
+ * done byte has KIN_DONE_TERMINATED or KIN_DONE_TRUNCATED set (done == NULL: every slot) -- the route env's auto-reset, one
+ * launch, no host round trip.  Draws are Philox4x32(seed, env, counter): distributionally, not bitwise, the reference's numpy
+ * stream.  obs [n_envs,80] (nullable): the rows of the reset slots are rewritten, the others untouched.                        */
+int kin_route_reset_sampled(void *handle, const KinRouteTable *host_route, const KinRouteResetParams *host_reset, float *state, int stride,
+                            int n_envs, const uint8_t *done, uint64_t seed, uint32_t counter, float *obs, void *stream);
+
 /* Replaces: RouteKinematicEnv.step (route/route_env.py:124-192; sequence_mode = 0) and RouteSequenceKinematicEnv.step
  * with the in-episode waypoint advance (route/route_sequence_env.py:139-257; sequence_mode = 1).
  * obs [n,80]; reward = route reward (route/reward_route.py:54-143); done = KIN_DONE_* with route semantics;

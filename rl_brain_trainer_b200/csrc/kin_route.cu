@@ -123,6 +123,59 @@ kin_route_reset_kernel(const __grid_constant__ KinEnvParams P, RouteView R, floa
     }
 }
 
+// sample_route_reset + reset for the finished slots (route/route_reset_samplers.py:43-117, route/route_env.py:60-97)
+__global__ void __launch_bounds__(128)
+kin_route_reset_sampled_kernel(const __grid_constant__ KinEnvParams P, RouteView R, const __grid_constant__ KinRouteResetParams C,
+                               float* __restrict__ state, int stride, int n_envs, const uint8_t* __restrict__ done, uint64_t seed,
+                               uint32_t counter, float* __restrict__ obs) {
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= n_envs) return;
+    if (done && !(done[env] & (KIN_DONE_TERMINATED | KIN_DONE_TRUNCATED))) return;
+    Philox rng(seed, (uint32_t)env, counter);
+    int mode = 4;
+    {
+        const float u = rng.uniform();
+#pragma unroll
+        for (int m = 3; m >= 0; --m) if (u < C.mode_cdf[m]) mode = m;
+    }
+    if (C.forced_mode >= 0) mode = C.forced_mode;
+    int ri = rng.integers(C.index_lo[mode], C.index_hi[mode]);
+    const int start = mode == 0 ? 0 : max(ri - 1, 0);
+    const int src = mode == 4 ? ri : start;
+    int last = ri;
+    if (C.sequence_length > 0) {
+        ri = min(max(ri, 1), C.max_route_index);
+        last = min(ri + C.sequence_length - 1, C.max_route_index);
+    }
+    float nz[24];
+#pragma unroll
+    for (int k = 0; k < 24; k += 2) nz[k] = gauss_pair(rng, &nz[k + 1]);
+    float r_iq[NJ], r_idq[NJ], r_ipa[NJ], r_gq[NJ], gq_out[NJ];
+    const float* sq = R.q + (size_t)wp_clamp(R, src) * NJ;
+    const float* gq = R.q + (size_t)wp_clamp(R, ri) * NJ;
+#pragma unroll
+    for (int k = 0; k < NJ; ++k) {
+        r_iq[k] = clampf(fmaf(nz[k], C.q_noise_std, __ldg(sq + k)), P.joint_lower[k], P.joint_upper[k]);
+        r_idq[k] = nz[7 + k] * C.dq_noise_std;
+        r_ipa[k] = clampf(nz[14 + k] * C.prev_action_noise_std, -1.0f, 1.0f);
+        r_gq[k] = __ldg(gq + k);
+    }
+    EnvRegs s;
+    s.flags = 0u;
+    reset_core(P, s, KIN_MODE_APPROACH, r_iq, r_idq, r_ipa, r_gq, nullptr, gq_out);
+    store_env_reset(state, stride, env, s, gq_out);
+    st_row_u(state, stride, KIN_ROW_ROUTE, env, (unsigned)ri);
+    st_row_u(state, stride, KIN_ROW_ROUTE2, env, (unsigned)last);
+    if (obs) {
+        float o56[OBS], o[ROBS];
+        build_obs(P, s, KIN_MODE_APPROACH, o56);
+        build_route_obs(P, R, s, ri, o56, o);
+        float4* dst = reinterpret_cast<float4*>(obs + (size_t)env * ROBS);
+#pragma unroll
+        for (int k = 0; k < ROBS / 4; ++k) dst[k] = make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+    }
+}
+
 struct DevPolicyR {
     const float *w0, *b0, *w1, *b1, *wo, *bo;
 };
@@ -216,6 +269,21 @@ extern "C" int kin_route_reset(void* handle, const KinRouteTable* host_route, fl
                                                                                     initial_dq, initial_prev_action, obs);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? KIN_OK : kin_fail_cuda(e, "kin_route_reset");
+}
+
+extern "C" int kin_route_reset_sampled(void* handle, const KinRouteTable* host_route, const KinRouteResetParams* host_reset, float* state, int stride,
+                                       int n_envs, const uint8_t* done, uint64_t seed, uint32_t counter, float* obs, void* stream) {
+    KinHandle* h = kin_handle(handle);
+    if (!h || !route_ok(host_route) || !host_reset) return kin_fail(KIN_ERR_INVALID_ARG, "kin_route_reset_sampled: bad handle, route table or reset parameters");
+    if (!state || n_envs <= 0 || stride < n_envs || (stride % 32) != 0) return kin_fail(KIN_ERR_INVALID_ARG, "kin_route_reset_sampled: bad sizes");
+    if (obs && ((uintptr_t)obs & 15u)) return kin_fail(KIN_ERR_INVALID_ARG, "kin_route_reset_sampled: obs must be 16-byte aligned");
+    for (int m = 0; m < 5; ++m)
+        if (host_reset->index_lo[m] < 0 || host_reset->index_hi[m] < host_reset->index_lo[m] || host_reset->index_hi[m] >= host_route->n_waypoints)
+            return kin_fail(KIN_ERR_INVALID_ARG, "kin_route_reset_sampled: waypoint range outside the route");
+    kin_route_reset_sampled_kernel<<<(n_envs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->params, view_of(host_route), *host_reset, state, stride, n_envs,
+                                                                                          done, seed, counter, obs);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? KIN_OK : kin_fail_cuda(e, "kin_route_reset_sampled");
 }
 
 extern "C" int kin_route_step(void* handle, const KinRouteTable* host_route, float* state, int stride, int n_envs, const float* action,

@@ -269,7 +269,7 @@ class PPOTrainer:
 
     def _collect_route(self) -> dict[str, float]:
         """Route env rollout: per step policy sample -> ``kin_route_step`` -> TimeLimit bootstrap from the terminal observation ->
-        masked sampled route reset (``sample_route_reset``) of the finished slots, all on the device with no host round trip.
+        sampled route reset of the finished slots in one launch (``kin_route_reset_sampled``), all on the device with no host round trip.
         The finished episodes' flags are kept per step and fed to the prefix curriculum in time order after the rollout, so a
         promotion widens the reset window from the next rollout on (the reference's callback widens it at the very step)."""
         L, env, hp = self._L, self.env, self.hp
@@ -293,7 +293,7 @@ class PPOTrainer:
                 fl = self._route_flags[t]
                 fl[0] = finished
                 fl[1], fl[2], fl[3], fl[4] = info["success"], info["route_ready"], info["route_orientation_hit"], info["route_regression"]
-                env.reset_where(finished)
+                env.reset_done(seed=self.seed ^ 0x5EED, counter=self.global_step)
                 self.obs_buf[t + 1].copy_(env.obs)
                 self.global_step += 1
             _lib.check(L.kin_policy_act(w, self.obs_buf[self.T].data_ptr(), self._scratch_act().data_ptr(),

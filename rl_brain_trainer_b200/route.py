@@ -192,25 +192,38 @@ class BatchedRouteKinematicEnv:
             self.obs[ids.long()] = out
         return self.obs
 
-    def reset_where(self, mask: torch.Tensor) -> torch.Tensor:
-        """Sampled reset (``sample_route_reset``) of the slots where ``mask`` is set, without a host round trip: every slot gets a
-        draw, the ones that keep running pass waypoint -1 and the reset kernel skips them (state and observation row untouched)."""
-        if not hasattr(self, "_gen"):
-            self._gen = torch.Generator(device=self.device)
-            self._gen.manual_seed(0)
-        n = self.num_envs
-        smp = sample_route_reset_batch(self.table, self.config.base_env_config.joint_specs, self.config.reset_config, n, self._gen)
-        ri = smp["route_index"]
-        last = None
-        if self.sequence is not None:  # route_sequence_env.py:120-124
-            max_index = min(self.config.reset_config.max_route_index, len(self.route) - 1)
-            ri = ri.clamp(1, max_index)
-            last = torch.clamp(ri + max(int(self.sequence.sequence_length), 1) - 1, max=max_index).to(torch.int32).contiguous()
-        ri = torch.where(mask.to(torch.bool), ri, torch.full_like(ri, -1)).to(torch.int32).contiguous()
-        st, iq, idq, ipa = (smp[k].contiguous() for k in ("start_route_index", "initial_q", "initial_dq", "initial_prev_action"))
+    def _reset_params(self) -> Any:
+        """``KinRouteResetParams`` of the current reset config / route window (rebuilt after ``set_route_window``)."""
+        cfg = self.config.reset_config
+        key = (cfg, self.sequence is not None)
+        if getattr(self, "_reset_params_key", None) != key:
+            c = _lib.c_struct("KinRouteResetParams")()
+            max_index = len(self.route) - 1
+            cdf = np.cumsum(_reset_mode_ratios(cfg))
+            cdf[-1] = 1.0
+            rng_tab = _reset_index_ranges(cfg, max_index)
+            c.forced_mode = int(_FORCED_MODE.get(cfg.mode, -1))
+            for m in range(5):
+                lo_m, hi_m = int(rng_tab[m, 0]), int(rng_tab[m, 1])
+                if hi_m < lo_m:       # a segment / replay range that starts beyond the current prefix window: the reference's
+                    lo_m = hi_m       # rng.integers would raise when that mode is drawn; like sample_route_reset_batch, pin the
+                                      # target to the window's upper end instead
+                c.mode_cdf[m] = float(cdf[m])
+                c.index_lo[m], c.index_hi[m] = lo_m, hi_m
+            c.q_noise_std, c.dq_noise_std, c.prev_action_noise_std = float(cfg.q_noise_std), float(cfg.dq_noise_std), float(cfg.prev_action_noise_std)
+            c.sequence_length = max(int(self.sequence.sequence_length), 1) if self.sequence is not None else 0
+            c.max_route_index = int(min(cfg.max_route_index, max_index))
+            self._reset_params_c, self._reset_params_key = c, key
+        return self._reset_params_c
+
+    def reset_done(self, *, seed: int, counter: int, done: torch.Tensor | None = None) -> torch.Tensor:
+        """The route env's auto-reset in one launch (``kin_route_reset_sampled``): every slot whose ``done`` byte (default: the last
+        step's) says terminated / truncated draws a fresh ``sample_route_reset`` start on the device (Philox(seed, env, counter));
+        state and observation rows of the other slots are untouched.  No host round trip."""
+        d = self.done if done is None else done
         with torch.cuda.device(self.device):
-            _lib.check(self._L.kin_route_reset(self._params.handle, ctypes.byref(self.table.c), _ptr(self.state), self.stride, n, None, n,
-                                               _ptr(ri), _ptr(st), _ptr(last), _ptr(iq), _ptr(idq), _ptr(ipa), _ptr(self.obs), _stream()))
+            _lib.check(self._L.kin_route_reset_sampled(self._params.handle, ctypes.byref(self.table.c), ctypes.byref(self._reset_params()), _ptr(self.state),
+                                                       self.stride, self.num_envs, _ptr(d), int(seed), int(counter) & 0xFFFFFFFF, _ptr(self.obs), _stream()))
         return self.obs
 
     def step(self, actions: torch.Tensor):

@@ -28,3 +28,19 @@ def pytest_collection_modifyitems(config, items):
             item.add_marker(pytest.mark.skip(reason="/root/reference not present"))
         if "gpu" in item.keywords and not have_gpu:
             item.add_marker(pytest.mark.skip(reason="no CUDA device"))
+
+
+@pytest.fixture(autouse=True)
+def _pin_global_rngs():
+    """Every test starts from the same global numpy / torch (CPU and CUDA) generator state: a test that draws without an explicit
+    generator sees the same problem instance whatever ran before it."""
+    import numpy as np
+
+    np.random.seed(12345)
+    try:
+        import torch
+
+        torch.manual_seed(12345)
+    except Exception:  # pragma: no cover
+        pass
+    yield

@@ -17,6 +17,7 @@ def _setup(seed=0, log_std=-0.5, in_dim=56):
     from rl_brain_trainer_b200 import ppo
 
     pol = ppo.random_policy(in_dim, seed=seed, log_std_init=log_std, device="cuda")
+    torch.manual_seed(1000 + seed)      # the in-place normal_() below draw from the global generators: pin the problem instance
     # make the action head non-trivial (SB3's 0.01 gain would hide errors in the actor gradient)
     pol.tensors["act_w"].mul_(30.0)
     pol.tensors["pi_b0"].normal_(0, 0.1)

@@ -207,3 +207,67 @@ def test_sampled_route_reset_and_route_window():
     # explicit waypoints still bypass the sampler
     env.reset(route_index=[5])
     assert env.last_reset is None
+
+
+def test_device_route_auto_reset_matches_the_sampler_distribution():
+    """kin_route_reset_sampled (the route env's auto-reset, one launch): only the finished slots are touched; the target waypoints,
+    the start-state noise and the reset-mode mix follow sample_route_reset; the sequence wrapper's window bookkeeping is applied."""
+    import dataclasses
+
+    from rl_brain_trainer_b200 import _lib
+    from rl_brain_trainer_b200 import config as kcfg
+    from rl_brain_trainer_b200.route import BatchedRouteKinematicEnv, _reset_index_ranges, _reset_mode_ratios
+
+    g, renv, _, route, _ = _setup()
+    n = 32768
+    D = _lib.define
+    for sequence in (False, True):
+        seq = kcfg.RouteSequenceConfig(enabled=True, sequence_length=3) if sequence else None
+        env = BatchedRouteKinematicEnv(route, renv, n, sequence_config=seq)
+        env.set_route_window(max_route_index=30, min_route_index=4)
+        env.reset(route_index=[7])
+        before_state, before_obs = env.state.clone(), env.obs.clone()
+        done = torch.zeros(n, dtype=torch.uint8, device="cuda")
+        done[::2] = D("KIN_DONE_TERMINATED")
+        done[1::4] = D("KIN_DONE_SUCCESS")            # a success flag alone is not "finished"
+        env.reset_done(seed=11, counter=5, done=done)
+        torch.cuda.synchronize()
+        hit = torch.arange(n, device="cuda") % 2 == 0
+        assert torch.equal(env.state[:, :n][:, ~hit], before_state[:, :n][:, ~hit]) and torch.equal(env.obs[~hit], before_obs[~hit])
+        ri = (env.state[D("KIN_ROW_ROUTE"), :n].view(torch.int32) & 0xFFFF).long()[hit]
+        last = (env.state[D("KIN_ROW_ROUTE2"), :n].view(torch.int32) & 0xFFFF).long()[hit]
+        cfg = env.config.reset_config
+        ranges = _reset_index_ranges(cfg, len(route) - 1)
+        assert int(ri.min()) >= int(ranges[:, 0].min()) and int(ri.max()) <= 30
+        if sequence:
+            assert bool((last == torch.clamp(ri + 2, max=30)).all())
+        else:
+            assert bool((last == ri).all())
+        # start state = waypoint(src) + N(0, q_noise_std): src is target - 1 (or 0 / the target itself for two of the modes)
+        q = env.state[0:7, :n].t()[hit]
+        tab = env.table.q
+        d_prev = (q - tab[(ri - 1).clamp_min(0)]).norm(dim=1)
+        d_zero = (q - tab[torch.zeros_like(ri)]).norm(dim=1)
+        d_self = (q - tab[ri]).norm(dim=1)
+        nearest = torch.stack([d_zero, d_prev, d_self]).min(dim=0).values
+        bound = 6.0 * cfg.q_noise_std * 7 ** 0.5
+        assert float(nearest.max()) < bound
+        ratios = _reset_mode_ratios(cfg)
+        frac_self = float(((d_self < bound) & (d_prev > bound)).float().mean())          # recovery mode starts AT the target
+        assert abs(frac_self - ratios[4]) < 0.02
+        # dq rows carry the dq noise, prev_action rows the clipped action noise
+        dq = env.state[D("KIN_ROW_DQ"):D("KIN_ROW_DQ") + 7, :n].t()[hit]
+        assert abs(float(dq.std()) - cfg.dq_noise_std) < 0.1 * cfg.dq_noise_std + 1e-9
+        assert float(env.state[D("KIN_ROW_PREV_ACTION"):D("KIN_ROW_PREV_ACTION") + 7, :n].abs().max()) <= 1.0
+        assert bool(torch.isfinite(env.obs).all())
+        # a different counter gives different draws, the same one the same draws
+        s1 = env.state.clone()
+        env.reset_done(seed=11, counter=5, done=done)
+        assert torch.equal(env.state, s1)
+        env.reset_done(seed=11, counter=6, done=done)
+        assert not torch.equal(env.state, s1)
+        # narrowing the window is picked up (the parameter block is rebuilt)
+        env.set_route_window(max_route_index=8)
+        env.reset_done(seed=11, counter=7, done=done)
+        ri8 = (env.state[D("KIN_ROW_ROUTE"), :n].view(torch.int32) & 0xFFFF).long()[hit]
+        assert int(ri8.max()) <= 8 and int(ri8.min()) >= 1

@@ -216,6 +216,26 @@ class BatchedRouteKinematicEnv:
             self._reset_params_c, self._reset_params_key = c, key
         return self._reset_params_c
 
+    def refresh_observation(self) -> torch.Tensor:
+        """Recompute ``self.obs`` from the device state (after the state was written from outside, e.g. a route index override)."""
+        n = self.num_envs
+        ri = (self.state[_D("KIN_ROW_ROUTE"), :n].view(torch.int32) & 0xFFFF).to(torch.int32)
+        r2 = self.state[_D("KIN_ROW_ROUTE2"), :n].view(torch.int32)
+        streak = (self.state[_D("KIN_ROW_ROUTE"), :n].view(torch.int32) >> 16) & 0xFFFF
+        q = self.state[_D("KIN_ROW_Q"):_D("KIN_ROW_Q") + 7, :n].t().contiguous()
+        dq = self.state[_D("KIN_ROW_DQ"):_D("KIN_ROW_DQ") + 7, :n].t().contiguous()
+        pa = self.state[_D("KIN_ROW_PREV_ACTION"):_D("KIN_ROW_PREV_ACTION") + 7, :n].t().contiguous()
+        keep = self.state[[_D("KIN_ROW_MIN_POS"), _D("KIN_ROW_CNT0"), _D("KIN_ROW_CNT1"), _D("KIN_ROW_FLAGS")], :n].clone()
+        last = (r2 & 0xFFFF).to(torch.int32).contiguous()
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.kin_route_reset(self._params.handle, ctypes.byref(self.table.c), _ptr(self.state), self.stride, n, None, n,
+                                               _ptr(ri.contiguous()), None, _ptr(last), _ptr(q), _ptr(dq), _ptr(pa), _ptr(self.obs), _stream()))
+        # the reset kernel re-derives the cached pose / entry metrics; the episode counters and the bookkeeping words are put back
+        self.state[[_D("KIN_ROW_MIN_POS"), _D("KIN_ROW_CNT0"), _D("KIN_ROW_CNT1"), _D("KIN_ROW_FLAGS")], :n] = keep
+        self.state[_D("KIN_ROW_ROUTE"), :n] = (ri | (streak << 16)).to(torch.int32).view(torch.float32)
+        self.state[_D("KIN_ROW_ROUTE2"), :n] = r2.view(torch.float32)
+        return self.obs
+
     def reset_done(self, *, seed: int, counter: int, done: torch.Tensor | None = None) -> torch.Tensor:
         """The route env's auto-reset in one launch (``kin_route_reset_sampled``): every slot whose ``done`` byte (default: the last
         step's) says terminated / truncated draws a fresh ``sample_route_reset`` start on the device (Philox(seed, env, counter));
@@ -252,6 +272,243 @@ class BatchedRouteKinematicEnv:
         if self.rcomp is not None:
             info["reward_components"] = self.rcomp[:, :n]
         return self.obs, self.reward, (d & _D("KIN_DONE_TERMINATED")) != 0, (d & _D("KIN_DONE_TRUNCATED")) != 0, info
+
+
+# SB3 flattens the Dict observation in alphabetical key order: slices of the 80-vector
+ROUTE_OBS_SLICES: dict[str, slice] = {
+    "dq": slice(0, 7), "goal_ori_err": slice(7, 10), "goal_pos_err": slice(10, 13), "joint_limit_margin": slice(13, 20),
+    "mode_flag": slice(20, 24), "next_wp_ori_err": slice(24, 27), "next_wp_pos_err": slice(27, 30), "prev_action": slice(30, 37),
+    "progress": slice(37, 40), "q": slice(40, 47), "route_q_error": slice(47, 54), "route_q_goal": slice(54, 61),
+    "route_scalar": slice(61, 64), "route_tangent": slice(64, 71), "task_type": slice(71, 74), "wp_ori_err": slice(74, 77),
+    "wp_pos_err": slice(77, 80),
+}
+
+
+class _RouteBaseEnvView:
+    """What the reference's evaluators reach for through ``env.base_env`` (eval_route_curriculum.py:73-87,134): the wrapped env's
+    private joint state and a ``reset(options=...)`` that re-seats the joint state while the route bookkeeping stays."""
+
+    def __init__(self, owner: "_SingleRouteEnv") -> None:
+        self._o = owner
+        self.config = owner.config.base_env_config
+        self.action_space, self.observation_space = owner.action_space, owner._base_observation_space
+
+    def _rows(self, name: str) -> np.ndarray:
+        r = _D(name)
+        return self._o._b.state[r:r + 7, 0].detach().cpu().numpy().astype(float)
+
+    _q = property(lambda self: self._rows("KIN_ROW_Q"))
+    _dq = property(lambda self: self._rows("KIN_ROW_DQ"))
+    _prev_action = property(lambda self: self._rows("KIN_ROW_PREV_ACTION"))
+    _goal_q = property(lambda self: self._rows("KIN_ROW_GOAL_Q"))
+
+    def reset(self, *, seed: int | None = None, options: dict[str, Any] | None = None):
+        o, opts = self._o, dict(options or {})
+        if "initial_q" not in opts:
+            raise ValueError("base_env.reset needs options['initial_q'] (the route wrappers own the sampled resets)")
+        goal = np.asarray(opts.get("goal_q", o.route.q_goal[o._target_index()]), dtype=float)
+        if np.abs(goal - o.route.q_goal[o._target_index()]).max() > 1e-9:
+            raise ValueError("base_env.reset: goal_q must be the current route waypoint's q_goal")
+        o._seat(o._target_index(), o._start_route_index, opts["initial_q"], opts.get("initial_dq"), opts.get("initial_prev_action"))
+        obs = o._obs_np()
+        return {k: v for k, v in obs.items() if not k.startswith("route_")}, o._base_info()
+
+    def close(self) -> None:
+        return None
+
+
+class _SingleRouteEnv:
+    """Shared 1-env plumbing of the two route wrappers (numpy in / out over a 1-replica ``BatchedRouteKinematicEnv``)."""
+
+    metadata = {"render_modes": []}
+
+    def __init__(self, *, route: RouteDataset, config: RouteEnvConfig, sequence_config: RouteSequenceConfig | None, seed: int | None,
+                 device: str | torch.device) -> None:
+        from .env import build_action_space, build_observation_space
+
+        self.route, self.config = route, config
+        n = config.base_env_config.n_joints
+        self.action_space = build_action_space(n)
+        self._base_observation_space = build_observation_space(n)
+        self.observation_space = self._base_observation_space
+        if config.observation_config.include_route_keys:      # route_observation.py:18-28
+            from .env import _Box, _DictSpace
+
+            sp = dict(self._base_observation_space.spaces)
+            sp.update({"route_q_goal": _Box(-1.0, 1.0, (n,)), "route_q_error": _Box(-1.0, 1.0, (n,)), "route_tangent": _Box(-1.0, 1.0, (n,)),
+                       "route_scalar": _Box(0.0, 1.0, (3,))})
+            self.observation_space = _DictSpace(sp)
+        self._b = BatchedRouteKinematicEnv(route, config, 1, device, sequence_config=sequence_config, with_components=True)
+        self._rng = np.random.default_rng(seed)
+        self._start_route_index = 0
+        self._prev_info: dict[str, Any] | None = None
+        self.base_env = _RouteBaseEnvView(self)
+        self._seat(1, 0, route.q_goal[0], None, None)
+
+    # ---- device state <-> the reference's private attributes
+    def _word(self, row: str) -> int:
+        return int(self._b.state[_D(row), 0].view(torch.int32).item()) & 0xFFFFFFFF
+
+    def _set_word(self, row: str, value: int) -> None:
+        v = int(value) & 0xFFFFFFFF
+        self._b.state[_D(row), 0] = torch.tensor(v if v < 2 ** 31 else v - 2 ** 32, dtype=torch.int32).view(torch.float32)
+
+    def _target_index(self) -> int:
+        return self._word("KIN_ROW_ROUTE") & 0xFFFF
+
+    def _set_target_index(self, value: int) -> None:
+        self._set_word("KIN_ROW_ROUTE", (self._word("KIN_ROW_ROUTE") & 0xFFFF0000) | (int(value) & 0xFFFF))
+
+    _ready_streak = property(lambda self: self._word("KIN_ROW_ROUTE") >> 16,
+                             lambda self, v: self._set_word("KIN_ROW_ROUTE", (self._word("KIN_ROW_ROUTE") & 0xFFFF) | ((int(v) & 0xFFFF) << 16)))
+
+    def _seat(self, route_index: int, start_index: int, initial_q: Any, initial_dq: Any, initial_prev_action: Any) -> None:
+        z = np.zeros(7)
+        self._b.reset(route_index=[int(route_index)], start_route_index=[int(start_index)], initial_q=np.asarray(initial_q, dtype=float),
+                      initial_dq=z if initial_dq is None else np.asarray(initial_dq, dtype=float),
+                      initial_prev_action=z if initial_prev_action is None else np.asarray(initial_prev_action, dtype=float))
+        self._start_route_index = int(start_index)
+
+    def _obs_np(self) -> dict[str, np.ndarray]:
+        flat = self._b.obs[0].detach().cpu().numpy()
+        keys = ROUTE_OBS_SLICES if self.config.observation_config.include_route_keys else {k: v for k, v in ROUTE_OBS_SLICES.items() if not k.startswith("route_")}
+        return {k: flat[sl].copy() for k, sl in keys.items()}
+
+    def _augment_obs(self, obs: dict[str, np.ndarray] | None = None) -> dict[str, np.ndarray]:
+        """``_augment_obs`` (route_env.py:194-207): the observation of the current device state including the route keys.  Meant
+        for the evaluator's use right after a (base) reset: the observation is rebuilt as an episode-start observation."""
+        self._b.refresh_observation()
+        return self._obs_np()
+
+    def _base_info(self) -> dict[str, Any]:
+        st = self._b.state[:, 0].detach().cpu().numpy()
+        f = lambda name, n: st[_D(name):_D(name) + n].astype(float)  # noqa: E731
+        goal, ee = f("KIN_ROW_GOAL_POSE", 6), f("KIN_ROW_EE_POSE", 6)
+        ori = (goal[3:] - ee[3:] + np.pi) % (2 * np.pi) - np.pi
+        return {"q": f("KIN_ROW_Q", 7), "dq": f("KIN_ROW_DQ", 7), "goal_q": f("KIN_ROW_GOAL_Q", 7), "goal_pose6": goal, "ee_pose6": ee,
+                "position_error_norm": float(np.linalg.norm(goal[:3] - ee[:3])), "orientation_error_norm": float(np.linalg.norm(ori)),
+                "success": False, "reason": "running"}
+
+    def _route_fields(self, index: int) -> dict[str, Any]:
+        return {"route_index": int(index), "start_route_index": int(self._start_route_index), "route_progress_m": float(self.route.progress_m[index]),
+                "route_chunk_id": int(self.route.chunk_id[index])}
+
+    def set_route_window(self, *, max_route_index: int, min_route_index: int = 1) -> None:
+        self._b.set_route_window(max_route_index=max_route_index, min_route_index=min_route_index)
+        self.config = self._b.config
+
+    def _step_device(self, action: Any):
+        a = np.asarray(action, dtype=float)
+        if a.shape != (self.config.base_env_config.n_joints,):
+            raise ValueError(f"Expected action shape {(self.config.base_env_config.n_joints,)}, got {a.shape}")
+        _, reward, term, trunc, info = self._b.step(torch.as_tensor(a[None], dtype=torch.float32))
+        out = self._base_info()
+        out.update({
+            "position_error_norm": float(info["position_error_norm"][0]), "orientation_error_norm": float(info["orientation_error_norm"][0]),
+            "action_l2": float(np.linalg.norm(self.base_env._prev_action)),        # the stored action is the clipped one that was executed
+            "executed_delta_q_l2": float(np.linalg.norm(out["dq"])),
+            "success": bool(info["success"][0]), "route_ready": bool(info["route_ready"][0]), "route_ready_streak": int(info["route_ready_streak"][0]),
+            "route_q_error_norm": float(info["route_q_error_norm"][0]), "route_orientation_hit": bool(info["route_orientation_hit"][0]),
+            "route_regression": bool(info["route_regression"][0]), "nearest_route_q_distance": float(info["nearest_route_q_distance"][0]),
+            "reward_components": info["reward_components"][:, 0].detach().cpu().numpy().astype(float),
+        })
+        return float(reward[0]), bool(term[0]), bool(trunc[0]), info, out
+
+    def render(self) -> None:
+        return None
+
+    def close(self) -> None:
+        return None
+
+
+class RouteKinematicEnv(_SingleRouteEnv):
+    """Drop-in for ``RouteKinematicEnv`` (route/route_env.py:27-212): same constructor keywords, ``reset(seed=, options=)`` /
+    ``step(action)`` / ``set_route_window``, dict observations with the four route keys, the ``info`` keys its readers use
+    (``eval_route_curriculum.py:88-132``, ``route_curriculum.py:96-99``) and the private attributes the evaluator touches
+    (``_route_index``, ``_start_route_index``, ``_ready_streak``, ``_prev_info``, ``_augment_obs``, ``base_env._q / _prev_action /
+    reset``).  Sampled resets consume the numpy PCG64 stream in the reference's order (``sample_route_reset``).  Conformance, not
+    throughput: every call is a 1-replica kernel launch plus a host copy."""
+
+    def __init__(self, *, route: RouteDataset, config: RouteEnvConfig, seed: int | None = None, device: str | torch.device = "cuda") -> None:
+        super().__init__(route=route, config=config, sequence_config=None, seed=seed, device=device)
+
+    _route_index = property(lambda self: self._target_index(), lambda self, v: self._set_target_index(v))
+
+    def reset(self, *, seed: int | None = None, options: dict[str, Any] | None = None):
+        if seed is not None:
+            self._rng = np.random.default_rng(seed)
+        opts = options or {}
+        if "route_index" in opts:           # route_env.py:53-59: explicit waypoint, start state = the start waypoint itself
+            ri = int(opts["route_index"])
+            st = int(opts.get("start_route_index", max(ri - 1, 0)))
+            self._seat(ri, st, self.route.q_goal[st], None, None)
+            mode = "explicit"
+        else:
+            smp = sample_route_reset(self._rng, self.route, self.config.base_env_config.joint_specs, self.config.reset_config)
+            self._seat(smp["route_index"], smp["start_route_index"], smp["initial_q"], smp["initial_dq"], smp["initial_prev_action"])
+            mode = smp["reset_mode"]
+        info = self._base_info()
+        info.update(self._route_fields(self._route_index))
+        info["route_reset_mode"] = mode
+        self._prev_info = dict(info)
+        return self._obs_np(), info
+
+    def step(self, action: Any):
+        reward, term, trunc, _, info = self._step_device(action)
+        if info["success"] and self.config.base_env_config.termination_config.terminate_on_success:
+            info["termination_reason"] = "route_ready_success"
+        info.update(self._route_fields(self._route_index))
+        self._prev_info = dict(info)
+        return self._obs_np(), reward, term, trunc, info
+
+
+class RouteSequenceKinematicEnv(_SingleRouteEnv):
+    """Drop-in for ``RouteSequenceKinematicEnv`` (route/route_sequence_env.py:27-278): the target advances to the next dense route
+    waypoint inside the episode when the current one is reached; ``_current_route_index`` / ``_last_route_index`` /
+    ``_completed_waypoints`` mirror the reference's attributes."""
+
+    def __init__(self, *, route: RouteDataset, config: RouteEnvConfig, sequence_config: RouteSequenceConfig | None = None, seed: int | None = None,
+                 device: str | torch.device = "cuda") -> None:
+        import dataclasses
+
+        self.sequence_config = sequence_config or RouteSequenceConfig()
+        super().__init__(route=route, config=config, sequence_config=dataclasses.replace(self.sequence_config, enabled=True), seed=seed, device=device)
+
+    _current_route_index = property(lambda self: self._target_index(), lambda self, v: self._set_target_index(v))
+    _last_route_index = property(lambda self: self._word("KIN_ROW_ROUTE2") & 0xFFFF)
+    _completed_waypoints = property(lambda self: self._word("KIN_ROW_ROUTE2") >> 16)
+
+    def _sequence_fields(self, *, waypoint_success: bool, sequence_success: bool) -> dict[str, Any]:
+        out = self._route_fields(self._current_route_index)
+        out.update({"route_last_index": int(self._last_route_index), "route_completed_waypoints": int(self._completed_waypoints),
+                    "route_waypoint_success": bool(waypoint_success), "route_sequence_success": bool(sequence_success)})
+        return out
+
+    def reset(self, *, seed: int | None = None, options: dict[str, Any] | None = None):
+        if seed is not None:
+            self._rng = np.random.default_rng(seed)
+        opts = options or {}
+        if "route_index" in opts:           # route_sequence_env.py:101-107: explicit start state allowed
+            ri = int(opts["route_index"])
+            st = int(opts.get("start_route_index", max(ri - 1, 0)))
+            self._seat(ri, st, opts.get("initial_q", self.route.q_goal[st]), opts.get("initial_dq"), opts.get("initial_prev_action"))
+            mode = "explicit_sequence"
+        else:
+            smp = sample_route_reset(self._rng, self.route, self.config.base_env_config.joint_specs, self.config.reset_config)
+            self._seat(smp["route_index"], smp["start_route_index"], smp["initial_q"], smp["initial_dq"], smp["initial_prev_action"])
+            mode = smp["reset_mode"]
+        info = self._base_info()
+        info.update(self._sequence_fields(waypoint_success=False, sequence_success=False))
+        info["route_reset_mode"] = mode
+        self._prev_info = dict(info)
+        return self._obs_np(), info
+
+    def step(self, action: Any):
+        reward, term, trunc, dev, info = self._step_device(action)
+        wp = bool(dev["route_waypoint_success"][0])
+        info.update(self._sequence_fields(waypoint_success=wp, sequence_success=bool(info["success"])))
+        self._prev_info = dict(info)
+        return self._obs_np(), reward, term, trunc, info
 
 
 ROUTE_RESET_MODES = ("prefix_start", "random_prefix", "segment", "replay", "recovery")

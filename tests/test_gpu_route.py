@@ -271,3 +271,65 @@ def test_device_route_auto_reset_matches_the_sampler_distribution():
         env.reset_done(seed=11, counter=7, done=done)
         ri8 = (env.state[D("KIN_ROW_ROUTE"), :n].view(torch.int32) & 0xFFFF).long()[hit]
         assert int(ri8.max()) <= 8 and int(ri8.min()) >= 1
+
+
+def _flags_of(term, trunc, info, index_key="route_index"):
+    return np.array([int(term), int(trunc), int(info["success"]), int(info["route_ready"]), int(info["route_ready_streak"]),
+                     int(info["route_regression"]), int(info["route_orientation_hit"]), int(info[index_key])])
+
+
+def _flat80(obs):
+    from rl_brain_trainer_b200.route import ROUTE_OBS_SLICES
+
+    return np.concatenate([np.asarray(obs[k], dtype=np.float32).reshape(-1) for k in sorted(ROUTE_OBS_SLICES)])
+
+
+def test_single_env_route_adapters_follow_the_reference_traces():
+    """The 1-env drop-ins for RouteKinematicEnv / RouteSequenceKinematicEnv driven exactly as the reference's evaluator drives them
+    (explicit reset, base_env.reset state override, private attribute writes, _augment_obs) against traces recorded from the live
+    reference: dict observations, rewards, flags, info scalars."""
+    from dataclasses import replace
+
+    from rl_brain_trainer_b200.route import RouteKinematicEnv, RouteSequenceKinematicEnv
+
+    g, renv, seq, route, _ = _setup()
+    env = RouteKinematicEnv(route=route, config=renv, seed=0)
+    assert set(env.observation_space.spaces) >= {"route_q_goal", "route_q_error", "route_tangent", "route_scalar", "q", "dq"}
+    starts = g["seq_episode_start"]
+    for e in range(len(starts) - 1):
+        gi = int(g["seq_reset_index"][e])
+        obs, info = env.reset(options={"route_index": gi, "start_route_index": 0, "policy_mode": "approach"})
+        assert info["route_index"] == gi and info["route_reset_mode"] == "explicit" and obs["route_q_goal"].shape == (7,)
+        # eval_route_curriculum.py:73-87: override the base state for sequential chaining
+        obs, info = env.base_env.reset(options={"initial_q": g["seq_reset_q"][e], "initial_dq": g["seq_reset_dq"][e],
+                                                "initial_prev_action": g["seq_reset_pa"][e], "goal_q": route.q_goal[gi], "policy_mode": "approach"})
+        env._route_index, env._start_route_index, env._ready_streak, env._prev_info = gi, 0, 0, dict(info)
+        obs = env._augment_obs(obs)
+        assert np.abs(_flat80(obs) - g["seq_reset_obs"][e]).max() < 5e-5
+        for t in range(starts[e], starts[e + 1]):
+            obs, reward, term, trunc, info = env.step(g["seq_action"][t])
+            assert np.array_equal(_flags_of(term, trunc, info), g["seq_flags"][t]), t
+            sc = np.array([info["route_q_error_norm"], info["nearest_route_q_distance"], info["position_error_norm"], info["orientation_error_norm"]])
+            assert np.abs(sc - g["seq_scalars"][t]).max() < 1e-5 and np.abs(_flat80(obs) - g["seq_obs"][t]).max() < 5e-5, t
+            assert abs(reward - g["seq_reward"][t]) < 5e-4 * max(1.0, abs(g["seq_reward"][t])) and isinstance(reward, float)
+            assert np.abs(info["q"] - g["seq_q"][t]).max() < 5e-6 and np.abs(env.base_env._q - g["seq_q"][t]).max() < 5e-6
+            assert env._ready_streak == int(g["seq_flags"][t][4]) and env._prev_info is not None
+    with pytest.raises(ValueError):
+        env.step(np.zeros(6))
+    # sampled resets draw from the numpy stream like the reference; the window can be narrowed
+    env.set_route_window(max_route_index=6)
+    _, info = env.reset(seed=3)
+    assert 1 <= info["route_index"] <= 6 and info["route_reset_mode"] in ("prefix_start", "random_prefix", "segment", "replay", "recovery")
+    # the sequence wrapper: in-episode waypoint advance
+    senv = RouteSequenceKinematicEnv(route=route, config=renv, sequence_config=replace(seq, enabled=True, sequence_length=4))
+    starts = g["adv_episode_start"]
+    for e in range(len(starts) - 1):
+        first = int(g["adv_reset_index"][e])
+        obs, info = senv.reset(options={"route_index": first, "start_route_index": first - 1})
+        assert np.abs(_flat80(obs) - g["adv_reset_obs"][e]).max() < 5e-5 and info["route_last_index"] == min(first + 3, len(route) - 1)
+        for t in range(starts[e], starts[e + 1]):
+            obs, reward, term, trunc, info = senv.step(g["adv_action"][t])
+            assert np.array_equal(_flags_of(term, trunc, info), g["adv_flags"][t]), t
+            assert np.abs(_flat80(obs) - g["adv_obs"][t]).max() < 5e-5 and abs(reward - g["adv_reward"][t]) < 5e-4 * max(1.0, abs(g["adv_reward"][t]))
+            assert info["route_completed_waypoints"] == int(g["adv_completed"][t]) == senv._completed_waypoints
+            assert senv._current_route_index == int(g["adv_flags"][t][7])

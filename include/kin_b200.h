@@ -577,6 +577,28 @@ int kin_route_probe(void *handle, const KinRouteTable *host_route, const KinPoli
                     int start_index, int end_index, int n, int *prefix, uint32_t *success_bits, unsigned long long *env_steps,
                     void *stream);
 
+/* kin_route_probe that also writes, for the first detail_replicas replicas, the per-waypoint row of _roll_one
+ * (eval/eval_route_curriculum.py:111-131) from which _summarize_rows / _failure_reason / _chunk_metrics (:127-186) are computed:
+ * rows [detail_replicas][end_index - start_index + 1][KIN_ROUTE_ROW_FIELDS] floats.                                            */
+#define KIN_ROUTE_ROW_SUCCESS 0
+#define KIN_ROUTE_ROW_READY_HIT 1
+#define KIN_ROUTE_ROW_READY_DWELL 2
+#define KIN_ROUTE_ROW_FIRST_READY_STEP 3 /* -1: never ready */
+#define KIN_ROUTE_ROW_MAX_READY_STREAK 4
+#define KIN_ROUTE_ROW_STEPS 5
+#define KIN_ROUTE_ROW_FINAL_POS 6
+#define KIN_ROUTE_ROW_FINAL_ORI 7
+#define KIN_ROUTE_ROW_FINAL_Q_ERR 8
+#define KIN_ROUTE_ROW_MIN_POS 9
+#define KIN_ROUTE_ROW_MIN_ORI 10
+#define KIN_ROUTE_ROW_MIN_Q_ERR 11
+#define KIN_ROUTE_ROW_FINAL_ACTION_L2 12
+#define KIN_ROUTE_ROW_FINAL_DQ_L2 13
+#define KIN_ROUTE_ROW_FIELDS 14
+int kin_route_probe_rows(void *handle, const KinRouteTable *host_route, const KinPolicyWeights *host_policy, const float *start_q,
+                         int start_index, int end_index, int n, int *prefix, uint32_t *success_bits, unsigned long long *env_steps,
+                         float *rows, int detail_replicas, void *stream);
+
 /* The same probe with the 80-input actor on tcgen05 (kind::tf32 operands, fp32 accumulation; csrc/kin_route_tc.cu): actions move by
  * O(1e-3) against the strict-fp32 probe, which stays the parity path.  Same arguments and outputs.                              */
 int kin_route_probe_tc(void *handle, const KinRouteTable *host_route, const KinPolicyWeights *host_policy, const float *start_q,

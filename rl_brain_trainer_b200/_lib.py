@@ -102,6 +102,7 @@ def lib() -> ctypes.CDLL:
     L.kin_route_reset_sampled.argtypes = [vp, vp, vp, vp, i32, i32, vp, u64, ctypes.c_uint32, vp, vp]
     L.kin_route_step.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, i32, i32, vp]
     L.kin_route_probe.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp]
+    L.kin_route_probe_rows.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, i32, vp]
     L.kin_route_probe_tc.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp]
     f32, i64, u32 = ctypes.c_float, ctypes.c_longlong, ctypes.c_uint32
     L.kin_ppo_param_count.argtypes = [i32]

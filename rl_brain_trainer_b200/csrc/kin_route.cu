@@ -180,11 +180,13 @@ struct DevPolicyR {
     const float *w0, *b0, *w1, *b1, *wo, *bo;
 };
 
-// evaluate_sequential_route for one replica per thread, policy in the loop (strict fp32 MLP)
+// evaluate_sequential_route for one replica per thread, policy in the loop (strict fp32 MLP).  DETAIL: the first detail_n replicas also
+// write the per-waypoint row of _roll_one (eval_route_curriculum.py:111-131), KIN_ROUTE_ROW_FIELDS floats each
+template <bool DETAIL>
 __global__ void __launch_bounds__(RT_THREADS)
 kin_route_probe_kernel(const __grid_constant__ KinEnvParams P, RouteView R, DevPolicyR pol, const float* __restrict__ start_q, int start_index,
                        int end_index, int n, int* __restrict__ prefix_out, uint32_t* __restrict__ success_bits, int words,
-                       unsigned long long* __restrict__ env_steps) {
+                       unsigned long long* __restrict__ env_steps, float* __restrict__ rows, int detail_n) {
     extern __shared__ __align__(16) float smem[];
     float* sw = smem;
     float* scratch = smem + MlpSmem<ROBS>::FLOATS + threadIdx.x;
@@ -216,7 +218,11 @@ kin_route_probe_kernel(const __grid_constant__ KinEnvParams P, RouteView R, DevP
         RouteRegs rr{idx, 0, idx, 0};
         RouteOut ro;
         ro.done = 0u;
+        ro.q_err = 0.0f;
         bool running = active;
+        // _roll_one's running minima start from the reset state (eval_route_curriculum.py:88-90)
+        float d_min_pos = s.entry[0], d_min_ori = s.entry[1], d_min_q = dist7(gq, cq), d_pos = s.entry[0], d_ori = s.entry[1], d_act = 0.0f, d_dq = 0.0f;
+        int d_first = -1, d_max_streak = 0, d_steps = 0;
         while (__any_sync(0xffffffffu, running)) {
             if (running) {
                 float o56[OBS], o[ROBS], act[ACT];
@@ -229,9 +235,33 @@ kin_route_probe_kernel(const __grid_constant__ KinEnvParams P, RouteView R, DevP
                 route_step_core<false, false>(P, R, nullptr, s, rr, act, true, so, ro, nullptr);   // eval needs no off-route term
                 steps += 1;
                 running = !(ro.done & (KIN_DONE_TERMINATED | KIN_DONE_TRUNCATED));
+                if (DETAIL) {
+                    d_steps += 1;
+                    d_pos = so.pos; d_ori = so.ori; d_act = so.action_l2; d_dq = so.dq_l2;
+                    d_min_pos = fminf(d_min_pos, so.pos); d_min_ori = fminf(d_min_ori, so.ori); d_min_q = fminf(d_min_q, ro.q_err);
+                    if ((ro.flags & 1u) && d_first < 0) d_first = d_steps;
+                    d_max_streak = max(d_max_streak, rr.streak);
+                }
             }
         }
         const bool ok = (ro.done & KIN_DONE_SUCCESS) != 0;
+        if (DETAIL && active && rep < detail_n) {
+            float* row = rows + ((size_t)rep * (final_end - start_index + 1) + (idx - start_index)) * KIN_ROUTE_ROW_FIELDS;
+            row[KIN_ROUTE_ROW_SUCCESS] = ok ? 1.0f : 0.0f;
+            row[KIN_ROUTE_ROW_READY_HIT] = d_first >= 0 ? 1.0f : 0.0f;
+            row[KIN_ROUTE_ROW_READY_DWELL] = d_max_streak >= P.term_success_dwell_steps ? 1.0f : 0.0f;
+            row[KIN_ROUTE_ROW_FIRST_READY_STEP] = (float)d_first;
+            row[KIN_ROUTE_ROW_MAX_READY_STREAK] = (float)d_max_streak;
+            row[KIN_ROUTE_ROW_STEPS] = (float)d_steps;
+            row[KIN_ROUTE_ROW_FINAL_POS] = d_pos;
+            row[KIN_ROUTE_ROW_FINAL_ORI] = d_ori;
+            row[KIN_ROUTE_ROW_FINAL_Q_ERR] = ro.q_err;
+            row[KIN_ROUTE_ROW_MIN_POS] = d_min_pos;
+            row[KIN_ROUTE_ROW_MIN_ORI] = d_min_ori;
+            row[KIN_ROUTE_ROW_MIN_Q_ERR] = d_min_q;
+            row[KIN_ROUTE_ROW_FINAL_ACTION_L2] = d_act;
+            row[KIN_ROUTE_ROW_FINAL_DQ_L2] = d_dq;
+        }
         if (ok && !broken) prefix += 1; else broken = true;
         const int k = idx - start_index;
         if (ok) word |= 1u << (k & 31);
@@ -311,21 +341,36 @@ extern "C" int kin_route_step(void* handle, const KinRouteTable* host_route, flo
     return e == cudaSuccess ? KIN_OK : kin_fail_cuda(e, "kin_route_step");
 }
 
+extern "C" int kin_route_probe_rows(void* handle, const KinRouteTable* host_route, const KinPolicyWeights* w, const float* start_q, int start_index,
+                                    int end_index, int n, int* prefix, uint32_t* success_bits, unsigned long long* env_steps, float* rows,
+                                    int detail_replicas, void* stream);
+
 extern "C" int kin_route_probe(void* handle, const KinRouteTable* host_route, const KinPolicyWeights* w, const float* start_q, int start_index,
                                int end_index, int n, int* prefix, uint32_t* success_bits, unsigned long long* env_steps, void* stream) {
+    return kin_route_probe_rows(handle, host_route, w, start_q, start_index, end_index, n, prefix, success_bits, env_steps, nullptr, 0, stream);
+}
+
+extern "C" int kin_route_probe_rows(void* handle, const KinRouteTable* host_route, const KinPolicyWeights* w, const float* start_q, int start_index,
+                                    int end_index, int n, int* prefix, uint32_t* success_bits, unsigned long long* env_steps, float* rows,
+                                    int detail_replicas, void* stream) {
     KinHandle* h = kin_handle(handle);
     if (!h || !route_ok(host_route)) return kin_fail(KIN_ERR_INVALID_ARG, "kin_route_probe: bad handle or route table");
+    if (detail_replicas < 0 || detail_replicas > n || (detail_replicas > 0 && !rows)) return kin_fail(KIN_ERR_INVALID_ARG, "kin_route_probe_rows: bad detail arguments");
     if (!w || w->in_dim != ROBS || !w->pi_w0 || !w->pi_b0 || !w->pi_w1 || !w->pi_b1 || !w->act_w || !w->act_b) return kin_fail(KIN_ERR_INVALID_ARG, "kin_route_probe: need an 80-input actor");
     if (!prefix || n <= 0 || start_index < 1 || end_index < start_index) return kin_fail(KIN_ERR_INVALID_ARG, "kin_route_probe: bad sizes / indices");
     const size_t smem = (size_t)(MlpSmem<ROBS>::FLOATS + HID * RT_THREADS) * sizeof(float);
-    cudaError_t e = cudaFuncSetAttribute(kin_route_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(kin_route_probe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(kin_route_probe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return kin_fail_cuda(e, "kin_route_probe: smem attribute");
     const int final_end = end_index < host_route->n_waypoints - 1 ? end_index : host_route->n_waypoints - 1;
     const int words = (final_end - start_index + 1 + 31) / 32;
     DevPolicyR p{w->pi_w0, w->pi_b0, w->pi_w1, w->pi_b1, w->act_w, w->act_b};
-    kin_route_probe_kernel<<<(n + RT_THREADS - 1) / RT_THREADS, RT_THREADS, smem, (cudaStream_t)stream>>>(h->params, view_of(host_route), p, start_q,
-                                                                                                        start_index, end_index, n, prefix, success_bits,
-                                                                                                        words, env_steps);
+    if (detail_replicas > 0)
+        kin_route_probe_kernel<true><<<(n + RT_THREADS - 1) / RT_THREADS, RT_THREADS, smem, (cudaStream_t)stream>>>(
+            h->params, view_of(host_route), p, start_q, start_index, end_index, n, prefix, success_bits, words, env_steps, rows, detail_replicas);
+    else
+        kin_route_probe_kernel<false><<<(n + RT_THREADS - 1) / RT_THREADS, RT_THREADS, smem, (cudaStream_t)stream>>>(
+            h->params, view_of(host_route), p, start_q, start_index, end_index, n, prefix, success_bits, words, env_steps, nullptr, 0);
     e = cudaGetLastError();
     return e == cudaSuccess ? KIN_OK : kin_fail_cuda(e, "kin_route_probe");
 }

@@ -640,20 +640,99 @@ class RoutePrefixCurriculum:
                 "stage_episode_count": int(self.stage_episode_count), **self.metrics(), "history": list(self.history)}
 
 
+ROUTE_EVAL_CHUNKS = ((1, 40), (41, 80), (81, 120), (121, 180), (181, 260), (261, 360), (361, 483))
+
+
+def route_failure_reason(row: dict[str, Any]) -> str:
+    """``_failure_reason`` (eval_route_curriculum.py:156-168)."""
+    if row["final_position_error"] > 0.010:
+        return "position"
+    if row["final_orientation_error"] > 0.150:
+        return "orientation"
+    if row.get("final_action_magnitude", 0.0) > 1.20 or row.get("final_dq_norm", 0.0) > 0.040:
+        return "motion_action"
+    if row["final_q_error"] > 0.500:
+        return "q_error"
+    if not row["route_ready_dwell"]:
+        return "dwell_or_motion"
+    return "unknown"
+
+
+def summarize_route_rows(rows: Sequence[dict[str, Any]], route: RouteDataset) -> dict[str, Any]:
+    """``_summarize_rows`` (eval_route_curriculum.py:127-153): same keys, same arithmetic."""
+    if not rows:
+        return {"target_count": 0}
+    first_failure = next((r for r in rows if not r["success"]), None)
+    longest = 0
+    for r in rows:
+        if not r["success"]:
+            break
+        longest += 1
+    mean = lambda k: float(np.mean([r[k] for r in rows]))  # noqa: E731
+    return {
+        "target_count": len(rows), "success_rate": mean("success"), "route_ready_hit_rate": mean("route_ready_hit"),
+        "route_ready_dwell_rate": mean("route_ready_dwell"), "longest_success_prefix": int(longest),
+        "cumulative_successful_route_distance_m": float(route.progress_m[min(longest, len(route) - 1)] - route.progress_m[0]),
+        "first_failure_index": None if first_failure is None else int(first_failure["route_index"]),
+        "first_failure_reason": None if first_failure is None else route_failure_reason(first_failure),
+        "mean_final_position_error": mean("final_position_error"), "mean_final_orientation_error": mean("final_orientation_error"),
+        "mean_final_q_error": mean("final_q_error"),
+        "max_final_position_error": float(np.max([r["final_position_error"] for r in rows])),
+        "max_final_orientation_error": float(np.max([r["final_orientation_error"] for r in rows])),
+    }
+
+
+def route_chunk_metrics(rows: Sequence[dict[str, Any]]) -> dict[str, Any]:
+    """``_chunk_metrics`` (eval_route_curriculum.py:171-186)."""
+    out: dict[str, Any] = {}
+    for idx, (lo, hi) in enumerate(ROUTE_EVAL_CHUNKS):
+        sub = [r for r in rows if lo <= r["route_index"] <= hi]
+        if not sub:
+            continue
+        mean = lambda k: float(np.mean([r[k] for r in sub]))  # noqa: E731
+        out[f"chunk_{idx}_{lo}_{hi}"] = {"target_count": len(sub), "success_rate": mean("success"), "route_ready_hit_rate": mean("route_ready_hit"),
+                                         "mean_final_position_error": mean("final_position_error"),
+                                         "mean_final_orientation_error": mean("final_orientation_error"), "mean_final_q_error": mean("final_q_error")}
+    return out
+
+
+def _rows_from_device(block: np.ndarray, start_index: int) -> list[dict[str, Any]]:
+    """[waypoints][KIN_ROUTE_ROW_FIELDS] floats of one replica -> the row dicts of ``_roll_one`` (eval_route_curriculum.py:111-128)."""
+    F = lambda name: _D("KIN_ROUTE_ROW_" + name)  # noqa: E731
+    rows = []
+    for k, r in enumerate(block):
+        first = int(r[F("FIRST_READY_STEP")])
+        rows.append({
+            "route_index": int(start_index + k), "success": bool(r[F("SUCCESS")] > 0.5), "route_ready_hit": bool(r[F("READY_HIT")] > 0.5),
+            "route_ready_dwell": bool(r[F("READY_DWELL")] > 0.5), "first_ready_step": None if first < 0 else first,
+            "max_ready_streak": int(r[F("MAX_READY_STREAK")]), "steps": int(r[F("STEPS")]),
+            "final_position_error": float(r[F("FINAL_POS")]), "final_orientation_error": float(r[F("FINAL_ORI")]),
+            "final_q_error": float(r[F("FINAL_Q_ERR")]), "min_position_error": float(r[F("MIN_POS")]),
+            "min_orientation_error": float(r[F("MIN_ORI")]), "min_q_error": float(r[F("MIN_Q_ERR")]),
+            "final_action_magnitude": float(r[F("FINAL_ACTION_L2")]), "final_dq_norm": float(r[F("FINAL_DQ_L2")]),
+        })
+    return rows
+
+
 def evaluate_sequential_route(route: RouteDataset, config: RouteEnvConfig, policy: PolicyWeights, *, n_replicas: int = 1, start_index: int = 1,
                               end_index: int | None = None, start_q_noise_std: float = 0.0, seed: int = 0,
-                              device: str | torch.device = "cuda", variant: str = "fp32") -> dict[str, Any]:
+                              device: str | torch.device = "cuda", variant: str = "fp32", detail_replicas: int = 0) -> dict[str, Any]:
     """``evaluate_sequential_route`` (eval_route_curriculum.py:188-246) for ``n_replicas`` independent chains in one launch.
 
     ``variant``: "fp32" = strict-fp32 policy in the loop (the parity path), "tc" = the actor on tcgen05 tensor cores (TF32 operands).
 
     Replica 0 starts exactly at waypoint ``start_index - 1`` like the reference; the others add N(0, std) joint noise.
     Returns per-replica ``longest_success_prefix``, the success bitmask, the prefix histogram and env-step count.
+    ``detail_replicas`` > 0 (strict variant): the first replicas also return the reference's per-waypoint ``rows`` and, for replica 0,
+    its ``summary`` / ``chunk_metrics`` / ``failure_report`` dicts (the JSON files ``evaluate_sequential_route`` writes, :222-245).
     """
     if not torch.cuda.is_available():
         raise _lib.KinError("evaluate_sequential_route needs a CUDA device; there is no CPU fallback")
     if variant not in ("fp32", "tc"):
         raise ValueError("variant must be 'fp32' or 'tc'")
+    detail_replicas = int(detail_replicas)
+    if detail_replicas and (variant != "fp32" or not 0 < detail_replicas <= n_replicas):
+        raise ValueError("detail_replicas needs the strict variant and 0 < detail_replicas <= n_replicas")
     device = torch.device(device)
     end = min(len(route) - 1, len(route) - 1 if end_index is None else int(end_index))
     m = end - start_index + 1
@@ -671,12 +750,31 @@ def evaluate_sequential_route(route: RouteDataset, config: RouteEnvConfig, polic
         prefix = torch.zeros(n_replicas, dtype=torch.int32, device=device)
         bits = torch.zeros((n_replicas, words), dtype=torch.int32, device=device)
         steps = torch.zeros(1, dtype=torch.int64, device=device)
-        probe = _lib.lib().kin_route_probe_tc if variant == "tc" else _lib.lib().kin_route_probe
-        _lib.check(probe(params.handle, ctypes.byref(table.c), ctypes.byref(policy.c), base.data_ptr(), int(start_index), end,
-                         n_replicas, prefix.data_ptr(), bits.data_ptr(), steps.data_ptr(), _stream()))
+        rows_dev = None
+        if detail_replicas:
+            rows_dev = torch.zeros((detail_replicas, m, _D("KIN_ROUTE_ROW_FIELDS")), dtype=torch.float32, device=device)
+            _lib.check(_lib.lib().kin_route_probe_rows(params.handle, ctypes.byref(table.c), ctypes.byref(policy.c), base.data_ptr(), int(start_index), end,
+                                                       n_replicas, prefix.data_ptr(), bits.data_ptr(), steps.data_ptr(), rows_dev.data_ptr(), detail_replicas,
+                                                       _stream()))
+        else:
+            probe = _lib.lib().kin_route_probe_tc if variant == "tc" else _lib.lib().kin_route_probe
+            _lib.check(probe(params.handle, ctypes.byref(table.c), ctypes.byref(policy.c), base.data_ptr(), int(start_index), end,
+                             n_replicas, prefix.data_ptr(), bits.data_ptr(), steps.data_ptr(), _stream()))
     hist = torch.bincount(prefix.long(), minlength=m + 1)
     p0 = int(prefix[0].item())
+    detail: dict[str, Any] = {}
+    if rows_dev is not None:
+        blocks = rows_dev.cpu().numpy()
+        all_rows = [_rows_from_device(b, int(start_index)) for b in blocks]
+        summary = summarize_route_rows(all_rows[0], route)
+        summary.update({"schema_version": "v5.route_curriculum.sequential_eval.v1", "mode": "sequential_actual_final_q_to_next_dense_q_goal",
+                        "start_index": int(start_index), "end_index": int(end)})
+        failure = next((r for r in all_rows[0] if not r["success"]), None)
+        detail = {"rows": all_rows, "summary": summary, "chunk_metrics": route_chunk_metrics(all_rows[0]),
+                  "failure_report": {"first_failure_index": summary["first_failure_index"], "first_failure_reason": summary["first_failure_reason"],
+                                     "first_failure": failure}}
     return {
+        **detail,
         "longest_success_prefix": prefix, "success_bits": bits, "prefix_histogram": hist, "env_steps": steps,
         "replica0_longest_success_prefix": p0,
         "replica0_cumulative_successful_route_distance_m": float(route.progress_m[min(p0, len(route) - 1)] - route.progress_m[0]),

@@ -333,3 +333,49 @@ def test_single_env_route_adapters_follow_the_reference_traces():
             assert np.abs(_flat80(obs) - g["adv_obs"][t]).max() < 5e-5 and abs(reward - g["adv_reward"][t]) < 5e-4 * max(1.0, abs(g["adv_reward"][t]))
             assert info["route_completed_waypoints"] == int(g["adv_completed"][t]) == senv._completed_waypoints
             assert senv._current_route_index == int(g["adv_flags"][t][7])
+
+
+def test_sequential_route_eval_rows_and_summary_match_the_reference():
+    """evaluate_sequential_route with per-waypoint rows against the live reference's run of the same chain (tests/golden/route_eval.json,
+    made by gen_golden_route_eval.py): _roll_one rows, _summarize_rows, _chunk_metrics, _failure_reason."""
+    import json
+
+    from rl_brain_trainer_b200.policy import PolicyWeights
+    from rl_brain_trainer_b200.route import evaluate_sequential_route, route_failure_reason
+
+    from ._util import GOLD
+
+    ref = json.loads((GOLD / "route_eval.json").read_text())
+    g, renv, _, route, _ = _setup()
+    pol = PolicyWeights.preset("route_prefix120", "cuda")
+    res = evaluate_sequential_route(route, renv, pol, n_replicas=3, start_index=1, end_index=len(route) - 1, start_q_noise_std=0.0008, seed=1,
+                                    detail_replicas=2)
+    rows, rrows = res["rows"][0], ref["rows"]
+    assert len(res["rows"]) == 2 and len(rows) == len(rrows) == len(route) - 1
+    # the chain is closed-loop: fp32 vs fp64 rounding can move a borderline waypoint, after which the two chains differ legitimately
+    same = 0
+    for a, b in zip(rows, rrows):
+        if a["success"] != b["success"] or a["steps"] != b["steps"]:
+            break
+        same += 1
+        assert a["route_index"] == b["route_index"] and a["route_ready_hit"] == b["route_ready_hit"] and a["route_ready_dwell"] == b["route_ready_dwell"]
+        assert a["first_ready_step"] == b["first_ready_step"] and a["max_ready_streak"] == b["max_ready_streak"]
+        for k in ("final_position_error", "final_orientation_error", "final_q_error", "min_position_error", "min_orientation_error", "min_q_error",
+                  "final_action_magnitude", "final_dq_norm"):
+            assert abs(a[k] - b[k]) < 2e-4 * max(1.0, abs(b[k])) + 2e-5, (a["route_index"], k, a[k], b[k])
+        if not b["success"]:
+            assert route_failure_reason(a) == ref["failure_reasons"][a["route_index"] - 1]
+    assert same >= ref["summary"]["longest_success_prefix"] + 1          # at least through the first failure
+    s, rs = res["summary"], ref["summary"]
+    assert set(rs) <= set(s)
+    assert s["longest_success_prefix"] == rs["longest_success_prefix"] == res["replica0_longest_success_prefix"]
+    assert s["first_failure_index"] == rs["first_failure_index"] and s["first_failure_reason"] == rs["first_failure_reason"]
+    assert abs(s["cumulative_successful_route_distance_m"] - rs["cumulative_successful_route_distance_m"]) < 1e-9
+    assert abs(s["success_rate"] - rs["success_rate"]) <= 3 / len(rows) and abs(s["route_ready_hit_rate"] - rs["route_ready_hit_rate"]) <= 3 / len(rows)
+    assert res["failure_report"]["first_failure"]["route_index"] == ref["failure_report"]["first_failure"]["route_index"]
+    assert set(res["chunk_metrics"]) == set(ref["chunk_metrics"])
+    for name, c in ref["chunk_metrics"].items():
+        assert res["chunk_metrics"][name]["target_count"] == c["target_count"]
+        assert abs(res["chunk_metrics"][name]["success_rate"] - c["success_rate"]) <= 3 / c["target_count"]
+    with pytest.raises(ValueError):
+        evaluate_sequential_route(route, renv, pol, n_replicas=2, variant="tc", detail_replicas=1)

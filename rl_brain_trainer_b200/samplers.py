@@ -277,3 +277,14 @@ def build_fixed_eval_suite(*, seed: int, n_episodes: int, joint_specs: Sequence[
         iq.append(sample_joint_configuration(rng, joint_specs, start_margin_fraction))
         gq.append(sample_joint_configuration(rng, joint_specs, goal_margin_fraction))
     return EvalSuite(initial_q=np.array(iq).reshape(-1, 7), goal_q=np.array(gq).reshape(-1, 7))
+
+
+def build_dock_eval_suite(config: Phase1EnvConfig, *, seed: int = 700001, n_episodes: int = 10, fk: FkFn | None = None) -> EvalSuite:
+    """``build_dock_eval_suite`` (fixed_eval_suite.py:108-134): ``n_episodes`` draws of ``sample_dock_reset`` at stage 0 from one
+    PCG64 stream (no handoff buffer).  ``fk`` is only needed when the config's close-bucket probability is > 0."""
+    rng = np.random.default_rng(seed)
+    rows = [sample_dock_reset(rng, config, 0, fk) for _ in range(int(n_episodes))]
+    stack = lambda name: None if any(getattr(r, name) is None for r in rows) else np.array([getattr(r, name) for r in rows], dtype=float).reshape(len(rows), -1)  # noqa: E731
+    return EvalSuite(initial_q=np.array([r.initial_q for r in rows], dtype=float).reshape(-1, 7),
+                     goal_q=np.array([r.goal_q for r in rows], dtype=float).reshape(-1, 7), goal_pose6=stack("goal_pose6"),
+                     initial_dq=stack("initial_dq"), initial_prev_action=stack("initial_prev_action"))

@@ -88,3 +88,18 @@ def test_randomstart_splits_match_reference_selection():
         assert np.array_equal(s.initial_q, ev[f"{split}_initial_q"]) and np.array_equal(s.goal_q, ev[f"{split}_goal_q"])
         assert np.array_equal(s.initial_dq, ev[f"{split}_initial_dq"])
         assert np.array_equal(s.initial_prev_action, ev[f"{split}_initial_prev_action"])
+
+
+def test_dock_eval_suite_matches_reference_stream():
+    """build_dock_eval_suite (fixed_eval_suite.py:108-134) on the finisher config: same PCG64 stream as the live reference, including
+    the close-bucket rejection sampler's FK calls (tests/golden/gen_golden_dock_suite.py)."""
+    from pathlib import Path
+
+    from rl_brain_trainer_b200 import config as kcfg, kinematics
+    from rl_brain_trainer_b200.samplers import build_dock_eval_suite
+
+    g = np.load(Path(__file__).resolve().parent / "golden" / "dock_suite.npz")
+    cfg = kcfg.load_preset("finisher_noop_ft")
+    suite = build_dock_eval_suite(cfg, seed=700001, n_episodes=24, fk=kinematics.fk_pose6_folded)
+    assert len(suite) == 24
+    assert np.abs(suite.initial_q - g["initial_q"]).max() < 1e-12 and np.abs(suite.goal_q - g["goal_q"]).max() < 1e-12

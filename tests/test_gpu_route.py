@@ -266,6 +266,13 @@ def test_device_route_auto_reset_matches_the_sampler_distribution():
         assert torch.equal(env.state, s1)
         env.reset_done(seed=11, counter=6, done=done)
         assert not torch.equal(env.state, s1)
+        if not sequence:      # explicit resets: a negative waypoint is a masked (skipped) entry
+            s2, o2 = env.state.clone(), env.obs.clone()
+            mixed = torch.full((n,), -1, dtype=torch.int32, device="cuda")
+            mixed[:3] = 9
+            env.reset(route_index=mixed)
+            assert torch.equal(env.state[:, 3:n], s2[:, 3:n]) and torch.equal(env.obs[3:], o2[3:])
+            assert bool(((env.state[D("KIN_ROW_ROUTE"), :3].view(torch.int32) & 0xFFFF) == 9).all())
         # narrowing the window is picked up (the parameter block is rebuilt)
         env.set_route_window(max_route_index=8)
         env.reset_done(seed=11, counter=7, done=done)

@@ -248,6 +248,7 @@ def measure_training(torch, dist, device, world: int, envs: int = 65536, n_steps
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     steps = S * iters * world
+    tr.close()
     return {"workload": "stage10_ppo_train", "envs_per_gpu": envs, "n_steps": n_steps, "epochs": 8, "minibatches_per_epoch": 16, "iters": iters,
             "rollout_env_steps_per_s": steps / float(t[0]), "update_env_steps_per_s": steps / float(t[1]),
             "e2e_env_steps_per_s": steps / float(t[0] + t[1]), "collect": "kin_ppo_collect (fused, tcgen05 bf16)", "update": "kin_ppo_grad_tc (tcgen05 bf16)",

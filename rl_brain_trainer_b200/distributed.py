@@ -121,6 +121,8 @@ class PeerGradExchange:
             raise _lib.KinError("PeerGradExchange: a peer rank never delivered its gradient (device-side wait timed out)")
 
     def close(self) -> None:
+        """Unmap the peers' buffers and free this rank's (after the stream drained).  Every rank must have finished its last
+        gather before any rank closes: call it at the same point of the program on all ranks (``PPOTrainer.close`` does)."""
         if getattr(self, "_own", None) is None:
             return
         torch.cuda.synchronize(self.device)
@@ -128,6 +130,12 @@ class PeerGradExchange:
             self._L.kin_peer_buffer_close(ptr)
         self._L.kin_peer_buffer_destroy(self._own)
         self._own, self._opened = None, []
+
+    def __del__(self) -> None:  # pragma: no cover - interpreter shutdown order is not ours
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class CurriculumTracker:

@@ -456,6 +456,17 @@ class PPOTrainer:
             log.append(row)
         return log
 
+    def close(self) -> None:
+        """Release the peer-exchange buffers (several ranks: call on every rank after the last ``update``)."""
+        if self.peer is not None:
+            if self.world > 1:
+                import torch.distributed as dist
+
+                torch.cuda.synchronize(self.device)
+                dist.barrier(group=self.group)       # nobody unmaps a buffer a peer may still be pushing into
+            self.peer.close()
+            self.peer = None
+
     def state_dict(self) -> dict[str, torch.Tensor]:
         """SB3 ``policy.pth`` key names, so a trained policy loads back into the reference (and vice versa)."""
         return {KEYS[f]: t.detach().clone() for f, t in self.policy.tensors.items()}

@@ -33,8 +33,7 @@ for ex in ("nccl", "peer"):
     torch.cuda.synchronize(dev)
     params[ex] = tr.params.clone()
     out[ex] = {"approx_kl": u["approx_kl"], "grad_norm": u["grad_norm"], "value_loss": u["value_loss"]}
-    if tr.peer:
-        tr.peer.close()
+    tr.close()
 rel = float((params["peer"] - params["nccl"]).norm() / params["nccl"].norm())
 gathered = [torch.zeros_like(params["peer"]) for _ in range(world)]
 dist.all_gather(gathered, params["peer"])

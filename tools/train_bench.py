@@ -69,5 +69,6 @@ if rank == 0:
                       "update_env_steps_per_s": steps / float(t[1]), "e2e_env_steps_per_s": steps / float(t[0] + t[1]),
                       "wall_env_steps_per_s": steps / float(t[2]), "rollout_s": float(t[0]) / a.iters, "update_s": float(t[1]) / a.iters,
                       "last": {**r, **u}}))
+tr.close()
 if world > 1:
     dist.destroy_process_group()

@@ -269,40 +269,44 @@ class PPOTrainer:
 
     def _collect_route(self) -> dict[str, float]:
         """Route env rollout: per step policy sample -> ``kin_route_step`` -> TimeLimit bootstrap from the terminal observation ->
-        sampled route reset of the finished slots in one launch (``kin_route_reset_sampled``), all on the device with no host round trip.
+        sampled route reset of the finished slots in one launch (``kin_route_reset_sampled``), all on the device with no host round trip
+        and every kernel writing straight into the rollout buffers.
         The finished episodes' flags are kept per step and fed to the prefix curriculum in time order after the rollout, so a
         promotion widens the reset window from the next rollout on (the reference's callback widens it at the very step)."""
         L, env, hp = self._L, self.env, self.hp
         stream = torch.cuda.current_stream(self.device).cuda_stream
         w = ctypes.byref(self.policy.c)
         done_bits = _D("KIN_DONE_TERMINATED") | _D("KIN_DONE_TRUNCATED")
-        if not hasattr(self, "_route_flags"):
-            self._route_flags = torch.zeros((self.T, 5, self.N), dtype=torch.bool, device=self.device)
+        if not hasattr(self, "_route_raw"):
+            self._route_raw = torch.zeros((self.T, self.N), dtype=torch.int32, device=self.device)      # KIN_RAUX_FLAGS word per step
+        flag_row = env.raux[_D("KIN_RAUX_FLAGS"), : self.N].view(torch.int32)
+        keep = env.obs, env.reward, env.done
         with torch.cuda.device(self.device):
-            for t in range(self.T):
-                self.start_buf[t].copy_(self._next_start)
+            self.start_buf[0].copy_(self._next_start)
+            for t in range(self.T):       # five launches per step: policy, route step, bootstrap, flag row, sampled reset
+                env.obs, env.reward, env.done = self.obs_buf[t + 1], self.rew_buf[t], self.done_buf[t]     # written in place by the kernels
                 _lib.check(L.kin_policy_act(w, self.obs_buf[t].data_ptr(), self.act_buf[t].data_ptr(), self.logp_buf[t].data_ptr(),
                                             self.val_buf[t].data_ptr(), self.N, self.seed, self.global_step, 0, stream))
-                _, reward, _, _, info = env.step(self.act_buf[t])
-                self.rew_buf[t].copy_(reward)
-                self.done_buf[t].copy_(env.done)
-                # env.obs is the terminal observation of the slots that just finished (no auto-reset inside the route kernels)
-                _lib.check(L.kin_ppo_bootstrap(w, env.obs.data_ptr(), self.done_buf[t].data_ptr(), self.rew_buf[t].data_ptr(), float(hp.gamma), self.N, stream))
-                finished = (env.done & done_bits) != 0
-                self._next_start = finished.to(torch.uint8)
-                fl = self._route_flags[t]
-                fl[0] = finished
-                fl[1], fl[2], fl[3], fl[4] = info["success"], info["route_ready"], info["route_orientation_hit"], info["route_regression"]
-                env.reset_done(seed=self.seed ^ 0x5EED, counter=self.global_step)
-                self.obs_buf[t + 1].copy_(env.obs)
+                env.step_raw(self.act_buf[t])
+                # env.obs now holds the terminal observation of the slots that just finished (no auto-reset inside the step kernel)
+                _lib.check(L.kin_ppo_bootstrap(w, env.obs.data_ptr(), env.done.data_ptr(), env.reward.data_ptr(), float(hp.gamma), self.N, stream))
+                self._route_raw[t].copy_(flag_row)
+                env.reset_done(seed=self.seed ^ 0x5EED, counter=self.global_step)       # rewrites the finished slots' rows of obs_buf[t + 1]
                 self.global_step += 1
+            env.obs, env.reward, env.done = keep
+            env.obs.copy_(self.obs_buf[self.T])
+            finished = (self.done_buf & done_bits) != 0
+            self.start_buf[1:].copy_(finished[:-1])
+            self._next_start = finished[-1].to(torch.uint8)
             _lib.check(L.kin_policy_act(w, self.obs_buf[self.T].data_ptr(), self._scratch_act().data_ptr(),
                                         self._scratch_logp().data_ptr(), self.last_val.data_ptr(), self.N, self.seed, self.global_step, 1, stream))
             _lib.check(L.kin_ppo_gae(self.rew_buf.data_ptr(), self.val_buf.data_ptr(), self.start_buf.data_ptr(), self.last_val.data_ptr(),
                                      self.done_buf[self.T - 1].data_ptr(), float(hp.gamma), float(hp.gae_lambda), self.T, self.N,
                                      self.adv_buf.data_ptr(), self.ret_buf.data_ptr(), self.tile_sums.data_ptr(), stream))
             self.obs_buf[0].copy_(self.obs_buf[self.T])
-            flags = self._route_flags.cpu().numpy()          # the rollout's one device -> host transfer
+            raw = self._route_raw
+            flags = torch.stack([finished, (self.done_buf & _D("KIN_DONE_SUCCESS")) != 0, (raw & 1) != 0, (raw & 4) != 0, (raw & 2) != 0],
+                                dim=1).cpu().numpy()          # [T, 5, N]: finished, success, route_ready, orientation_hit, regression
         fin = flags[:, 0]
         episodes, successes = float(fin.sum()), float((flags[:, 1] & fin).sum())
         if self.route_curriculum is not None:

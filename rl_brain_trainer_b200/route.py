@@ -246,6 +246,14 @@ class BatchedRouteKinematicEnv:
                                                        self.stride, self.num_envs, _ptr(d), int(seed), int(counter) & 0xFFFFFFFF, _ptr(self.obs), _stream()))
         return self.obs
 
+    def step_raw(self, actions: torch.Tensor) -> None:
+        """One ``kin_route_step`` launch with no host-side post-processing: results land in ``self.obs / reward / done / raux`` (which
+        a rollout loop may point at slices of its own buffers).  ``actions``: contiguous float32 ``[num_envs, 7]`` on this device."""
+        seq = self.sequence is not None
+        _lib.check(self._L.kin_route_step(self._params.handle, ctypes.byref(self.table.c), self.state.data_ptr(), self.stride, self.num_envs,
+                                          actions.data_ptr(), self.obs.data_ptr(), self.reward.data_ptr(), self.done.data_ptr(), _ptr(self.raux),
+                                          _ptr(self.rcomp), int(seq), int(bool(self.sequence.reset_ready_streak_on_advance)) if seq else 1, _stream()))
+
     def step(self, actions: torch.Tensor):
         a = torch.as_tensor(actions, dtype=torch.float32, device=self.device)
         if a.shape != (self.num_envs, 7):

@@ -104,3 +104,80 @@ def test_step_kernel_full_size_matches_small_batches():
         os_, rs, ts, us, _ = small.step(a[idx].contiguous())
         assert torch.equal(ob[idx], os_) and torch.equal(rb[idx], rs) and torch.equal(tb[idx], ts) and torch.equal(ub[idx], us)
     assert torch.equal(big.state[:, idx], small.state[:, :k])
+
+
+def test_randomstart_full_size_shard_invariance_and_reference_draw():
+    """Config 3 (mixed random-start, KNOWN split): a 262 144-pair sweep of the seed-940001 maps gives the same per-episode results
+    whether run as one batch or as eight shards (the 8-GPU layout); the success rate sits where the 1 M-pair sweep (0.833) and the
+    reference's 96-episode draw (0.802, reproduced exactly in tests/test_gpu_rollout.py) put it."""
+    from rl_brain_trainer_b200 import config as kcfg
+    from rl_brain_trainer_b200 import workspace as ws
+    from rl_brain_trainer_b200.distributed import shard_slice
+    from rl_brain_trainer_b200.policy import PolicyWeights
+    from rl_brain_trainer_b200.rollout import VARIANT_TC, ApproachFinisherRollout
+    from rl_brain_trainer_b200.samplers import EvalSuite
+
+    acfg, fcfg = kcfg.load_preset("randomstart_overnight"), kcfg.load_preset("finisher_noop_ft")
+    seed, n = 940001, 262144
+    targets = ws.generate_workspace_target_map(acfg, seed=seed + 1, stage_samples_per_stage=96, random_samples=384)
+    starts = ws.generate_workspace_start_state_map(acfg, seed=seed + 2, stage_samples_per_stage=48, random_samples=384)
+    pairs = ws.build_pair_table(starts, targets, seed=seed + 3, pair_count=int(n * 3.2))
+    tstage0 = np.where(targets.stage[pairs.target] < 0, 0, targets.stage[pairs.target])
+    pool = np.nonzero((tstage0 <= 8) & np.isin(pairs.klass, (0, 1, 2)))[0][:n]
+    assert pool.size == n
+    suite = ws.pairs_to_suite(starts, targets, pairs, pool)
+    ro = ApproachFinisherRollout(acfg, PolicyWeights.preset("randomstart", "cuda"), fcfg, PolicyWeights.preset("finisher", "cuda"), variant=VARIANT_TC)
+    whole = ro.evaluate_suite(suite).to_numpy()
+    assert 0.78 < whole["success"].mean() < 0.88                     # 0.8329 on the 1 M-pair sweep, 0.802 on the reference's 96
+    for r in (0, 3, 7):                                              # three of the eight shards
+        sl = shard_slice(n, r, 8)
+        sub = EvalSuite(initial_q=suite.initial_q[sl], goal_q=suite.goal_q[sl], goal_pose6=None if suite.goal_pose6 is None else suite.goal_pose6[sl],
+                        initial_dq=suite.initial_dq[sl], initial_prev_action=suite.initial_prev_action[sl])
+        part = ro.evaluate_suite(sub).to_numpy()
+        for key in ("success", "final_position_error", "approach_steps", "finisher_steps"):
+            assert np.array_equal(part[key], whole[key][sl]), (r, key)
+
+
+def test_route_probe_full_size_properties():
+    """Config 4 (262 144 route replicas x 170 waypoints, tensor-core probe): replica 0 (no start noise) is independent of the batch it
+    runs in, the prefix histogram accounts for every replica, and the env-step count is the sum of the per-waypoint episodes."""
+    from rl_brain_trainer_b200 import config as kcfg
+    from rl_brain_trainer_b200.policy import PolicyWeights
+    from rl_brain_trainer_b200.route import evaluate_sequential_route, synthetic_route
+
+    route = synthetic_route(483, seed=7)
+    renv, _ = kcfg.to_route_env_config(kcfg.preset_dict("route_prefix120"), max_route_index=len(route) - 1)
+    pol = PolicyWeights.preset("route_prefix120", "cuda")
+    n = 262144
+    big = evaluate_sequential_route(route, renv, pol, n_replicas=n, start_index=1, end_index=170, start_q_noise_std=0.0008, seed=11, variant="tc")
+    one = evaluate_sequential_route(route, renv, pol, n_replicas=1, start_index=1, end_index=170, variant="tc")
+    assert torch.equal(big["success_bits"][0], one["success_bits"][0]) and big["replica0_longest_success_prefix"] == one["replica0_longest_success_prefix"]
+    assert int(big["prefix_histogram"].sum()) == n and int(big["longest_success_prefix"].min()) >= 0 and int(big["longest_success_prefix"].max()) <= 170
+    steps = int(big["env_steps"].item())
+    assert 170 * n <= steps <= 170 * n * 120                         # at least one step per waypoint, at most the episode length
+    # the strict probe on a sample of the same replicas agrees on almost every waypoint flag
+    k = 4096
+    a = evaluate_sequential_route(route, renv, pol, n_replicas=k, start_index=1, end_index=170, start_q_noise_std=0.0008, seed=11, variant="fp32")
+    ba, bb = a["success_bits"].cpu().numpy().view(np.uint32), big["success_bits"][:k].cpu().numpy().view(np.uint32)
+    flips = int(np.unpackbits((ba ^ bb).view(np.uint8)).sum())
+    assert flips <= 0.02 * k * 170, flips
+
+
+def test_training_full_size_is_reproducible():
+    """Config 5 (Stage-10 shell, 65 536 envs x 128 steps, 16 minibatches): two trainers from the same seeds produce bitwise
+    identical parameters after a rollout + update (fused collection, tensor-core update, deterministic reductions), and the
+    first-epoch probability ratio is 1 (the update consumes the operand images with the arithmetic that sampled them)."""
+    from rl_brain_trainer_b200 import config as kcfg, ppo
+
+    cfg = kcfg.load_preset("approach_dynamic_scale_big")
+    envs, T = 65536, 128
+    hp = ppo.PPOHyper(learning_rate=4e-6, n_steps=T, batch_size=envs * T // 16, n_epochs=1, gamma=0.995, gae_lambda=0.95, clip_range=0.1, ent_coef=0.0003)
+    params, stats = [], []
+    for _ in range(2):
+        tr = ppo.PPOTrainer(cfg, ppo.random_policy(56, seed=0, log_std_init=-1.0, device="cuda"), num_envs=envs, hyper=hp, seed=1, stage_index=10)
+        r = tr.collect()
+        stats.append(tr.update())
+        params.append(tr.params.clone())
+        assert r["episodes"] > 0 and np.isfinite(list(stats[-1].values())).all()
+    assert torch.equal(params[0], params[1])
+    assert stats[0]["minibatches"] == 16 and stats[0]["approx_kl"] < 1e-4 and stats[0]["clip_fraction"] < 0.02

@@ -58,3 +58,27 @@ def test_prefix_curriculum_promotion_rules():
     with pytest.raises(ValueError):
         RoutePrefixCurriculum([], promotion_success_rate=1, promotion_route_ready_hit_rate=1, promotion_orientation_hit_rate=1,
                               promotion_max_regression_rate=0, window_episodes=1)
+
+
+def test_route_eval_summaries_reproduce_the_reference_on_its_own_rows():
+    """summarize_route_rows / route_chunk_metrics / route_failure_reason (eval_route_curriculum.py:127-186) fed with the per-waypoint
+    rows the live reference produced (tests/golden/route_eval.json) must give the reference's own summary, chunk table and reasons."""
+    import json
+    from pathlib import Path
+
+    import numpy as np
+
+    from rl_brain_trainer_b200.route import RouteDataset, route_chunk_metrics, route_failure_reason, summarize_route_rows
+
+    gold = Path(__file__).resolve().parent / "golden"
+    ref = json.loads((gold / "route_eval.json").read_text())
+    route = RouteDataset.from_q(np.load(gold / "trace_route.npz")["route_q"])
+    got = summarize_route_rows(ref["rows"], route)
+    for k, v in ref["summary"].items():
+        if isinstance(v, float):
+            assert abs(got[k] - v) < 1e-9, k
+        else:
+            assert got[k] == v, k
+    assert route_chunk_metrics(ref["rows"]) == ref["chunk_metrics"]
+    assert [None if r["success"] else route_failure_reason(r) for r in ref["rows"]] == ref["failure_reasons"]
+    assert summarize_route_rows([], route) == {"target_count": 0}

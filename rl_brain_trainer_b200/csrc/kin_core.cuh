@@ -48,6 +48,7 @@ struct StepOut {
     float margin_min;
     float pe[3], oe[3];      // pose error components after the step (reused by the observation)
     float margin[NJ];        // per-joint limit margins after the step (reused by the observation)
+    float qn[NJ];            // FAST flavour only: normalised joint positions 2(q-lo)/span-1 after the step (observation "q")
     unsigned done;           // KIN_DONE_* bits
 };
 
@@ -58,6 +59,50 @@ __device__ __forceinline__ float norm7(const float* v) {
 #pragma unroll
     for (int i = 1; i < NJ; ++i) acc = fmaf(v[i], v[i], acc);
     return sqrtf(acc);
+}
+
+// ---- FAST flavour (the tensor-core rollout / collection kernels) -----------------------------------------------------
+// Same formulas, cheaper instruction sequences: single-MUFU sqrt / reciprocal (relative error 2^-23, no slow path), a
+// branch-free atan2 (minimax polynomial, |error| < 1e-7 rad), margins from the normalised joint position, and the previous
+// step's pose-error norms carried instead of recomputed.  Differences from the strict flavour are a few ulp (<= 2e-7),
+// far inside the 1e-5 m / 1e-5 rad pose tolerance; the strict kernels (K1, kin_rollout_ffma) do not use it.
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+template <bool FAST>
+__device__ __forceinline__ float sqrt_sel(float x) {
+    if constexpr (FAST) return sqrt_approx(x);
+    else return sqrtf(x);
+}
+template <bool FAST>
+__device__ __forceinline__ float norm3_sel(float a, float b, float c) { return sqrt_sel<FAST>(fmaf(a, a, fmaf(b, b, c * c))); }
+
+// atan2 for the Euler extraction: t = min/max in [0, 1], atan(t) = t + t^3 Q(t^2) (Remez fit, max |error| 7.5e-8 in fp32),
+// then the octant / quadrant / sign fixes.  atan2(0, 0) = 0 like the reference's math.atan2.
+__device__ __forceinline__ float atan2_fast(float y, float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    const float t = mn * rcp_approx(fmaxf(mx, 1e-30f));
+    const float s = t * t;
+    float p = 0.0026222446467727423f;
+    p = fmaf(p, s, -0.015132537111639977f);
+    p = fmaf(p, s, 0.04112186282873154f);
+    p = fmaf(p, s, -0.07366706430912018f);
+    p = fmaf(p, s, 0.10573931783437729f);
+    p = fmaf(p, s, -0.1418597549200058f);
+    p = fmaf(p, s, 0.1999039649963379f);
+    p = fmaf(p, s, -0.33332985639572144f);
+    float r = fmaf(t * s, p, t);
+    r = (ay > ax) ? 1.57079632679489661923f - r : r;
+    r = (x < 0.0f) ? kPi - r : r;
+    return copysignf(r, y);
 }
 
 // pose_utils.py:11-12: (v + pi) mod 2pi - pi with a floored modulo.  Written as v - 2pi*floor((v+pi)/2pi)
@@ -90,12 +135,43 @@ __device__ __forceinline__ void sincos_joint(float x, float* sp, float* cp) {
     *cp = ((k + 1) & 2) ? -c0 : c0;
 }
 
+// FAST flavour: two-term Cody-Waite (|k| <= 2, the third term is 5e-15 * k) or, with -DKIN_FAST_MUFU_SINCOS, the MUFU units.
+__device__ __forceinline__ void sincos_joint_fast(float x, float* sp, float* cp) {
+#ifdef KIN_FAST_MUFU_SINCOS
+    *sp = __sinf(x);
+    *cp = __cosf(x);
+#else
+    const float kf = rintf(x * 0.63661977236758134f);
+    const int k = (int)kf;
+    float r = fmaf(kf, -1.57079601287841796875f, x);
+    r = fmaf(kf, -3.1391647326017846353e-07f, r);
+    const float r2 = r * r;
+    float ps = fmaf(r2, -1.9515295891e-4f, 8.3321608736e-3f);
+    ps = fmaf(ps, r2, -1.6666654611e-1f);
+    ps = fmaf(ps * r2, r, r);
+    float pc = fmaf(r2, 2.4433157117e-5f, -1.3887316255e-3f);
+    pc = fmaf(pc, r2, 4.1666645683e-2f);
+    pc = fmaf(pc, r2, -0.5f);
+    pc = fmaf(pc, r2, 1.0f);
+    const float s0 = (k & 1) ? pc : ps;
+    const float c0 = (k & 1) ? ps : pc;
+    *sp = (k & 2) ? -s0 : s0;
+    *cp = ((k + 1) & 2) ? -c0 : c0;
+#endif
+}
+template <bool FAST>
+__device__ __forceinline__ void sincos_sel(float x, float* sp, float* cp) {
+    if constexpr (FAST) sincos_joint_fast(x, sp, cp);
+    else sincos_joint(x, sp, cp);
+}
+
 // ee_fk.py:98-134 with the constant transforms folded on the host (see KinEnvParams::fk_*):
 // one sincos + 12 flops per revolute joint for the Rz, 27 for the constant 3x3, 9 for the offset.
+template <bool FAST = false>
 __device__ __forceinline__ void fk_pose6(const KinEnvParams& P, const float* q, float* pose) {
     float s, c;
     float R[9], M[9];
-    sincos_joint(q[1], &s, &c);
+    sincos_sel<FAST>(q[1], &s, &c);
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
         float m0 = P.fk_C[3 * r], m1 = P.fk_C[3 * r + 1];
@@ -118,7 +194,7 @@ __device__ __forceinline__ void fk_pose6(const KinEnvParams& P, const float* q, 
 #pragma unroll
             for (int k = 0; k < 3; ++k)
                 M[3 * r + k] = fmaf(R[3 * r], C[k], fmaf(R[3 * r + 1], C[3 + k], R[3 * r + 2] * C[6 + k]));
-        sincos_joint(q[j], &s, &c);
+        sincos_sel<FAST>(q[j], &s, &c);
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
             R[3 * r] = fmaf(c, M[3 * r], s * M[3 * r + 1]);
@@ -135,9 +211,15 @@ __device__ __forceinline__ void fk_pose6(const KinEnvParams& P, const float* q, 
     pose[0] = p0;
     pose[1] = p1;
     pose[2] = p2;
-    pose[3] = atan2f(r21, r22);
-    pose[4] = atan2f(-r20, sqrtf(fmaf(r00, r00, r10 * r10)));
-    pose[5] = atan2f(r10, r00);
+    if constexpr (FAST) {
+        pose[3] = atan2_fast(r21, r22);
+        pose[4] = atan2_fast(-r20, sqrt_approx(fmaf(r00, r00, r10 * r10)));
+        pose[5] = atan2_fast(r10, r00);
+    } else {
+        pose[3] = atan2f(r21, r22);
+        pose[4] = atan2f(-r20, sqrtf(fmaf(r00, r00, r10 * r10)));
+        pose[5] = atan2f(r10, r00);
+    }
 }
 
 // pose_utils.py:15-26 -> (|pos_err|, |ori_err|) and the components
@@ -170,6 +252,18 @@ __device__ __forceinline__ float interp_control(float pos, float near_thr, float
     if (pos >= far_thr) return far_v;
     float alpha = (pos - near_thr) / fmaxf(far_thr - near_thr, 1e-9f);
     return fmaf(alpha, far_v - near_v, near_v);
+}
+
+// FAST flavour: the division becomes a multiplication by a loop-invariant reciprocal
+__device__ __forceinline__ float interp_control_fast(float pos, float near_thr, float far_thr, float near_v, float far_v, float fallback) {
+    if (near_thr <= 0.0f || far_thr <= near_thr) return fallback;
+    const float alpha = clampf((pos - near_thr) * rcp_approx(fmaxf(far_thr - near_thr, 1e-9f)), 0.0f, 1.0f);
+    return fmaf(alpha, far_v - near_v, near_v);
+}
+template <bool FAST>
+__device__ __forceinline__ float interp_sel(float pos, float near_thr, float far_thr, float near_v, float far_v, float fallback) {
+    if constexpr (FAST) return interp_control_fast(pos, near_thr, far_thr, near_v, far_v, fallback);
+    else return interp_control(pos, near_thr, far_thr, near_v, far_v, fallback);
 }
 
 // AKE:425-430
@@ -555,7 +649,9 @@ __device__ __forceinline__ float dock_reward(const KinEnvParams& P, const Reward
 
 // AKE:213-365.  MODE: KIN_MODE_APPROACH / KIN_MODE_DOCK compile the other reward away;
 // KIN_MODE_PER_ENV reads the mode bits of s.flags.  c[] receives info["reward_components"] (COMP only).
-template <int MODE, bool COMP>
+// FAST (tensor-core rollout / collection kernels): `out` must hold the previous step's (or the reset's) pos / ori on entry --
+// they are the "previous" pose-error norms the reference recomputes from the cached ee pose -- and s.ee is not maintained.
+template <int MODE, bool COMP, bool FAST = false>
 __device__ __forceinline__ void step_core(const KinEnvParams& P, EnvRegs& s, const float* action_in, StepOut& out, float* c) {
     const int mode = (MODE == KIN_MODE_PER_ENV) ? (int)((s.flags >> KIN_FLAG_MODE_SHIFT) & 3u) : MODE;
     const bool dock = (mode == KIN_MODE_DOCK);
@@ -563,15 +659,22 @@ __device__ __forceinline__ void step_core(const KinEnvParams& P, EnvRegs& s, con
 #pragma unroll
     for (int i = 0; i < NJ; ++i) a[i] = clampf(action_in[i], -1.0f, 1.0f);
     float pe[3], oe[3];
-    pose_error(s.ee, s.goal, pe, oe);
-    const float prev_pos = norm3(pe[0], pe[1], pe[2]), prev_ori = norm3(oe[0], oe[1], oe[2]);
+    float prev_pos, prev_ori;
+    if constexpr (FAST) {
+        prev_pos = out.pos;
+        prev_ori = out.ori;
+    } else {
+        pose_error(s.ee, s.goal, pe, oe);
+        prev_pos = norm3(pe[0], pe[1], pe[2]);
+        prev_ori = norm3(oe[0], oe[1], oe[2]);
+    }
     float dock_limit = clampf(P.dock_residual_action_limit, 0.0f, 1.0f);
     float dqc_scale = fmaxf(P.dock_delta_q_change_limit_scale, 0.0f);
     if (dock) {
-        dock_limit = clampf(interp_control(prev_pos, P.dock_dynamic_action_limit_near_pos_threshold_m, P.dock_dynamic_action_limit_far_pos_threshold_m,
+        dock_limit = clampf(interp_sel<FAST>(prev_pos, P.dock_dynamic_action_limit_near_pos_threshold_m, P.dock_dynamic_action_limit_far_pos_threshold_m,
                                            P.dock_dynamic_residual_action_limit_near, P.dock_dynamic_residual_action_limit_far,
                                            P.dock_residual_action_limit), 0.0f, 1.0f);
-        dqc_scale = fmaxf(interp_control(prev_pos, P.dock_dynamic_action_limit_near_pos_threshold_m, P.dock_dynamic_action_limit_far_pos_threshold_m,
+        dqc_scale = fmaxf(interp_sel<FAST>(prev_pos, P.dock_dynamic_action_limit_near_pos_threshold_m, P.dock_dynamic_action_limit_far_pos_threshold_m,
                                          P.dock_dynamic_delta_q_change_limit_scale_near, P.dock_dynamic_delta_q_change_limit_scale_far,
                                          P.dock_delta_q_change_limit_scale), 0.0f);
 #pragma unroll
@@ -582,13 +685,15 @@ __device__ __forceinline__ void step_core(const KinEnvParams& P, EnvRegs& s, con
     if (dock) {
         if (P.dock_action_delta_scale > 0.0f) scale = P.dock_action_delta_scale;
     } else if (P.dynamic_action_delta_scale_enabled) {
-        float mult = interp_control(prev_pos, P.dynamic_action_delta_scale_near_pos_threshold_m, P.dynamic_action_delta_scale_far_pos_threshold_m,
+        float mult = interp_sel<FAST>(prev_pos, P.dynamic_action_delta_scale_near_pos_threshold_m, P.dynamic_action_delta_scale_far_pos_threshold_m,
                                     P.dynamic_action_delta_scale_near_multiplier, P.dynamic_action_delta_scale_far_multiplier, 1.0f);
         scale = P.action_delta_scale * fmaxf(mult, 0.0f);
     }
     RewardIn in;
-    in.prev_action_norm = norm7(s.pa);
-    in.prev_dq_norm = norm7(s.dq);
+    in.prev_action_norm = FAST ? sqrt_approx(fmaf(s.pa[0], s.pa[0], fmaf(s.pa[1], s.pa[1], fmaf(s.pa[2], s.pa[2], fmaf(s.pa[3], s.pa[3], fmaf(s.pa[4], s.pa[4], fmaf(s.pa[5], s.pa[5], s.pa[6] * s.pa[6])))))))
+                               : norm7(s.pa);
+    in.prev_dq_norm = FAST ? sqrt_approx(fmaf(s.dq[0], s.dq[0], fmaf(s.dq[1], s.dq[1], fmaf(s.dq[2], s.dq[2], fmaf(s.dq[3], s.dq[3], fmaf(s.dq[4], s.dq[4], fmaf(s.dq[5], s.dq[5], s.dq[6] * s.dq[6])))))))
+                           : norm7(s.dq);
     float msq = 0.0f, dmsq = 0.0f, dq_sq = 0.0f, dchg_sq = 0.0f, margin = 1.0f;
     float qn[NJ];
 #pragma unroll
@@ -608,15 +713,26 @@ __device__ __forceinline__ void step_core(const KinEnvParams& P, EnvRegs& s, con
         dmsq = fmaf(da, da, dmsq);
         dq_sq = fmaf(dqi, dqi, dq_sq);
         dchg_sq = fmaf(dch, dch, dchg_sq);
-        out.margin[i] = joint_margin(P, qn[i], i);
+        if constexpr (FAST) {   // margin = clip(2 min(q - lo, hi - q) / span, 0, 1) = 1 - |2 (q - lo) / span - 1| for q inside its limits
+            out.qn[i] = fmaf(2.0f * P.k_inv_span[i], qn[i] - P.joint_lower[i], -1.0f);
+            out.margin[i] = 1.0f - fabsf(out.qn[i]);
+        } else {
+            out.margin[i] = joint_margin(P, qn[i], i);
+        }
         margin = fminf(margin, out.margin[i]);
         s.q[i] = qn[i];
         s.dq[i] = dqi;
         s.pa[i] = a[i];
     }
-    fk_pose6(P, s.q, s.ee);
-    pose_error(s.ee, s.goal, pe, oe);
-    const float curr_pos = norm3(pe[0], pe[1], pe[2]), curr_ori = norm3(oe[0], oe[1], oe[2]);
+    if constexpr (FAST) {
+        float ee[6];
+        fk_pose6<true>(P, s.q, ee);
+        pose_error(ee, s.goal, pe, oe);
+    } else {
+        fk_pose6(P, s.q, s.ee);
+        pose_error(s.ee, s.goal, pe, oe);
+    }
+    const float curr_pos = norm3_sel<FAST>(pe[0], pe[1], pe[2]), curr_ori = norm3_sel<FAST>(oe[0], oe[1], oe[2]);
     const bool curr_pre = is_pre_near_goal(P, curr_pos, curr_ori);
     const bool curr_near = is_near_goal(P, curr_pos, curr_ori);
     s.min_pos = fminf(s.min_pos, curr_pos);
@@ -649,9 +765,9 @@ __device__ __forceinline__ void step_core(const KinEnvParams& P, EnvRegs& s, con
 
     in.prev_pos = prev_pos; in.prev_ori = prev_ori; in.curr_pos = curr_pos; in.curr_ori = curr_ori;
     in.act_msq = msq * (1.0f / NJ); in.act_dmsq = dmsq * (1.0f / NJ);
-    in.action_norm = sqrtf(msq);
-    in.dq_norm = sqrtf(dq_sq);
-    in.dq_change_l2 = sqrtf(dchg_sq);
+    in.action_norm = sqrt_sel<FAST>(msq);
+    in.dq_norm = sqrt_sel<FAST>(dq_sq);
+    in.dq_change_l2 = sqrt_sel<FAST>(dchg_sq);
     in.margin_min = margin;
     in.pre = curr_pre; in.pn = prev_in_near; in.cn = curr_near; in.success = success;
     in.dwell = s.dwell; in.entry_cnt = s.entry_cnt; in.drift_cnt = s.drift_cnt;

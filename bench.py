@@ -43,9 +43,11 @@ SUITE_SEED = 700001 + STAGE * 1009
 STEP_BYTES_APPROACH = 532
 # measured DRAM traffic per launch (ncu --set full captures committed under profiles/): read + write bytes
 NCU_TRAFFIC_STEP_KERNEL = 369_136_896 + 690_771_968     # kin_step_kernel<approach>, 2 097 152 envs: 1 060 MB vs 1 116 MB algorithmic
-NCU_TRAFFIC_ROLLOUT_TC = 4_509_696 + 158_464            # kin_rollout_tc_kernel, 65 536 episodes: inputs + result rows only
+NCU_TRAFFIC_ROLLOUT_TC = 4_111_360 + 0                  # kin_rollout_tc16_kernel, 65 536 episodes (profiles/r2_rollout_tc16_raw.csv): inputs only, the 6 MB of result rows stay in L2
 ACTOR_FLOPS = 2 * (56 * 64 + 64 * 64 + 64 * 7)   # 16256
 ENV_FLOPS = 1800
+XU_OPS_PER_ENV_STEP = 160     # MUFU-class instructions per env-step of the tensor-core rollout: 128 tanh + 12 sin/cos + ~20 rcp / sqrt / conversions (SASS count)
+THRESHOLD_BAND = 0.01         # parity: an episode is "within tolerance of a threshold" if scaling the decision thresholds by 1 -+ 1 % flips the ORACLE
 
 
 def peaks() -> dict:
@@ -134,6 +136,44 @@ def _oracle_setup():
     return ko, acfg, fcfg, ko.params_from_config(acfg), ko.params_from_config(fcfg), ko.OracleMlp(w("approach_stage8_11")), ko.OracleMlp(w("finisher"))
 
 
+def bench_config(episodes_per_gpu: int, world: int) -> dict:
+    """The `config` object of the JSON line -- the same dict on both arms (b200 and --impl reference)."""
+    return {"workload": "stage5_approach_finisher_eval_65536env", "episodes_per_gpu": episodes_per_gpu, "env_steps_per_episode": 164,
+            "approach_config": "workspace_expansion_dynamic_scale_big", "finisher_config": "dock_workspace_handoff_noop_ft_12env",
+            "policies": "bundled approach stage8-11 + finisher checkpoints", "parallelism": f"env-sharded x{world}",
+            "l2": "256 MB flush between timed iterations"}
+
+
+def cpu_config1(threads_all: int) -> dict:
+    """BASELINE.json configs[0]: Stage-0 Approach env, random-init 56-64-64-7 tanh MLP in the loop, auto-reset, >= 1 000 env-steps on
+    the reference CPU path -- here the C port (fp64 env + fp32 MLP) on ONE host thread, then one independent env per host core."""
+    from oracle import kin_oracle as ko
+    from rl_brain_trainer_b200 import config as kcfg
+    from rl_brain_trainer_b200.samplers import build_curriculum_local_eval_suite
+
+    cfg = kcfg.load_preset("approach_dynamic_scale_big")
+    params = ko.params_from_config(cfg)
+    rng = np.random.default_rng(0)
+    K = ko.OracleMlp.KEYS
+    w = {K["pi_w0"]: rng.standard_normal((64, 56)) * 0.1, K["pi_b0"]: np.zeros(64), K["pi_w1"]: rng.standard_normal((64, 64)) * 0.1,
+         K["pi_b1"]: np.zeros(64), K["act_w"]: rng.standard_normal((7, 64)) * 0.01, K["act_b"]: np.zeros(7)}
+    mlp = ko.OracleMlp({k: v.astype(np.float32) for k, v in w.items()})
+    ep_len = cfg.termination_config.max_episode_steps
+    out = {}
+    for label, threads, episodes in (("single_thread", 1, -(-1000 // ep_len)), ("all_cores", threads_all, threads_all * 8 * -(-1000 // ep_len))):
+        suite = build_curriculum_local_eval_suite(cfg, seed=0, stage_index=0, n_episodes=episodes)
+        t0 = time.perf_counter()
+        _, steps = ko.eval_approach_finisher(params, None, mlp, None, initial_q=suite.initial_q, goal_q=suite.goal_q, n_threads=threads)
+        dt = time.perf_counter() - t0
+        out[label] = {"env_steps_per_s": steps / dt, "env_steps": steps, "seconds": dt, "threads": threads}
+    out["what"] = ("Stage-0 approach env, random-init MLP policy in the loop, episodes run back to back (auto-reset), C port of the reference's "
+                   "Python env; os.cpu_count() = %d" % threads_all)
+    rec = ROOT / "profiles" / "r2_config1_reference_python.json"
+    if rec.exists():
+        out["python_reference_recorded"] = json.loads(rec.read_text())   # the reference itself, timed where /root/reference exists (build container)
+    return out
+
+
 def cpu_reference_steps_per_sec(n_episodes: int, threads: int, offset: int = 0):
     """Oracle port of the reference CPU path on `n_episodes` of the same suite -> (env-steps/s, env_steps, seconds, success_rate)."""
     from rl_brain_trainer_b200.samplers import build_curriculum_local_eval_suite
@@ -170,11 +210,10 @@ def run_reference_arm(args) -> None:
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * total_s / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": "stage5_approach_finisher_eval_65536env", "episodes_per_gpu": EPISODES_PER_GPU, "env_steps_per_episode": 164,
-                   "approach_config": "workspace_expansion_dynamic_scale_big", "finisher_config": "dock_workspace_handoff_noop_ft_12env",
-                   "policies": "bundled approach stage8-11 + finisher checkpoints", "episodes_per_step_sampled": n_ep,
-                   "note": "each step is a bounded sample of the same 65,536-episode suite; CPU port (C, fp64) of the reference's pure-Python "
-                           "env + fp32 MLP on all host threads (the Python reference itself runs ~1,000 env-steps/s per core)"},
+        "config": bench_config(EPISODES_PER_GPU, max(args.gpus, 1)),
+        "reference_arm": {"episodes_per_step_sampled": n_ep,
+                          "note": "each step is a bounded sample of the same 65,536-episode suite; CPU port (C, fp64) of the reference's pure-Python "
+                                  "env + fp32 MLP on all host threads (the Python reference itself runs ~1,000 env-steps/s per core)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{args.steps} x {n_ep} episodes x 164 env-steps, {threads} host threads"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -295,7 +334,7 @@ def main() -> None:
     os.dup2(2, 1)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = os.environ.get("KIN_NCCL_DEBUG", "WARN")
+        os.environ.setdefault("NCCL_DEBUG", "INFO")     # an inherited setting wins; INFO prints the rank / channel lines the driver greps
         dist.init_process_group("nccl", device_id=device)
     pk = peaks()
 
@@ -393,6 +432,26 @@ def main() -> None:
         torch.cuda.empty_cache()
         train = measure_training(torch, dist, device, world, grad_exchange=args.grad_exchange)
 
+    # ---- the strict-fp32 variant of the same rollout, timed the same way (rank 0, a few launches): the parity path beside the headline
+    strict = None
+    res_strict = None
+    if rank == 0 and variant == VARIANT_TC:
+        ro_s = ApproachFinisherRollout(acfg, pol_a, fcfg, pol_f, device=device, variant=VARIANT_FFMA)
+        out_s = RolloutResult(raw=torch.zeros((24, stride), dtype=torch.int32, device=device), n=n, env_steps=torch.zeros(1, dtype=torch.int64, device=device))
+        ro_s.run(dev_in, out=out_s)
+        torch.cuda.synchronize(device)
+        out_s.env_steps.zero_()
+        ev_s = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(3)]
+        for a, b in ev_s:
+            a.record()
+            ro_s.run(dev_in, out=out_s)
+            b.record()
+        torch.cuda.synchronize(device)
+        s_sec = sum(a.elapsed_time(b) for a, b in ev_s) * 1e-3
+        res_strict = out_s.to_numpy()
+        strict = {"kernel": "kin_rollout_ffma_kernel", "value": int(out_s.env_steps.item()) / s_sec, "unit": UNIT, "launches": 3,
+                  "success_rate": float(res_strict["success"].mean())}
+
     step_roof = None
     cpu_base = None
     parity = None
@@ -401,19 +460,30 @@ def main() -> None:
     clocks.__exit__(None, None, None)
     if rank == 0:
         if world == 1 and not args.skip_cpu_baseline:
+            from oracle.parity import threshold_sensitive_episodes
+
             threads = os.cpu_count() or 1
             n_cpu = 4096
             rate, steps_cpu, dt, sr = cpu_reference_steps_per_sec(n_cpu, threads)
             cpu_base = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                         "sample": f"first {n_cpu} episodes of the same suite x 164 env-steps ({steps_cpu} env-steps in {dt:.2f} s), "
-                                  f"C port (fp64) of the reference's Python env + fp32 MLP, {threads} host threads"}
-            ko, _, _, pa, pf, A, F = _oracle_setup()
-            ref, _ = ko.eval_approach_finisher(pa, pf, A, F, initial_q=suite.initial_q[:n_cpu].astype(np.float32).astype(float),
-                                               goal_q=suite.goal_q[:n_cpu].astype(np.float32).astype(float), n_threads=threads)
-            parity = {"episodes_checked": n_cpu, "success_flag_mismatches": int(np.sum(res["success"][:n_cpu].astype(int) != ref["success"])),
-                      "gpu_success_rate": float(res["success"][:n_cpu].mean()), "oracle_success_rate": float(ref["success"].mean()),
-                      "mean_final_pos_err_gpu": float(res["final_position_error"][:n_cpu].mean()),
-                      "mean_final_pos_err_oracle": float(ref["final_position_error"].mean())}
+                                  f"C port (fp64) of the reference's Python env + fp32 MLP, {threads} host threads",
+                        "config1": cpu_config1(threads)}
+            # parity of EVERY episode of the timed suite against the fp64 oracle; a differing success flag is "explained" only if the
+            # oracle's own verdict for that episode changes when the decision thresholds are scaled by 1 -+ THRESHOLD_BAND
+            ko, _, _, _, _, A, F = _oracle_setup()
+            t0 = time.perf_counter()
+            ref, sensitive = threshold_sensitive_episodes(acfg, fcfg, A, F, suite, THRESHOLD_BAND, n_threads=threads)
+            flips = res["success"].astype(int) != ref["success"]
+            parity = {"episodes_checked": n, "threshold_band": THRESHOLD_BAND, "threshold_sensitive_episodes": int(sensitive.sum()),
+                      "success_flag_mismatches": int(flips.sum()), "unexplained_mismatches": int((flips & ~sensitive).sum()),
+                      "gpu_success_rate": float(res["success"].mean()), "oracle_success_rate": float(ref["success"].mean()),
+                      "mean_final_pos_err_gpu": float(res["final_position_error"].mean()),
+                      "mean_final_pos_err_oracle": float(ref["final_position_error"].mean()), "oracle_seconds": time.perf_counter() - t0}
+            if res_strict is not None:
+                f_s = res_strict["success"].astype(int) != ref["success"]
+                strict["flips"] = int(f_s.sum())
+                strict["unexplained_flips"] = int((f_s & ~sensitive).sum())
 
     if rank == 0:
         steps_per_launch = env_steps / max(args.steps, 1)
@@ -421,12 +491,19 @@ def main() -> None:
         tc = variant == VARIANT_TC
         flops = (ACTOR_FLOPS + (0 if tc else ENV_FLOPS)) * steps_per_launch
         if tc:
-            peak_tf = pk["bf16_tflops_sustained"] / 2.0   # kind::tf32 runs at half the bf16 rate
-            roof = {"kernel": "kin_rollout_tc_kernel", "bound": "tensor", "achieved": flops / t_launch / 1e12, "peak": peak_tf,
+            # each launch is a sub-millisecond kernel timed alone between L2 flushes: the BURST fp16/bf16 peak applies (kind::f16 runs at the bf16 rate)
+            peak_tf = pk["bf16_tflops"]
+            xu_ceiling = 148 * 16 * pk["sm_max_mhz"] * 1e6 / XU_OPS_PER_ENV_STEP      # 16 MUFU lanes / clk / SM
+            roof = {"kernel": "kin_rollout_tc16_kernel", "bound": "tensor", "achieved": flops / t_launch / 1e12, "peak": peak_tf,
                     "unit": "TFLOP/s", "frac": flops / t_launch / 1e12 / peak_tf,
                     "traffic": NCU_TRAFFIC_ROLLOUT_TC if n == EPISODES_PER_GPU else None,
-                    "traffic_source": "dram bytes per launch, profiles/r1_rollout_tc_v2_raw.csv (ncu --set full, 65 536 episodes)", "peak_source": pk["source"],
-                    "note": "actor MLP 16,256 FLOP/env-step on tcgen05 kind::tf32; peak = measured sustained bf16 / 2"}
+                    "traffic_source": "dram bytes per launch, profiles/r2_rollout_tc16_raw.csv (ncu --set full, 65 536 episodes)", "peak_source": pk["source"],
+                    "peak_kind": "burst (bf16_tflops): the kernel is timed in isolation",
+                    "note": "actor MLP 16,256 FLOP/env-step on tcgen05 kind::f16 (fp16 operands, fp32 accumulate)",
+                    "limiter": {"pipe": "xu (MUFU)", "ops_per_env_step": XU_OPS_PER_ENV_STEP, "ceiling_env_steps_per_s": xu_ceiling,
+                                "frac": (steps_per_launch / t_launch) / xu_ceiling,
+                                "note": "128 tanh + the FK's sin/cos per env-step go through the 16-lane/clk/SM special-function pipe; with the "
+                                        "issue slots (ncu: profiles/r2_rollout_tc16_raw.csv) it, not the tensor pipe, bounds this kernel"}}
         else:
             fp32_peak = 148 * 128 * 2 * pk["sm_max_mhz"] * 1e6 / 1e12
             roof = {"kernel": "kin_rollout_ffma_kernel", "bound": "fp32", "achieved": flops / t_launch / 1e12, "peak": fp32_peak,
@@ -435,13 +512,10 @@ def main() -> None:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dev_s_max / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32" if not tc else "f32 env + tf32 MLP (f32 accumulate)", "data": "synthetic",
-            "config": {"workload": "stage5_approach_finisher_eval_65536env", "episodes_per_gpu": n, "env_steps_per_episode": 164,
-                       "approach_config": "workspace_expansion_dynamic_scale_big", "finisher_config": "dock_workspace_handoff_noop_ft_12env",
-                       "policies": "bundled approach stage8-11 + finisher checkpoints", "rollout_variant": "tc" if tc else "ffma",
-                       "parallelism": f"env-sharded x{world}", "l2": "256 MB flush between timed iterations"},
+            "dtype": "f32" if not tc else "f32 env + f16 MLP operands (f32 accumulate)", "data": "synthetic",
+            "config": bench_config(n, world), "rollout_variant": "tc" if tc else "ffma",
             "env_steps_per_step": env_steps / max(args.steps, 1), "success_rate": success_all, "wall_s_timed_region": t_wall,
-            "roofline": roof, "step_kernel_roofline": step_roof, "cpu_baseline": cpu_base, "parity": parity,
+            "roofline": roof, "step_kernel_roofline": step_roof, "cpu_baseline": cpu_base, "parity": parity, "strict_fp32": strict,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "success_rate": e2e_success},
             "clocks": clocks.summary(), "gpu_launches": launches, "train": train,
         }

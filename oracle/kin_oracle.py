@@ -383,13 +383,8 @@ def eval_approach_finisher(pa, pf, approach: OracleMlp, finisher: OracleMlp | No
                                      ctypes.byref(approach.c), ctypes.byref(finisher.c) if finisher is not None else None,
                                      _dptr(iq), _dptr(idq), _dptr(ipa), _dptr(gq), _dptr(gp), n,
                                      int(handoff_confirm_steps), int(n_threads), res, ctypes.byref(steps))
-    raw = np.frombuffer(res, dtype=np.dtype(EpisodeResult)) if False else None  # noqa: F841 (kept simple below)
-    out: dict[str, np.ndarray] = {}
-    for name in _RESULT_FIELDS:
-        if name == "final_q":
-            out[name] = np.array([[r.final_q[i] for i in range(7)] for r in res])
-        else:
-            out[name] = np.array([getattr(r, name) for r in res])
+    raw = np.frombuffer(res, dtype=np.dtype(EpisodeResult))   # structured view of the C array (65 536 episodes convert in milliseconds)
+    out: dict[str, np.ndarray] = {name: np.array(raw[name]) for name in _RESULT_FIELDS}
     return out, int(steps.value)
 
 

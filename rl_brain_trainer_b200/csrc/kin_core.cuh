@@ -76,12 +76,12 @@ __device__ __forceinline__ float rcp_approx(float x) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-template <bool FAST>
+template <int FAST>
 __device__ __forceinline__ float sqrt_sel(float x) {
     if constexpr (FAST) return sqrt_approx(x);
     else return sqrtf(x);
 }
-template <bool FAST>
+template <int FAST>
 __device__ __forceinline__ float norm3_sel(float a, float b, float c) { return sqrt_sel<FAST>(fmaf(a, a, fmaf(b, b, c * c))); }
 
 // atan2 for the Euler extraction: t = min/max in [0, 1], atan(t) = t + t^3 Q(t^2) (Remez fit, max |error| 7.5e-8 in fp32),
@@ -135,12 +135,8 @@ __device__ __forceinline__ void sincos_joint(float x, float* sp, float* cp) {
     *cp = ((k + 1) & 2) ? -c0 : c0;
 }
 
-// FAST flavour: two-term Cody-Waite (|k| <= 2, the third term is 5e-15 * k) or, with -DKIN_FAST_MUFU_SINCOS, the MUFU units.
+// FAST flavour: two-term Cody-Waite (|k| <= 2, the third term is 5e-15 * k).
 __device__ __forceinline__ void sincos_joint_fast(float x, float* sp, float* cp) {
-#ifdef KIN_FAST_MUFU_SINCOS
-    *sp = __sinf(x);
-    *cp = __cosf(x);
-#else
     const float kf = rintf(x * 0.63661977236758134f);
     const int k = (int)kf;
     float r = fmaf(kf, -1.57079601287841796875f, x);
@@ -157,17 +153,23 @@ __device__ __forceinline__ void sincos_joint_fast(float x, float* sp, float* cp)
     const float c0 = (k & 1) ? ps : pc;
     *sp = (k & 2) ? -s0 : s0;
     *cp = ((k + 1) & 2) ? -c0 : c0;
-#endif
 }
-template <bool FAST>
+// FAST: 0 strict, 1 fast, 2 fast with the MUFU sine / cosine (sin.approx / cos.approx: |error| <= 2^-20.9 on [-pi, pi], ~5e-7)
+template <int FAST>
 __device__ __forceinline__ void sincos_sel(float x, float* sp, float* cp) {
-    if constexpr (FAST) sincos_joint_fast(x, sp, cp);
-    else sincos_joint(x, sp, cp);
+    if constexpr (FAST == 2) {
+        *sp = __sinf(x);
+        *cp = __cosf(x);
+    } else if constexpr (FAST == 1) {
+        sincos_joint_fast(x, sp, cp);
+    } else {
+        sincos_joint(x, sp, cp);
+    }
 }
 
 // ee_fk.py:98-134 with the constant transforms folded on the host (see KinEnvParams::fk_*):
 // one sincos + 12 flops per revolute joint for the Rz, 27 for the constant 3x3, 9 for the offset.
-template <bool FAST = false>
+template <int FAST = 0>
 __device__ __forceinline__ void fk_pose6(const KinEnvParams& P, const float* q, float* pose) {
     float s, c;
     float R[9], M[9];
@@ -260,7 +262,7 @@ __device__ __forceinline__ float interp_control_fast(float pos, float near_thr, 
     const float alpha = clampf((pos - near_thr) * rcp_approx(fmaxf(far_thr - near_thr, 1e-9f)), 0.0f, 1.0f);
     return fmaf(alpha, far_v - near_v, near_v);
 }
-template <bool FAST>
+template <int FAST>
 __device__ __forceinline__ float interp_sel(float pos, float near_thr, float far_thr, float near_v, float far_v, float fallback) {
     if constexpr (FAST) return interp_control_fast(pos, near_thr, far_thr, near_v, far_v, fallback);
     else return interp_control(pos, near_thr, far_thr, near_v, far_v, fallback);
@@ -651,7 +653,7 @@ __device__ __forceinline__ float dock_reward(const KinEnvParams& P, const Reward
 // KIN_MODE_PER_ENV reads the mode bits of s.flags.  c[] receives info["reward_components"] (COMP only).
 // FAST (tensor-core rollout / collection kernels): `out` must hold the previous step's (or the reset's) pos / ori on entry --
 // they are the "previous" pose-error norms the reference recomputes from the cached ee pose -- and s.ee is not maintained.
-template <int MODE, bool COMP, bool FAST = false>
+template <int MODE, bool COMP, int FAST = 0>
 __device__ __forceinline__ void step_core(const KinEnvParams& P, EnvRegs& s, const float* action_in, StepOut& out, float* c) {
     const int mode = (MODE == KIN_MODE_PER_ENV) ? (int)((s.flags >> KIN_FLAG_MODE_SHIFT) & 3u) : MODE;
     const bool dock = (mode == KIN_MODE_DOCK);
@@ -726,7 +728,7 @@ __device__ __forceinline__ void step_core(const KinEnvParams& P, EnvRegs& s, con
     }
     if constexpr (FAST) {
         float ee[6];
-        fk_pose6<true>(P, s.q, ee);
+        fk_pose6<FAST>(P, s.q, ee);
         pose_error(ee, s.goal, pe, oe);
     } else {
         fk_pose6(P, s.q, s.ee);

@@ -263,10 +263,6 @@ using namespace kin;
 int kin_rollout_tc16_launch(const KinHandle* ha, const KinHandle* hf, const KinPolicyWeights* pa, const KinPolicyWeights* pf,
                             const float* iq, const float* idq, const float* ipa, const float* gq, const float* gpose, int n, int stride,
                             int confirm, uint32_t* result, unsigned long long* env_steps, cudaStream_t st);
-// implemented in kin_rollout_tc.cu (tcgen05 kind::tf32 / TMEM variant)
-int kin_rollout_tc_launch(const KinHandle* ha, const KinHandle* hf, const KinPolicyWeights* pa, const KinPolicyWeights* pf,
-                          const float* iq, const float* idq, const float* ipa, const float* gq, const float* gpose, int n, int stride,
-                          int confirm, int variant, uint32_t* result, unsigned long long* env_steps, cudaStream_t st);
 
 extern "C" int kin_rollout_approach_finisher(void* approach_handle, void* finisher_handle, const KinPolicyWeights* host_approach,
                                              const KinPolicyWeights* host_finisher, const float* initial_q, const float* initial_dq,
@@ -282,12 +278,9 @@ extern "C" int kin_rollout_approach_finisher(void* approach_handle, void* finish
     if (!initial_q || (!goal_q && !goal_pose6) || !result || n <= 0 || stride < n) return kin_fail(KIN_ERR_INVALID_ARG, "kin_rollout_approach_finisher: bad buffers / sizes");
     if (handoff_confirm_steps < 1) return kin_fail(KIN_ERR_INVALID_ARG, "kin_rollout_approach_finisher: handoff_confirm_steps >= 1");
     cudaStream_t st = (cudaStream_t)stream;
-    if (variant == 2)
+    if (variant != 0)
         return kin_rollout_tc16_launch(ha, has_f ? hf : nullptr, host_approach, has_f ? host_finisher : nullptr, initial_q, initial_dq,
                                        initial_prev_action, goal_q, goal_pose6, n, stride, handoff_confirm_steps, result, env_steps, st);
-    if (variant != 0)
-        return kin_rollout_tc_launch(ha, has_f ? hf : nullptr, host_approach, has_f ? host_finisher : nullptr, initial_q, initial_dq,
-                                     initial_prev_action, goal_q, goal_pose6, n, stride, handoff_confirm_steps, variant, result, env_steps, st);
     const size_t smem = (size_t)(MlpSmem<OBS>::FLOATS + HID * RO_THREADS) * sizeof(float);
     static bool attr_set[KIN_MAX_DEVICES] = {};
     const int dev_slot = kin_device_slot();

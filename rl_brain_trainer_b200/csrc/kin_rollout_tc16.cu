@@ -31,10 +31,21 @@ namespace kin {
 
 using namespace tc16;
 
+#ifdef KIN_TC16_TRACE
+// cycle trace (debug builds only, tools/tc16_trace.py): SM-clock stamps of every warp of CTA 0 around the three GEMM round trips
+// of approach steps 10..17: [step][warp][0..2 = before arrive L1/L2/L3 | 3..5 = after wake L1/L2/L3 | 6..8 = MMAs committed (issuing warp)]
+__device__ long long kin_tc16_trace_buf[8][16][12];   // 9..11 = issuer warp woke up for L1/L2/L3 (issuer-warp mode)
+#define TC16_STAMP(slot) do { if (blockIdx.x == 0 && c.step_id >= 10 && c.step_id < 18 && (threadIdx.x & 31) == 0) \
+        kin_tc16_trace_buf[c.step_id - 10][threadIdx.x >> 5][slot] = clock64(); } while (0)
+#else
+#define TC16_STAMP(slot)
+#endif
+
 struct Tile16 {
     unsigned char *X, *H;
     float* snap;                 // [21][128] floats, column = row
-    unsigned x_saddr, h_saddr, w0_saddr, w1_saddr, wo_saddr, wob_saddr, mbar_saddr, cnt_saddr, tmem_d, tmem_row;
+    unsigned x_lo, h_lo, w0_lo, w1_lo, wo_lo, wob_lo;   // descriptor low words (tc16::desc_lo)
+    unsigned mbar_saddr, cnt_saddr, full_saddr, tmem_d, tmem_row;
     volatile int* stamp;
     int row, n_warps;
     unsigned parity, arrivals;
@@ -69,9 +80,61 @@ __device__ __forceinline__ void obs_pack(const KinEnvParams& P, const EnvRegs& s
         if (!((i >= 7 && i <= 9) || i >= 15)) w[i] = clamp1_h2(w[i]);
 }
 
+// The MMAs of one layer of one tile (one elected lane).  layer 0: X . W0^T (K = 48, bias in column 36); layer 1: H . W1^T + b1
+// (bias: X[:, 32:48] . W0img[:, 48:64]^T); layer 2: H . WO^T + bo (N = 16; bias: X[:, 32:48] . WOB[:, 32:48]^T).
+__device__ __forceinline__ void issue_layer16(int layer, unsigned tmem_d, unsigned x_lo, unsigned h_lo, unsigned w0_lo, unsigned w1_lo,
+                                              unsigned wo_lo, unsigned wob_lo, unsigned mbar_saddr) {
+    if (layer == 0) {
+        constexpr unsigned id = idesc_f16(TILE, HID);
+#pragma unroll
+        for (int k = 0; k < X_K / 16; ++k) mma_f16(tmem_d, x_lo + 2 * k, w0_lo + 2 * k, id, k > 0 ? 1u : 0u);
+    } else if (layer == 1) {
+        constexpr unsigned id = idesc_f16(TILE, HID);
+#pragma unroll
+        for (int k = 0; k < HID / 16; ++k) mma_f16(tmem_d, h_lo + 2 * k, w1_lo + 2 * k, id, k > 0 ? 1u : 0u);
+        mma_f16(tmem_d, x_lo + 4, w0_lo + 6, id, 1u);
+    } else {
+        constexpr unsigned id = idesc_f16(TILE, 16);
+#pragma unroll
+        for (int k = 0; k < HID / 16; ++k) mma_f16(tmem_d, h_lo + 2 * k, wo_lo + 2 * k, id, k > 0 ? 1u : 0u);
+        mma_f16(tmem_d, x_lo + 4, wob_lo + 4, id, 1u);
+    }
+    umma::commit(mbar_saddr);
+}
+
+// "My rows of the operand tile are written; wake me when the accumulator is ready."
+//   ISS  (dedicated issuer warps): proxy fence, warp converges, lane 0 arrives on the tile's `full` mbarrier -- the issuer warp
+//        that sleeps on it issues the MMAs;
+//   !ISS (16-warp CTAs, no room for issuer warps): lane 0 bumps the tile's arrival counter and the warp that arrives last issues.
+template <bool ISS>
+__device__ __forceinline__ void tile_sync16(Tile16& c, int layer, int sid) {
+    TC16_STAMP(layer);
+    if constexpr (ISS) {
+        umma::fence_async_smem();
+        umma::fence_before();
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(c.full_saddr);
+    } else {
+        c.arrivals += (unsigned)c.n_warps;
+        if (const int last = tile_arrive(c.cnt_saddr, c.arrivals, layer == 0 ? c.stamp : nullptr, sid)) {
+            umma::fence_after();
+            if (elect_one()) {
+                if (last == 1) issue_layer16(layer, c.tmem_d, c.x_lo, c.h_lo, c.w0_lo, c.w1_lo, c.wo_lo, c.wob_lo, c.mbar_saddr);
+                else mbar_arrive(c.mbar_saddr);
+            }
+            __syncwarp();
+            TC16_STAMP(6 + layer);
+        }
+    }
+    mbar_wait(c.mbar_saddr, c.parity);
+    TC16_STAMP(3 + layer);
+    c.parity ^= 1u;
+}
+
 // One policy forward for the tile: X row <- observation, three GEMMs, act[7] out.  Collective over the tile's warps.
 // Returns false (without running the MLP) once no episode of the tile is still running.
-__device__ __forceinline__ bool mlp16(Smem& S, Tile16& c, const unsigned* w, float* act, bool running) {
+template <bool ISS>
+__device__ __forceinline__ bool mlp16(Tile16& c, const unsigned* w, float* act, bool running) {
     const int sid = ++c.step_id;
     if (__any_sync(0xffffffffu, running) && (threadIdx.x & 31) == 0) *c.stamp = sid;
     // ---- layer 1: X = [obs36 | 1 | 0 ...]; chunk 5 (columns 40..47) stays zero from the prologue
@@ -80,58 +143,16 @@ __device__ __forceinline__ bool mlp16(Smem& S, Tile16& c, const unsigned* w, flo
     st_chunk(c.X, c.row, 2, w[8], w[9], w[10], w[11]);
     st_chunk(c.X, c.row, 3, w[12], w[13], w[14], w[15]);
     st_chunk(c.X, c.row, 4, w[16], w[17], 0x00003C00u, 0u);
-    c.arrivals += (unsigned)c.n_warps;
-    if (const int last = tile_arrive(c.cnt_saddr, c.arrivals, c.stamp, sid)) {
-        umma::fence_after();
-        if (elect_one()) {
-            if (last == 1) {
-                constexpr unsigned id = idesc_f16(TILE, HID);
-#pragma unroll
-                for (int k = 0; k < X_K / 16; ++k) mma_f16(c.tmem_d, c.x_saddr + 32 * k, c.w0_saddr + 32 * k, id, k > 0 ? 1u : 0u);
-                umma::commit(c.mbar_saddr);
-            } else {
-                mbar_arrive(c.mbar_saddr);
-            }
-        }
-        __syncwarp();
-    }
-    mbar_wait(c.mbar_saddr, c.parity);
-    c.parity ^= 1u;
+    tile_sync16<ISS>(c, 0, sid);
     if (*c.stamp != sid) return false;
     umma::fence_after();
     epilogue_tanh(c.tmem_row, c.H, c.row);
-    // ---- layer 2: H1 . W1^T + b1 (bias: X[:, 32:48] . W0img[:, 48:64]^T)
-    c.arrivals += (unsigned)c.n_warps;
-    if (tile_arrive(c.cnt_saddr, c.arrivals)) {
-        umma::fence_after();
-        if (elect_one()) {
-            constexpr unsigned id = idesc_f16(TILE, HID);
-#pragma unroll
-            for (int k = 0; k < HID / 16; ++k) mma_f16(c.tmem_d, c.h_saddr + 32 * k, c.w1_saddr + 32 * k, id, k > 0 ? 1u : 0u);
-            mma_f16(c.tmem_d, c.x_saddr + 64, c.w0_saddr + 96, id, 1u);
-            umma::commit(c.mbar_saddr);
-        }
-        __syncwarp();
-    }
-    mbar_wait(c.mbar_saddr, c.parity);
-    c.parity ^= 1u;
+    // ---- layer 2
+    tile_sync16<ISS>(c, 1, sid);
     umma::fence_after();
     epilogue_tanh(c.tmem_row, c.H, c.row);
-    // ---- layer 3 (N = 16: 7 action means + zero rows) + action bias
-    c.arrivals += (unsigned)c.n_warps;
-    if (tile_arrive(c.cnt_saddr, c.arrivals)) {
-        umma::fence_after();
-        if (elect_one()) {
-            constexpr unsigned id = idesc_f16(TILE, 16);
-#pragma unroll
-            for (int k = 0; k < HID / 16; ++k) mma_f16(c.tmem_d, c.h_saddr + 32 * k, c.wo_saddr + 32 * k, id, k > 0 ? 1u : 0u);
-            mma_f16(c.tmem_d, c.x_saddr + 64, c.wob_saddr + 64, id, 1u);
-            umma::commit(c.mbar_saddr);
-        }
-        __syncwarp();
-    }
-    mbar_wait(c.mbar_saddr, c.parity);
-    c.parity ^= 1u;
+    // ---- layer 3 (N = 16: 7 action means + zero rows)
+    tile_sync16<ISS>(c, 2, sid);
     umma::fence_after();
     {
         unsigned r[8];
@@ -142,6 +163,56 @@ __device__ __forceinline__ bool mlp16(Smem& S, Tile16& c, const unsigned* w, flo
         for (int i = 0; i < NJ; ++i) act[i] = clampf(__uint_as_float(r[i]), -1.0f, 1.0f);
     }
     return true;
+}
+
+// ---- issuer warps (ISS mode): warp `iw` (0 / 1) serves tiles 2 iw and 2 iw + 1 of the CTA -------------------------------------
+struct IssTile {
+    unsigned x_lo, h_lo, tmem_d, full_saddr, mbar_saddr;
+    volatile int* stamp;
+    unsigned parity;
+    int sid, layer, tile;
+    bool exists, live;
+};
+
+// Serve one tile if its operands are ready.  Sleeps at most ~hint_ns on the tile's `full` mbarrier.
+__device__ __forceinline__ void issuer_poll(IssTile& t, unsigned w0_lo, unsigned w1_lo, unsigned wo_lo, unsigned wob_lo, unsigned hint_ns) {
+    if (!(hint_ns ? mbar_try_wait_hint(t.full_saddr, t.parity, hint_ns) : mbar_test_wait(t.full_saddr, t.parity))) return;
+    t.parity ^= 1u;
+    umma::fence_after();
+    bool go = true;
+    if (t.layer == 0) {
+        t.sid += 1;
+        go = (*t.stamp == t.sid);
+    }
+#ifdef KIN_TC16_TRACE
+    if (blockIdx.x == 0 && t.sid >= 10 && t.sid < 18 && (threadIdx.x & 31) == 0) kin_tc16_trace_buf[t.sid - 10][4 * t.tile][9 + t.layer] = clock64();
+#endif
+    if (elect_one()) {
+        if (go) issue_layer16(t.layer, t.tmem_d, t.x_lo, t.h_lo, w0_lo, w1_lo, wo_lo, wob_lo, t.mbar_saddr);
+        else mbar_arrive(t.mbar_saddr);
+#ifdef KIN_TC16_TRACE
+        if (blockIdx.x == 0 && t.sid >= 10 && t.sid < 18) kin_tc16_trace_buf[t.sid - 10][4 * t.tile][6 + t.layer] = clock64();
+#endif
+    }
+    __syncwarp();
+    if (!go) t.live = false;
+    else t.layer = t.layer == 2 ? 0 : t.layer + 1;
+}
+
+__device__ unsigned kin_tc16_poll_hint = 32u;   // experiment knob (KIN_TC16_POLL_HINT): 0 = non-blocking test_wait, else nap length in ns
+
+// one phase (approach or finisher): until both tiles have reported "nobody running"
+__device__ __forceinline__ void issuer_phase(IssTile& a, IssTile& b, unsigned w0_lo, unsigned w1_lo, unsigned wo_lo, unsigned wob_lo) {
+    a.live = a.exists;
+    b.live = b.exists;
+    a.layer = b.layer = 0;
+    unsigned spins = 0u;
+    while (a.live || b.live) {
+        const unsigned hint = (a.live && b.live) ? kin_tc16_poll_hint : 1000u;   // two tiles to watch: probe each in turn
+        if (a.live) issuer_poll(a, w0_lo, w1_lo, wo_lo, wob_lo, hint);
+        if (b.live) issuer_poll(b, w0_lo, w1_lo, wo_lo, wob_lo, hint);
+        if (++spins > (1u << 28)) __trap();   // watchdog: a protocol bug must fail the launch, not hang the GPU
+    }
 }
 
 __device__ __forceinline__ bool ready_pred16(float pos_thr, float ori_thr, float a_thr, float dq_thr, float pos, float ori, float an, float dqn) {
@@ -162,6 +233,8 @@ __device__ __forceinline__ void prime_step_out(const KinEnvParams& P, const EnvR
     }
 }
 
+// ISS: the CTA's last two warps are issuer warps (<= 14 env warps, the balanced one-wave shape): blockDim.x = 32 (env warps + 2)
+template <int FAST, bool ISS>
 __global__ void __launch_bounds__(MAX_THREADS, 1)
 kin_rollout_tc16_kernel(const __grid_constant__ KinEnvParams PA, const __grid_constant__ KinEnvParams PF, DevPolicy pol_a, DevPolicy pol_f,
                         int has_finisher, const float* __restrict__ iq, const float* __restrict__ idq, const float* __restrict__ ipa,
@@ -172,14 +245,15 @@ kin_rollout_tc16_kernel(const __grid_constant__ KinEnvParams PA, const __grid_co
     Smem& S = *reinterpret_cast<Smem*>(base);
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
-    const int n_tiles_cta = ((int)blockDim.x + TILE - 1) / TILE;
+    const int env_threads = (int)blockDim.x - (ISS ? 64 : 0);
+    const int n_tiles_cta = (env_threads + TILE - 1) / TILE;
     unsigned char* tiles = base + ((sizeof(Smem) + 1023) / 1024) * 1024;
     float* snaps = reinterpret_cast<float*>(tiles + (size_t)n_tiles_cta * 2 * TILE_BYTES);
 
     Tile16 c;
     const int tile = tid >> 7;
     c.row = tid & (TILE - 1);
-    c.n_warps = (min(TILE, (int)blockDim.x - tile * TILE) + 31) >> 5;
+    c.n_warps = (min(TILE, env_threads - tile * TILE) + 31) >> 5;
     c.X = tiles + (size_t)tile * 2 * TILE_BYTES;
     c.H = c.X + TILE_BYTES;
     c.snap = snaps + (size_t)tile * SNAP_FLOATS * TILE + c.row;
@@ -194,19 +268,23 @@ kin_rollout_tc16_kernel(const __grid_constant__ KinEnvParams PA, const __grid_co
 #pragma unroll
         for (int i = 0; i < MAX_TILES; ++i) {
             umma::mbar_init(umma::smem_u32(&S.mbar[i]), 1);
+            umma::mbar_init(umma::smem_u32(&S.full[i]), (unsigned)max(1, (min(TILE, env_threads - i * TILE) + 31) >> 5));
             S.arrive[i] = 0u;
             S.run_stamp[i] = 0;
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     load_weights(S, pol_a, KIN_MODE_APPROACH, tid, (int)blockDim.x);
+    const bool env_thread = tid < env_threads;
     // this thread's rows of the X / H images start as zeros (the K padding of X is never written again)
+    if (env_thread) {
 #pragma unroll
-    for (int ch = 0; ch < 8; ++ch) {
-        st_chunk(c.X, c.row, ch, 0u, 0u, 0u, 0u);
-        st_chunk(c.H, c.row, ch, 0u, 0u, 0u, 0u);
+        for (int ch = 0; ch < 8; ++ch) {
+            st_chunk(c.X, c.row, ch, 0u, 0u, 0u, 0u);
+            st_chunk(c.H, c.row, ch, 0u, 0u, 0u, 0u);
+        }
     }
-    if (c.n_warps < 4) {   // partial tile: the rows nobody owns still feed the M = 128 GEMMs -- keep them finite
+    if (env_thread && c.n_warps < 4) {   // partial tile: the rows nobody owns still feed the M = 128 GEMMs -- keep them finite
         for (int r = c.n_warps * 32 + c.row; r < TILE; r += c.n_warps * 32)
 #pragma unroll
             for (int ch = 0; ch < 8; ++ch) {
@@ -219,18 +297,52 @@ kin_rollout_tc16_kernel(const __grid_constant__ KinEnvParams PA, const __grid_co
     __syncthreads();
     umma::fence_after();
     const unsigned tmem_base = S.tmem_base;
-    c.x_saddr = umma::smem_u32(c.X);
-    c.h_saddr = umma::smem_u32(c.H);
-    c.w0_saddr = umma::smem_u32(S.W0);
-    c.w1_saddr = umma::smem_u32(S.W1);
-    c.wo_saddr = umma::smem_u32(S.WO);
-    c.wob_saddr = umma::smem_u32(S.WOB);
+    c.x_lo = desc_lo(umma::smem_u32(c.X));
+    c.h_lo = desc_lo(umma::smem_u32(c.H));
+    c.w0_lo = desc_lo(umma::smem_u32(S.W0));
+    c.w1_lo = desc_lo(umma::smem_u32(S.W1));
+    c.wo_lo = desc_lo(umma::smem_u32(S.WO));
+    c.wob_lo = desc_lo(umma::smem_u32(S.WOB));
     c.mbar_saddr = umma::smem_u32(&S.mbar[tile]);
     c.cnt_saddr = umma::smem_u32(&S.arrive[tile]);
+    c.full_saddr = umma::smem_u32(&S.full[tile]);
     c.tmem_d = tmem_base + tile * HID;                                        // lane 0, this tile's 64 columns
     c.tmem_row = c.tmem_d + ((unsigned)((warp & 3) * 32) << 16);              // this warp's 32-lane slice
 
-    const int ep = blockIdx.x * (int)blockDim.x + tid;
+    if constexpr (ISS) {
+        if (!env_thread) {   // ---- issuer warp: serve two tiles through both phases, keep step with the CTA barriers
+            const int iw = (tid - env_threads) >> 5;
+            IssTile it[2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int t = 2 * iw + j;
+                it[j].exists = t < n_tiles_cta;
+                it[j].tile = t;
+                unsigned char* X = tiles + (size_t)t * 2 * TILE_BYTES;
+                it[j].x_lo = desc_lo(umma::smem_u32(X));
+                it[j].h_lo = desc_lo(umma::smem_u32(X + TILE_BYTES));
+                it[j].tmem_d = tmem_base + t * HID;
+                it[j].full_saddr = umma::smem_u32(&S.full[t]);
+                it[j].mbar_saddr = umma::smem_u32(&S.mbar[t]);
+                it[j].stamp = &S.run_stamp[t];
+                it[j].parity = 0u;
+                it[j].sid = 0;
+            }
+            issuer_phase(it[0], it[1], c.w0_lo, c.w1_lo, c.wo_lo, c.wob_lo);
+            __syncthreads();
+            if (has_finisher) {
+                load_weights(S, pol_f, KIN_MODE_DOCK, tid, (int)blockDim.x);
+                umma::fence_async_smem();
+                __syncthreads();
+                issuer_phase(it[0], it[1], c.w0_lo, c.w1_lo, c.wo_lo, c.wob_lo);
+            }
+            umma::fence_before();
+            __syncthreads();
+            return;
+        }
+    }
+
+    const int ep = blockIdx.x * env_threads + tid;
     const bool active = ep < n;
     const int epc = active ? ep : n - 1;
 
@@ -266,9 +378,9 @@ kin_rollout_tc16_kernel(const __grid_constant__ KinEnvParams PA, const __grid_co
         unsigned w[X_DYN / 2];
         float act[NJ];
         obs_pack(PA, s, so, w);
-        if (!mlp16(S, c, w, act, running)) break;
+        if (!mlp16<ISS>(c, w, act, running)) break;
         if (running) {
-            step_core<KIN_MODE_APPROACH, false, true>(PA, s, act, so, nullptr);
+            step_core<KIN_MODE_APPROACH, false, FAST>(PA, s, act, so, nullptr);
             const float an = so.action_l2;
             steps += 1;
             min_pos = fminf(min_pos, so.pos);
@@ -338,12 +450,12 @@ kin_rollout_tc16_kernel(const __grid_constant__ KinEnvParams PA, const __grid_co
             unsigned w[X_DYN / 2];
             float act[NJ];
             obs_pack(PF, s, so, w);
-            if (!mlp16(S, c, w, act, running)) break;
+            if (!mlp16<ISS>(c, w, act, running)) break;
             if (running) {
                 float an2 = 0.0f;   // the policy's own action (the step clips it to the dock limit before it reports action_l2)
 #pragma unroll
                 for (int i = 0; i < NJ; ++i) an2 = fmaf(act[i], act[i], an2);
-                step_core<KIN_MODE_DOCK, false, true>(PF, s, act, so, nullptr);
+                step_core<KIN_MODE_DOCK, false, FAST>(PF, s, act, so, nullptr);
                 steps += 1;
                 final_an = sqrt_approx(an2);
                 running = !(so.done & (KIN_DONE_TERMINATED | KIN_DONE_TRUNCATED));
@@ -388,15 +500,35 @@ kin_rollout_tc16_kernel(const __grid_constant__ KinEnvParams PA, const __grid_co
 
 using namespace kin;
 
+#ifdef KIN_TC16_TRACE
+extern "C" int kin_debug_tc16_trace(long long* out) {
+    return cudaMemcpyFromSymbol(out, kin_tc16_trace_buf, sizeof(kin_tc16_trace_buf)) == cudaSuccess ? KIN_OK : KIN_ERR_INVALID_ARG;
+}
+#endif
+
 int kin_rollout_tc16_launch(const KinHandle* ha, const KinHandle* hf, const KinPolicyWeights* pa, const KinPolicyWeights* pf,
                             const float* iq, const float* idq, const float* ipa, const float* gq, const float* gpose, int n, int stride,
                             int confirm, uint32_t* result, unsigned long long* env_steps, cudaStream_t st) {
+    using Kernel = void (*)(KinEnvParams, KinEnvParams, tc16::DevPolicy, tc16::DevPolicy, int, const float*, const float*, const float*, const float*,
+                            const float*, int, int, int, uint32_t*, unsigned long long*);
+    static const Kernel kernels[2][2] = {{kin_rollout_tc16_kernel<1, false>, kin_rollout_tc16_kernel<1, true>},
+                                         {kin_rollout_tc16_kernel<2, false>, kin_rollout_tc16_kernel<2, true>}};
     static bool attr_set[KIN_MAX_DEVICES] = {};
     const int dev_slot = kin_device_slot();
     if (!attr_set[dev_slot]) {
-        cudaError_t e = cudaFuncSetAttribute(kin_rollout_tc16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc16::smem_bytes(tc16::MAX_TILES));
-        if (e != cudaSuccess) return kin_fail_cuda(e, "kin_rollout_approach_finisher(tc16): smem attribute");
+        for (int i = 0; i < 4; ++i) {
+            cudaError_t e = cudaFuncSetAttribute(kernels[i >> 1][i & 1], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc16::smem_bytes(tc16::MAX_TILES));
+            if (e != cudaSuccess) return kin_fail_cuda(e, "kin_rollout_approach_finisher(tc16): smem attribute");
+        }
         attr_set[dev_slot] = true;
+    }
+    // KIN_TC16_EXACT_SINCOS=1: polynomial sine / cosine in the FK instead of the MUFU units (the default: 6 % faster, same flip count)
+    static const bool exact_sincos = kin_env_flag("KIN_TC16_EXACT_SINCOS");
+    static const bool no_issuer = kin_env_flag("KIN_TC16_NO_ISSUER_WARPS");
+    static bool hint_set = false;
+    if (!hint_set) {
+        if (const char* v = getenv("KIN_TC16_POLL_HINT")) { const unsigned h = (unsigned)atoi(v); cudaMemcpyToSymbol(kin_tc16_poll_hint, &h, sizeof(h)); }
+        hint_set = true;
     }
     tc16::DevPolicy da{pa->pi_w0, pa->pi_b0, pa->pi_w1, pa->pi_b1, pa->act_w, pa->act_b};
     tc16::DevPolicy df = pf ? tc16::DevPolicy{pf->pi_w0, pf->pi_b0, pf->pi_w1, pf->pi_b1, pf->act_w, pf->act_b} : da;
@@ -406,15 +538,18 @@ int kin_rollout_tc16_launch(const KinHandle* ha, const KinHandle* hf, const KinP
         int dev = 0;
         if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
     }
-    // one wave: spread the warps evenly over the SMs; several waves: full 16-warp CTAs, one per SM
+    // one wave: spread the warps evenly over the SMs; several waves: full 16-warp CTAs, one per SM.  Up to 14 env warps leave room
+    // (registers: 16 warps x 128) for two issuer warps, which then sit on the two schedulers that carry one env warp fewer.
     const int warps = (n + 31) / 32;
     int w_per_cta = (warps + n_sm - 1) / n_sm;
     if (w_per_cta > 16) w_per_cta = 16;
     if (const char* v = getenv("KIN_TC_WARPS")) { const int f = atoi(v); if (f >= 1 && f <= 16) w_per_cta = f; }
-    const int threads = 32 * w_per_cta;
-    const size_t smem = tc16::smem_bytes((threads + tc16::TILE - 1) / tc16::TILE);
-    kin_rollout_tc16_kernel<<<(n + threads - 1) / threads, threads, smem, st>>>(ha->params, PF, da, df, (hf && pf) ? 1 : 0, iq, idq, ipa, gq,
-                                                                                      gpose, n, stride, confirm, result, env_steps);
+    const bool iss = w_per_cta <= 14 && !no_issuer;
+    const int env_threads = 32 * w_per_cta;
+    const int threads = env_threads + (iss ? 64 : 0);
+    const size_t smem = tc16::smem_bytes((env_threads + tc16::TILE - 1) / tc16::TILE);
+    kernels[exact_sincos ? 0 : 1][iss ? 1 : 0]<<<(n + env_threads - 1) / env_threads, threads, smem, st>>>(
+        ha->params, PF, da, df, (hf && pf) ? 1 : 0, iq, idq, ipa, gq, gpose, n, stride, confirm, result, env_steps);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? KIN_OK : kin_fail_cuda(e, "kin_rollout_approach_finisher(tc16)");
 }

@@ -38,6 +38,7 @@ struct Smem {
     alignas(1024) unsigned char WO[16 * 128];    // rows 0..6 action head, rows 7..15 zero (N = 16)
     alignas(1024) unsigned char WOB[16 * 128];   // column 36 = action bias (multiplies the X tile's constant-one column)
     unsigned long long mbar[MAX_TILES];          // "accumulator ready", one per tile
+    unsigned long long full[MAX_TILES];          // issuer-warp mode: "operand tile written" (one arrival per warp of the tile)
     unsigned arrive[MAX_TILES];                  // monotonically increasing arrival counters ("operand tile written")
     int run_stamp[MAX_TILES];                    // id of the last step in which some episode of the tile was still running
     unsigned tmem_base;
@@ -100,8 +101,19 @@ __device__ __forceinline__ void load_weights(Smem& S, const DevPolicy& p, int mo
     }
 }
 
-__device__ __forceinline__ void mma_f16(unsigned tmem_d, unsigned a_saddr, unsigned b_saddr, unsigned idesc, unsigned accumulate) {
-    umma::mma_bf16(tmem_d, umma::desc_k(a_saddr), umma::desc_k(b_saddr), idesc, accumulate);   // same instruction; the idesc selects fp16
+// Low word of a K-major SWIZZLE_128B descriptor (start >> 4 | LBO); the high word is the constant DESC_HI.  A K slice of 16
+// halves is 32 bytes further along the row: + 2 in the low word.  Precomputed once per tile so the issue path is a handful of
+// uniform adds instead of shift / mask chains per MMA.
+constexpr unsigned DESC_HI = 64u | (1u << 14) | (2u << 29);      // SBO = 1024 B >> 4, version 1 (bit 46), SWIZZLE_128B (bits 61..63 = 2)
+__device__ __forceinline__ unsigned desc_lo(unsigned saddr) { return ((saddr >> 4) & 0x3FFFu) | (1u << 16); }
+__device__ __forceinline__ void mma_f16(unsigned tmem_d, unsigned a_lo, unsigned b_lo, unsigned idesc, unsigned accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(DESC_HI) : "memory");
 }
 __device__ __forceinline__ bool elect_one() {
     unsigned pred;
@@ -121,12 +133,31 @@ __device__ __forceinline__ void mbar_wait(unsigned saddr, unsigned parity) {
         if (spins > (1u << 24)) __trap();   // each failed try_wait already suspends for a bounded time: >> seconds
     }
 }
+// non-blocking-ish probe: returns after at most ~`hint_ns` (the hardware suspends the warp meanwhile, no issue slots burnt)
+__device__ __forceinline__ bool mbar_try_wait_hint(unsigned saddr, unsigned parity, unsigned hint_ns) {
+    unsigned done;
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t}"
+        : "=r"(done) : "r"(saddr), "r"(parity), "r"(hint_ns) : "memory");
+    return done != 0u;
+}
+__device__ __forceinline__ bool mbar_test_wait(unsigned saddr, unsigned parity) {
+    unsigned done;
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t}"
+        : "=r"(done) : "r"(saddr), "r"(parity) : "memory");
+    return done != 0u;
+}
 __device__ __forceinline__ void mbar_arrive(unsigned saddr) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(saddr) : "memory");
 }
 
 // "My part of the operand tile is written": every lane makes its generic-proxy stores visible to the async proxy, the warp
-// converges, lane 0 bumps the tile's counter (acq_rel).  Returns non-zero -- to the whole warp -- on the warp that arrived last;
+// converges, lane 0 bumps the tile's counter.  Returns non-zero -- to the whole warp -- on the warp that arrived last;
 // that warp issues the tile's MMAs, nobody blocks on a CTA barrier.  With `stamp` the last arriver also reports whether some
 // episode of the tile stamped step `sid` as still running (1) or not (2); the stamps were stored before their writers' arrivals.
 __device__ __forceinline__ int tile_arrive(unsigned cnt_saddr, unsigned target, const volatile int* stamp = nullptr, int sid = 0) {
@@ -136,7 +167,9 @@ __device__ __forceinline__ int tile_arrive(unsigned cnt_saddr, unsigned target, 
     int last = 0;
     if ((threadIdx.x & 31) == 0) {
         unsigned old;
-        asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(cnt_saddr) : "memory");
+        // relaxed: shared-memory operations of one warp are performed in order, and the proxy fence above is what makes the stores
+        // visible to the tensor core; an acq_rel atomic costs two MEMBAR.ALL.CTA on the critical path of every GEMM round trip
+        asm volatile("atom.relaxed.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(cnt_saddr) : "memory");
         if (old + 1u == target) last = (stamp == nullptr || *stamp == sid) ? 1 : 2;
     }
     return __shfl_sync(0xffffffffu, last, 0);

@@ -23,8 +23,7 @@ from .policy import PolicyWeights
 from .samplers import EvalSuite
 
 VARIANT_FFMA = 0   # strict fp32 on the FP32 pipe
-VARIANT_TC = 1     # MLP on the 5th-gen tensor cores (tcgen05 kind::tf32, TMEM accumulators) -- round-1 kernel
-VARIANT_TC16 = 2   # tcgen05 kind::f16 (fp16 operands, fp32 accumulate), constants folded, barrier-free issue -- round-2 kernel
+VARIANT_TC = 1     # MLP on the 5th-gen tensor cores (tcgen05 kind::f16: fp16 operands, fp32 accumulators in TMEM), csrc/kin_rollout_tc16.cu
 
 
 def _D(name: str) -> int:

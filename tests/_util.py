@@ -37,3 +37,6 @@ def policy_weights(name: str) -> dict[str, np.ndarray]:
 
 def oracle_policy(name: str) -> ko.OracleMlp:
     return ko.OracleMlp(policy_weights(name))
+
+
+from oracle.parity import scale_decision_thresholds, threshold_sensitive_episodes  # noqa: E402,F401  (re-exported for the tests)

@@ -92,6 +92,21 @@ def test_library_is_sm100_and_loaded():
     assert major.value == 10, f"expected a Blackwell sm_100 device, got {major.value}.{minor.value} ({name.value})"
 
 
+def _rot(rpy: np.ndarray) -> np.ndarray:
+    """Rz(yaw) Ry(pitch) Rx(roll) for rows of (roll, pitch, yaw) -- the reference's Euler convention (ee_fk.py:64-71)."""
+    cr, sr, cp, sp, cy, sy = np.cos(rpy[:, 0]), np.sin(rpy[:, 0]), np.cos(rpy[:, 1]), np.sin(rpy[:, 1]), np.cos(rpy[:, 2]), np.sin(rpy[:, 2])
+    return np.stack([np.stack([cy * cp, cy * sp * sr - sy * cr, cy * sp * cr + sy * sr], -1),
+                     np.stack([sy * cp, sy * sp * sr + cy * cr, sy * sp * cr - cy * sr], -1),
+                     np.stack([-sp, cp * sr, cp * cr], -1)], -2)
+
+
+def _geodesic(rpy_a: np.ndarray, rpy_b: np.ndarray) -> np.ndarray:
+    """Angle of the rotation taking orientation a to orientation b (singularity-free, unlike Euler differences)."""
+    rel = np.einsum("nij,nkj->nik", _rot(rpy_a), _rot(rpy_b))
+    skew = np.stack([rel[:, 2, 1] - rel[:, 1, 2], rel[:, 0, 2] - rel[:, 2, 0], rel[:, 1, 0] - rel[:, 0, 1]], -1)
+    return np.arctan2(0.5 * np.linalg.norm(skew, axis=1), 0.5 * (np.trace(rel, axis1=1, axis2=2) - 1.0))
+
+
 def test_fk_matches_oracle():
     g = golden("fk.npz")
     env = _make_env(env_config("approach_dynamic_scale_big"), 1)
@@ -99,12 +114,14 @@ def test_fk_matches_oracle():
     ref = ko.fk_pose6(g["q"].astype(np.float32).astype(float))  # oracle on the same fp32-rounded inputs
     assert np.abs(pose[:, :3] - ref[:, :3]).max() < POS_TOL
     d = np.abs((pose[:, 3:] - ref[:, 3:] + np.pi) % (2 * np.pi) - np.pi)
-    # near pitch = +-pi/2 the Euler extraction is ill-conditioned; inside the curriculum shells it is not
+    # inside the curriculum shells the Euler extraction is well conditioned
     shell = slice(2, 130)
     assert d[shell].max() < 2e-6
-    well = np.abs(np.abs(ref[:, 4]) - np.pi / 2) > 0.05
-    assert d[well].max() < ANG_TOL
     assert np.median(d) < 5e-7
+    # EVERY pose, the gimbal-lock neighbourhood included: the orientation itself agrees to 1e-5 rad (geodesic angle between
+    # the two rotations), and each Euler component to 1e-5 rad scaled by its conditioning 1 / cos(pitch) -- a bound, not a mask
+    assert _geodesic(pose[:, 3:], ref[:, 3:]).max() < ANG_TOL
+    assert (d * np.maximum(np.abs(np.cos(ref[:, 4:5])), 1e-4)).max() < ANG_TOL
 
 
 def _compare_rollout(cfg, mode, iq, gq, actions, gp=None, idq=None, ipa=None, names=ko.APPROACH_COMPONENT_NAMES, mode_hint_mixed=False):
@@ -145,8 +162,9 @@ def _compare_rollout(cfg, mode, iq, gq, actions, gp=None, idq=None, ipa=None, na
         stats["max_q"] = max(stats["max_q"], np.abs(q - rq).max(), np.abs(dq - rdq).max())
         stats["max_pos"] = max(stats["max_pos"], np.abs(ee[:, :3] - ree[:, :3]).max())
         ang = np.abs((ee[:, 3:] - ree[:, 3:] + np.pi) % (2 * np.pi) - np.pi)
-        well = np.abs(np.abs(ree[:, 4]) - np.pi / 2) > 0.05
-        stats["max_ang"] = max(stats["max_ang"], ang[well].max() if well.any() else 0.0)
+        # no pose is skipped: Euler components are bounded with their conditioning (1 / cos(pitch) near gimbal lock), and the
+        # rotation itself (geodesic angle) with the plain tolerance
+        stats["max_ang"] = max(stats["max_ang"], (ang * np.maximum(np.abs(np.cos(ree[:, 4:5])), 1e-4)).max(), _geodesic(ee[:, 3:], ree[:, 3:]).max())
         r_pos = np.array([o.position_error_norm for o in routs])
         r_ori = np.array([o.orientation_error_norm for o in routs])
         r_an = np.array([o.action_l2 for o in routs])
@@ -162,7 +180,10 @@ def _compare_rollout(cfg, mode, iq, gq, actions, gp=None, idq=None, ipa=None, na
         gpos = info["position_error_norm"].cpu().numpy().astype(float)
         gori = info["orientation_error_norm"].cpu().numpy().astype(float)
         assert np.abs(gpos - r_pos).max() < POS_TOL
-        assert np.abs(gori - r_ori)[well].max() < 2 * ANG_TOL if well.any() else True
+        # the orientation-error norm is what every predicate consumes: bounded for EVERY pose, with the Euler conditioning of the
+        # current and the goal pose (1 / cos(pitch); 1 inside the curriculum shells) -- no pose is masked out
+        cond = np.maximum(np.minimum(np.abs(np.cos(ree[:, 4])), np.abs(np.cos(orc.field("goal_pose6", 6)[:, 4]))), 1e-4)
+        assert (np.abs(gori - r_ori) * cond).max() < 2 * ANG_TOL
         sel = clean
         if sel.any():
             r_flags = np.array([[o.terminated, o.truncated, o.success, o.curr_in_pre_near_goal, o.curr_in_near_goal, o.reason] for o in routs])

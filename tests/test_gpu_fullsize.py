@@ -59,28 +59,40 @@ def test_stage5_full_size_properties(variant):
     assert steps == int(res["approach_steps"].sum() + res["finisher_steps"].sum()) and steps <= N_FULL * 164
 
 
-def test_stage5_full_size_variants_agree_and_sampled_oracle_check():
-    """The tensor-core rollout (TF32 MLP) against the strict-fp32 one on all 65 536 episodes, and 512 episodes sampled from the
-    whole suite against the CPU oracle."""
-    from oracle import kin_oracle as ko
+THRESHOLD_BAND = 0.01   # an episode is "within tolerance of a threshold" if scaling every decision threshold by 1 -+ 1 % changes the oracle's verdict
 
-    from ._util import oracle_params, oracle_policy
+
+def test_stage5_full_size_every_episode_against_the_oracle():
+    """All 65 536 Stage-5 episodes through the fp64 oracle (north_star: "flags identical except for episodes within tolerance of a
+    threshold").  Strict-fp32 rollout: ZERO success flags differ.  Tensor-core rollout (fp16 operands, fp32 accumulate): every
+    differing episode must be one whose ORACLE verdict itself changes when the decision thresholds (near-goal zone, ready predicates,
+    success pose) are scaled by 1 -+ 1 % -- a flip on a threshold-robust episode fails the test."""
+    import os
+
+    from ._util import oracle_policy, threshold_sensitive_episodes
 
     suite = _suite(N_FULL)
+    acfg, fcfg = env_config("approach_dynamic_scale_big"), env_config("finisher_noop_ft")
+    ref, sensitive = threshold_sensitive_episodes(acfg, fcfg, oracle_policy("approach_stage8_11"), oracle_policy("finisher"), suite,
+                                                  THRESHOLD_BAND, n_threads=os.cpu_count() or 8)
+    assert 0 < sensitive.sum() < 0.01 * N_FULL                       # the band is narrow: well under 1 % of the suite sits inside it
     strict, tc = _rollout(0).evaluate_suite(suite).to_numpy(), _rollout(1).evaluate_suite(suite).to_numpy()
-    flips = int(np.sum(strict["success"] != tc["success"]))
-    assert flips < 0.001 * N_FULL, flips
-    assert abs(strict["success"].mean() - tc["success"].mean()) < 5e-4
-    assert abs(strict["final_position_error"].mean() - tc["final_position_error"].mean()) < 2e-5
-    idx = np.sort(np.random.default_rng(5).choice(N_FULL, 512, replace=False))
-    ref, _ = ko.eval_approach_finisher(oracle_params(env_config("approach_dynamic_scale_big")), oracle_params(env_config("finisher_noop_ft")),
-                                       oracle_policy("approach_stage8_11"), oracle_policy("finisher"),
-                                       initial_q=suite.initial_q[idx].astype(np.float32).astype(float),
-                                       goal_q=suite.goal_q[idx].astype(np.float32).astype(float), n_threads=8)
-    assert int(np.sum(strict["success"][idx].astype(int) != ref["success"])) <= 2
-    same = strict["success"][idx].astype(int) == ref["success"]
-    assert np.quantile(np.abs(strict["final_position_error"][idx][same] - ref["final_position_error"][same]), 0.99) < 2e-5
-    assert np.array_equal(strict["approach_steps"][idx], ref["approach_steps"])
+    # ---- strict fp32: identical flags, step counts and handoff decisions on every episode that is not threshold-sensitive; in
+    # practice on all of them
+    flips = strict["success"].astype(int) != ref["success"]
+    assert int(flips.sum()) == 0, np.nonzero(flips)[0][:20]
+    robust = ~sensitive
+    assert np.array_equal(strict["approach_steps"], ref["approach_steps"])
+    assert np.array_equal(strict["handoff_kind"][robust], ref["handoff_kind"][robust])
+    assert np.quantile(np.abs(strict["final_position_error"] - ref["final_position_error"]), 0.999) < 2e-5
+    # ---- tensor-core variant: flips only inside the band
+    flips = tc["success"].astype(int) != ref["success"]
+    unexplained = flips & robust
+    assert int(unexplained.sum()) == 0, (np.nonzero(unexplained)[0][:20], int(flips.sum()))
+    assert int(flips.sum()) <= int(sensitive.sum()) and int(flips.sum()) < 0.001 * N_FULL
+    assert abs(tc["success"].mean() - ref["success"].mean()) < 5e-4
+    assert abs(tc["final_position_error"].mean() - ref["final_position_error"].mean()) < 2e-5
+    assert np.array_equal(tc["approach_steps"], ref["approach_steps"])
 
 
 def test_step_kernel_full_size_matches_small_batches():
@@ -129,6 +141,23 @@ def test_randomstart_full_size_shard_invariance_and_reference_draw():
     ro = ApproachFinisherRollout(acfg, PolicyWeights.preset("randomstart", "cuda"), fcfg, PolicyWeights.preset("finisher", "cuda"), variant=VARIANT_TC)
     whole = ro.evaluate_suite(suite).to_numpy()
     assert 0.78 < whole["success"].mean() < 0.88                     # 0.8329 on the 1 M-pair sweep, 0.802 on the reference's 96
+    # the first 32 768 KNOWN-split pairs through the fp64 oracle: strict fp32 flips nothing outside the threshold band, the
+    # tensor-core variant only flips threshold-sensitive episodes
+    import os
+
+    from ._util import oracle_policy, threshold_sensitive_episodes
+
+    k = 32768
+    head = EvalSuite(initial_q=suite.initial_q[:k], goal_q=suite.goal_q[:k], goal_pose6=None if suite.goal_pose6 is None else suite.goal_pose6[:k],
+                     initial_dq=suite.initial_dq[:k], initial_prev_action=suite.initial_prev_action[:k])
+    ref, sensitive = threshold_sensitive_episodes(acfg, fcfg, oracle_policy("randomstart"), oracle_policy("finisher"), head, THRESHOLD_BAND,
+                                                  n_threads=os.cpu_count() or 8)
+    strict = ApproachFinisherRollout(acfg, PolicyWeights.preset("randomstart", "cuda"), fcfg, PolicyWeights.preset("finisher", "cuda"),
+                                     variant=0).evaluate_suite(head).to_numpy()
+    for name, res in (("strict", strict), ("tc", {key: v[:k] for key, v in whole.items()})):
+        flips = res["success"].astype(int) != ref["success"]
+        assert int((flips & ~sensitive).sum()) == 0, (name, np.nonzero(flips & ~sensitive)[0][:20], int(flips.sum()), int(sensitive.sum()))
+    assert int((strict["success"].astype(int) != ref["success"]).sum()) <= 2
     for r in (0, 3, 7):                                              # three of the eight shards
         sl = shard_slice(n, r, 8)
         sub = EvalSuite(initial_q=suite.initial_q[sl], goal_q=suite.goal_q[sl], goal_pose6=None if suite.goal_pose6 is None else suite.goal_pose6[sl],

@@ -14,7 +14,7 @@ acfg, fcfg = kcfg.load_preset("approach_dynamic_scale_big"), kcfg.load_preset("f
 pa, pf = PolicyWeights.preset("approach_stage8_11"), PolicyWeights.preset("finisher")
 suite = build_curriculum_local_eval_suite(acfg, seed=700001 + 5 * 1009, stage_index=5, n_episodes=n)
 out = {}
-for name, variant in (("ffma", 0), ("tc", 1), ("tc16", 2)):
+for name, variant in (("ffma", 0), ("tc", 1)):
     ro = ApproachFinisherRollout(acfg, pa, fcfg, pf, variant=variant)
     dev = ro.upload(suite)
     r = ro.run(dev); torch.cuda.synchronize()
@@ -27,7 +27,7 @@ for name, variant in (("ffma", 0), ("tc", 1), ("tc16", 2)):
     steps = int(out[name]["approach_steps"].sum() + out[name]["finisher_steps"].sum())
     print(f"{name}: {dt*1e3:.3f} ms/pass, {steps/dt/1e9:.3f} G env-steps/s, success {out[name]['success'].mean():.4f}, "
           f"final pos {out[name]['final_position_error'].mean()*1e3:.4f} mm ori {out[name]['final_orientation_error'].mean():.5f}")
-for other in ("tc", "tc16"):
+for other in ("tc",):
   a, b = out["ffma"], out[other]
   print("----", other, "vs ffma")
   print("success flips:", int((a["success"] != b["success"]).sum()), "of", n)

@@ -2,7 +2,8 @@
 
 * evaluation: no data-path collective; one all-reduce (sum) of a small statistics vector at the end.
 * training: one all-reduce (sum) of the flat gradient (+ the statistics) per minibatch; every rank then applies the
-  identical Adam step.  Curriculum promotion uses an all-reduced (successes, episodes) pair so all ranks switch stage together.
+  identical Adam step.  Curriculum promotion replays the reference's per-episode windowed rule on the rollout's ordered outcome
+  stream, gathered over ranks in env order, so all ranks switch stage together (``CurriculumTracker``).
 
 All helpers take plain tensors and an optional process group, so they run under NCCL (one rank per GPU) and under gloo on
 CPU tensors (tests/test_distributed_gloo.py, world_size 2).
@@ -16,6 +17,7 @@ from __future__ import annotations
 
 from typing import Any
 
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -139,48 +141,106 @@ class PeerGradExchange:
 
 
 class CurriculumTracker:
-    """Windowed success-rate promotion (``PointCurriculumTracker`` / ``PointCurriculumCallback``, curriculum.py:104-154,
-    training/callbacks.py:54-92), fed with per-iteration (successes, episodes) counts that are summed over ranks first.
+    """``PointCurriculumTracker`` / ``PointCurriculumCallback`` (envs/curriculum.py:104-154, training/callbacks.py:54-92), exact:
+    a deque of the last ``window_episodes`` episode outcomes, checked after EVERY finished episode in the order SB3's callback sees
+    them (time step, then env index); promotion needs ``min_episodes_per_stage`` episodes since the last promotion, a full window and
+    a windowed rate >= the threshold, and clears the window.
 
-    The reference keeps a deque of the last ``window_episodes`` episode outcomes; with tens of thousands of envs finishing
-    together the window is filled many times per iteration, so the rate of the latest batch of finished episodes is used
-    when that batch alone is at least a window long, otherwise batches are accumulated until it is.
+    The batched trainer finishes thousands of episodes per rollout, so the tracker takes the rollout's ordered outcome stream
+    (``record_stream``) and replays the per-episode rule on it with prefix sums -- the decisions (which episode triggers, the trigger
+    rate, the history) are the reference's; several promotions inside one rollout are possible, as in the reference.  With several
+    ranks the per-rank streams are gathered and merged in (time step, rank, env) order = the single-process env order, so every rank
+    takes the same decisions.  The env's stage is switched by the caller after the rollout (the fused collection runs a whole rollout
+    in one launch), i.e. up to ``n_steps`` later than the reference's callback switches it.
     """
 
     def __init__(self, n_stages: int, success_rate_threshold: float, window_episodes: int, min_episodes_per_stage: int, stage_index: int = 0) -> None:
         self.n_stages, self.threshold = int(n_stages), float(success_rate_threshold)
-        self.window, self.min_episodes = int(window_episodes), int(min_episodes_per_stage)
+        self.window, self.min_episodes = max(int(window_episodes), 1), max(int(min_episodes_per_stage), 1)
         self.stage_index = int(stage_index)
         self.stage_episode_count = 0
-        self._succ = 0.0
-        self._eps = 0.0
+        self.recent = np.zeros(0, dtype=np.int64)      # the deque: at most `window` latest outcomes, oldest first
         self.history: list[dict[str, float | int]] = []
 
-    def record(self, successes: torch.Tensor | float, episodes: torch.Tensor | float, group: Any = None) -> bool:
-        v = torch.as_tensor([float(successes), float(episodes)], dtype=torch.float64)
-        if world(group)[1] > 1:
-            dev = successes.device if isinstance(successes, torch.Tensor) else None
-            backend = dist.get_backend(group)
-            v = v.to(dev) if (backend == "nccl" and dev is not None) else v
-            allreduce_sum_(v, group)
-        s, e = float(v[0]), float(v[1])
-        if e <= 0:
-            return False
-        if e >= self.window:
-            self._succ, self._eps = s, e
+    @property
+    def max_stage_index(self) -> int:
+        return max(self.n_stages - 1, 0)
+
+    def record_episode(self, success: bool) -> bool:
+        """One finished episode (the reference's ``record_episode``)."""
+        return self.record_stream(np.array([1 if success else 0], dtype=np.int64)) > 0
+
+    def record_stream(self, outcomes: np.ndarray | torch.Tensor, total_timesteps: int | None = None) -> int:
+        """Feed finished episodes in callback order (1 = success).  Returns the number of promotions it caused."""
+        x = outcomes.detach().cpu().numpy() if isinstance(outcomes, torch.Tensor) else np.asarray(outcomes)
+        x = (x != 0).astype(np.int64).reshape(-1)
+        promotions = 0
+        W = self.window
+        while x.size:
+            if self.stage_index >= self.max_stage_index:      # the last stage only keeps the window current
+                self.stage_episode_count += int(x.size)
+                self.recent = np.concatenate([self.recent, x])[-W:]
+                return promotions
+            seq = np.concatenate([self.recent, x])
+            c = np.concatenate([[0], np.cumsum(seq)])
+            k = np.arange(x.size)
+            end = self.recent.size + k + 1                    # window [end - W, end) after episode k
+            full = end >= W
+            wsum = c[end] - c[np.maximum(end - W, 0)]
+            ok = full & (self.stage_episode_count + k + 1 >= self.min_episodes) & (wsum.astype(np.float64) / float(W) >= self.threshold)
+            hit = np.nonzero(ok)[0]
+            if hit.size == 0:
+                self.stage_episode_count += int(x.size)
+                self.recent = seq[-W:]
+                return promotions
+            j = int(hit[0])
+            rec: dict[str, float | int] = {"from_stage_index": self.stage_index, "to_stage_index": self.stage_index + 1,
+                                            "trigger_success_rate": float(wsum[j]) / float(W)}
+            if total_timesteps is not None:
+                rec["total_timesteps"] = int(total_timesteps)
+            self.history.append(rec)
+            self.stage_index += 1
+            self.stage_episode_count = 0
+            self.recent = np.zeros(0, dtype=np.int64)
+            promotions += 1
+            x = x[j + 1:]
+        return promotions
+
+    def record_rollout(self, finished: torch.Tensor, success: torch.Tensor, group: Any = None, total_timesteps: int | None = None) -> int:
+        """``finished`` / ``success``: bool ``[T, N_local]`` of one rollout.  Builds the ordered outcome stream -- over all ranks of
+        ``group`` in (time step, rank, env) order -- and replays it.  Identical result on every rank."""
+        t_idx, _ = torch.nonzero(finished, as_tuple=True)     # row-major: time step, then env
+        outcome = success[finished].to(torch.int32)
+        rank, n_ranks = world(group)
+        if n_ranks > 1:
+            dev = finished.device if dist.get_backend(group) == "nccl" else torch.device("cpu")
+            count = torch.tensor([int(t_idx.numel())], dtype=torch.int64, device=dev)
+            counts = [torch.zeros_like(count) for _ in range(n_ranks)]
+            dist.all_gather(counts, count, group=group)
+            m = int(max(int(c.item()) for c in counts))
+            pad = torch.full((2, max(m, 1)), -1, dtype=torch.int32, device=dev)
+            pad[0, : t_idx.numel()] = t_idx.to(device=dev, dtype=torch.int32)
+            pad[1, : t_idx.numel()] = outcome.to(dev)
+            parts = [torch.zeros_like(pad) for _ in range(n_ranks)]
+            dist.all_gather(parts, pad, group=group)
+            ts = torch.cat([p_[0, : int(c.item())] for p_, c in zip(parts, counts)]).cpu().numpy()
+            oc = torch.cat([p_[1, : int(c.item())] for p_, c in zip(parts, counts)]).cpu().numpy()
+            order = np.argsort(ts, kind="stable")             # per-rank lists are time-ordered: stable sort = (t, rank, env)
+            stream = oc[order]
         else:
-            self._succ += s
-            self._eps += e
-        self.stage_episode_count += int(e)
-        if self.stage_index >= self.n_stages - 1 or self.stage_episode_count < self.min_episodes or self._eps < self.window:
-            return False
-        rate = self._succ / self._eps
-        if rate < self.threshold:
-            if self._eps >= 4 * self.window:
-                self._succ, self._eps = 0.0, 0.0
-            return False
-        self.history.append({"from_stage_index": self.stage_index, "to_stage_index": self.stage_index + 1, "trigger_success_rate": rate})
-        self.stage_index += 1
-        self.stage_episode_count = 0
-        self._succ, self._eps = 0.0, 0.0
-        return True
+            stream = outcome.cpu().numpy()
+        return self.record_stream(stream, total_timesteps)
+
+    def snapshot(self) -> dict[str, object]:
+        rate = float(self.recent.sum()) / float(self.recent.size) if self.recent.size else 0.0
+        return {"stage_index": self.stage_index, "stage_episode_count": self.stage_episode_count, "recent_success_rate": rate,
+                "history": list(self.history)}
+
+    def state_dict(self) -> dict[str, Any]:
+        return {"stage_index": self.stage_index, "stage_episode_count": self.stage_episode_count, "recent": self.recent.tolist(),
+                "history": list(self.history)}
+
+    def load_state_dict(self, d: dict[str, Any]) -> None:
+        self.stage_index, self.stage_episode_count = int(d["stage_index"]), int(d["stage_episode_count"])
+        self.recent = np.asarray(d.get("recent", []), dtype=np.int64)
+        self.history = list(d.get("history", []))

@@ -264,6 +264,7 @@ class PPOTrainer:
         self.num_timesteps += self.S * self.world
         finished = (self.done_buf & done_bits) != 0
         succ = ((self.done_buf & _D("KIN_DONE_SUCCESS")) != 0) & finished
+        self._finished, self._success = finished, succ      # [T, N] bool: the rollout's episode outcomes in callback order
         self.last_rollout = {"episodes": float(finished.sum()), "successes": float(succ.sum()), "mean_reward": float(self.rew_buf.mean())}
         return self.last_rollout
 
@@ -344,6 +345,7 @@ class PPOTrainer:
         done_bits = _D("KIN_DONE_TERMINATED") | _D("KIN_DONE_TRUNCATED")
         finished = (self.done_buf & done_bits) != 0
         succ = ((self.done_buf & _D("KIN_DONE_SUCCESS")) != 0) & finished
+        self._finished, self._success = finished, succ      # [T, N] bool: the rollout's episode outcomes in callback order
         self.last_rollout = {"episodes": float(finished.sum()), "successes": float(succ.sum()), "mean_reward": float(self.rew_buf.mean())}
         return self.last_rollout
 
@@ -448,7 +450,7 @@ class PPOTrainer:
         for _ in range(int(iterations)):
             r = self.collect()
             u = self.update()
-            if self.curriculum is not None and self.curriculum.record(r["successes"], r["episodes"], self.group):
+            if self.curriculum is not None and self.curriculum.record_rollout(self._finished, self._success, self.group, self.num_timesteps):
                 self.env.set_curriculum_stage(self.curriculum.stage_index)
             stage = float(self.route_curriculum.current_stage_index) if (self.is_route and self.route_curriculum is not None) else (
                 0.0 if self.is_route else float(self.env.get_curriculum_stage()))

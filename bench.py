@@ -255,6 +255,72 @@ def measure_step_kernel(torch, device, pk, n_envs: int = 1 << 21, launches: int 
             "note": "working set %.0f MB per launch (> L2), CUDA events on the launching stream" % (STEP_BYTES_APPROACH * n_envs / 1e6)}
 
 
+def _time_launches(torch, device, fn, launches: int) -> float:
+    """Mean seconds per call of `fn` (CUDA events on the launching stream, after 3 warm-up calls)."""
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize(device)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(launches)]
+    for a, b in ev:
+        a.record()
+        fn()
+        b.record()
+    torch.cuda.synchronize(device)
+    return float(np.mean([a.elapsed_time(b) for a, b in ev])) * 1e-3
+
+
+def measure_step_variants(torch, device, pk, n_envs: int = 1 << 21, launches: int = 10) -> dict:
+    """The other instances of the step kernel family at an HBM-resident size, each against its own algorithmic bytes (SURVEY 8d:
+    dock 548 B, approach with in-kernel auto-reset 532 B, route step 644 B), plus the documented per-step API (`env.step`, lazy
+    info) at the same size and at 65 536 envs where launch overhead shows."""
+    from rl_brain_trainer_b200 import config as kcfg
+    from rl_brain_trainer_b200.env import BatchedArmKinematicEnv
+    from rl_brain_trainer_b200.route import BatchedRouteKinematicEnv, synthetic_route
+
+    out = {}
+    g = torch.Generator(device=device)
+    g.manual_seed(2)
+    actions = torch.rand((n_envs, 7), device=device, generator=g) * 2 - 1
+
+    def entry(kernel, bytes_per_step, t, n):
+        gbs = bytes_per_step * n / t / 1e9
+        return {"kernel": kernel, "bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
+                "bytes_per_env_step": bytes_per_step, "n_envs": n, "us_per_launch": t * 1e6, "env_steps_per_sec": n / t, "peak_source": pk["source"]}
+
+    acfg, fcfg = kcfg.load_preset("approach_dynamic_scale_big"), kcfg.load_preset("finisher_noop_ft")
+    env = BatchedArmKinematicEnv(fcfg, n_envs, device, with_aux=False, seed=3, host_sampler=False)
+    env.reset()
+    out["dock"] = entry("kin_step_kernel<dock>", 548, _time_launches(torch, device, lambda: env.step_raw(actions), launches), n_envs)
+    del env
+    env = BatchedArmKinematicEnv(acfg, n_envs, device, with_aux=False, seed=3, host_sampler=False, auto_reset=True)
+    env.set_curriculum_stage(STAGE)
+    env.reset()
+    out["approach_autoreset"] = entry("kin_step_kernel<approach, AUTORESET>", 532, _time_launches(torch, device, lambda: env.step_raw(actions), launches), n_envs)
+    # the public per-step API on the same env: kernel + lazily decoded info (only the two done-bit tests run per call)
+    t_api = _time_launches(torch, device, lambda: env.step(actions), launches)
+    out["step_api"] = {"call": "BatchedArmKinematicEnv.step (auto-reset, lazy info)", "n_envs": n_envs, "us_per_call": t_api * 1e6,
+                       "env_steps_per_sec": n_envs / t_api, "frac_of_hbm_peak": 532 * n_envs / t_api / 1e9 / pk["hbm_gbs"]}
+    del env
+    small = BatchedArmKinematicEnv(acfg, 65536, device, with_aux=False, seed=3, host_sampler=False, auto_reset=True)
+    small.set_curriculum_stage(STAGE)
+    small.reset()
+    a_small = actions[:65536].contiguous()
+    t_small = _time_launches(torch, device, lambda: small.step(a_small), 50)
+    out["step_api_65536"] = {"call": "BatchedArmKinematicEnv.step (auto-reset, lazy info)", "n_envs": 65536, "us_per_call": t_small * 1e6,
+                             "env_steps_per_sec": 65536 / t_small, "note": "35 MB working set: L2-resident, launch-latency bound"}
+    del small
+    route = synthetic_route(483, seed=7)
+    renv, _ = kcfg.to_route_env_config(kcfg.preset_dict("route_prefix120"), max_route_index=len(route) - 1)
+    n_route = n_envs // 2
+    renv_b = BatchedRouteKinematicEnv(route, renv, n_route, device)
+    renv_b.reset(seed=5)
+    a_route = actions[:n_route].contiguous()
+    out["route_step"] = entry("kin_route_step_kernel", 644, _time_launches(torch, device, lambda: renv_b.step_raw(a_route), launches), n_route)
+    del renv_b
+    torch.cuda.empty_cache()
+    return out
+
+
 def measure_training(torch, dist, device, world: int, envs: int = 65536, n_steps: int = 128, iters: int = 2, grad_exchange: str = "peer") -> dict:
     """BASELINE config 5: Stage-10 stress-shell PPO (fused collection K4 + tensor-core update K3-TC, 8 epochs x 16 minibatches,
     one gradient sum over ranks per minibatch when world > 1: NVLink peer-memory push (csrc/kin_peer.cu) or NCCL all-reduce).
@@ -455,8 +521,10 @@ def main() -> None:
     step_roof = None
     cpu_base = None
     parity = None
+    step_variants = None
     if rank == 0 and not args.skip_step_kernel:
         step_roof = measure_step_kernel(torch, device, pk)
+        step_variants = measure_step_variants(torch, device, pk)
     clocks.__exit__(None, None, None)
     if rank == 0:
         if world == 1 and not args.skip_cpu_baseline:
@@ -515,7 +583,7 @@ def main() -> None:
             "dtype": "f32" if not tc else "f32 env + f16 MLP operands (f32 accumulate)", "data": "synthetic",
             "config": bench_config(n, world), "rollout_variant": "tc" if tc else "ffma",
             "env_steps_per_step": env_steps / max(args.steps, 1), "success_rate": success_all, "wall_s_timed_region": t_wall,
-            "roofline": roof, "step_kernel_roofline": step_roof, "cpu_baseline": cpu_base, "parity": parity, "strict_fp32": strict,
+            "roofline": roof, "step_kernel_roofline": step_roof, "step_kernel_variants": step_variants, "cpu_baseline": cpu_base, "parity": parity, "strict_fp32": strict,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "success_rate": e2e_success},
             "clocks": clocks.summary(), "gpu_launches": launches, "train": train,
         }

@@ -427,6 +427,14 @@ typedef struct KinRouteTable {
     const float *pose6;
     const float *next_q_delta;
     const float *progress_m;
+    /* Optional pruning table for the nearest-waypoint scan of the route reward (route_env.py:135 scans the whole route every step):
+     * nearest_lb[i * nearest_lb_k + k] <= min over waypoints j with |j - i| >= k of |q_goal[j] - q_goal[i]| (k = 0 .. nearest_lb_k - 1,
+     * +inf where no such j exists).  With it the step kernels visit waypoints outward from the env's current target and stop as soon
+     * as the triangle inequality rules the rest out -- the SAME minimum, a handful of candidates instead of all of them.
+     * NULL / 0: every waypoint is visited. */
+    const float *nearest_lb;
+    int nearest_lb_k;
+    int pad1;
 } KinRouteTable;
 
 /* per-step scalars of the route wrappers: raux[row * stride + env] (route/route_env.py:175-190 info keys) */
@@ -621,6 +629,7 @@ int kin_route_probe_tc(void *handle, const KinRouteTable *host_route, const KinP
 #define KIN_PPO_STAT_CLIP_FRACTION 4
 #define KIN_PPO_STAT_GRAD_NORM 5
 #define KIN_PPO_STAT_SAMPLES 6
+#define KIN_PPO_STAT_SKIP 7         /* set by kin_peer_grad_gather after a peer timed out: kin_ppo_adam then leaves the parameters untouched */
 
 typedef struct KinPpoHyper {
     float gamma;

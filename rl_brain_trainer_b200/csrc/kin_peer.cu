@@ -13,6 +13,7 @@
 //     [128..]  float    slot[2][world][row]   row = n_params + 8 (gradient, then the 5 loss statistics); slot = exchange parity
 //   A slot is rewritten two exchanges later; by then every reader has passed the wait of the exchange in between, which its
 //   sender only reaches after its own gather of this exchange (stream order), so two slots suffice.
+#include <cstdlib>
 #include <cstring>
 
 #include "kin_internal.h"
@@ -98,6 +99,9 @@ kin_peer_gather_kernel(const unsigned char* __restrict__ local, int world, unsig
         }
     }
     __syncthreads();
+    // a peer that never delivered leaves stale slots behind: mark the minibatch so kin_ppo_adam skips it on this rank (the sticky
+    // flag makes every later exchange skip too -- parameters stay where they were until the host raises, they never diverge)
+    if (blockIdx.x == 0 && threadIdx.x == 0 && stats) stats[KIN_PPO_STAT_SKIP] = *reinterpret_cast<volatile int*>(timed_out) ? 1.0f : 0.0f;
     const int p = blockIdx.x * 256 + threadIdx.x;
     if (p >= P + 5) return;
     const float* slot = reinterpret_cast<const float*>(local + PEER_HEADER) + (size_t)(epoch & 1u) * world * peer_row(P);
@@ -172,7 +176,14 @@ extern "C" int kin_peer_grad_gather(const void* local_buffer, int n_params, int 
     if (!local_buffer || !grad || !timed_out || n_params <= 0 || world < 1 || world > PEER_MAX || epoch == 0u)
         return kin_fail(KIN_ERR_INVALID_ARG, "kin_peer_grad_gather: bad arguments");
     const int blocks = (n_params + 5 + 255) / 256;
-    const unsigned long long timeout = 20ull * 1000ull * 1000ull * 1000ull;      // ~10 s of SM clocks
+    // device-side wait limit in SM clocks: KIN_PEER_TIMEOUT_S seconds (default 30) at ~2 GHz; first-call module loads, checkpoint
+    // writes or a throttled peer can skew ranks by seconds
+    static unsigned long long timeout = 0ull;
+    if (timeout == 0ull) {
+        double sec = 30.0;
+        if (const char* v = getenv("KIN_PEER_TIMEOUT_S")) { const double f = atof(v); if (f > 0.0) sec = f; }
+        timeout = (unsigned long long)(sec * 2.0e9);
+    }
     kin_peer_gather_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(static_cast<const unsigned char*>(local_buffer), world, epoch, n_params, grad, stats,
                                                                      timeout, timed_out);
     cudaError_t e = cudaGetLastError();

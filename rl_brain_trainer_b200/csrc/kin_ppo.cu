@@ -596,6 +596,7 @@ kin_ppo_adam_kernel(float* __restrict__ params, const float* __restrict__ grad, 
                     unsigned short* __restrict__ wimg, int in_dim) {
     __shared__ float red[32];
     __shared__ float coef;
+    if (stats && stats[KIN_PPO_STAT_SKIP] != 0.0f) return;      // the gradient exchange timed out (kin_peer.cu): leave the parameters alone
     // this thread's own parameter: fetch its optimiser state now, so the loads fly while the norm is being reduced
     const int own = blockIdx.x * blockDim.x + threadIdx.x;
     const bool has_own = own < P && gridDim.x * blockDim.x >= P;      // the usual launch: one parameter per thread

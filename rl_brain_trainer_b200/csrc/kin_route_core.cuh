@@ -21,6 +21,8 @@ struct RouteView {
     const float* pose;   // [n][6]
     const float* tan;    // [n][7] next_q_delta
     const float* prog;   // [n]
+    const float* lb;     // [n][lb_k] pruning bounds of the nearest-waypoint scan (KinRouteTable::nearest_lb), or nullptr
+    int lb_k;
 };
 
 struct RouteRegs {
@@ -107,15 +109,38 @@ __device__ __forceinline__ void route_step_core(const KinEnvParams& P, const Rou
     const float an = sqrtf(an2), dqn = so.dq_l2, tn = sqrtf(tn2);
     float nearest = 0.0f;
     if (q_table) {
-        nearest = CUDART_INF_F;
-        for (int w = 0; w < R.n; ++w) {
+        // route_env.py:135: min over ALL waypoints of |q_w - q|.  Every candidate's squared distance is computed by the same
+        // expression in either branch and min is order-independent, so the pruned scan returns the full scan's value bit for bit.
+        auto d2 = [&](int w) {
             const float* qw = q_table + w * NJ;
             float acc = 0.0f;
 #pragma unroll
             for (int i = 0; i < NJ; ++i) acc = fmaf(qw[i] - s.q[i], qw[i] - s.q[i], acc);
-            nearest = fminf(nearest, acc);
+            return acc;
+        };
+        if (R.lb != nullptr && R.lb_k > 1) {
+            // outward from the current target i: |q_j - q| >= |q_j - q_i| - |q_i - q| >= lb[i][k] - r for every j with |j - i| >= k
+            const int i0 = wp_clamp(R, target);
+            float best = d2(i0);
+            const float r = sqrtf(best) * 1.00001f;
+            const float* lb = R.lb + (size_t)i0 * R.lb_k;
+            int k = 1;
+            for (; k < R.lb_k; ++k) {
+                const float slack = __ldg(lb + k) * 0.99999f - r;
+                if (slack > 0.0f && slack * slack >= best) break;       // also breaks on +inf (no waypoint that far from i)
+                if (i0 - k >= 0) best = fminf(best, d2(i0 - k));
+                if (i0 + k < R.n) best = fminf(best, d2(i0 + k));
+            }
+            if (k == R.lb_k) {                                           // far off the route: finish with the plain scan
+                for (int w = 0; w <= i0 - k; ++w) best = fminf(best, d2(w));
+                for (int w = i0 + k; w < R.n; ++w) best = fminf(best, d2(w));
+            }
+            nearest = sqrtf(best);
+        } else {
+            nearest = CUDART_INF_F;
+            for (int w = 0; w < R.n; ++w) nearest = fminf(nearest, d2(w));
+            nearest = sqrtf(nearest);
         }
-        nearest = sqrtf(nearest);
     }
     const bool ready = route_ready(P, q_err, so.pos, so.ori, an, dqn);
     rr.streak = ready ? rr.streak + 1 : 0;
@@ -207,6 +232,8 @@ __device__ __forceinline__ void load_q_table(float* dst, const RouteView& R, int
 }
 
 static inline bool route_ok(const KinRouteTable* r) { return r && r->n_waypoints >= 2 && r->n_waypoints <= 65535 && r->q_goal && r->pose6 && r->next_q_delta && r->progress_m; }
-static inline RouteView view_of(const KinRouteTable* r) { return RouteView{r->n_waypoints, r->q_goal, r->pose6, r->next_q_delta, r->progress_m}; }
+static inline RouteView view_of(const KinRouteTable* r) {
+    return RouteView{r->n_waypoints, r->q_goal, r->pose6, r->next_q_delta, r->progress_m, r->nearest_lb, r->nearest_lb ? r->nearest_lb_k : 0};
+}
 
 }  // namespace kin

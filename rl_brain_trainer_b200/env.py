@@ -126,6 +126,31 @@ class ParamsHandle:
             pass
 
 
+class LazyInfo(Mapping):
+    """Read-only ``info`` mapping whose values are produced on first access (and then cached).  Behaves like the dict the reference
+    returns for every reader (``info[key]``, ``key in info``, ``info.get``, iteration, ``dict(info)``)."""
+
+    __slots__ = ("_thunks", "_cache")
+
+    def __init__(self, thunks: dict[str, Any]) -> None:
+        self._thunks = thunks
+        self._cache: dict[str, Any] = {}
+
+    def __getitem__(self, key: str) -> Any:
+        if key not in self._cache:
+            self._cache[key] = self._thunks[key]()
+        return self._cache[key]
+
+    def __iter__(self):
+        return iter(self._thunks)
+
+    def __len__(self) -> int:
+        return len(self._thunks)
+
+    def __contains__(self, key: object) -> bool:
+        return key in self._thunks
+
+
 class BatchedArmKinematicEnv:
     """``num_envs`` independent kinematic envs resident on one GPU.
 
@@ -354,42 +379,42 @@ class BatchedArmKinematicEnv:
                 "near_goal_drift_count": (c1 >> 16) & 0xFFFF, "pre_near_goal_hit": (fl & 1) != 0, "near_goal_hit": (fl & 2) != 0,
                 "mode": (fl >> _D("KIN_FLAG_MODE_SHIFT")) & 3, "stage": (fl >> _D("KIN_FLAG_STAGE_SHIFT")) & 15}
 
-    def _info(self, *, reset: bool) -> dict[str, Any]:
-        """Batched ``info``: tensors keyed like the reference's ``_base_info`` (AKE:384-423); views where possible."""
-        info: dict[str, Any] = {"q": self.q, "dq": self.dq, "goal_q": self.goal_q, "goal_pose6": self.goal_pose6, "ee_pose6": self.ee_pose6,
-                                "min_position_error": self.state[_D("KIN_ROW_MIN_POS"), : self.num_envs]}
+    def _info(self, *, reset: bool) -> "LazyInfo":
+        """Batched ``info`` keyed like the reference's ``_base_info`` (AKE:384-423), decoded LAZILY: ``step()`` is the kernel launch
+        plus the two done-bit tests; a key costs its one or two elementwise ops only when somebody reads it.  Values are views of
+        (or derived from) the env's buffers as they are at first access, valid until the next ``step`` / ``reset``."""
+        n, st, d = self.num_envs, self.state, self.done
         e = _D("KIN_ROW_ENTRY")
-        info["entry_position_error_norm"] = self.state[e, : self.num_envs]
-        info["entry_orientation_error_norm"] = self.state[e + 1, : self.num_envs]
-        info["entry_action_l2"] = self.state[e + 2, : self.num_envs]
-        info["entry_dq_norm"] = self.state[e + 3, : self.num_envs]
+        t: dict[str, Any] = {
+            "q": lambda: self.q, "dq": lambda: self.dq, "goal_q": lambda: self.goal_q, "goal_pose6": lambda: self.goal_pose6,
+            "ee_pose6": lambda: self.ee_pose6, "min_position_error": lambda: st[_D("KIN_ROW_MIN_POS"), :n],
+            "entry_position_error_norm": lambda: st[e, :n], "entry_orientation_error_norm": lambda: st[e + 1, :n],
+            "entry_action_l2": lambda: st[e + 2, :n], "entry_dq_norm": lambda: st[e + 3, :n],
+        }
         if reset:
-            info["position_error_norm"] = info["entry_position_error_norm"]
-            info["orientation_error_norm"] = info["entry_orientation_error_norm"]
-            info["success"] = torch.zeros(self.num_envs, dtype=torch.bool, device=self.device)
+            t["position_error_norm"] = t["entry_position_error_norm"]
+            t["orientation_error_norm"] = t["entry_orientation_error_norm"]
+            t["success"] = lambda: torch.zeros(n, dtype=torch.bool, device=self.device)
         else:
-            d = self.done
-            info["success"] = (d & _D("KIN_DONE_SUCCESS")) != 0
-            info["curr_in_pre_near_goal"] = (d & _D("KIN_DONE_PRE_NEAR")) != 0
-            info["curr_in_near_goal"] = (d & _D("KIN_DONE_NEAR")) != 0
-            info["reason_code"] = (d >> _D("KIN_DONE_REASON_SHIFT")) & 3
-            info["auto_reset"] = (d & _D("KIN_DONE_AUTORESET")) != 0
+            t["success"] = lambda: (d & _D("KIN_DONE_SUCCESS")) != 0
+            t["curr_in_pre_near_goal"] = lambda: (d & _D("KIN_DONE_PRE_NEAR")) != 0
+            t["curr_in_near_goal"] = lambda: (d & _D("KIN_DONE_NEAR")) != 0
+            t["reason_code"] = lambda: (d >> _D("KIN_DONE_REASON_SHIFT")) & 3
+            t["auto_reset"] = lambda: (d & _D("KIN_DONE_AUTORESET")) != 0
             if self.aux is not None:
-                ax = self.aux[:, : self.num_envs]
-                info["position_error_norm"] = ax[_D("KIN_AUX_POS_ERR")]
-                info["orientation_error_norm"] = ax[_D("KIN_AUX_ORI_ERR")]
-                info["action_l2"] = ax[_D("KIN_AUX_ACTION_L2")]
-                info["executed_delta_q_l2"] = ax[_D("KIN_AUX_DQ_L2")]
-                info["delta_q_change_l2"] = ax[_D("KIN_AUX_DQ_CHANGE_L2")]
-                info["dock_action_limit"] = ax[_D("KIN_AUX_DOCK_LIMIT")]
-                info["dock_delta_q_change_limit_scale"] = ax[_D("KIN_AUX_DQC_SCALE")]
-                info["joint_limit_margin_min"] = ax[_D("KIN_AUX_MARGIN_MIN")]
+                ax = self.aux
+                for key, row in (("position_error_norm", "KIN_AUX_POS_ERR"), ("orientation_error_norm", "KIN_AUX_ORI_ERR"),
+                                 ("action_l2", "KIN_AUX_ACTION_L2"), ("executed_delta_q_l2", "KIN_AUX_DQ_L2"),
+                                 ("delta_q_change_l2", "KIN_AUX_DQ_CHANGE_L2"), ("dock_action_limit", "KIN_AUX_DOCK_LIMIT"),
+                                 ("dock_delta_q_change_limit_scale", "KIN_AUX_DQC_SCALE"), ("joint_limit_margin_min", "KIN_AUX_MARGIN_MIN")):
+                    t[key] = (lambda r: (lambda: ax[_D(r), :n]))(row)
             if self.components is not None:
-                info["reward_components"] = self.components[:, : self.num_envs]
+                t["reward_components"] = lambda: self.components[:, :n]
             if self.terminal_obs is not None:
-                info["terminal_observation"] = self.terminal_obs
-        info.update(self.counters())
-        return info
+                t["terminal_observation"] = lambda: self.terminal_obs
+        for key in ("step_count", "dwell_count", "near_goal_entry_count", "near_goal_drift_count", "pre_near_goal_hit", "near_goal_hit", "mode", "stage"):
+            t[key] = (lambda k: (lambda: self.counters()[k]))(key)
+        return LazyInfo(t)
 
     # ------------------------------------------------------------------ helpers
     def fk_pose6(self, q: torch.Tensor) -> torch.Tensor:

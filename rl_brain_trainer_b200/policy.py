@@ -66,9 +66,14 @@ class PolicyWeights:
     def save_npz(self, path: str | Path) -> None:
         np.savez_compressed(path, **{k: v.detach().cpu().numpy() for k, v in self.state_dict().items()})
 
-    def save_sb3_zip(self, path: str | Path, data: dict | None = None) -> None:
-        """Write an SB3-style ``model.zip`` (``policy.pth`` with the reference's key names + a ``data`` JSON), so the
-        reference's ``PPO.load`` / its evaluators can pick a policy trained here back up (``training/callbacks.py:17-29``)."""
+    def save_weights_zip(self, path: str | Path, data: dict | None = None, extra: Mapping[str, bytes] | None = None) -> None:
+        """Write a WEIGHTS-ONLY zip laid out like an SB3 ``model.zip``: ``policy.pth`` holds the state dict under the reference's key
+        names, ``data`` a plain JSON of hyper-parameters.  It is NOT a full SB3 archive -- SB3's ``PPO.load`` also wants the pickled
+        observation / action spaces and schedules, which need stable-baselines3 + gymnasium (absent here) to produce.  To take a
+        policy trained here into the reference: build ``PPO("MultiInputPolicy", env, **hyper)`` as ``train_workspace_expansion.py:199``
+        does and ``model.policy.load_state_dict(torch.load(<policy.pth from this zip>))`` (the keys and shapes are SB3's own);
+        ``PPOTrainer.save_checkpoint`` adds ``policy.optimizer.pth`` in torch-Adam layout for ``model.policy.optimizer.load_state_dict``.
+        ``PolicyWeights.load`` reads these zips and the reference's own ``model.zip`` checkpoints alike."""
         import json
 
         buf = io.BytesIO()
@@ -77,7 +82,9 @@ class PolicyWeights:
             z.writestr("policy.pth", buf.getvalue())
             z.writestr("data", json.dumps(data or {"policy_class": "MultiInputPolicy", "n_envs": 1}))
             z.writestr("_stable_baselines3_version", "2.8.0")
-            z.writestr("system_info.txt", "written by rl_brain_trainer_b200")
+            z.writestr("system_info.txt", "written by rl_brain_trainer_b200 (weights-only archive)")
+            for name, blob in (extra or {}).items():
+                z.writestr(name, blob)
 
     @classmethod
     def load(cls, path: str | Path, device: str | torch.device = "cuda") -> "PolicyWeights":

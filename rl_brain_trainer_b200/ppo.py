@@ -328,7 +328,9 @@ class PPOTrainer:
         L, env, hp = self._L, self.env, self.hp
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream(self.device).cuda_stream
-            mode = _D("KIN_MODE_APPROACH") if env._mode_all is None else env._mode_all
+            if env._mode_all is None:
+                raise _lib.KinError("the fused collection runs ONE policy mode for all envs; per-env mixed modes need collect_variant='steps'")
+            mode = env._mode_all
             _lib.check(L.kin_ppo_collect(env._params.handle, env.state.data_ptr(), env.stride, self.N, mode, self.params.data_ptr(), self.weight_image.data_ptr(), 56,
                                          self.T,
                                          self.seed, self.global_step, env._seed, self.obs_img.data_ptr(), self.act_buf.data_ptr(),
@@ -342,6 +344,9 @@ class PPOTrainer:
                                      self.adv_buf.data_ptr(), self.ret_buf.data_ptr(), self.tile_sums.data_ptr(), stream))
         self.global_step += self.T
         self.num_timesteps += self.S * self.world
+        if int(self.boot_count.item()) > self.boot_cap:       # the kernel drops entries past the capacity: returns would be biased
+            raise _lib.KinError(f"TimeLimit bootstrap list overflow ({int(self.boot_count.item())} > {self.boot_cap}): the env's episode limit "
+                                "changed after the trainer was built; rebuild the trainer")
         done_bits = _D("KIN_DONE_TERMINATED") | _D("KIN_DONE_TRUNCATED")
         finished = (self.done_buf & done_bits) != 0
         succ = ((self.done_buf & _D("KIN_DONE_SUCCESS")) != 0) & finished
@@ -436,6 +441,8 @@ class PPOTrainer:
                 for m in range(mb_per_epoch):
                     self._grad_launch(perm.data_ptr() + 4 * m * tiles_per_mb, tiles_per_mb, adv.data_ptr() + 8 * m)
                     self.apply_update()
+                if self.peer:
+                    self.peer.check()        # once per epoch: a dead peer surfaces after at most one epoch of skipped updates
             a = self.stats_accum.cpu().numpy().astype(np.float64)
             if self.peer:
                 self.peer.check()
@@ -476,6 +483,89 @@ class PPOTrainer:
     def state_dict(self) -> dict[str, torch.Tensor]:
         """SB3 ``policy.pth`` key names, so a trained policy loads back into the reference (and vice versa)."""
         return {KEYS[f]: t.detach().clone() for f, t in self.policy.tensors.items()}
+
+    # SB3's ``policy.parameters()`` order for MultiInputPolicy (= the index of each tensor in ``policy.optimizer.pth``)
+    SB3_PARAM_ORDER = ("log_std", "pi_w0", "pi_b0", "pi_w1", "pi_b1", "vf_w0", "vf_b0", "vf_w1", "vf_b1", "act_w", "act_b", "val_w", "val_b")
+
+    def _flat_views(self, flat: torch.Tensor) -> dict[str, torch.Tensor]:
+        out, off = {}, 0
+        for k in PARAM_ORDER:
+            n = self.policy.tensors[k].numel()
+            out[k] = flat[off:off + n].view_as(self.policy.tensors[k])
+            off += n
+        return out
+
+    def save_checkpoint(self, path: str) -> None:
+        """Everything a resume needs -- what SB3's ``model.save`` keeps (``train_workspace_expansion.py:187-196`` resumes with
+        ``PPO.load``: weights AND Adam state AND the run's own hyper-parameters): ``policy.pth`` (SB3 key names),
+        ``policy.optimizer.pth`` (torch-Adam state dict in SB3's parameter order), ``data`` (hyper-parameters, counters) and
+        ``trainer_state.json`` (curriculum tracker, step counters)."""
+        import io
+        import json
+        from dataclasses import asdict
+
+        m, v = self._flat_views(self.adam_m), self._flat_views(self.adam_v)
+        opt = {"state": {i: {"step": torch.tensor(float(self.update_count)), "exp_avg": m[k].detach().cpu().clone(),
+                             "exp_avg_sq": v[k].detach().cpu().clone()} for i, k in enumerate(self.SB3_PARAM_ORDER)},
+               "param_groups": [{"lr": self.hp.learning_rate, "betas": (self.hp.adam_beta1, self.hp.adam_beta2), "eps": self.hp.adam_eps,
+                                 "weight_decay": 0, "amsgrad": False, "params": list(range(len(self.SB3_PARAM_ORDER)))}]}
+        buf = io.BytesIO()
+        torch.save(opt, buf)
+        state = {"update_count": self.update_count, "num_timesteps": self.num_timesteps, "global_step": self.global_step,
+                 "curriculum": None if self.curriculum is None else self.curriculum.state_dict(),
+                 "stage_index": None if self.is_route else int(self.env.get_curriculum_stage())}
+        data = {"policy_class": "MultiInputPolicy", "n_envs": self.N, "num_timesteps": self.num_timesteps, **asdict(self.hp)}
+        self.policy.save_weights_zip(path, data=data, extra={"policy.optimizer.pth": buf.getvalue(), "trainer_state.json": json.dumps(state).encode()})
+
+    def load_checkpoint(self, path: str, *, load_hyper: bool = True, learning_rate: float | None = None) -> None:
+        """Resume from ``save_checkpoint`` output or from one of the REFERENCE's own ``model.zip`` files: weights, Adam moments and
+        step count, and (``load_hyper``) the checkpoint's own gamma / gae_lambda / clip_range / ent_coef / vf_coef / max_grad_norm /
+        n_epochs -- ``PPO.load(path, env, learning_rate=...)`` keeps all of those and only overrides the learning rate
+        (``train_workspace_expansion.py:187-196``)."""
+        import io
+        import json
+        import zipfile
+
+        with zipfile.ZipFile(path) as z:
+            names = set(z.namelist())
+            sd = torch.load(io.BytesIO(z.read("policy.pth")), weights_only=True, map_location="cpu")
+            opt = torch.load(io.BytesIO(z.read("policy.optimizer.pth")), weights_only=True, map_location="cpu") if "policy.optimizer.pth" in names else None
+            data = json.loads(z.read("data")) if "data" in names else {}
+            state = json.loads(z.read("trainer_state.json")) if "trainer_state.json" in names else {}
+        for f, key in KEYS.items():
+            if f in self.policy.tensors and key in sd:
+                self.policy.tensors[f].copy_(sd[key].to(self.device))
+        if opt is not None and opt.get("state"):
+            m, v = self._flat_views(self.adam_m), self._flat_views(self.adam_v)
+            steps = []
+            for i, k in enumerate(self.SB3_PARAM_ORDER):
+                st = opt["state"].get(i)
+                if st is None:
+                    continue
+                m[k].copy_(st["exp_avg"].to(self.device))
+                v[k].copy_(st["exp_avg_sq"].to(self.device))
+                steps.append(int(float(st["step"])))
+            if steps:
+                self.update_count = max(steps)
+        if load_hyper:
+            for k in ("gamma", "gae_lambda", "ent_coef", "vf_coef", "max_grad_norm", "n_epochs", "normalize_advantage"):
+                if isinstance(data.get(k), (int, float, bool)):
+                    setattr(self.hp, k, type(getattr(self.hp, k))(data[k]))
+            if isinstance(data.get("clip_range"), (int, float)):
+                self.hp.clip_range = float(data["clip_range"])
+            if isinstance(data.get("learning_rate"), (int, float)):
+                self.hp.learning_rate = float(data["learning_rate"])
+        if learning_rate is not None:
+            self.hp.learning_rate = float(learning_rate)
+        self.update_count = int(state.get("update_count", self.update_count))
+        self.num_timesteps = int(state.get("num_timesteps", data.get("num_timesteps", self.num_timesteps)) or 0)
+        self.global_step = int(state.get("global_step", self.global_step))
+        if self.curriculum is not None and state.get("curriculum"):
+            self.curriculum.load_state_dict(state["curriculum"])
+            self.env.set_curriculum_stage(self.curriculum.stage_index)
+        elif state.get("stage_index") is not None and not self.is_route:
+            self.env.set_curriculum_stage(int(state["stage_index"]))
+        self.pack_weights()
 
 
 def decode_obs_images(images: torch.Tensor) -> torch.Tensor:

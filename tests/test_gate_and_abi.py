@@ -90,7 +90,7 @@ def test_policy_checkpoint_round_trip(tmp_path):
 
     pol = PolicyWeights.preset("finisher", "cpu")
     z = tmp_path / "model.zip"
-    pol.save_sb3_zip(z)
+    pol.save_weights_zip(z)
     back = PolicyWeights.load(z, "cpu")
     for k in KEYS.values():
         assert torch.equal(pol.state_dict()[k], back.state_dict()[k])

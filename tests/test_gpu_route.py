@@ -386,3 +386,41 @@ def test_sequential_route_eval_rows_and_summary_match_the_reference():
         assert abs(res["chunk_metrics"][name]["success_rate"] - c["success_rate"]) <= 3 / c["target_count"]
     with pytest.raises(ValueError):
         evaluate_sequential_route(route, renv, pol, n_replicas=2, variant="tc", detail_replicas=1)
+
+
+def test_pruned_nearest_waypoint_scan_is_the_full_scan():
+    """The route reward's nearest-waypoint distance (route_env.py:135 scans the whole route): the step kernel's pruned outward scan
+    (KinRouteTable.nearest_lb, triangle inequality) returns the full scan's value BIT FOR BIT -- on-route replicas, replicas pushed
+    far off the route (the pruning table runs out and the kernel finishes with the plain scan) and every route index."""
+    from rl_brain_trainer_b200 import config as kcfg
+    from rl_brain_trainer_b200.route import BatchedRouteKinematicEnv, nearest_scan_bounds, synthetic_route
+
+    route = synthetic_route(483, seed=7)
+    renv, _ = kcfg.to_route_env_config(kcfg.preset_dict("route_prefix120"), max_route_index=len(route) - 1)
+    n = 8192
+    lb = nearest_scan_bounds(route.q_goal)
+    d = np.linalg.norm(route.q_goal[:, None] - route.q_goal[None], axis=2)
+    for k in (0, 1, 5, 63):       # the table is a lower bound of the true minimum, and tight to fp32 rounding
+        true = np.where(np.abs(np.arange(483)[:, None] - np.arange(483)[None]) >= k, d, np.inf).min(1)
+        assert (lb[:, k] <= true).all() and (lb[:, k] >= true * (1 - 1e-6)).all()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    idx = torch.randint(1, len(route), (n,), generator=g, device="cuda").cpu().numpy()
+    out = []
+    for pruned in (True, False):
+        env = BatchedRouteKinematicEnv(route, renv, n)
+        if not pruned:
+            env.table.c.nearest_lb, env.table.c.nearest_lb_k = None, 0
+        gq = torch.Generator(device="cuda").manual_seed(5)
+        q0 = torch.as_tensor(route.q_goal[np.maximum(idx - 1, 0)], dtype=torch.float32, device="cuda")
+        spread = torch.cat([torch.full((n // 2,), 0.01), torch.full((n // 4,), 0.3), torch.full((n - n // 2 - n // 4,), 2.0)]).to("cuda")[:, None]
+        q0 = q0 + spread * torch.randn((n, 7), generator=gq, device="cuda")
+        env.reset(route_index=idx, start_route_index=np.maximum(idx - 1, 0), initial_q=q0)
+        rows = []
+        for _ in range(3):
+            a = torch.rand((n, 7), generator=gq, device="cuda") * 2 - 1
+            _, reward, _, _, info = env.step(a)
+            rows.append((info["nearest_route_q_distance"].clone(), reward.clone()))
+        out.append(rows)
+    for (na, ra), (nb, rb) in zip(*out):
+        assert torch.equal(na, nb) and torch.equal(ra, rb)
+    assert float(out[0][0][0].max()) > 0.5 and float(out[0][0][0].min()) < 0.05     # both regimes were exercised

@@ -312,10 +312,14 @@ def measure_step_variants(torch, device, pk, n_envs: int = 1 << 21, launches: in
     route = synthetic_route(483, seed=7)
     renv, _ = kcfg.to_route_env_config(kcfg.preset_dict("route_prefix120"), max_route_index=len(route) - 1)
     n_route = n_envs // 2
-    renv_b = BatchedRouteKinematicEnv(route, renv, n_route, device)
-    renv_b.reset(seed=5)
-    a_route = actions[:n_route].contiguous()
-    out["route_step"] = entry("kin_route_step_kernel", 644, _time_launches(torch, device, lambda: renv_b.step_raw(a_route), launches), n_route)
+    # two regimes of the route reward's nearest-waypoint term: replicas tracking the route (small actions, as under a trained policy:
+    # pruned walk over a few waypoints) and replicas driven off it by uniform +-1 actions (the plain scan over all 483 waypoints)
+    for key, scale in (("route_step", 0.1), ("route_step_random_actions", 1.0)):
+        renv_b = BatchedRouteKinematicEnv(route, renv, n_route, device)
+        renv_b.reset(seed=5)
+        a_route = (actions[:n_route] * scale).contiguous()
+        out[key] = entry("kin_route_step_kernel", 644, _time_launches(torch, device, lambda: renv_b.step_raw(a_route), launches), n_route)
+        out[key]["action_scale"] = scale
     del renv_b
     torch.cuda.empty_cache()
     return out

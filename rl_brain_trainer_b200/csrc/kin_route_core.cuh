@@ -13,6 +13,8 @@ constexpr int ROBS = KIN_ROUTE_OBS_DIM;
 constexpr int ROBS_TILE_FLOATS = WARP * ROBS;   // 2560 floats = 10 240 B per warp
 constexpr int RT_THREADS = 128;
 constexpr int RT_WARPS = RT_THREADS / WARP;
+constexpr int ROUTE_PRUNE_RINGS = 24;            // pruned nearest-waypoint scan: rings (2 candidates each) checked around the pivot
+constexpr int ROUTE_DESCENT_MAX = 32;            // ... and moves of the descent along the route index that finds the pivot
 constexpr int ROUTE_MAX_SMEM_WP = 1024;         // waypoint joint vectors staged in smem for the nearest-waypoint scan
 
 struct RouteView {
@@ -118,28 +120,69 @@ __device__ __forceinline__ void route_step_core(const KinEnvParams& P, const Rou
             for (int i = 0; i < NJ; ++i) acc = fmaf(qw[i] - s.q[i], qw[i] - s.q[i], acc);
             return acc;
         };
+        // Pruned form (needs KinRouteTable::nearest_lb): (1) from the current target walk along the route index while the distance
+        // falls -- a replica tracking the route sits a few waypoints behind its target, so this finds a pivot j next to it in a
+        // handful of evaluations; (2) ring check around the pivot: every waypoint w with |w - j| >= k satisfies
+        // |q_w - q| >= |q_w - q_j| - |q_j - q| >= lb[j][k] - r, so once lb[j][k] - r >= sqrt(best) nothing further out can win.
+        // Any pivot makes (2) a proof; (1) only makes it short.  Replicas far off the route (the rings run out) take the plain scan.
+        bool done_scan = false;
         if (R.lb != nullptr && R.lb_k > 1) {
-            // outward from the current target i: |q_j - q| >= |q_j - q_i| - |q_i - q| >= lb[i][k] - r for every j with |j - i| >= k
-            const int i0 = wp_clamp(R, target);
-            float best = d2(i0);
-            const float r = sqrtf(best) * 1.00001f;
-            const float* lb = R.lb + (size_t)i0 * R.lb_k;
-            int k = 1;
-            for (; k < R.lb_k; ++k) {
-                const float slack = __ldg(lb + k) * 0.99999f - r;
-                if (slack > 0.0f && slack * slack >= best) break;       // also breaks on +inf (no waypoint that far from i)
-                if (i0 - k >= 0) best = fminf(best, d2(i0 - k));
-                if (i0 + k < R.n) best = fminf(best, d2(i0 + k));
+            int j = wp_clamp(R, target);
+            float best = d2(j);
+            {
+                const float dl = j > 0 ? d2(j - 1) : CUDART_INF_F, dr = j + 1 < R.n ? d2(j + 1) : CUDART_INF_F;
+                const int dir = dl < dr ? -1 : 1;
+                float dn = fminf(dl, dr);
+                for (int moves = 0; dn < best && moves < ROUTE_DESCENT_MAX; ++moves) {
+                    best = dn;
+                    j += dir;
+                    const int nx = j + dir;
+                    dn = (nx >= 0 && nx < R.n) ? d2(nx) : CUDART_INF_F;
+                }
             }
-            if (k == R.lb_k) {                                           // far off the route: finish with the plain scan
-                for (int w = 0; w <= i0 - k; ++w) best = fminf(best, d2(w));
-                for (int w = i0 + k; w < R.n; ++w) best = fminf(best, d2(w));
+            const float r = sqrtf(best) * 1.00001f;
+            const float* lb = R.lb + (size_t)j * R.lb_k;
+            int rings = min(R.lb_k - 1, ROUTE_PRUNE_RINGS);
+            if (!(__ldg(lb + rings) * 0.99999f - r >= r)) rings = 0;      // the table cannot settle this replica: straight to the plain scan
+            for (int k = 1; k <= rings; ++k) {
+                const float slack = __ldg(lb + k) * 0.99999f - r;
+                if (slack > 0.0f && slack * slack >= best) { done_scan = true; break; }     // also on +inf: no waypoint that far from j
+                if (j - k >= 0) best = fminf(best, d2(j - k));
+                if (j + k < R.n) best = fminf(best, d2(j + k));
             }
             nearest = sqrtf(best);
-        } else {
-            nearest = CUDART_INF_F;
-            for (int w = 0; w < R.n; ++w) nearest = fminf(nearest, d2(w));
-            nearest = sqrtf(nearest);
+        }
+        // Replicas the ring check could not settle get the plain scan over ALL waypoints -- done by the whole warp for one such
+        // lane at a time (its q broadcast, every lane takes the waypoints w = lane, lane + 32, ..., shuffle-min at the end), so a
+        // single far-off replica costs its warp ~16 strided iterations instead of a 483-iteration serial loop.
+        // NOTE: warp-collective -- every lane of the warp calls route_step_core (the kernels keep inactive lanes in step).
+        unsigned todo = __ballot_sync(0xffffffffu, !done_scan);
+        const int lane = (int)(threadIdx.x & 31u);
+        if (__popc(todo) > 16) {          // most of the warp is off the route: the classic loop, one broadcast waypoint per iteration
+            if (!done_scan) {
+                float m = CUDART_INF_F;
+                for (int w = 0; w < R.n; ++w) m = fminf(m, d2(w));
+                nearest = sqrtf(m);
+            }
+            todo = 0u;
+        }
+        while (todo) {
+            const int src = __ffs((int)todo) - 1;
+            todo &= todo - 1u;
+            float qs[NJ];
+#pragma unroll
+            for (int i = 0; i < NJ; ++i) qs[i] = __shfl_sync(0xffffffffu, s.q[i], src);
+            float m = CUDART_INF_F;
+            for (int w = lane; w < R.n; w += 32) {
+                const float* qw = q_table + w * NJ;
+                float acc = 0.0f;
+#pragma unroll
+                for (int i = 0; i < NJ; ++i) acc = fmaf(qw[i] - qs[i], qw[i] - qs[i], acc);
+                m = fminf(m, acc);
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, off));
+            if (lane == src) nearest = sqrtf(m);
         }
     }
     const bool ready = route_ready(P, q_err, so.pos, so.ori, an, dqn);

@@ -143,8 +143,10 @@ class EvalGate:
         self.best_state: dict[str, torch.Tensor] | None = None
         self.history: list[dict[str, Any]] = []
 
-    def maybe_eval(self, num_timesteps: int, policy: PolicyWeights) -> dict[str, Any] | None:
-        if num_timesteps < self.next_eval:
+    def maybe_eval(self, num_timesteps: int, policy: PolicyWeights, *, force: bool = False) -> dict[str, Any] | None:
+        """``force=True`` evaluates regardless of the interval -- e.g. the policy a fine-tune STARTS from, so that the best checkpoint is
+        never worse than the initial one (the reference's callback only sees checkpoints after the first interval)."""
+        if num_timesteps < self.next_eval and not force:
             return None
         while self.next_eval <= num_timesteps:
             self.next_eval += self.eval_interval

@@ -43,6 +43,7 @@ class PPOHyper:
     adam_beta1: float = 0.9
     adam_beta2: float = 0.999
     adam_eps: float = 1e-5
+    target_kl: float | None = None      # SB3's early stop: no further epochs once the mean approx. KL of an epoch exceeds 1.5 x target_kl
 
     @classmethod
     def from_config(cls, cfg: dict[str, Any]) -> "PPOHyper":
@@ -429,6 +430,7 @@ class PPOTrainer:
             if self.update_variant == "tc" and not img:   # the fused collection already sampled with the tensor-core forward
                 self.refresh_old_logp()
             adv = self._adv_stats
+            kl_seen = mb_seen = 0.0
             for _ in range(self.hp.n_epochs):
                 if img:   # minibatches are unions of whole 128-sample images: permute pairs of 64-sample tiles
                     p2 = torch.randperm(n_tiles_total // 2, generator=self._gen, device=self.device, dtype=torch.int64)
@@ -443,6 +445,14 @@ class PPOTrainer:
                     self.apply_update()
                 if self.peer:
                     self.peer.check()        # once per epoch: a dead peer surfaces after at most one epoch of skipped updates
+                if self.hp.target_kl is not None:
+                    # SB3 checks after every minibatch (ppo.py:262-267); here once per epoch, so the rollout stays one host sync per
+                    # epoch instead of one per minibatch (the statistics are sums over the minibatches seen so far)
+                    acc = self.stats_accum.cpu().numpy().astype(np.float64)
+                    kl_epoch = (acc[3] - kl_seen) / max(acc[7] - mb_seen, 1.0)
+                    kl_seen, mb_seen = acc[3], acc[7]
+                    if kl_epoch > 1.5 * float(self.hp.target_kl):
+                        break
             a = self.stats_accum.cpu().numpy().astype(np.float64)
             if self.peer:
                 self.peer.check()

@@ -713,7 +713,23 @@ int kin_ppo_collect(void *handle, float *state, int stride, int n_envs, int mode
                     float *reward, uint8_t *done, uint8_t *episode_start, uint8_t *start_io, float *last_value, int *boot_count,
                     int *boot_index, float *boot_obs, int boot_cap, int tiles_per_cta, void *stream);
 
-/* reward[boot_index[i]] += gamma * V(boot_obs[i]) for i < min(*boot_count, boot_cap) (strict-fp32 critic of the flat params). */
+/* Replaces: collect_rollouts over a VecEnv of RouteKinematicEnv / RouteSequenceKinematicEnv (kinematic_phase1/train_route_curriculum.py:
+ * 113-145; route/route_env.py:49-212, route/route_sequence_env.py:96-278, route/route_reset_samplers.py:43-117), fused into ONE launch:
+ * n_steps x (80-input actor + critic forward on tcgen05, Gaussian sample + log-prob, kin_route_step semantics with the in-episode
+ * waypoint advance when sequence_mode != 0, sampled route reset of finished slots as kin_route_reset_sampled draws it with
+ * Philox(reset_seed, env, first_step + t)).  n_envs must be a multiple of 128.  Outputs, time-major: obs [n_steps + 1][n_envs][80] fp32
+ * (row t = the observation the policy saw at step t, row n_steps = the observation after the last step), action [T][n][7],
+ * logp / value / reward [T][n], done / episode_start [T][n] u8, route_flags [T][n] (the KIN_RAUX_FLAGS word of the step: bit0
+ * route_ready, bit1 regression, bit2 orientation hit, bit3 waypoint success), start_io / last_value [n].  Time-limit episodes append
+ * (t * n + env, terminal observation [80]) to boot_index / boot_obs for kin_ppo_bootstrap_list(in_dim = 80).                     */
+int kin_route_collect(void *handle, const KinRouteTable *host_route, const KinRouteResetParams *host_reset, float *state, int stride, int n_envs,
+                      const float *params, int n_steps, uint64_t noise_seed, uint32_t first_step, uint64_t reset_seed, int sequence_mode,
+                      int reset_ready_streak_on_advance, float *obs, float *action, float *logp, float *value, float *reward, uint8_t *done,
+                      uint8_t *episode_start, int *route_flags, uint8_t *start_io, float *last_value, int *boot_count, int *boot_index,
+                      float *boot_obs, int boot_cap, int tiles_per_cta, void *stream);
+
+/* reward[boot_index[i]] += gamma * V(boot_obs[i]) for i < min(*boot_count, boot_cap) (strict-fp32 critic of the flat params);
+ * in_dim 56 or 80 (boot_obs rows of in_dim floats). */
 int kin_ppo_bootstrap_list(const float *params, int in_dim, const float *boot_obs, const int *boot_index, const int *boot_count, int boot_cap,
                            float *reward, float gamma, void *stream);
 

@@ -351,10 +351,10 @@ kin_collect_kernel(const __grid_constant__ KinEnvParams P, const KinSamplerParam
 }
 
 // r[idx] += gamma * V(terminal_obs) for the truncated episodes the collection kernel listed (strict fp32 critic)
+template <int IN>
 __global__ void __launch_bounds__(128)
 kin_bootstrap_list_kernel(const float* __restrict__ params, const float* __restrict__ boot_obs, const int* __restrict__ boot_index,
                           const int* __restrict__ boot_count, int cap, float* __restrict__ reward, float gamma) {
-    constexpr int IN = 56;
     const PpoOffsets O = ppo_offsets(IN);
     const int count = min(*boot_count, cap);
     const int i = blockIdx.x * 128 + threadIdx.x;
@@ -449,8 +449,9 @@ extern "C" int kin_ppo_collect(void* handle, float* state, int stride, int n_env
 extern "C" int kin_ppo_bootstrap_list(const float* params, int in_dim, const float* boot_obs, const int* boot_index, const int* boot_count, int boot_cap,
                                       float* reward, float gamma, void* stream) {
     if (!params || !boot_obs || !boot_index || !boot_count || !reward || boot_cap <= 0) return kin_fail(KIN_ERR_INVALID_ARG, "kin_ppo_bootstrap_list: bad arguments");
-    if (in_dim != 56) return kin_fail(KIN_ERR_UNSUPPORTED, "kin_ppo_bootstrap_list: in_dim must be 56");
-    kin_bootstrap_list_kernel<<<(boot_cap + 127) / 128, 128, 0, (cudaStream_t)stream>>>(params, boot_obs, boot_index, boot_count, boot_cap, reward, gamma);
+    if (in_dim != 56 && in_dim != 80) return kin_fail(KIN_ERR_UNSUPPORTED, "kin_ppo_bootstrap_list: in_dim must be 56 or 80");
+    if (in_dim == 56) kin_bootstrap_list_kernel<56><<<(boot_cap + 127) / 128, 128, 0, (cudaStream_t)stream>>>(params, boot_obs, boot_index, boot_count, boot_cap, reward, gamma);
+    else kin_bootstrap_list_kernel<80><<<(boot_cap + 127) / 128, 128, 0, (cudaStream_t)stream>>>(params, boot_obs, boot_index, boot_count, boot_cap, reward, gamma);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? KIN_OK : kin_fail_cuda(e, "kin_ppo_bootstrap_list");
 }

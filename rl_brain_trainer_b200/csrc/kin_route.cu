@@ -132,37 +132,11 @@ kin_route_reset_sampled_kernel(const __grid_constant__ KinEnvParams P, RouteView
     if (env >= n_envs) return;
     if (done && !(done[env] & (KIN_DONE_TERMINATED | KIN_DONE_TRUNCATED))) return;
     Philox rng(seed, (uint32_t)env, counter);
-    int mode = 4;
-    {
-        const float u = rng.uniform();
-#pragma unroll
-        for (int m = 3; m >= 0; --m) if (u < C.mode_cdf[m]) mode = m;
-    }
-    if (C.forced_mode >= 0) mode = C.forced_mode;
-    int ri = rng.integers(C.index_lo[mode], C.index_hi[mode]);
-    const int start = mode == 0 ? 0 : max(ri - 1, 0);
-    const int src = mode == 4 ? ri : start;
-    int last = ri;
-    if (C.sequence_length > 0) {
-        ri = min(max(ri, 1), C.max_route_index);
-        last = min(ri + C.sequence_length - 1, C.max_route_index);
-    }
-    float nz[24];
-#pragma unroll
-    for (int k = 0; k < 24; k += 2) nz[k] = gauss_pair(rng, &nz[k + 1]);
-    float r_iq[NJ], r_idq[NJ], r_ipa[NJ], r_gq[NJ], gq_out[NJ];
-    const float* sq = R.q + (size_t)wp_clamp(R, src) * NJ;
-    const float* gq = R.q + (size_t)wp_clamp(R, ri) * NJ;
-#pragma unroll
-    for (int k = 0; k < NJ; ++k) {
-        r_iq[k] = clampf(fmaf(nz[k], C.q_noise_std, __ldg(sq + k)), P.joint_lower[k], P.joint_upper[k]);
-        r_idq[k] = nz[7 + k] * C.dq_noise_std;
-        r_ipa[k] = clampf(nz[14 + k] * C.prev_action_noise_std, -1.0f, 1.0f);
-        r_gq[k] = __ldg(gq + k);
-    }
     EnvRegs s;
-    s.flags = 0u;
-    reset_core(P, s, KIN_MODE_APPROACH, r_iq, r_idq, r_ipa, r_gq, nullptr, gq_out);
+    RouteRegs rr;
+    float gq_out[NJ];
+    sample_route_reset_dev(P, R, C, rng, s, rr, gq_out);
+    const int ri = rr.index, last = rr.last;
     store_env_reset(state, stride, env, s, gq_out);
     st_row_u(state, stride, KIN_ROW_ROUTE, env, (unsigned)ri);
     st_row_u(state, stride, KIN_ROW_ROUTE2, env, (unsigned)last);

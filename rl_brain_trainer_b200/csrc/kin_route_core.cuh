@@ -274,6 +274,46 @@ __device__ __forceinline__ void load_q_table(float* dst, const RouteView& R, int
     for (int i = tid; i < n; i += nthreads) dst[i] = __ldg(R.q + i);
 }
 
+// sample_route_reset + RouteKinematicEnv.reset for one slot (route/route_reset_samplers.py:43-117, route/route_env.py:60-97,
+// route/route_sequence_env.py:120-124): draws from `rng`, fills the env registers and the route registers, returns goal_q.
+__device__ __forceinline__ void sample_route_reset_dev(const KinEnvParams& P, const RouteView& R, const KinRouteResetParams& C, Philox& rng, EnvRegs& s,
+                                                       RouteRegs& rr, float* gq_out) {
+    int mode = 4;
+    {
+        const float u = rng.uniform();
+#pragma unroll
+        for (int m = 3; m >= 0; --m) if (u < C.mode_cdf[m]) mode = m;
+    }
+    if (C.forced_mode >= 0) mode = C.forced_mode;
+    int ri = rng.integers(C.index_lo[mode], C.index_hi[mode]);
+    const int start = mode == 0 ? 0 : max(ri - 1, 0);
+    const int src = mode == 4 ? ri : start;
+    int last = ri;
+    if (C.sequence_length > 0) {
+        ri = min(max(ri, 1), C.max_route_index);
+        last = min(ri + C.sequence_length - 1, C.max_route_index);
+    }
+    float nz[24];
+#pragma unroll
+    for (int k = 0; k < 24; k += 2) nz[k] = gauss_pair(rng, &nz[k + 1]);
+    float r_iq[NJ], r_idq[NJ], r_ipa[NJ], r_gq[NJ];
+    const float* sq = R.q + (size_t)wp_clamp(R, src) * NJ;
+    const float* gq = R.q + (size_t)wp_clamp(R, ri) * NJ;
+#pragma unroll
+    for (int k = 0; k < NJ; ++k) {
+        r_iq[k] = clampf(fmaf(nz[k], C.q_noise_std, __ldg(sq + k)), P.joint_lower[k], P.joint_upper[k]);
+        r_idq[k] = nz[7 + k] * C.dq_noise_std;
+        r_ipa[k] = clampf(nz[14 + k] * C.prev_action_noise_std, -1.0f, 1.0f);
+        r_gq[k] = __ldg(gq + k);
+    }
+    s.flags = 0u;
+    reset_core(P, s, KIN_MODE_APPROACH, r_iq, r_idq, r_ipa, r_gq, nullptr, gq_out);
+    rr.index = ri;
+    rr.streak = 0;
+    rr.last = last;
+    rr.completed = 0;
+}
+
 static inline bool route_ok(const KinRouteTable* r) { return r && r->n_waypoints >= 2 && r->n_waypoints <= 65535 && r->q_goal && r->pose6 && r->next_q_delta && r->progress_m; }
 static inline RouteView view_of(const KinRouteTable* r) {
     return RouteView{r->n_waypoints, r->q_goal, r->pose6, r->next_q_delta, r->progress_m, r->nearest_lb, r->nearest_lb ? r->nearest_lb_k : 0};

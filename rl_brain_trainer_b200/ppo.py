@@ -121,9 +121,11 @@ class PPOTrainer:
         if self.in_dim != (80 if self.is_route else 56):
             raise _lib.KinError("PPOTrainer: 56-input policies train on the arm env, the 80-input route policy needs route=<RouteDataset>")
         if self.is_route:
-            if update_variant != "tc" or collect_variant not in (None, "steps"):
-                raise ValueError("route training uses update_variant='tc' and the per-step collection")
-            collect_variant = "steps"
+            if update_variant != "tc":
+                raise ValueError("route training uses update_variant='tc'")
+            # "fused": ONE kin_route_collect launch per rollout (or per `route_chunk_steps` steps when a prefix curriculum must be able
+            # to widen the reset window mid-rollout); "steps": five launches per time step (the restatement the fused kernel is tested against)
+            collect_variant = collect_variant or ("fused" if num_envs % 128 == 0 else "steps")
         tile = _D("KIN_PPO_TILE")
         if num_envs % tile:
             raise ValueError(f"num_envs must be a multiple of {tile}")
@@ -138,7 +140,7 @@ class PPOTrainer:
         if self.collect_variant not in ("fused", "steps"):
             raise ValueError("collect_variant must be 'fused' or 'steps'")
         if self.collect_variant == "fused" and (update_variant != "tc" or num_envs % 128):
-            raise ValueError("the fused collection writes bf16 operand images: it needs update_variant='tc' and num_envs % 128 == 0")
+            raise ValueError("the fused collection runs 128-env GEMM tiles and feeds the tensor-core update: it needs update_variant='tc' and num_envs % 128 == 0")
         self.device = torch.device(device)
         self.group = process_group
         self.rank, self.world = world(process_group)
@@ -187,15 +189,17 @@ class PPOTrainer:
                 if handoff_states is not None:       # Finisher training: dock resets replay Approach handoff states (handoff.py)
                     self.env.set_handoff_states(handoff_states)
             f32 = dict(dtype=torch.float32, device=self.device)
-            fused = self.collect_variant == "fused"
+            fused = self.collect_variant == "fused" and not self.is_route      # the arm path's fused collection stores bf16 operand images
             self.obs_buf = None if fused else torch.zeros((self.T + 1, self.N, self.in_dim), **f32)
-            if fused:
-                self.obs_img = torch.zeros((self.T, self.N // 128, 128 * 128), dtype=torch.uint8, device=self.device)
-                limit = max(int(getattr(config.termination_config, "max_episode_steps", config.episode_length)), 1)
+            if self.collect_variant == "fused":
+                base_cfg = config.base_env_config if self.is_route else config
+                limit = max(int(getattr(base_cfg.termination_config, "max_episode_steps", base_cfg.episode_length)), 1)
                 self.boot_cap = self.N * (self.T // limit + 2)     # an env hits the time limit at most once per `limit` steps
                 self.boot_count = torch.zeros(1, dtype=torch.int32, device=self.device)
                 self.boot_index = torch.zeros(self.boot_cap, dtype=torch.int32, device=self.device)
-                self.boot_obs = torch.zeros((self.boot_cap, 56), **f32)
+                self.boot_obs = torch.zeros((self.boot_cap, self.in_dim), **f32)
+            if fused:
+                self.obs_img = torch.zeros((self.T, self.N // 128, 128 * 128), dtype=torch.uint8, device=self.device)
             self.act_buf = torch.zeros((self.T, self.N, 7), **f32)
             self.logp_buf = torch.zeros((self.T, self.N), **f32)
             self.val_buf = torch.zeros((self.T, self.N), **f32)
@@ -216,6 +220,7 @@ class PPOTrainer:
                 self.obs_buf[0].copy_(self.env.obs)
         self._next_start = torch.ones(self.N, dtype=torch.uint8, device=self.device)
         self.tiles_per_cta = 0              # fused collection: 128-env tiles per CTA (0 = fewest that fit one wave)
+        self.route_chunk_steps = 16         # fused route collection with a prefix curriculum: steps per launch (promotion latency)
         self.num_timesteps = 0
         self.update_count = 0
         self.global_step = 0
@@ -235,7 +240,7 @@ class PPOTrainer:
     def collect(self) -> dict[str, float]:
         """``collect_rollouts``: T steps of (sample action, env step with auto-reset, TimeLimit bootstrap), then GAE."""
         if self.is_route:
-            return self._collect_route()
+            return self._collect_route_fused() if self.collect_variant == "fused" else self._collect_route()
         self.env._ensure_sampler()          # a curriculum promotion since the last rollout re-uploads the device sampler
         if self.collect_variant == "fused":
             return self._collect_fused()
@@ -324,6 +329,62 @@ class PPOTrainer:
         self.last_rollout = {"episodes": episodes, "successes": successes, "mean_reward": float(self.rew_buf.mean())}
         return self.last_rollout
 
+    def _collect_route_fused(self) -> dict[str, float]:
+        """Route env rollout in fused launches (``kin_route_collect``): policy forward on tcgen05, route step with waypoint advance,
+        sampled route resets -- same draws, same arithmetic as the per-step path (``_collect_route``), which the kernel is replayed
+        against.  Without a prefix curriculum the whole rollout is ONE launch.  With one, the rollout runs in chunks of
+        ``route_chunk_steps`` steps and the finished episodes of each chunk are fed to the curriculum in time order before the next
+        chunk starts, so a promotion widens the reset window at most ``route_chunk_steps`` steps after the step that triggered it
+        (the reference's callback widens it at that very step, route/route_curriculum.py:85-99; chunk 1 reproduces that)."""
+        L, env, hp = self._L, self.env, self.hp
+        done_bits = _D("KIN_DONE_TERMINATED") | _D("KIN_DONE_TRUNCATED")
+        if not hasattr(self, "_route_raw"):
+            self._route_raw = torch.zeros((self.T, self.N), dtype=torch.int32, device=self.device)
+        chunk = self.T if self.route_curriculum is None else max(1, min(int(self.route_chunk_steps), self.T))
+        seq = env.sequence is not None
+        episodes = successes = 0.0
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            t0 = 0
+            while t0 < self.T:
+                tc = min(chunk, self.T - t0)
+                _lib.check(L.kin_route_collect(
+                    env._params.handle, ctypes.byref(env.table.c), ctypes.byref(env._reset_params()), env.state.data_ptr(), env.stride, self.N,
+                    self.params.data_ptr(), tc, self.seed, self.global_step, self.seed ^ 0x5EED, int(seq),
+                    int(bool(env.sequence.reset_ready_streak_on_advance)) if seq else 1, self.obs_buf[t0].data_ptr(), self.act_buf[t0].data_ptr(),
+                    self.logp_buf[t0].data_ptr(), self.val_buf[t0].data_ptr(), self.rew_buf[t0].data_ptr(), self.done_buf[t0].data_ptr(),
+                    self.start_buf[t0].data_ptr(), self._route_raw[t0].data_ptr(), self._next_start.data_ptr(), self.last_val.data_ptr(),
+                    self.boot_count.data_ptr(), self.boot_index.data_ptr(), self.boot_obs.data_ptr(), self.boot_cap, int(self.tiles_per_cta), stream))
+                # time-limit episodes of this chunk: r += gamma * V(terminal observation); indices are relative to the chunk's first row
+                _lib.check(L.kin_ppo_bootstrap_list(self.params.data_ptr(), 80, self.boot_obs.data_ptr(), self.boot_index.data_ptr(), self.boot_count.data_ptr(),
+                                                    self.boot_cap, self.rew_buf[t0].data_ptr(), float(hp.gamma), stream))
+                self.global_step += tc
+                if self.route_curriculum is not None:
+                    d, raw = self.done_buf[t0:t0 + tc], self._route_raw[t0:t0 + tc]
+                    fin = (d & done_bits) != 0
+                    flags = torch.stack([fin, (d & _D("KIN_DONE_SUCCESS")) != 0, (raw & 1) != 0, (raw & 4) != 0, (raw & 2) != 0], dim=1).cpu().numpy()
+                    promoted = False
+                    for t in range(tc):
+                        ids = np.nonzero(flags[t, 0])[0]
+                        if ids.size:
+                            promoted |= self.route_curriculum.record(flags[t, 1, ids], flags[t, 2, ids], flags[t, 3, ids], flags[t, 4, ids],
+                                                                    total_timesteps=self.num_timesteps + (t0 + t + 1) * self.N * self.world)
+                    if promoted:
+                        env.set_route_window(max_route_index=self.route_curriculum.prefix_end_index)
+                if int(self.boot_count.item()) > self.boot_cap:
+                    raise _lib.KinError("TimeLimit bootstrap list overflow in the fused route collection: rebuild the trainer")
+                t0 += tc
+            _lib.check(L.kin_ppo_gae(self.rew_buf.data_ptr(), self.val_buf.data_ptr(), self.start_buf.data_ptr(), self.last_val.data_ptr(),
+                                     self.done_buf[self.T - 1].data_ptr(), float(hp.gamma), float(hp.gae_lambda), self.T, self.N,
+                                     self.adv_buf.data_ptr(), self.ret_buf.data_ptr(), self.tile_sums.data_ptr(), stream))
+            env.obs.copy_(self.obs_buf[self.T])
+        finished = (self.done_buf & done_bits) != 0
+        succ = ((self.done_buf & _D("KIN_DONE_SUCCESS")) != 0) & finished
+        self._finished, self._success = finished, succ
+        self.num_timesteps += self.S * self.world
+        self.last_rollout = {"episodes": float(finished.sum()), "successes": float(succ.sum()), "mean_reward": float(self.rew_buf.mean())}
+        return self.last_rollout
+
     def _collect_fused(self) -> dict[str, float]:
         """The whole rollout in one launch (``kin_ppo_collect``), then the TimeLimit bootstrap of the listed episodes and GAE."""
         L, env, hp = self._L, self.env, self.hp
@@ -371,7 +432,7 @@ class PPOTrainer:
         hp = self._c_hyper
         global_batch = n_tiles * _D("KIN_PPO_TILE") * self.world
         if self.update_variant == "tc":
-            img = self.collect_variant == "fused"
+            img = self.collect_variant == "fused" and not self.is_route
             _lib.check(self._L.kin_ppo_grad_tc(self.params.data_ptr(), self.in_dim, ctypes.byref(hp), (self.obs_img if img else self.obs_buf).data_ptr(),
                                                self.act_buf.data_ptr(), self.logp_buf.data_ptr(), self.adv_buf.data_ptr(), self.ret_buf.data_ptr(),
                                                self.tile_sums.data_ptr(), tile_ptr, n_tiles, global_batch, self.partials.data_ptr(),
@@ -426,8 +487,8 @@ class PPOTrainer:
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream(self.device).cuda_stream
             self.stats_accum.zero_()
-            img = self.collect_variant == "fused"
-            if self.update_variant == "tc" and not img:   # the fused collection already sampled with the tensor-core forward
+            img = self.collect_variant == "fused" and not self.is_route
+            if self.update_variant == "tc" and not img:   # the arm path's fused collection already sampled with the update's own forward
                 self.refresh_old_logp()
             adv = self._adv_stats
             kl_seen = mb_seen = 0.0

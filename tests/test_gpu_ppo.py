@@ -447,6 +447,89 @@ def test_fused_collection_replays_through_the_step_kernel(tiles_per_cta, num_env
     assert stats["grad_norm"] > 0
 
 
+@pytest.mark.parametrize("tiles_per_cta,num_envs,sequence,chunk", [(1, 256, True, 0), (2, 512, True, 8), (4, 640, False, 0)])
+def test_fused_route_collection_replays_through_the_step_kernels(tiles_per_cta, num_envs, sequence, chunk):
+    """kin_route_collect (fused rollout of the 80-input route policy) against the per-step kernels it replaces: replaying its recorded
+    actions through kin_route_step + kin_route_reset_sampled from the same start state reproduces observations, rewards (the TimeLimit
+    bootstrap included), done flags, route flags, reset draws and the final SoA state BIT FOR BIT; sampled actions / log-probs / values
+    agree with the fp32 policy to bf16 accuracy.  `chunk` > 0 runs the rollout in several launches (the prefix-curriculum mode)."""
+    import dataclasses
+
+    from rl_brain_trainer_b200 import config as kcfg, ppo
+    from rl_brain_trainer_b200.policy import PolicyWeights
+    from rl_brain_trainer_b200.route import BatchedRouteKinematicEnv, RouteCurriculumStage, RoutePrefixCurriculum, synthetic_route
+
+    route = synthetic_route(160, seed=7)
+    renv, seq = kcfg.to_route_env_config(kcfg.preset_dict("route_prefix120"), max_route_index=len(route) - 1)
+    base = renv.base_env_config       # short episodes: time-limit truncations inside the rollout
+    renv = dataclasses.replace(renv, base_env_config=dataclasses.replace(base, episode_length=20, termination_config=dataclasses.replace(
+        base.termination_config, max_episode_steps=20)))
+    seq = dataclasses.replace(seq, enabled=bool(sequence))
+    T = 48
+    pol = PolicyWeights.preset("route_prefix120", "cuda")
+    hp = ppo.PPOHyper(n_steps=T, batch_size=num_envs * T // 4, n_epochs=1, gamma=0.97, learning_rate=0.0)
+    cur = None
+    if chunk:   # a curriculum that never promotes: it only switches the chunked launch mode on
+        cur = RoutePrefixCurriculum([RouteCurriculumStage("all", len(route) - 1)], promotion_success_rate=2.0, promotion_route_ready_hit_rate=2.0,
+                                    promotion_orientation_hit_rate=2.0, promotion_max_regression_rate=-1.0, window_episodes=64, min_episodes_per_stage=64)
+    tr = ppo.PPOTrainer(renv, pol, num_envs=num_envs, hyper=hp, seed=11, route=route, route_sequence_config=seq, collect_variant="fused", route_curriculum=cur)
+    assert tr.collect_variant == "fused"
+    tr.tiles_per_cta = tiles_per_cta
+    if chunk:
+        tr.route_chunk_steps = chunk
+    replay = BatchedRouteKinematicEnv(route, renv, num_envs, "cuda", sequence_config=seq)
+    if cur is not None:
+        replay.set_route_window(max_route_index=cur.prefix_end_index)
+    for rollout in range(2):
+        replay.state.copy_(tr.env.state)
+        start0 = tr._next_start.clone()
+        step0 = tr.global_step
+        tr.collect()
+        torch.cuda.synchronize()
+        obs_t = tr.obs_buf[0]
+        n_trunc = 0
+        for t in range(T):
+            mean, value = _torch_forward(pol, obs_t)
+            sigma = pol.tensors["log_std"].exp()
+            lp = torch.distributions.Normal(mean, sigma).log_prob(tr.act_buf[t]).sum(-1)
+            assert float((tr.val_buf[t] - value).abs().max()) < 0.05 * max(1.0, float(value.abs().max()))
+            smin = float(sigma.min())
+            assert float((tr.logp_buf[t] - lp).abs().mean()) < 0.01 / smin
+            replay.step_raw(tr.act_buf[t].contiguous())
+            torch.cuda.synchronize()
+            assert torch.equal(replay.done, tr.done_buf[t]), (rollout, t)
+            assert torch.equal(replay.raux[_lib_define("KIN_RAUX_FLAGS"), :num_envs].view(torch.int32), tr._route_raw[t]), (rollout, t)
+            trunc = ((replay.done & 2) != 0) & ((replay.done & 1) == 0)
+            expect = replay.reward.clone()
+            if bool(trunc.any()):
+                _, tv = _torch_forward(pol, replay.obs)           # the observation after the step IS the terminal observation
+                expect[trunc] += hp.gamma * tv[trunc]
+                n_trunc += int(trunc.sum())
+            assert torch.equal(tr.rew_buf[t][~trunc], replay.reward[~trunc]), (rollout, t)
+            assert torch.allclose(tr.rew_buf[t], expect, atol=2e-5), (rollout, t)
+            replay.reset_done(seed=tr.seed ^ 0x5EED, counter=step0 + t)
+            torch.cuda.synchronize()
+            assert torch.equal(replay.obs, tr.obs_buf[t + 1]), (rollout, t)
+            exp_start = start0 if t == 0 else ((tr.done_buf[t - 1] & 3) != 0).to(torch.uint8)
+            assert torch.equal(tr.start_buf[t], exp_start)
+            obs_t = tr.obs_buf[t + 1]
+        assert n_trunc > 0 and bool(((tr.done_buf & 4) != 0).any())        # time limits were hit and waypoints were reached
+        assert torch.equal(replay.state[:, :num_envs], tr.env.state[:, :num_envs])
+        _, v_last = _torch_forward(pol, obs_t)
+        assert float((tr.last_val - v_last).abs().max()) < 0.05 * max(1.0, float(v_last.abs().max()))
+        ra, rr = ppo.numpy_gae(tr.rew_buf.cpu().numpy(), tr.val_buf.cpu().numpy(), tr.start_buf.cpu().numpy(), tr.last_val.cpu().numpy(),
+                               ((tr.done_buf[T - 1] & 3) != 0).cpu().numpy(), hp.gamma, hp.gae_lambda)
+        assert np.abs(tr.adv_buf.cpu().numpy() - ra).max() < 5e-4
+    stats = tr.update()
+    assert np.isfinite(list(stats.values())).all() and stats["approx_kl"] < 1e-5
+
+
+def _lib_define(name):
+    from rl_brain_trainer_b200 import _lib
+
+    return _lib.define(name)
+
+
 def test_gate_eval_and_finetune_retention():
     """Multi-stage gate evaluation in one launch; a short fine-tune at the reference's learning rate keeps the gate's retention
     (the acceptance SURVEY 8c asks for: a policy touched by the new trainer still passes when evaluated by the ORACLE env)."""

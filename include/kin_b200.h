@@ -698,6 +698,18 @@ int kin_ppo_grad_tc(const float *params, int in_dim, const KinPpoHyper *host_hyp
                     long long global_batch, float *partials, int grid, float *grad, float *stats, float *logp_out, float *value_out,
                     int forward_only, int obs_is_image, const float *adv_stats, const void *weight_image, void *stream);
 
+/* kin_ppo_grad_tc with the gradient exchange over NVLink peer memory (kin_peer_* buffers) fused into the kernel's tail: after a grid
+ * barrier every CTA reduces a column slice of the partial rows, stores it into every rank's receive buffer, waits for the same slice
+ * from every rank and writes grad / stats = the sum over ranks in RANK ORDER (bitwise identical on all ranks; with world == 1 bitwise
+ * the plain reduction).  Replaces the kin_peer_grad_push + kin_peer_grad_gather launches between the gradient kernel and kin_ppo_adam.
+ * epoch counts exchanges from 1 and must advance by one per call on every rank; *timed_out is the sticky device flag of
+ * kin_peer_grad_gather (a dead peer marks stats[KIN_PPO_STAT_SKIP], kin_ppo_adam then leaves the parameters untouched).            */
+int kin_ppo_grad_tc_exchange(const float *params, int in_dim, const KinPpoHyper *host_hyper, const void *obs, const float *action,
+                             const float *old_logp, const float *advantage, const float *returns, const double *tile_sums, const int *tile_ids,
+                             int n_tiles, long long global_batch, float *partials, int grid, float *grad, float *stats, int obs_is_image,
+                             const float *adv_stats, const void *weight_image, void *const *peer_buffers, int rank, int world, unsigned epoch,
+                             int *timed_out, void *stream);
+
 /* Replaces: OnPolicyAlgorithm.collect_rollouts (SB3 on_policy_algorithm.py) over a VecEnv of ArmKinematicEnv, fused into ONE
  * launch: n_steps x (actor + critic forward on tcgen05, a = mean + exp(log_std) * eps, log-prob, env step with reward and
  * termination, in-register auto-reset from the device sampler).  n_envs must be a multiple of 128.  Outputs, time-major:

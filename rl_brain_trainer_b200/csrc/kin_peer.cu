@@ -7,34 +7,16 @@
 // of each rank waits for the counters of all senders and adds the slots in rank order, so every rank computes the bitwise
 // identical sum and the parameters never drift apart.  One exchange = two small kernels, no host involvement, no ring.
 //
-//   receive buffer of a rank (cudaMalloc'ed by kin_peer_buffer_create, opened by the peers through CUDA IPC):
-//     [0]      unsigned arrived[8]      arrived[s] = number of pushes of sender s that have fully landed here
-//     [64]     unsigned local_count     CTAs of this rank's push kernel that have finished (reset by the last one)
-//     [128..]  float    slot[2][world][row]   row = n_params + 8 (gradient, then the 5 loss statistics); slot = exchange parity
+// The receive-buffer layout and the in-kernel form of the exchange (the gradient kernel's tail) live in kin_peer.cuh; this file
+// keeps the buffer management and the two-kernel form (push + gather), which the strict-fp32 update still uses.
 //   A slot is rewritten two exchanges later; by then every reader has passed the wait of the exchange in between, which its
 //   sender only reaches after its own gather of this exchange (stream order), so two slots suffice.
 #include <cstdlib>
 #include <cstring>
 
-#include "kin_internal.h"
-#include "kin_ppo_layout.cuh"
+#include "kin_peer.cuh"
 
 namespace kin {
-
-constexpr int PEER_MAX = 8;
-constexpr size_t PEER_HEADER = 128;
-
-struct PeerTable {
-    unsigned char* base[PEER_MAX];
-};
-
-__host__ __device__ inline int peer_row(int P) { return (P + KIN_PPO_STATS + 3) & ~3; }
-
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
 
 // reduce the per-CTA partial gradients (as kin_ppo_reduce_kernel) and store the result into slot[parity][rank] of EVERY rank
 __global__ void __launch_bounds__(256)
@@ -113,6 +95,18 @@ kin_peer_gather_kernel(const unsigned char* __restrict__ local, int world, unsig
 
 }  // namespace kin
 
+// device-side wait limit in SM clocks: KIN_PEER_TIMEOUT_S seconds (default 30) at ~2 GHz; first-call module loads, checkpoint writes
+// or a throttled peer can skew ranks by seconds
+unsigned long long kin::kin_peer_timeout_cycles() {
+    static unsigned long long timeout = 0ull;
+    if (timeout == 0ull) {
+        double sec = 30.0;
+        if (const char* v = getenv("KIN_PEER_TIMEOUT_S")) { const double f = atof(v); if (f > 0.0) sec = f; }
+        timeout = (unsigned long long)(sec * 2.0e9);
+    }
+    return timeout;
+}
+
 using namespace kin;
 
 extern "C" int kin_peer_buffer_bytes(int n_params, int world) {
@@ -176,14 +170,7 @@ extern "C" int kin_peer_grad_gather(const void* local_buffer, int n_params, int 
     if (!local_buffer || !grad || !timed_out || n_params <= 0 || world < 1 || world > PEER_MAX || epoch == 0u)
         return kin_fail(KIN_ERR_INVALID_ARG, "kin_peer_grad_gather: bad arguments");
     const int blocks = (n_params + 5 + 255) / 256;
-    // device-side wait limit in SM clocks: KIN_PEER_TIMEOUT_S seconds (default 30) at ~2 GHz; first-call module loads, checkpoint
-    // writes or a throttled peer can skew ranks by seconds
-    static unsigned long long timeout = 0ull;
-    if (timeout == 0ull) {
-        double sec = 30.0;
-        if (const char* v = getenv("KIN_PEER_TIMEOUT_S")) { const double f = atof(v); if (f > 0.0) sec = f; }
-        timeout = (unsigned long long)(sec * 2.0e9);
-    }
+    const unsigned long long timeout = kin_peer_timeout_cycles();
     kin_peer_gather_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(static_cast<const unsigned char*>(local_buffer), world, epoch, n_params, grad, stats,
                                                                      timeout, timed_out);
     cudaError_t e = cudaGetLastError();

@@ -42,6 +42,7 @@
 // relative per tensor (tests/test_gpu_ppo.py::test_minibatch_gradient_tc_*); log-probs move by O(1e-3), so a trainer whose
 // rollout sampled with the fp32 policy refreshes old_logp with THIS kernel's forward (forward_only); the fused collection
 // (kin_collect.cu) samples with the same bf16 arithmetic, so there the first-epoch ratio is 1 by construction.
+#include "kin_peer.cuh"
 #include "kin_ppo_layout.cuh"
 #include "kin_umma.cuh"
 
@@ -146,13 +147,16 @@ __device__ __forceinline__ void epilogue_store(unsigned char* tile, int row, int
 }
 
 // IMG: obs is the rollout buffer of bf16 operand images written by kin_ppo_collect (one 16 KB image per 128 consecutive samples)
-template <bool IMG, int IN>
+// PEER: the kernel ends with the in-kernel gradient exchange over NVLink peer memory (kin_peer.cuh::peer_exchange_tail): grid barrier,
+// per-CTA column slices reduced over the partial rows and pushed to every rank, rank-ordered sum into px.grad -- no separate push /
+// gather launches between this kernel and Adam.
+template <bool IMG, int IN, bool PEER = false>
 __global__ void __launch_bounds__(TCG_THREADS, IN == 56 ? 2 : 1)
 kin_ppo_grad_tc_kernel(const float* __restrict__ params, KinPpoHyper hp, const float* __restrict__ obs, const float* __restrict__ action,
                        const float* __restrict__ old_logp, const float* __restrict__ advantage, const float* __restrict__ returns,
                        const double* __restrict__ tile_sums, const int* __restrict__ tile_ids, int n_pairs, float inv_global_batch,
                        float* __restrict__ partials, float* __restrict__ logp_out, float* __restrict__ value_out, int forward_only, int net_base,
-                       const float* __restrict__ adv_stats, const unsigned char* __restrict__ wimg) {
+                       const float* __restrict__ adv_stats, const unsigned char* __restrict__ wimg, const PeerFused px) {
     static_assert(IN == 56 || (IN == 80 && !IMG), "56-input policies (fp32 observations or images) or the 80-input route policy (fp32 observations)");
     constexpr int KT = IN > 63 ? 2 : 1;              // K tiles of layer 1
     constexpr int K1 = IN == 56 ? 64 : 96;           // padded reduction width of layer 1 (IN inputs | 1 | zeros)
@@ -600,6 +604,10 @@ kin_ppo_grad_tc_kernel(const float* __restrict__ params, KinPpoHyper hp, const f
             out[P + 1] = S.scal[2];
             out[O.val_b] = S.scal[16];
         }
+        if constexpr (PEER) {       // every tile buffer is dead by now: the exchange borrows the X tile for its 1 KB of scratch
+            float(*part)[32] = reinterpret_cast<float(*)[32]>(S.X[0]);
+            peer_exchange_tail(px, partials, (int)gridDim.x, P, inv_global_batch, part, reinterpret_cast<int*>(S.X[0] + 2048));
+        }
     }
     fence_before();
     __syncthreads();
@@ -616,10 +624,10 @@ extern "C" int kin_debug_ppo_trace(unsigned long long* out) {      // 4 x 16 cou
 }
 #endif
 
-extern "C" int kin_ppo_grad_tc(const float* params, int in_dim, const KinPpoHyper* hp, const void* obs_any, const float* action, const float* old_logp,
-                               const float* advantage, const float* returns, const double* tile_sums, const int* tile_ids, int n_tiles,
-                               long long global_batch, float* partials, int grid, float* grad, float* stats, float* logp_out, float* value_out,
-                               int forward_only, int obs_is_image, const float* adv_stats, const void* weight_image, void* stream) {
+static int grad_tc_launch(const float* params, int in_dim, const KinPpoHyper* hp, const void* obs_any, const float* action, const float* old_logp,
+                          const float* advantage, const float* returns, const double* tile_sums, const int* tile_ids, int n_tiles,
+                          long long global_batch, float* partials, int grid, float* grad, float* stats, float* logp_out, float* value_out,
+                          int forward_only, int obs_is_image, const float* adv_stats, const void* weight_image, const PeerFused& px, void* stream) {
     const float* obs = static_cast<const float*>(obs_any);
     if (!params || !hp || !obs || !action || !tile_ids || n_tiles <= 0 || grid <= 0)
         return kin_fail(KIN_ERR_INVALID_ARG, "kin_ppo_grad_tc: bad arguments");
@@ -641,6 +649,9 @@ extern "C" int kin_ppo_grad_tc(const float* params, int in_dim, const KinPpoHype
         cudaError_t e = cudaFuncSetAttribute(kin_ppo_grad_tc_kernel<false, 56>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(TcGradSmem<1>) + 1024));
         if (e == cudaSuccess) e = cudaFuncSetAttribute(kin_ppo_grad_tc_kernel<true, 56>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(TcGradSmem<1>) + 1024));
         if (e == cudaSuccess) e = cudaFuncSetAttribute(kin_ppo_grad_tc_kernel<false, 80>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(TcGradSmem<2>) + 1024));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(kin_ppo_grad_tc_kernel<false, 56, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(TcGradSmem<1>) + 1024));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(kin_ppo_grad_tc_kernel<true, 56, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(TcGradSmem<1>) + 1024));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(kin_ppo_grad_tc_kernel<false, 80, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(TcGradSmem<2>) + 1024));
         if (e != cudaSuccess) return kin_fail_cuda(e, "kin_ppo_grad_tc: smem attribute");
         attr_set[dev_slot] = true;
     }
@@ -656,14 +667,54 @@ extern "C" int kin_ppo_grad_tc(const float* params, int in_dim, const KinPpoHype
         net_base = logp_out ? 0 : 1;
     }
     const unsigned char* wimg = static_cast<const unsigned char*>(weight_image);
-#define KIN_GRAD_TC_LAUNCH(IMG, IN)                                                                                                              \
-    kin_ppo_grad_tc_kernel<IMG, IN><<<dg, TCG_THREADS, smem, st>>>(params, *hp, obs, action, old_logp, advantage, returns, tile_sums, tile_ids, n_pairs, inv, \
-                                                                   partials, logp_out, value_out, forward_only, net_base, adv_stats, wimg)
-    if (in_dim == 80) KIN_GRAD_TC_LAUNCH(false, 80);
-    else if (obs_is_image) KIN_GRAD_TC_LAUNCH(true, 56);
-    else KIN_GRAD_TC_LAUNCH(false, 56);
+    const bool fused = px.world > 0 && !forward_only;
+    if (fused && (int)(dg.x * dg.y) > PEER_MAX_CTA) return kin_fail(KIN_ERR_INVALID_ARG, "kin_ppo_grad_tc_exchange: at most 512 CTAs");
+#define KIN_GRAD_TC_LAUNCH(IMG, IN, PEER)                                                                                                        \
+    kin_ppo_grad_tc_kernel<IMG, IN, PEER><<<dg, TCG_THREADS, smem, st>>>(params, *hp, obs, action, old_logp, advantage, returns, tile_sums, tile_ids, n_pairs, \
+                                                                         inv, partials, logp_out, value_out, forward_only, net_base, adv_stats, wimg, px)
+    if (fused) {
+        if (in_dim == 80) KIN_GRAD_TC_LAUNCH(false, 80, true);
+        else if (obs_is_image) KIN_GRAD_TC_LAUNCH(true, 56, true);
+        else KIN_GRAD_TC_LAUNCH(false, 56, true);
+    } else {
+        if (in_dim == 80) KIN_GRAD_TC_LAUNCH(false, 80, false);
+        else if (obs_is_image) KIN_GRAD_TC_LAUNCH(true, 56, false);
+        else KIN_GRAD_TC_LAUNCH(false, 56, false);
+    }
 #undef KIN_GRAD_TC_LAUNCH
-    if (!forward_only && grad) kin_ppo_reduce_launch(partials, g, P, grad, stats, inv, st);      // grad == NULL: the caller reduces `partials` (kin_peer_grad_push)
+    if (!forward_only && grad && !fused) kin_ppo_reduce_launch(partials, g, P, grad, stats, inv, st);      // grad == NULL: the caller reduces `partials` (kin_peer_grad_push)
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? KIN_OK : kin_fail_cuda(e, "kin_ppo_grad_tc");
+}
+
+extern "C" int kin_ppo_grad_tc(const float* params, int in_dim, const KinPpoHyper* hp, const void* obs_any, const float* action, const float* old_logp,
+                               const float* advantage, const float* returns, const double* tile_sums, const int* tile_ids, int n_tiles,
+                               long long global_batch, float* partials, int grid, float* grad, float* stats, float* logp_out, float* value_out,
+                               int forward_only, int obs_is_image, const float* adv_stats, const void* weight_image, void* stream) {
+    PeerFused none{};
+    return grad_tc_launch(params, in_dim, hp, obs_any, action, old_logp, advantage, returns, tile_sums, tile_ids, n_tiles, global_batch, partials, grid, grad,
+                          stats, logp_out, value_out, forward_only, obs_is_image, adv_stats, weight_image, none, stream);
+}
+
+extern "C" int kin_ppo_grad_tc_exchange(const float* params, int in_dim, const KinPpoHyper* hp, const void* obs_any, const float* action, const float* old_logp,
+                                        const float* advantage, const float* returns, const double* tile_sums, const int* tile_ids, int n_tiles,
+                                        long long global_batch, float* partials, int grid, float* grad, float* stats, int obs_is_image,
+                                        const float* adv_stats, const void* weight_image, void* const* peer_buffers, int rank, int world, unsigned epoch,
+                                        int* timed_out, void* stream) {
+    if (!peer_buffers || !grad || !timed_out || world < 1 || world > PEER_MAX || rank < 0 || rank >= world || epoch == 0u)
+        return kin_fail(KIN_ERR_INVALID_ARG, "kin_ppo_grad_tc_exchange: bad exchange arguments (epoch counts exchanges from 1)");
+    PeerFused px{};
+    for (int i = 0; i < world; ++i) {
+        if (!peer_buffers[i]) return kin_fail(KIN_ERR_INVALID_ARG, "kin_ppo_grad_tc_exchange: null peer buffer");
+        px.peers.base[i] = static_cast<unsigned char*>(peer_buffers[i]);
+    }
+    px.rank = rank;
+    px.world = world;
+    px.epoch = epoch;
+    px.grad = grad;
+    px.stats = stats;
+    px.timed_out = timed_out;
+    px.timeout_cycles = kin_peer_timeout_cycles();
+    return grad_tc_launch(params, in_dim, hp, obs_any, action, old_logp, advantage, returns, tile_sums, tile_ids, n_tiles, global_batch, partials, grid, grad,
+                          stats, nullptr, nullptr, 0, obs_is_image, adv_stats, weight_image, px, stream);
 }

@@ -67,9 +67,11 @@ def reduce_eval_stats(success: torch.Tensor, final_pos: torch.Tensor, final_ori:
 class PeerGradExchange:
     """Per-minibatch gradient all-reduce (sum) over CUDA-IPC peer buffers of the GPUs of one node (``kin_peer_*`` in the C ABI).
 
+    Two forms.  Fused (the tensor-core update): ``kin_ppo_grad_tc_exchange`` does the whole exchange in the gradient kernel's tail --
+    ``next_epoch()`` hands it the exchange counter, ``buffers`` / ``timed_out`` the rest.  Two-kernel (the strict-fp32 update):
     ``push(partials, n_cta, global_batch)`` reduces this rank's per-CTA rows and stores them into every rank's buffer;
     ``gather(grad, stats)`` waits on the device for all ranks and writes the rank-ordered sum (bitwise identical everywhere).
-    Both only enqueue kernels on the current stream.  ``check()`` raises if a peer never arrived (device-side timeout).
+    Everything only enqueues kernels on the current stream.  ``check()`` raises if a peer never arrived (device-side timeout).
     """
 
     def __init__(self, n_params: int, device: torch.device, group: Any = None) -> None:
@@ -91,7 +93,7 @@ class PeerGradExchange:
             handles: list[Any] = [None] * self.world
             if self.world > 1:
                 dist.all_gather_object(handles, bytes(handle.raw), group=group)
-            self._bufs = (ctypes.c_void_p * self.world)()
+            self._bufs = self.buffers = (ctypes.c_void_p * self.world)()
             self._opened: list[int] = []
             for r in range(self.world):
                 if r == self.rank:
@@ -110,6 +112,11 @@ class PeerGradExchange:
         self.epoch += 1
         self._check(self._L.kin_peer_grad_push(partials.data_ptr(), int(n_cta), self.P, int(global_batch), self._bufs, self.rank, self.world,
                                                self.epoch, torch.cuda.current_stream(self.device).cuda_stream))
+
+    def next_epoch(self) -> int:
+        """Exchange counter for the fused form (``kin_ppo_grad_tc_exchange``: push + gather inside the gradient kernel's tail)."""
+        self.epoch += 1
+        return self.epoch
 
     def gather(self, grad: torch.Tensor, stats: torch.Tensor | None) -> None:
         self._check(self._L.kin_peer_grad_gather(self._own, self.P, self.world, self.epoch, grad.data_ptr(),

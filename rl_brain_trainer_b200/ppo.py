@@ -220,6 +220,7 @@ class PPOTrainer:
                 self.obs_buf[0].copy_(self.env.obs)
         self._next_start = torch.ones(self.N, dtype=torch.uint8, device=self.device)
         self.tiles_per_cta = 0              # fused collection: 128-env tiles per CTA (0 = fewest that fit one wave)
+        self.fused_exchange = True          # tensor-core update with grad_exchange="peer": the exchange runs inside the gradient kernel's tail
         self.route_chunk_steps = 16         # fused route collection with a prefix curriculum: steps per launch (promotion latency)
         self.num_timesteps = 0
         self.update_count = 0
@@ -433,11 +434,20 @@ class PPOTrainer:
         global_batch = n_tiles * _D("KIN_PPO_TILE") * self.world
         if self.update_variant == "tc":
             img = self.collect_variant == "fused" and not self.is_route
-            _lib.check(self._L.kin_ppo_grad_tc(self.params.data_ptr(), self.in_dim, ctypes.byref(hp), (self.obs_img if img else self.obs_buf).data_ptr(),
+            obs = (self.obs_img if img else self.obs_buf).data_ptr()
+            wimg = None if self.weight_image is None else self.weight_image.data_ptr()
+            if self.peer and self.fused_exchange:     # reduce + push + rank-ordered gather inside the gradient kernel's tail
+                _lib.check(self._L.kin_ppo_grad_tc_exchange(self.params.data_ptr(), self.in_dim, ctypes.byref(hp), obs, self.act_buf.data_ptr(),
+                                                            self.logp_buf.data_ptr(), self.adv_buf.data_ptr(), self.ret_buf.data_ptr(), self.tile_sums.data_ptr(),
+                                                            tile_ptr, n_tiles, global_batch, self.partials.data_ptr(), self.grad_ctas, self.grad.data_ptr(),
+                                                            self.stats.data_ptr(), int(img), adv_ptr, wimg, self.peer.buffers, self.peer.rank, self.peer.world,
+                                                            self.peer.next_epoch(), self.peer.timed_out.data_ptr(), stream))
+                return
+            _lib.check(self._L.kin_ppo_grad_tc(self.params.data_ptr(), self.in_dim, ctypes.byref(hp), obs,
                                                self.act_buf.data_ptr(), self.logp_buf.data_ptr(), self.adv_buf.data_ptr(), self.ret_buf.data_ptr(),
                                                self.tile_sums.data_ptr(), tile_ptr, n_tiles, global_batch, self.partials.data_ptr(),
                                                self.grad_ctas, None if self.peer else self.grad.data_ptr(), self.stats.data_ptr(), None, None, 0,
-                                               int(img), adv_ptr, None if self.weight_image is None else self.weight_image.data_ptr(), stream))
+                                               int(img), adv_ptr, wimg, stream))
             if self.peer:
                 self.peer.push(self.partials, min(self.grad_ctas, n_tiles // 2), global_batch)
             return
@@ -466,7 +476,7 @@ class PPOTrainer:
 
     def apply_update(self) -> None:
         """All-reduce the gradient (sum over ranks), clip by global norm, Adam step -- identical on every rank."""
-        if self.peer:
+        if self.peer and not (self.fused_exchange and self.update_variant == "tc"):
             self.peer.gather(self.grad, self.stats)                        # waits for every rank's push, rank-ordered sum
         elif self.world > 1:
             allreduce_sum_(self._gradstats[: self.P + 5], self.group)      # gradient + the five loss statistics

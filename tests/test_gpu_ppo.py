@@ -328,11 +328,16 @@ def test_route_policy_training_runs_end_to_end():
     assert float(after["longest_success_prefix"].float().mean()) >= float(before["longest_success_prefix"].float().mean()) - 6.0
 
 
-@pytest.mark.parametrize("variant", ["tc", "fp32"])
+@pytest.mark.parametrize("variant", ["tc", "tc_two_kernel", "fp32"])
 def test_peer_gradient_exchange_single_rank_is_the_plain_reduction(variant):
-    """The NVLink peer-memory exchange (kin_peer_grad_push / kin_peer_grad_gather, csrc/kin_peer.cu) with one rank pushes into its own
-    buffer: the update must be bitwise the one of the in-kernel reduction (the N-rank sum is checked by tools/peer_check.py)."""
+    """The NVLink peer-memory exchange with one rank pushes into its own buffer: the update must be bitwise the one of the plain
+    reduction.  "tc": the exchange fused into the gradient kernel's tail (kin_ppo_grad_tc_exchange: grid barrier, per-CTA column slices,
+    per-slice flags); "tc_two_kernel" / "fp32": kin_peer_grad_push + kin_peer_grad_gather (csrc/kin_peer.cu).  The N-rank sum is
+    checked by tools/peer_check.py under torchrun."""
     from rl_brain_trainer_b200 import ppo
+
+    two_kernel = variant == "tc_two_kernel"
+    variant = "tc" if two_kernel else variant
 
     cfg = env_config("approach_dynamic_scale_big")
     hp = ppo.PPOHyper(learning_rate=1e-3, n_steps=16, batch_size=2048, n_epochs=2, gamma=0.98, clip_range=0.2)
@@ -341,6 +346,8 @@ def test_peer_gradient_exchange_single_rank_is_the_plain_reduction(variant):
         tr = ppo.PPOTrainer(cfg, ppo.random_policy(56, seed=1, log_std_init=-1.0, device="cuda"), num_envs=512, hyper=hp, seed=3, update_variant=variant,
                             grad_exchange=ex)
         assert (tr.peer is not None) == (ex == "peer")
+        if two_kernel:
+            tr.fused_exchange = False
         tr.learn(2)
         params[ex] = tr.params.clone()
         if tr.peer:

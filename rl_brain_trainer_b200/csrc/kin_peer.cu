@@ -47,9 +47,9 @@ kin_peer_push_kernel(const float* __restrict__ partials, int n_cta, int P, float
         float* slot = reinterpret_cast<float*>(peers.base[w] + PEER_HEADER) + ((size_t)(epoch & 1u) * world + rank) * peer_row(P);
         slot[p] = a;
     }
-    __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
+        __threadfence_system();      // cumulative: after the block barrier it also orders the other threads' peer stores
         unsigned* count = reinterpret_cast<unsigned*>(peers.base[rank] + 64);
         last = atomicAdd(count, 1u) == gridDim.x - 1;
     }

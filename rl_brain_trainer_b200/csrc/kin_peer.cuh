@@ -73,7 +73,6 @@ __device__ __forceinline__ void peer_exchange_tail(const PeerFused& px, const fl
         const long long t0 = clock64();
         while ((int)(ld_acquire_gpu(cnt) - target) < 0) {
             if ((unsigned long long)(clock64() - t0) > px.timeout_cycles) { atomicExch(px.timed_out, 1); break; }
-            __nanosleep(32);
         }
     }
     __syncthreads();
@@ -85,12 +84,26 @@ __device__ __forceinline__ void peer_exchange_tail(const PeerFused& px, const fl
         const int p = base + lane;
         float a0 = 0.0f, a1 = 0.0f;
         if (w < 8 && p < cols) {
+            // rows w, w + 16, ... into a0 and w + 8, w + 24, ... into a1, added in that order (kin_ppo_reduce_kernel's order); the loads
+            // of a batch are all issued before the first add, so the L2 latency is paid once per batch, not once per row
+            constexpr int B = 6;
             int c = w;
-            for (; c + 8 < n_rows; c += 16) {
-                a0 += __ldcg(partials + (size_t)c * prow + p);
-                a1 += __ldcg(partials + (size_t)(c + 8) * prow + p);
+            while (c < n_rows) {
+                float v0[B], v1[B];
+#pragma unroll
+                for (int k = 0; k < B; ++k) {
+                    const int r0 = c + 16 * k, r1 = r0 + 8;
+                    v0[k] = r0 < n_rows ? __ldcg(partials + (size_t)r0 * prow + p) : 0.0f;
+                    v1[k] = (r1 < n_rows && r0 + 8 < n_rows) ? __ldcg(partials + (size_t)r1 * prow + p) : 0.0f;
+                }
+#pragma unroll
+                for (int k = 0; k < B; ++k) {
+                    const int r0 = c + 16 * k;
+                    if (r0 + 8 < n_rows) { a0 += v0[k]; a1 += v1[k]; }
+                    else if (r0 < n_rows) a0 += v0[k];
+                }
+                c += 16 * B;
             }
-            if (c < n_rows) a0 += __ldcg(partials + (size_t)c * prow + p);
         }
         if (w < 8) part[w][lane] = a0 + a1;
         __syncthreads();
@@ -104,8 +117,8 @@ __device__ __forceinline__ void peer_exchange_tail(const PeerFused& px, const fl
         }
         __syncthreads();
     }
-    __threadfence_system();
-    __syncthreads();
+    // the release stores below are the only system-scope fences of the CTA: release is cumulative, so coming after the CTA barrier it
+    // also orders the other threads' slot stores before the flag
     if (tid < px.world) {
         unsigned* flag = reinterpret_cast<unsigned*>(px.peers.base[tid] + PEER_FLAGS) + px.rank * PEER_MAX_CTA + cta;
         asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(px.epoch) : "memory");
@@ -118,7 +131,6 @@ __device__ __forceinline__ void peer_exchange_tail(const PeerFused& px, const fl
         const long long t0 = clock64();
         while ((int)(ld_acquire_sys(flag) - px.epoch) < 0) {
             if ((unsigned long long)(clock64() - t0) > px.timeout_cycles) { atomicExch(px.timed_out, 1); break; }
-            __nanosleep(64);
         }
     }
     __syncthreads();

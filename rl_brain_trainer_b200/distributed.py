@@ -123,6 +123,15 @@ class PeerGradExchange:
                                                  None if stats is None else stats.data_ptr(), self.timed_out.data_ptr(),
                                                  torch.cuda.current_stream(self.device).cuda_stream))
 
+    def poll(self) -> None:
+        """Non-blocking form of ``check``: enqueue a copy of the device flag into pinned host memory and look at the PREVIOUS poll's copy
+        (no stream synchronisation; a dead peer is noticed one poll late at worst, the blocking ``check`` at the end of the update still runs)."""
+        if not hasattr(self, "_host_flag"):
+            self._host_flag = torch.zeros(1, dtype=torch.int32).pin_memory()
+        if int(self._host_flag[0]):
+            self.check()
+        self._host_flag.copy_(self.timed_out, non_blocking=True)
+
     def check(self) -> None:
         if int(self.timed_out.item()):
             from . import _lib

@@ -220,7 +220,10 @@ class PPOTrainer:
                 self.obs_buf[0].copy_(self.env.obs)
         self._next_start = torch.ones(self.N, dtype=torch.uint8, device=self.device)
         self.tiles_per_cta = 0              # fused collection: 128-env tiles per CTA (0 = fewest that fit one wave)
-        self.fused_exchange = True          # tensor-core update with grad_exchange="peer": the exchange runs inside the gradient kernel's tail
+        # grad_exchange="peer" with the tensor-core update: True runs the exchange inside the gradient kernel's tail
+        # (kin_ppo_grad_tc_exchange) instead of the push + gather kernels: two launches per minibatch instead of four, bitwise the same
+        # sums (2 x B200, 65 536 envs: update 20.06 vs 20.42 ms; NCCL 19.87 ms; one GPU 18.45 ms)
+        self.fused_exchange = True
         self.route_chunk_steps = 16         # fused route collection with a prefix curriculum: steps per launch (promotion latency)
         self.num_timesteps = 0
         self.update_count = 0
@@ -476,8 +479,9 @@ class PPOTrainer:
 
     def apply_update(self) -> None:
         """All-reduce the gradient (sum over ranks), clip by global norm, Adam step -- identical on every rank."""
-        if self.peer and not (self.fused_exchange and self.update_variant == "tc"):
-            self.peer.gather(self.grad, self.stats)                        # waits for every rank's push, rank-ordered sum
+        if self.peer:
+            if not (self.fused_exchange and self.update_variant == "tc"):  # (the fused form already left the rank-ordered sum in self.grad)
+                self.peer.gather(self.grad, self.stats)                    # waits for every rank's push, rank-ordered sum
         elif self.world > 1:
             allreduce_sum_(self._gradstats[: self.P + 5], self.group)      # gradient + the five loss statistics
         self.update_count += 1
@@ -515,7 +519,7 @@ class PPOTrainer:
                     self._grad_launch(perm.data_ptr() + 4 * m * tiles_per_mb, tiles_per_mb, adv.data_ptr() + 8 * m)
                     self.apply_update()
                 if self.peer:
-                    self.peer.check()        # once per epoch: a dead peer surfaces after at most one epoch of skipped updates
+                    self.peer.poll()         # once per epoch, without a host sync: a dead peer surfaces after at most two epochs of skipped updates
                 if self.hp.target_kl is not None:
                     # SB3 checks after every minibatch (ppo.py:262-267); here once per epoch, so the rollout stays one host sync per
                     # epoch instead of one per minibatch (the statistics are sums over the minibatches seen so far)

@@ -331,8 +331,8 @@ def test_route_policy_training_runs_end_to_end():
 @pytest.mark.parametrize("variant", ["tc", "tc_two_kernel", "fp32"])
 def test_peer_gradient_exchange_single_rank_is_the_plain_reduction(variant):
     """The NVLink peer-memory exchange with one rank pushes into its own buffer: the update must be bitwise the one of the plain
-    reduction.  "tc": the exchange fused into the gradient kernel's tail (kin_ppo_grad_tc_exchange: grid barrier, per-CTA column slices,
-    per-slice flags); "tc_two_kernel" / "fp32": kin_peer_grad_push + kin_peer_grad_gather (csrc/kin_peer.cu).  The N-rank sum is
+    reduction.  "tc" / "fp32": kin_peer_grad_push + kin_peer_grad_gather (csrc/kin_peer.cu); "tc_two_kernel": the opt-in form with the
+    exchange inside the gradient kernel's tail (kin_ppo_grad_tc_exchange: grid barrier, per-CTA column slices, per-slice flags).  The N-rank sum is
     checked by tools/peer_check.py under torchrun."""
     from rl_brain_trainer_b200 import ppo
 

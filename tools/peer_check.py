@@ -24,9 +24,10 @@ N, T = 4096, 32
 hp = ppo.PPOHyper(learning_rate=3e-4, n_steps=T, batch_size=N * T // 4, n_epochs=2, gamma=0.995, gae_lambda=0.95, clip_range=0.1, ent_coef=0.0003)
 out = {}
 params = {}
-for ex in ("nccl", "peer"):
+for ex in ("nccl", "peer", "peer_two_kernel"):
     pol = ppo.random_policy(56, seed=0, log_std_init=-1.0, device=dev)
-    tr = ppo.PPOTrainer(cfg, pol, num_envs=N, hyper=hp, device=dev, seed=1, stage_index=10, update_variant="tc", grad_exchange=ex)
+    tr = ppo.PPOTrainer(cfg, pol, num_envs=N, hyper=hp, device=dev, seed=1, stage_index=10, update_variant="tc", grad_exchange=ex.split("_")[0])
+    tr.fused_exchange = not ex.endswith("two_kernel")
     for _ in range(2):
         tr.collect()
         u = tr.update()
@@ -35,10 +36,12 @@ for ex in ("nccl", "peer"):
     out[ex] = {"approx_kl": u["approx_kl"], "grad_norm": u["grad_norm"], "value_loss": u["value_loss"]}
     tr.close()
 rel = float((params["peer"] - params["nccl"]).norm() / params["nccl"].norm())
+fused_equal = bool(torch.equal(params["peer"], params["peer_two_kernel"]))      # same summation orders: bitwise the two-kernel form
 gathered = [torch.zeros_like(params["peer"]) for _ in range(world)]
 dist.all_gather(gathered, params["peer"])
 identical = all(bool(torch.equal(gathered[0], g)) for g in gathered)
 if rank == 0:
-    print(json.dumps({"world": world, "peer_vs_nccl_rel_diff": rel, "peer_params_bitwise_identical_across_ranks": identical, **out}))
+    print(json.dumps({"world": world, "peer_vs_nccl_rel_diff": rel, "peer_params_bitwise_identical_across_ranks": identical,
+                      "fused_tail_bitwise_equals_two_kernel": fused_equal, **out}))
 dist.destroy_process_group()
-assert rel < 1e-5 and identical
+assert rel < 1e-5 and identical and fused_equal

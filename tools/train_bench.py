@@ -22,6 +22,8 @@ ap.add_argument("--iters", type=int, default=3)
 ap.add_argument("--stage", type=int, default=10)
 ap.add_argument("--update", default="tc", choices=("tc", "fp32"))
 ap.add_argument("--grad-exchange", default="peer", choices=("peer", "nccl"), help="per-minibatch gradient sum over ranks: NVLink peer buffers or NCCL")
+ap.add_argument("--force-peer", action="store_true", help="use the peer-memory exchange even with one rank (it then pushes into its own buffer)")
+ap.add_argument("--two-kernel", action="store_true", help="peer exchange as separate push + gather kernels instead of the gradient kernel's fused tail")
 ap.add_argument("--route", action="store_true", help="train the 80-input route policy on the batched RouteSequence env (train_route_curriculum.py)")
 ap.add_argument("--from-checkpoint", action="store_true", help="fine-tune the bundled approach checkpoint instead of a random init")
 a = ap.parse_args()
@@ -44,7 +46,9 @@ else:
 S = a.envs * a.n_steps
 hp = ppo.PPOHyper(learning_rate=4e-6, n_steps=a.n_steps, batch_size=S // 16, n_epochs=a.epochs, gamma=0.995, gae_lambda=0.95, clip_range=0.1, ent_coef=0.0003)
 tr = ppo.PPOTrainer(cfg, pol, num_envs=a.envs, hyper=hp, device=dev, seed=1, stage_index=a.stage, update_variant=a.update,
-                    grad_exchange=a.grad_exchange if world > 1 else "nccl", **route_kw)
+                    grad_exchange=a.grad_exchange if (world > 1 or a.force_peer) else "nccl", **route_kw)
+if a.two_kernel:
+    tr.fused_exchange = False
 tr.collect(); tr.update()          # warm-up
 torch.cuda.synchronize(dev)
 ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731

@@ -357,8 +357,29 @@ def measure_training(torch, dist, device, world: int, envs: int = 65536, n_steps
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     steps = S * iters * world
+    # multi-rank correctness in the same line: every rank must hold bitwise the same parameters after the timed updates, and the
+    # peer-memory exchange must reproduce the NCCL all-reduce (small side run from identical seeds, both exchanges)
+    check = {"param_checksum": float(tr.params.double().sum())}
+    if world > 1:
+        mine = tr.params.clone()
+        allp = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allp, mine)
+        check["params_bitwise_identical_across_ranks"] = all(bool(torch.equal(allp[0], q)) for q in allp)
+        check["param_checksums"] = [float(q.double().sum()) for q in allp]
     tr.close()
-    return {"workload": "stage10_ppo_train", "envs_per_gpu": envs, "n_steps": n_steps, "epochs": 8, "minibatches_per_epoch": 16, "iters": iters,
+    if world > 1:
+        side = {}
+        hp2 = ppo.PPOHyper(learning_rate=3e-4, n_steps=32, batch_size=4096 * 32 // 4, n_epochs=2, gamma=0.995, gae_lambda=0.95, clip_range=0.1, ent_coef=0.0003)
+        for ex in ("nccl", "peer"):
+            t2 = ppo.PPOTrainer(cfg, ppo.random_policy(56, seed=0, log_std_init=-1.0, device=device), num_envs=4096, hyper=hp2, device=device, seed=1,
+                                stage_index=10, process_group=dist.group.WORLD, grad_exchange=ex)
+            t2.collect()
+            t2.update()
+            torch.cuda.synchronize(device)
+            side[ex] = t2.params.clone()
+            t2.close()
+        check["peer_vs_nccl_rel_diff"] = float((side["peer"] - side["nccl"]).norm() / side["nccl"].norm())
+    return {"workload": "stage10_ppo_train", "exchange_check": check, "envs_per_gpu": envs, "n_steps": n_steps, "epochs": 8, "minibatches_per_epoch": 16, "iters": iters,
             "rollout_env_steps_per_s": steps / float(t[0]), "update_env_steps_per_s": steps / float(t[1]),
             "e2e_env_steps_per_s": steps / float(t[0] + t[1]), "collect": "kin_ppo_collect (fused, tcgen05 bf16)", "update": "kin_ppo_grad_tc (tcgen05 bf16)",
             "grad_exchange": (grad_exchange if world > 1 else "none"), "approx_kl": stats["approx_kl"], "value_loss": stats["value_loss"]}

@@ -691,8 +691,10 @@ int kin_ppo_adv_stats(const double *tile_sums, const int *tile_ids, int n_tiles_
  * samples -- and every pair (tile_ids[2j], tile_ids[2j+1]) must be (2m, 2m+1), i.e. one whole image.
  * weight_image (nullable): the bf16 operand image of params (kin_ppo_pack_weights / kin_ppo_adam keep it current); each CTA then
  * fetches its weights with bulk copies instead of converting them from fp32.
- * in_dim: 56 (Approach / Finisher policies) or 80 (the route policy of train_route_curriculum.py: obs [S,80] fp32 only, layer 1 runs
- * over two K tiles and dW0 is an N = 96 GEMM; obs_is_image and weight_image must be 0 / NULL).                                  */
+ * in_dim: 56 (Approach / Finisher policies) or 80 (the route policy of train_route_curriculum.py).  The route policy runs layer 1 on
+ * its 60 live observation columns -- the 20 constant columns are folded into the bias (csrc/kin_ppo_layout.cuh), gradients come back
+ * in the full 80-column layout -- so obs must be the folded images of kin_route_obs_images (obs_is_image = 1) and weight_image, when
+ * given, the folded image kin_ppo_pack_weights(in_dim = 80) builds.                                                               */
 int kin_ppo_grad_tc(const float *params, int in_dim, const KinPpoHyper *host_hyper, const void *obs, const float *action, const float *old_logp,
                     const float *advantage, const float *returns, const double *tile_sums, const int *tile_ids, int n_tiles,
                     long long global_batch, float *partials, int grid, float *grad, float *stats, float *logp_out, float *value_out,
@@ -724,6 +726,11 @@ int kin_ppo_collect(void *handle, float *state, int stride, int n_envs, int mode
                     uint64_t noise_seed, uint32_t first_step, uint64_t reset_seed, void *obs_tiles, float *action, float *logp, float *value,
                     float *reward, uint8_t *done, uint8_t *episode_start, uint8_t *start_io, float *last_value, int *boot_count,
                     int *boot_index, float *boot_obs, int boot_cap, int tiles_per_cta, void *stream);
+
+/* Route observations [n_rows][80] fp32 -> folded bf16 operand images [n_rows / 128][16 KB]: rows of [60 live columns | 1 | 0 0 0]
+ * (20 of the 80 columns are constants of the path and are folded into the layer-1 bias, see csrc/kin_ppo_layout.cuh), SWIZZLE_128B.
+ * kin_ppo_grad_tc(in_dim = 80, obs_is_image = 1) consumes them; n_rows must be a multiple of 128.                               */
+int kin_route_obs_images(const float *obs, long long n_rows, void *images, void *stream);
 
 /* Replaces: collect_rollouts over a VecEnv of RouteKinematicEnv / RouteSequenceKinematicEnv (kinematic_phase1/train_route_curriculum.py:
  * 113-145; route/route_env.py:49-212, route/route_sequence_env.py:96-278, route/route_reset_samplers.py:43-117), fused into ONE launch:

@@ -117,6 +117,7 @@ def lib() -> ctypes.CDLL:
     L.kin_ppo_adv_stats.argtypes = [vp, vp, i32, i32, i32, vp, vp]
     L.kin_ppo_collect.argtypes = [vp, vp, i32, i32, i32, vp, vp, i32, i32, u64, u32, u64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp]
     L.kin_ppo_bootstrap_list.argtypes = [vp, i32, vp, vp, vp, i32, vp, f32, vp]
+    L.kin_route_obs_images.argtypes = [vp, i64, vp, vp]
     L.kin_route_collect.argtypes = [vp, vp, vp, vp, i32, i32, vp, i32, u64, u32, u64, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp]
     L.kin_peer_buffer_bytes.argtypes = [i32, i32]
     L.kin_peer_buffer_create.argtypes = [i32, i32, ctypes.POINTER(vp), ctypes.c_char_p]

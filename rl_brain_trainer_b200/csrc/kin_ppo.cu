@@ -659,10 +659,52 @@ __global__ void __launch_bounds__(256)
 kin_ppo_pack_weights_kernel(const float* __restrict__ params, int in_dim, unsigned short* __restrict__ wimg) {
     const PpoOffsets O = ppo_offsets(in_dim);
     const int i = blockIdx.x * 256 + threadIdx.x;
+    if (in_dim == 80) {       // folded layer 1: one thread per image element of the two W0 blocks; the rest as for 56 inputs
+        if (i < 2 * 64 * 64) {
+            const int net = i >> 12, u = (i >> 6) & 63, k = i & 63;
+            const int w0 = net ? O.vf_w0 : O.pi_w0, b0 = net ? O.vf_b0 : O.pi_b0;
+            float v = 0.0f;
+            if (k < KIN_ROUTE_DYN) v = params[w0 + u * 80 + route_unfold_col(k)];
+            else if (k == KIN_ROUTE_DYN) v = params[b0 + u] + params[w0 + u * 80 + KIN_ROUTE_ONE_A] + params[w0 + u * 80 + KIN_ROUTE_ONE_B];
+            wimg[(KIN_WIMG_W0 + net * 8192 + wimg_elem(u, k)) >> 1] = __bfloat16_as_ushort(__float2bfloat16_rn(v));
+        }
+        if (i < O.total) {
+            const bool layer1 = (i >= O.pi_w0 && i < O.pi_w1) || (i >= O.vf_w0 && i < O.vf_w1);
+            if (!layer1) {
+                // the 56-input offsets of the blocks behind layer 1 are the same image positions: map through a 56-layout twin
+                const PpoOffsets T = ppo_offsets(56);
+                const int twin = i < O.vf_w0 ? i - (O.pi_w1 - T.pi_w1) : i - (O.vf_w1 - T.vf_w1);
+                const int off = wimg_offset(T, 56, twin);
+                if (off >= 0) wimg[off >> 1] = __bfloat16_as_ushort(__float2bfloat16_rn(params[i]));
+            }
+        }
+        return;
+    }
     if (i < O.total) {
         const int off = wimg_offset(O, in_dim, i);
         if (off >= 0) wimg[off >> 1] = __bfloat16_as_ushort(__float2bfloat16_rn(params[i]));
     }
+}
+
+// route observations [n_rows][80] fp32 -> folded bf16 operand images [n_rows / 128][16 KB] ([60 live columns | 1 | 0 0 0] rows,
+// SWIZZLE_128B): what kin_ppo_grad_tc(in_dim = 80, obs_is_image = 1) stages with one bulk copy per tile.  One thread per 16-byte chunk.
+__global__ void __launch_bounds__(256)
+kin_route_obs_images_kernel(const float* __restrict__ obs, long long n_rows, unsigned char* __restrict__ img) {
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;      // row * 8 + chunk
+    if (i >= n_rows * 8) return;
+    const long long row = i >> 3;
+    const int ch = (int)(i & 7), r = (int)(row & 127);
+    const float* o = obs + row * 80;
+    unsigned short h[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int k = ch * 8 + e;
+        const float v = k < KIN_ROUTE_DYN ? __ldg(o + route_unfold_col(k)) : (k == KIN_ROUTE_DYN ? 1.0f : 0.0f);
+        h[e] = __bfloat16_as_ushort(__float2bfloat16_rn(v));
+    }
+    uint4 w;
+    w.x = h[0] | ((unsigned)h[1] << 16); w.y = h[2] | ((unsigned)h[3] << 16); w.z = h[4] | ((unsigned)h[5] << 16); w.w = h[6] | ((unsigned)h[7] << 16);
+    *reinterpret_cast<uint4*>(img + (row >> 7) * 16384 + r * 128 + ((ch ^ (r & 7)) << 4)) = w;
 }
 
 int kin_ppo_reduce_launch(const float* partials, int n_cta, int P, float* grad, float* stats, float inv_global_batch, cudaStream_t st) {
@@ -767,7 +809,7 @@ extern "C" int kin_ppo_adv_stats(const double* tile_sums, const int* tile_ids, i
 
 extern "C" int kin_ppo_pack_weights(const float* params, int in_dim, void* weight_image, void* stream) {
     if (!params || !weight_image) return kin_fail(KIN_ERR_INVALID_ARG, "kin_ppo_pack_weights: bad arguments");
-    if (in_dim != 56) return kin_fail(KIN_ERR_UNSUPPORTED, "kin_ppo_pack_weights: in_dim must be 56");
+    if (in_dim != 56 && in_dim != 80) return kin_fail(KIN_ERR_UNSUPPORTED, "kin_ppo_pack_weights: in_dim must be 56 or 80");
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = cudaMemsetAsync(weight_image, 0, KIN_WIMG_BYTES, st);
     if (e != cudaSuccess) return kin_fail_cuda(e, "kin_ppo_pack_weights: memset");
@@ -777,9 +819,19 @@ extern "C" int kin_ppo_pack_weights(const float* params, int in_dim, void* weigh
     return e == cudaSuccess ? KIN_OK : kin_fail_cuda(e, "kin_ppo_pack_weights");
 }
 
+extern "C" int kin_route_obs_images(const float* obs, long long n_rows, void* images, void* stream) {
+    if (!obs || !images || n_rows <= 0 || (n_rows % 128) != 0) return kin_fail(KIN_ERR_INVALID_ARG, "kin_route_obs_images: n_rows must be a positive multiple of 128");
+    if (((uintptr_t)images & 15u)) return kin_fail(KIN_ERR_INVALID_ARG, "kin_route_obs_images: images must be 16-byte aligned");
+    const long long chunks = n_rows * 8;
+    kin_route_obs_images_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, (cudaStream_t)stream>>>(obs, n_rows, static_cast<unsigned char*>(images));
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? KIN_OK : kin_fail_cuda(e, "kin_route_obs_images");
+}
+
 extern "C" int kin_ppo_adam(float* params, const float* grad, float* adam_m, float* adam_v, int n_params, const KinPpoHyper* hp, int step,
                             float* stats, float* stats_accum, void* weight_image, int in_dim, void* stream) {
-    if (weight_image && in_dim != 56) return kin_fail(KIN_ERR_UNSUPPORTED, "kin_ppo_adam: the weight image is built for in_dim 56");
+    if (weight_image && in_dim != 56)
+        return kin_fail(KIN_ERR_UNSUPPORTED, "kin_ppo_adam: only the 56-input image is kept current in place; the folded route image is rebuilt with kin_ppo_pack_weights");
     if (!params || !grad || !adam_m || !adam_v || !hp || n_params <= 0 || step < 1) return kin_fail(KIN_ERR_INVALID_ARG, "kin_ppo_adam: bad arguments");
     const float bc1 = 1.0f - powf(hp->adam_beta1, (float)step), bc2 = 1.0f - powf(hp->adam_beta2, (float)step);
     kin_ppo_adam_kernel<<<(n_params + 1023) / 1024, 1024, 0, (cudaStream_t)stream>>>(params, grad, adam_m, adam_v, n_params, *hp, bc1, bc2, stats, stats_accum,

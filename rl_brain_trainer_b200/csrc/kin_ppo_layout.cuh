@@ -28,9 +28,25 @@ __host__ __device__ inline PpoOffsets ppo_offsets(int in_dim) {
     return o;
 }
 
+// ---- constant-folded layer-1 input of the 80-input route policy ---------------------------------------------------------------------
+// 20 of the 80 route-observation columns are constants of the path (mode_flag one-hot = approach -> column 20 is 1, task_type = [1, 0, 0]
+// -> column 71 is 1, the next_wp / wp blocks, progress[2], mode_flag[1..3], task_type[1..2] are 0).  The tensor-core kernels run layer 1 on
+// the 60 live columns + a constant-one column (K = 64, ONE operand tile, like the 56-input policies) with the bias column holding
+// b0 + W0[:, 20] + W0[:, 71]; the gradient of that column IS d b0 = d W0[:, 20] = d W0[:, 71], the zero columns get zero gradient --
+// exactly what SB3 computes on the full 80 columns.
+constexpr int KIN_ROUTE_DYN = 60;
+// live column k (0..59) of the folded input -> column of the 80-float route observation
+__host__ __device__ inline int route_unfold_col(int k) { return k < 20 ? k : (k < 29 ? k + 10 : k + 11); }
+// column c (0..79) of the route observation -> folded column, or -1 for the constant columns
+__host__ __device__ inline int route_fold_col(int c) { return c < 20 ? c : (c < 30 ? -1 : (c < 39 ? c - 10 : (c == 39 ? -1 : (c < 71 ? c - 11 : -1)))); }
+constexpr int KIN_ROUTE_ONE_A = 20, KIN_ROUTE_ONE_B = 71;       // the two columns that are the constant 1
+// effective layer-1 width of the tensor-core kernels (live columns; the bias rides in column `ppo_in_eff`)
+__host__ __device__ inline int ppo_in_eff(int in_dim) { return in_dim == 80 ? KIN_ROUTE_DYN : in_dim; }
+
 // ---- bf16 operand image of the weights (the B operands of the tensor-core kernels), 36 KB:
 //   [W0 actor 8 KB][W0 critic 8 KB][W1 actor 8 KB][W1 critic 8 KB][WO actor 2 KB][WO critic 2 KB]
-// every block a [rows][64 bf16] SWIZZLE_128B tile (kin_umma.cuh): W0 rows = hidden unit, col 56 = its bias, cols 57.. zero;
+// every block a [rows][64 bf16] SWIZZLE_128B tile (kin_umma.cuh): W0 rows = hidden unit, col 56 = its bias, cols 57.. zero (the route
+// policy: its 60 live columns, col 60 = the folded bias, see above -- built by kin_ppo_pack_weights only, not by wimg_offset);
 // WO actor rows 0..6 = act_w, WO critic row 7 = val_w, other rows zero.  b1 / act_b / val_b / log_std stay fp32 in `params`.
 constexpr int KIN_WIMG_BYTES = 36864;
 constexpr int KIN_WIMG_W0 = 0, KIN_WIMG_W1 = 16384, KIN_WIMG_WO = 32768;

@@ -77,8 +77,8 @@ __device__ unsigned long long kin_ppo_trace_buf[4][16];
 #define TRACE_FLUSH(n)
 #endif
 
-// KT = K tiles of layer 1: 1 for the 56-input policies (K = 64), 2 for the 80-input route policy (K = 96: X[0] | X[1] are then the
-// two K tiles of ONE X operand, fp32 observations only -- there is no image / double buffering for that policy)
+// Layer 1 always runs K = 64 on ONE operand tile: the 56-input policies as [obs56 | 1 | 0..], the 80-input route policy constant-folded
+// to its 60 live columns ([live60 | 1 | 0 0 0], kin_ppo_layout.cuh) -- so both take the same image path, two CTAs per SM.
 template <int KT>
 struct __align__(1024) TcGradSmem {
     unsigned char X[2][TILE_BYTES];      // double-buffered in image mode (the next tile's image is prefetched by the TMA engine)
@@ -151,15 +151,17 @@ __device__ __forceinline__ void epilogue_store(unsigned char* tile, int row, int
 // per-CTA column slices reduced over the partial rows and pushed to every rank, rank-ordered sum into px.grad -- no separate push /
 // gather launches between this kernel and Adam.
 template <bool IMG, int IN, bool PEER = false>
-__global__ void __launch_bounds__(TCG_THREADS, IN == 56 ? 2 : 1)
+__global__ void __launch_bounds__(TCG_THREADS, 2)
 kin_ppo_grad_tc_kernel(const float* __restrict__ params, KinPpoHyper hp, const float* __restrict__ obs, const float* __restrict__ action,
                        const float* __restrict__ old_logp, const float* __restrict__ advantage, const float* __restrict__ returns,
                        const double* __restrict__ tile_sums, const int* __restrict__ tile_ids, int n_pairs, float inv_global_batch,
                        float* __restrict__ partials, float* __restrict__ logp_out, float* __restrict__ value_out, int forward_only, int net_base,
                        const float* __restrict__ adv_stats, const unsigned char* __restrict__ wimg, const PeerFused px) {
-    static_assert(IN == 56 || (IN == 80 && !IMG), "56-input policies (fp32 observations or images) or the 80-input route policy (fp32 observations)");
-    constexpr int KT = IN > 63 ? 2 : 1;              // K tiles of layer 1
-    constexpr int K1 = IN == 56 ? 64 : 96;           // padded reduction width of layer 1 (IN inputs | 1 | zeros)
+    static_assert(IN == 56 || (IN == 80 && IMG), "56-input policies (fp32 observations or images) or the 80-input route policy (folded images)");
+    constexpr int KT = 1;                            // K tiles of layer 1
+    constexpr int K1 = 64;                           // padded reduction width of layer 1 (live inputs | 1 | zeros)
+    constexpr bool FOLD = IN == 80;                  // route policy: layer 1 sees its 60 live columns, the constants are folded into the bias
+    constexpr int INE = FOLD ? KIN_ROUTE_DYN : IN;   // live columns of the X tile; column INE carries the bias
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // round up to 1024 bytes WITHOUT leaving the shared address space (pointer + offset, not an integer round trip), so every
     // access below compiles to LDS / STS rather than generic LD / ST with 64-bit address arithmetic
@@ -181,7 +183,9 @@ kin_ppo_grad_tc_kernel(const float* __restrict__ params, KinPpoHyper hp, const f
     if (!wimg) {       // no prebuilt operand image: convert this net's weights here (latency-bound; the trainer passes the image)
         for (int i = tid; i < 64 * KT * 64; i += TCG_THREADS) {
             const int u = i / (KT * 64), k = i - u * (KT * 64);
-            const float v = k < IN ? __ldg(params + o_w0 + u * IN + k) : (k == IN ? __ldg(params + o_b0 + u) : 0.0f);
+            float v = 0.0f;
+            if (k < INE) v = __ldg(params + o_w0 + u * IN + (FOLD ? route_unfold_col(k) : k));
+            else if (k == INE) v = __ldg(params + o_b0 + u) + (FOLD ? __ldg(params + o_w0 + u * IN + KIN_ROUTE_ONE_A) + __ldg(params + o_w0 + u * IN + KIN_ROUTE_ONE_B) : 0.0f);
             st_bf16(S.W0[k >> 6], u, k & 63, v);
         }
         for (int i = tid; i < 64 * 64; i += TCG_THREADS) st_bf16(S.W1, i >> 6, i & 63, __ldg(params + o_w1 + i));
@@ -383,7 +387,7 @@ kin_ppo_grad_tc_kernel(const float* __restrict__ params, KinPpoHyper hp, const f
             int t0 = 0, t1 = 0;
             if (!IMG || logp_out || value_out) { t0 = __ldg(tile_ids + 2 * j); t1 = __ldg(tile_ids + 2 * j + 1); }
             const size_t g = (size_t)(row < 64 ? t0 : t1) * 64 + (row & 63);      // only used by the X conversion / the forward outputs
-            if (!IMG) {
+            if constexpr (!IMG) {
                 // ---- X tile: obs fp32 -> bf16, coalesced float4 reads; column 56 = 1 carries the layer-1 bias ---------------
                 if (it > 0 && !forward_only) mbar_wait(mb_wg, (unsigned)(it - 1) & 1u);    // the previous tile's dW0 batch still reads X
                 constexpr int Q = IN / 4;                                    // float4 per observation row
@@ -396,8 +400,7 @@ kin_ppo_grad_tc_kernel(const float* __restrict__ params, KinPpoHyper hp, const f
                     *reinterpret_cast<uint2*>(S.X[c4 >> 6] + sw_chunk(r, (c4 & 63) >> 3) + (c4 & 4) * 2) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
                 }
                 if (tid < 128) {      // column IN = 1 (carries the bias), zero up to K1
-                    *reinterpret_cast<uint4*>(S.X[IN >> 6] + sw_chunk(tid, (IN & 63) >> 3)) = make_uint4(0x00003F80u, 0u, 0u, 0u);
-                    if (IN == 80) *reinterpret_cast<uint4*>(S.X[1] + sw_chunk(tid, 3)) = make_uint4(0u, 0u, 0u, 0u);
+                    *reinterpret_cast<uint4*>(S.X[0] + sw_chunk(tid, IN >> 3)) = make_uint4(0x00003F80u, 0u, 0u, 0u);
                 }
                 fence_async_smem();
                 fence_before();
@@ -573,8 +576,18 @@ kin_ppo_grad_tc_kernel(const float* __restrict__ params, KinPpoHyper hp, const f
 #pragma unroll
                     for (int c = 0; c < 32; ++c) {
                         const int k = cb * 32 + c;
-                        if (k < IN) out[o_w0 + u * IN + k] = v[c];
-                        else if (k == IN) out[o_b0 + u] = v[c];
+                        if (k < INE) {
+                            out[o_w0 + u * IN + (FOLD ? route_unfold_col(k) : k)] = v[c];
+                        } else if (k == INE) {
+                            out[o_b0 + u] = v[c];
+                            if (FOLD) {       // the inputs of these two columns are the constant 1: their gradient is the bias gradient
+                                out[o_w0 + u * IN + KIN_ROUTE_ONE_A] = v[c];
+                                out[o_w0 + u * IN + KIN_ROUTE_ONE_B] = v[c];
+#pragma unroll
+                                for (int z = 0; z < IN; ++z)      // ... and the constant-zero inputs give zero gradient
+                                    if (route_fold_col(z) < 0 && z != KIN_ROUTE_ONE_A && z != KIN_ROUTE_ONE_B) out[o_w0 + u * IN + z] = 0.0f;
+                            }
+                        }
                     }
                 }
             }
@@ -635,23 +648,23 @@ static int grad_tc_launch(const float* params, int in_dim, const KinPpoHyper* hp
         return kin_fail(KIN_ERR_INVALID_ARG, "kin_ppo_grad_tc: the gradient pass needs old_logp, advantage, returns, tile_sums, partials and grad");
     if (forward_only && !logp_out && !value_out) return kin_fail(KIN_ERR_INVALID_ARG, "kin_ppo_grad_tc: forward_only without an output");
     if (in_dim != 56 && in_dim != 80) return kin_fail(KIN_ERR_UNSUPPORTED, "kin_ppo_grad_tc: in_dim must be 56 or 80");
-    if (in_dim == 80 && (obs_is_image || weight_image))
-        return kin_fail(KIN_ERR_UNSUPPORTED, "kin_ppo_grad_tc: the 80-input route policy takes fp32 observations and converts its weights itself");
+    if (in_dim == 80 && !obs_is_image)
+        return kin_fail(KIN_ERR_UNSUPPORTED, "kin_ppo_grad_tc: the 80-input route policy takes folded bf16 observation images (kin_route_obs_images)");
     if (n_tiles & 1) return kin_fail(KIN_ERR_INVALID_ARG, "kin_ppo_grad_tc: n_tiles must be even (two 64-sample tiles per 128-row GEMM tile)");
     if (((uintptr_t)obs & 15u)) return kin_fail(KIN_ERR_INVALID_ARG, "kin_ppo_grad_tc: obs must be 16-byte aligned");
     if (((uintptr_t)action | (uintptr_t)old_logp | (uintptr_t)advantage | (uintptr_t)returns) & 15u)      // staged by the TMA engine
         return kin_fail(KIN_ERR_INVALID_ARG, "kin_ppo_grad_tc: action / old_logp / advantage / returns must be 16-byte aligned");
     const int P = ppo_offsets(in_dim).total;
-    const size_t smem = (in_dim == 56 ? sizeof(TcGradSmem<1>) : sizeof(TcGradSmem<2>)) + 1024;
+    const size_t smem = sizeof(TcGradSmem<1>) + 1024;
     static bool attr_set[KIN_MAX_DEVICES] = {};
     const int dev_slot = kin_device_slot();
     if (!attr_set[dev_slot]) {
         cudaError_t e = cudaFuncSetAttribute(kin_ppo_grad_tc_kernel<false, 56>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(TcGradSmem<1>) + 1024));
         if (e == cudaSuccess) e = cudaFuncSetAttribute(kin_ppo_grad_tc_kernel<true, 56>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(TcGradSmem<1>) + 1024));
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(kin_ppo_grad_tc_kernel<false, 80>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(TcGradSmem<2>) + 1024));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(kin_ppo_grad_tc_kernel<true, 80>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(TcGradSmem<1>) + 1024));
         if (e == cudaSuccess) e = cudaFuncSetAttribute(kin_ppo_grad_tc_kernel<false, 56, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(TcGradSmem<1>) + 1024));
         if (e == cudaSuccess) e = cudaFuncSetAttribute(kin_ppo_grad_tc_kernel<true, 56, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(TcGradSmem<1>) + 1024));
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(kin_ppo_grad_tc_kernel<false, 80, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(TcGradSmem<2>) + 1024));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(kin_ppo_grad_tc_kernel<true, 80, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(TcGradSmem<1>) + 1024));
         if (e != cudaSuccess) return kin_fail_cuda(e, "kin_ppo_grad_tc: smem attribute");
         attr_set[dev_slot] = true;
     }
@@ -673,11 +686,11 @@ static int grad_tc_launch(const float* params, int in_dim, const KinPpoHyper* hp
     kin_ppo_grad_tc_kernel<IMG, IN, PEER><<<dg, TCG_THREADS, smem, st>>>(params, *hp, obs, action, old_logp, advantage, returns, tile_sums, tile_ids, n_pairs, \
                                                                          inv, partials, logp_out, value_out, forward_only, net_base, adv_stats, wimg, px)
     if (fused) {
-        if (in_dim == 80) KIN_GRAD_TC_LAUNCH(false, 80, true);
+        if (in_dim == 80) KIN_GRAD_TC_LAUNCH(true, 80, true);
         else if (obs_is_image) KIN_GRAD_TC_LAUNCH(true, 56, true);
         else KIN_GRAD_TC_LAUNCH(false, 56, true);
     } else {
-        if (in_dim == 80) KIN_GRAD_TC_LAUNCH(false, 80, false);
+        if (in_dim == 80) KIN_GRAD_TC_LAUNCH(true, 80, false);
         else if (obs_is_image) KIN_GRAD_TC_LAUNCH(true, 56, false);
         else KIN_GRAD_TC_LAUNCH(false, 56, false);
     }

@@ -121,8 +121,8 @@ class PPOTrainer:
         if self.in_dim != (80 if self.is_route else 56):
             raise _lib.KinError("PPOTrainer: 56-input policies train on the arm env, the 80-input route policy needs route=<RouteDataset>")
         if self.is_route:
-            if update_variant != "tc":
-                raise ValueError("route training uses update_variant='tc'")
+            if update_variant != "tc" or num_envs % 128:
+                raise ValueError("route training uses update_variant='tc' (folded bf16 observation images: num_envs must be a multiple of 128)")
             # "fused": ONE kin_route_collect launch per rollout (or per `route_chunk_steps` steps when a prefix curriculum must be able
             # to widen the reset window mid-rollout); "steps": five launches per time step (the restatement the fused kernel is tested against)
             collect_variant = collect_variant or ("fused" if num_envs % 128 == 0 else "steps")
@@ -163,8 +163,8 @@ class PPOTrainer:
             self._gradstats = torch.zeros(self.P + _D("KIN_PPO_STATS"), dtype=torch.float32, device=self.device)
             self.grad = self._gradstats[: self.P]
             self.stats = self._gradstats[self.P:]
-            # bf16 operand image of `params` (56-input policies; the route policy's kernel converts its weights itself)
-            self.weight_image = None if self.is_route else torch.zeros(36864, dtype=torch.uint8, device=self.device)
+            # bf16 operand image of `params` (the route policy's is constant-folded: rebuilt after every Adam step, not patched in place)
+            self.weight_image = torch.zeros(36864, dtype=torch.uint8, device=self.device)
             self.pack_weights()
             self.stats_accum = torch.zeros(_D("KIN_PPO_STATS"), dtype=torch.float32, device=self.device)
             self._adv_stats = torch.zeros((max(self.S // self.local_batch, 1), 2), dtype=torch.float32, device=self.device)
@@ -198,7 +198,7 @@ class PPOTrainer:
                 self.boot_count = torch.zeros(1, dtype=torch.int32, device=self.device)
                 self.boot_index = torch.zeros(self.boot_cap, dtype=torch.int32, device=self.device)
                 self.boot_obs = torch.zeros((self.boot_cap, self.in_dim), **f32)
-            if fused:
+            if fused or (self.is_route and self.N % 128 == 0):
                 self.obs_img = torch.zeros((self.T, self.N // 128, 128 * 128), dtype=torch.uint8, device=self.device)
             self.act_buf = torch.zeros((self.T, self.N, 7), **f32)
             self.logp_buf = torch.zeros((self.T, self.N), **f32)
@@ -224,6 +224,8 @@ class PPOTrainer:
         # (kin_ppo_grad_tc_exchange) instead of the push + gather kernels: two launches per minibatch instead of four, bitwise the same
         # sums (2 x B200, 65 536 envs: update 20.06 vs 20.42 ms; NCCL 19.87 ms; one GPU 18.45 ms)
         self.fused_exchange = True
+        # the tensor-core update reads bf16 operand images: written by the fused arm collection, or built from the route observations
+        self._img = self.update_variant == "tc" and (self.is_route or self.collect_variant == "fused")
         self.route_chunk_steps = 16         # fused route collection with a prefix curriculum: steps per launch (promotion latency)
         self.num_timesteps = 0
         self.update_count = 0
@@ -235,9 +237,7 @@ class PPOTrainer:
 
     def pack_weights(self) -> None:
         """Rebuild the bf16 operand image from ``self.params`` (needed after the parameters were written from outside the trainer)."""
-        if self.weight_image is None:
-            return
-        _lib.check(self._L.kin_ppo_pack_weights(self.params.data_ptr(), 56, self.weight_image.data_ptr(),
+        _lib.check(self._L.kin_ppo_pack_weights(self.params.data_ptr(), self.in_dim, self.weight_image.data_ptr(),
                                                 torch.cuda.current_stream(self.device).cuda_stream))
 
     # ------------------------------------------------------------------ rollout
@@ -436,9 +436,9 @@ class PPOTrainer:
         hp = self._c_hyper
         global_batch = n_tiles * _D("KIN_PPO_TILE") * self.world
         if self.update_variant == "tc":
-            img = self.collect_variant == "fused" and not self.is_route
+            img = self._img
             obs = (self.obs_img if img else self.obs_buf).data_ptr()
-            wimg = None if self.weight_image is None else self.weight_image.data_ptr()
+            wimg = self.weight_image.data_ptr()
             if self.peer and self.fused_exchange:     # reduce + push + rank-ordered gather inside the gradient kernel's tail
                 _lib.check(self._L.kin_ppo_grad_tc_exchange(self.params.data_ptr(), self.in_dim, ctypes.byref(hp), obs, self.act_buf.data_ptr(),
                                                             self.logp_buf.data_ptr(), self.adv_buf.data_ptr(), self.ret_buf.data_ptr(), self.tile_sums.data_ptr(),
@@ -472,9 +472,9 @@ class PPOTrainer:
         if not hasattr(self, "_all_tiles"):
             self._all_tiles = torch.arange(self.S // _D("KIN_PPO_TILE"), dtype=torch.int32, device=self.device)
         hp = self.hp.c()
-        _lib.check(self._L.kin_ppo_grad_tc(self.params.data_ptr(), self.in_dim, ctypes.byref(hp), self.obs_buf.data_ptr(), self.act_buf.data_ptr(), None, None,
-                                           None, None, self._all_tiles.data_ptr(), int(self._all_tiles.numel()), 0, None, self.grad_ctas, None, None,
-                                           self.logp_buf.data_ptr(), None, 1, 0, None, None if self.weight_image is None else self.weight_image.data_ptr(),
+        _lib.check(self._L.kin_ppo_grad_tc(self.params.data_ptr(), self.in_dim, ctypes.byref(hp), (self.obs_img if self._img else self.obs_buf).data_ptr(),
+                                           self.act_buf.data_ptr(), None, None, None, None, self._all_tiles.data_ptr(), int(self._all_tiles.numel()), 0, None,
+                                           self.grad_ctas, None, None, self.logp_buf.data_ptr(), None, 1, int(self._img), None, self.weight_image.data_ptr(),
                                            torch.cuda.current_stream(self.device).cuda_stream))
 
     def apply_update(self) -> None:
@@ -486,10 +486,12 @@ class PPOTrainer:
             allreduce_sum_(self._gradstats[: self.P + 5], self.group)      # gradient + the five loss statistics
         self.update_count += 1
         hp = getattr(self, "_c_hyper", None) or self.hp.c()
+        stream = torch.cuda.current_stream(self.device).cuda_stream
         _lib.check(self._L.kin_ppo_adam(self.params.data_ptr(), self.grad.data_ptr(), self.adam_m.data_ptr(), self.adam_v.data_ptr(), self.P,
                                         ctypes.byref(hp), self.update_count, self.stats.data_ptr(), self.stats_accum.data_ptr(),
-                                        None if self.weight_image is None else self.weight_image.data_ptr(), self.in_dim,
-                                        torch.cuda.current_stream(self.device).cuda_stream))
+                                        None if self.is_route else self.weight_image.data_ptr(), self.in_dim, stream))
+        if self.is_route and self.update_variant == "tc":      # the folded bias column mixes three parameters: rebuild the image
+            _lib.check(self._L.kin_ppo_pack_weights(self.params.data_ptr(), self.in_dim, self.weight_image.data_ptr(), stream))
 
     def update(self) -> dict[str, float]:
         """``PPO.train``: n_epochs passes over the rollout in random minibatches; no host synchronisation until the statistics are read."""
@@ -501,9 +503,11 @@ class PPOTrainer:
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream(self.device).cuda_stream
             self.stats_accum.zero_()
-            img = self.collect_variant == "fused" and not self.is_route
-            if self.update_variant == "tc" and not img:   # the arm path's fused collection already sampled with the update's own forward
-                self.refresh_old_logp()
+            img = self._img
+            if self.is_route and self.update_variant == "tc":      # fp32 route observations -> folded bf16 operand images, once per rollout
+                _lib.check(self._L.kin_route_obs_images(self.obs_buf.data_ptr(), self.S, self.obs_img.data_ptr(), stream))
+            if self.update_variant == "tc" and not (self.collect_variant == "fused" and not self.is_route):
+                self.refresh_old_logp()        # (the arm path's fused collection already sampled with the update's own forward)
             adv = self._adv_stats
             kl_seen = mb_seen = 0.0
             for _ in range(self.hp.n_epochs):

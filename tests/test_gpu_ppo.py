@@ -157,6 +157,10 @@ def test_minibatch_gradient_tc_matches_autograd(in_dim):
     S = 64 * 48
     g = torch.Generator(device="cuda").manual_seed(2)
     obs = (torch.rand((S, in_dim), device="cuda", generator=g) * 2 - 1).contiguous()
+    if in_dim == 80:       # the route observation's constant columns (the kernel folds them into the layer-1 bias)
+        const = [c for c in range(80) if c in range(20, 30) or c == 39 or c >= 71]
+        obs[:, const] = 0.0
+        obs[:, [20, 71]] = 1.0
     with torch.no_grad():
         mean, value = _torch_forward(pol, obs)
     sigma = pol.tensors["log_std"].exp()
@@ -167,6 +171,11 @@ def test_minibatch_gradient_tc_matches_autograd(in_dim):
     ret = (value + torch.randn(S, device="cuda", generator=g)).contiguous()
     sums = torch.stack([adv.reshape(-1, 64).double().sum(1), (adv.reshape(-1, 64).double() ** 2).sum(1)], dim=1).contiguous()
     tile_ids = torch.tensor([3, 17, 0, 39, 8, 21, 22, 5, 30, 11, 12, 1, 47, 40], dtype=torch.int32, device="cuda")
+    kobs, is_img = obs, 0
+    if in_dim == 80:       # folded bf16 images, whole images per pair of 64-sample tiles
+        tile_ids = torch.tensor([2, 3, 16, 17, 0, 1, 38, 39, 8, 9, 20, 21, 46, 47, 10, 11], dtype=torch.int32, device="cuda")
+        kobs, is_img = torch.zeros((S // 128, 16384), dtype=torch.uint8, device="cuda"), 1
+        _lib.check(_lib.lib().kin_route_obs_images(obs.data_ptr(), S, kobs.data_ptr(), torch.cuda.current_stream().cuda_stream))
     idx = (tile_ids.long()[:, None] * 64 + torch.arange(64, device="cuda")[None]).reshape(-1)
     P = flat.numel()
     c_hp = hp.c()
@@ -174,8 +183,8 @@ def test_minibatch_gradient_tc_matches_autograd(in_dim):
     stream = torch.cuda.current_stream().cuda_stream
     # forward only: log-prob and value of the visited samples
     lp_out, v_out = torch.full((S,), 123.0, device="cuda"), torch.full((S,), 123.0, device="cuda")
-    _lib.check(L.kin_ppo_grad_tc(flat.data_ptr(), in_dim, ctypes.byref(c_hp), obs.data_ptr(), act.data_ptr(), None, None, None, None,
-                                 tile_ids.data_ptr(), tile_ids.numel(), 0, None, 3, None, None, lp_out.data_ptr(), v_out.data_ptr(), 1, 0, None, None, stream))
+    _lib.check(L.kin_ppo_grad_tc(flat.data_ptr(), in_dim, ctypes.byref(c_hp), kobs.data_ptr(), act.data_ptr(), None, None, None, None,
+                                 tile_ids.data_ptr(), tile_ids.numel(), 0, None, 3, None, None, lp_out.data_ptr(), v_out.data_ptr(), 1, is_img, None, None, stream))
     torch.cuda.synchronize()
     assert float((v_out[idx] - value[idx]).abs().max()) < 0.03 and float((lp_out[idx] - exact_logp[idx]).abs().max()) < 0.06
     assert float((lp_out[idx] - exact_logp[idx]).abs().mean()) < 0.008
@@ -197,9 +206,9 @@ def test_minibatch_gradient_tc_matches_autograd(in_dim):
         for ctas in (2, 7, 148):      # several GEMM tiles per CTA (TMEM accumulation across tiles), one per CTA, more CTAs than tiles
             partials = torch.zeros((ctas, P + 16), device="cuda")
             grad, stats = torch.zeros(P, device="cuda"), torch.zeros(8, device="cuda")
-            _lib.check(L.kin_ppo_grad_tc(flat.data_ptr(), in_dim, ctypes.byref(c_hp), obs.data_ptr(), act.data_ptr(), old_logp.data_ptr(), adv.data_ptr(),
+            _lib.check(L.kin_ppo_grad_tc(flat.data_ptr(), in_dim, ctypes.byref(c_hp), kobs.data_ptr(), act.data_ptr(), old_logp.data_ptr(), adv.data_ptr(),
                                          ret.data_ptr(), sums.data_ptr(), tile_ids.data_ptr(), tile_ids.numel(), tile_ids.numel() * 64,
-                                         partials.data_ptr(), ctas, grad.data_ptr(), stats.data_ptr(), None, None, 0, 0, None, None, stream))
+                                         partials.data_ptr(), ctas, grad.data_ptr(), stats.data_ptr(), None, None, 0, is_img, None, None, stream))
             torch.cuda.synchronize()
             off = 0
             for k, gk in zip(ppo.PARAM_ORDER, grads):
@@ -214,10 +223,23 @@ def test_minibatch_gradient_tc_matches_autograd(in_dim):
             for i, key in enumerate(("policy_loss", "value_loss", "entropy", "approx_kl", "clip_fraction")):
                 assert abs(got_stats[i] - ref_stats[key]) < 3e-2 * max(1.0, abs(ref_stats[key])), (key, got_stats[i], ref_stats[key])
     # odd tile counts are refused (two 64-sample tiles per GEMM tile)
-    rc = L.kin_ppo_grad_tc(flat.data_ptr(), in_dim, ctypes.byref(c_hp), obs.data_ptr(), act.data_ptr(), old_logp.data_ptr(), adv.data_ptr(),
+    rc = L.kin_ppo_grad_tc(flat.data_ptr(), in_dim, ctypes.byref(c_hp), kobs.data_ptr(), act.data_ptr(), old_logp.data_ptr(), adv.data_ptr(),
                            ret.data_ptr(), sums.data_ptr(), tile_ids.data_ptr(), 3, 192, partials.data_ptr(), 2, grad.data_ptr(), stats.data_ptr(),
-                           None, None, 0, 0, None, None, stream)
+                           None, None, 0, is_img, None, None, stream)
     assert rc != 0
+    if in_dim == 80:       # the route policy without folded images is refused, and its folded weight image gives the same gradient
+        rc = L.kin_ppo_grad_tc(flat.data_ptr(), in_dim, ctypes.byref(c_hp), obs.data_ptr(), act.data_ptr(), old_logp.data_ptr(), adv.data_ptr(),
+                               ret.data_ptr(), sums.data_ptr(), tile_ids.data_ptr(), 4, 256, partials.data_ptr(), 2, grad.data_ptr(), stats.data_ptr(),
+                               None, None, 0, 0, None, None, stream)
+        assert rc != 0
+        wimg = torch.zeros(36864, dtype=torch.uint8, device="cuda")
+        _lib.check(L.kin_ppo_pack_weights(flat.data_ptr(), 80, wimg.data_ptr(), stream))
+        g2 = torch.zeros(P, device="cuda")
+        _lib.check(L.kin_ppo_grad_tc(flat.data_ptr(), in_dim, ctypes.byref(c_hp), kobs.data_ptr(), act.data_ptr(), old_logp.data_ptr(), adv.data_ptr(),
+                                     ret.data_ptr(), sums.data_ptr(), tile_ids.data_ptr(), tile_ids.numel(), tile_ids.numel() * 64,
+                                     partials.data_ptr(), 148, g2.data_ptr(), stats.data_ptr(), None, None, 0, 1, None, wimg.data_ptr(), stream))
+        torch.cuda.synchronize()
+        assert torch.equal(g2, grad)
 
 
 def test_adam_matches_torch():
@@ -303,7 +325,7 @@ def test_route_policy_training_runs_end_to_end():
     pol = ppo.random_policy(80, seed=2, log_std_init=-1.0, device="cuda")
     hp = ppo.PPOHyper(learning_rate=1e-3, n_steps=32, batch_size=4096, n_epochs=4, gamma=0.98, clip_range=0.2)
     tr = ppo.PPOTrainer(renv, pol, num_envs=512, hyper=hp, seed=3, route=route, route_sequence_config=seq)
-    assert tr.is_route and tr.in_dim == 80 and tr.obs_buf.shape == (33, 512, 80) and tr.weight_image is None
+    assert tr.is_route and tr.in_dim == 80 and tr.obs_buf.shape == (33, 512, 80) and tr.obs_img.shape == (32, 4, 16384)
     p0 = tr.params.clone()
     log = tr.learn(4)
     assert all(np.isfinite(list(row.values())).all() for row in log)

@@ -46,6 +46,7 @@ struct Tile16 {
     float* snap;                 // [21][128] floats, column = row
     unsigned x_lo, h_lo, w0_lo, w1_lo, wo_lo, wob_lo;   // descriptor low words (tc16::desc_lo)
     unsigned mbar_saddr, cnt_saddr, full_saddr, tmem_d, tmem_row;
+    unsigned x_row, h_row;       // AT: this thread's lane of the X / H operands in tensor memory
     volatile int* stamp;
     int row, n_warps;
     unsigned parity, arrivals;
@@ -82,22 +83,29 @@ __device__ __forceinline__ void obs_pack(const KinEnvParams& P, const EnvRegs& s
 
 // The MMAs of one layer of one tile (one elected lane).  layer 0: X . W0^T (K = 48, bias in column 36); layer 1: H . W1^T + b1
 // (bias: X[:, 32:48] . W0img[:, 48:64]^T); layer 2: H . WO^T + bo (N = 16; bias: X[:, 32:48] . WOB[:, 32:48]^T).
+// AT: the A operands (X, H) live in tensor memory -- x_lo / h_lo are then TMEM addresses (lane 0, first column of the operand) and a
+// K slice of 16 halves is 8 columns further on.
+template <bool AT>
 __device__ __forceinline__ void issue_layer16(int layer, unsigned tmem_d, unsigned x_lo, unsigned h_lo, unsigned w0_lo, unsigned w1_lo,
                                               unsigned wo_lo, unsigned wob_lo, unsigned mbar_saddr) {
+    auto mma = [&](unsigned a, int ka, unsigned b_lo, unsigned id, unsigned acc) {
+        if constexpr (AT) mma_f16_ts(tmem_d, a + 8u * ka, b_lo, id, acc);
+        else mma_f16(tmem_d, a + 2u * ka, b_lo, id, acc);
+    };
     if (layer == 0) {
         constexpr unsigned id = idesc_f16(TILE, HID);
 #pragma unroll
-        for (int k = 0; k < X_K / 16; ++k) mma_f16(tmem_d, x_lo + 2 * k, w0_lo + 2 * k, id, k > 0 ? 1u : 0u);
+        for (int k = 0; k < X_K / 16; ++k) mma(x_lo, k, w0_lo + 2 * k, id, k > 0 ? 1u : 0u);
     } else if (layer == 1) {
         constexpr unsigned id = idesc_f16(TILE, HID);
 #pragma unroll
-        for (int k = 0; k < HID / 16; ++k) mma_f16(tmem_d, h_lo + 2 * k, w1_lo + 2 * k, id, k > 0 ? 1u : 0u);
-        mma_f16(tmem_d, x_lo + 4, w0_lo + 6, id, 1u);
+        for (int k = 0; k < HID / 16; ++k) mma(h_lo, k, w1_lo + 2 * k, id, k > 0 ? 1u : 0u);
+        mma(x_lo, 2, w0_lo + 6, id, 1u);
     } else {
         constexpr unsigned id = idesc_f16(TILE, 16);
 #pragma unroll
-        for (int k = 0; k < HID / 16; ++k) mma_f16(tmem_d, h_lo + 2 * k, wo_lo + 2 * k, id, k > 0 ? 1u : 0u);
-        mma_f16(tmem_d, x_lo + 4, wob_lo + 4, id, 1u);
+        for (int k = 0; k < HID / 16; ++k) mma(h_lo, k, wo_lo + 2 * k, id, k > 0 ? 1u : 0u);
+        mma(x_lo, 2, wob_lo + 4, id, 1u);
     }
     umma::commit(mbar_saddr);
 }
@@ -106,11 +114,12 @@ __device__ __forceinline__ void issue_layer16(int layer, unsigned tmem_d, unsign
 //   ISS  (dedicated issuer warps): proxy fence, warp converges, lane 0 arrives on the tile's `full` mbarrier -- the issuer warp
 //        that sleeps on it issues the MMAs;
 //   !ISS (16-warp CTAs, no room for issuer warps): lane 0 bumps the tile's arrival counter and the warp that arrives last issues.
-template <bool ISS>
+template <bool ISS, bool AT>
 __device__ __forceinline__ void tile_sync16(Tile16& c, int layer, int sid) {
     TC16_STAMP(layer);
+    if constexpr (AT) tmem_st_wait();      // the operand rows went to tensor memory: no generic -> async proxy fence to pay
     if constexpr (ISS) {
-        umma::fence_async_smem();
+        if constexpr (!AT) umma::fence_async_smem();
         umma::fence_before();
         __syncwarp();
         if ((threadIdx.x & 31) == 0) mbar_arrive(c.full_saddr);
@@ -119,7 +128,7 @@ __device__ __forceinline__ void tile_sync16(Tile16& c, int layer, int sid) {
         if (const int last = tile_arrive(c.cnt_saddr, c.arrivals, layer == 0 ? c.stamp : nullptr, sid)) {
             umma::fence_after();
             if (elect_one()) {
-                if (last == 1) issue_layer16(layer, c.tmem_d, c.x_lo, c.h_lo, c.w0_lo, c.w1_lo, c.wo_lo, c.wob_lo, c.mbar_saddr);
+                if (last == 1) issue_layer16<AT>(layer, c.tmem_d, c.x_lo, c.h_lo, c.w0_lo, c.w1_lo, c.wo_lo, c.wob_lo, c.mbar_saddr);
                 else mbar_arrive(c.mbar_saddr);
             }
             __syncwarp();
@@ -133,26 +142,34 @@ __device__ __forceinline__ void tile_sync16(Tile16& c, int layer, int sid) {
 
 // One policy forward for the tile: X row <- observation, three GEMMs, act[7] out.  Collective over the tile's warps.
 // Returns false (without running the MLP) once no episode of the tile is still running.
-template <bool ISS>
+template <bool ISS, bool AT>
 __device__ __forceinline__ bool mlp16(Tile16& c, const unsigned* w, float* act, bool running) {
     const int sid = ++c.step_id;
     if (__any_sync(0xffffffffu, running) && (threadIdx.x & 31) == 0) *c.stamp = sid;
-    // ---- layer 1: X = [obs36 | 1 | 0 ...]; chunk 5 (columns 40..47) stays zero from the prologue
-    st_chunk(c.X, c.row, 0, w[0], w[1], w[2], w[3]);
-    st_chunk(c.X, c.row, 1, w[4], w[5], w[6], w[7]);
-    st_chunk(c.X, c.row, 2, w[8], w[9], w[10], w[11]);
-    st_chunk(c.X, c.row, 3, w[12], w[13], w[14], w[15]);
-    st_chunk(c.X, c.row, 4, w[16], w[17], 0x00003C00u, 0u);
-    tile_sync16<ISS>(c, 0, sid);
+    // ---- layer 1: X = [obs36 | 1 | 0 ...]; columns 40..47 stay zero from the prologue
+    if constexpr (AT) {
+        tmem_st8(c.x_row, w);
+        tmem_st8(c.x_row + 8u, w + 8);
+        tmem_st4(c.x_row + 16u, w[16], w[17], 0x00003C00u, 0u);
+    } else {
+        st_chunk(c.X, c.row, 0, w[0], w[1], w[2], w[3]);
+        st_chunk(c.X, c.row, 1, w[4], w[5], w[6], w[7]);
+        st_chunk(c.X, c.row, 2, w[8], w[9], w[10], w[11]);
+        st_chunk(c.X, c.row, 3, w[12], w[13], w[14], w[15]);
+        st_chunk(c.X, c.row, 4, w[16], w[17], 0x00003C00u, 0u);
+    }
+    tile_sync16<ISS, AT>(c, 0, sid);
     if (*c.stamp != sid) return false;
     umma::fence_after();
-    epilogue_tanh(c.tmem_row, c.H, c.row);
+    if constexpr (AT) epilogue_tanh_tmem(c.tmem_row, c.h_row);
+    else epilogue_tanh(c.tmem_row, c.H, c.row);
     // ---- layer 2
-    tile_sync16<ISS>(c, 1, sid);
+    tile_sync16<ISS, AT>(c, 1, sid);
     umma::fence_after();
-    epilogue_tanh(c.tmem_row, c.H, c.row);
+    if constexpr (AT) epilogue_tanh_tmem(c.tmem_row, c.h_row);
+    else epilogue_tanh(c.tmem_row, c.H, c.row);
     // ---- layer 3 (N = 16: 7 action means + zero rows)
-    tile_sync16<ISS>(c, 2, sid);
+    tile_sync16<ISS, AT>(c, 2, sid);
     umma::fence_after();
     {
         unsigned r[8];
@@ -175,6 +192,7 @@ struct IssTile {
 };
 
 // Serve one tile if its operands are ready.  Sleeps at most ~hint_ns on the tile's `full` mbarrier.
+template <bool AT>
 __device__ __forceinline__ void issuer_poll(IssTile& t, unsigned w0_lo, unsigned w1_lo, unsigned wo_lo, unsigned wob_lo, unsigned hint_ns) {
     if (!(hint_ns ? mbar_try_wait_hint(t.full_saddr, t.parity, hint_ns) : mbar_test_wait(t.full_saddr, t.parity))) return;
     t.parity ^= 1u;
@@ -188,7 +206,7 @@ __device__ __forceinline__ void issuer_poll(IssTile& t, unsigned w0_lo, unsigned
     if (blockIdx.x == 0 && t.sid >= 10 && t.sid < 18 && (threadIdx.x & 31) == 0) kin_tc16_trace_buf[t.sid - 10][4 * t.tile][9 + t.layer] = clock64();
 #endif
     if (elect_one()) {
-        if (go) issue_layer16(t.layer, t.tmem_d, t.x_lo, t.h_lo, w0_lo, w1_lo, wo_lo, wob_lo, t.mbar_saddr);
+        if (go) issue_layer16<AT>(t.layer, t.tmem_d, t.x_lo, t.h_lo, w0_lo, w1_lo, wo_lo, wob_lo, t.mbar_saddr);
         else mbar_arrive(t.mbar_saddr);
 #ifdef KIN_TC16_TRACE
         if (blockIdx.x == 0 && t.sid >= 10 && t.sid < 18) kin_tc16_trace_buf[t.sid - 10][4 * t.tile][6 + t.layer] = clock64();
@@ -202,6 +220,7 @@ __device__ __forceinline__ void issuer_poll(IssTile& t, unsigned w0_lo, unsigned
 __device__ unsigned kin_tc16_poll_hint = 32u;   // experiment knob (KIN_TC16_POLL_HINT): 0 = non-blocking test_wait, else nap length in ns
 
 // one phase (approach or finisher): until both tiles have reported "nobody running"
+template <bool AT>
 __device__ __forceinline__ void issuer_phase(IssTile& a, IssTile& b, unsigned w0_lo, unsigned w1_lo, unsigned wo_lo, unsigned wob_lo) {
     a.live = a.exists;
     b.live = b.exists;
@@ -209,8 +228,8 @@ __device__ __forceinline__ void issuer_phase(IssTile& a, IssTile& b, unsigned w0
     unsigned spins = 0u;
     while (a.live || b.live) {
         const unsigned hint = (a.live && b.live) ? kin_tc16_poll_hint : 1000u;   // two tiles to watch: probe each in turn
-        if (a.live) issuer_poll(a, w0_lo, w1_lo, wo_lo, wob_lo, hint);
-        if (b.live) issuer_poll(b, w0_lo, w1_lo, wo_lo, wob_lo, hint);
+        if (a.live) issuer_poll<AT>(a, w0_lo, w1_lo, wo_lo, wob_lo, hint);
+        if (b.live) issuer_poll<AT>(b, w0_lo, w1_lo, wo_lo, wob_lo, hint);
         if (++spins > (1u << 28)) __trap();   // watchdog: a protocol bug must fail the launch, not hang the GPU
     }
 }
@@ -234,7 +253,9 @@ __device__ __forceinline__ void prime_step_out(const KinEnvParams& P, const EnvR
 }
 
 // ISS: the CTA's last two warps are issuer warps (<= 14 env warps, the balanced one-wave shape): blockDim.x = 32 (env warps + 2)
-template <int FAST, bool ISS>
+// AT: the activations (X, H) are A operands in TENSOR MEMORY (tcgen05.st from the epilogue, tcgen05.mma with a TMEM A operand) instead of
+// swizzled shared-memory images: 128 TMEM columns per tile (64 accumulator | 32 H | 24 X)
+template <int FAST, bool ISS, bool AT>
 __global__ void __launch_bounds__(MAX_THREADS, 1)
 kin_rollout_tc16_kernel(const __grid_constant__ KinEnvParams PA, const __grid_constant__ KinEnvParams PF, DevPolicy pol_a, DevPolicy pol_f,
                         int has_finisher, const float* __restrict__ iq, const float* __restrict__ idq, const float* __restrict__ ipa,
@@ -262,7 +283,8 @@ kin_rollout_tc16_kernel(const __grid_constant__ KinEnvParams PA, const __grid_co
     c.step_id = 0;
     c.stamp = &S.run_stamp[tile];
 
-    const unsigned tmem_cols = n_tiles_cta == 1 ? 64u : (n_tiles_cta == 2 ? 128u : 256u);   // 64 accumulator columns per tile
+    constexpr unsigned TCOLS = AT ? 128u : 64u;      // TMEM columns per tile
+    const unsigned tmem_cols = n_tiles_cta == 1 ? TCOLS : (n_tiles_cta == 2 ? 2u * TCOLS : 4u * TCOLS);
     if (warp == 0) umma::tmem_alloc(umma::smem_u32(&S.tmem_base), tmem_cols);
     if (tid == 0) {
 #pragma unroll
@@ -306,8 +328,20 @@ kin_rollout_tc16_kernel(const __grid_constant__ KinEnvParams PA, const __grid_co
     c.mbar_saddr = umma::smem_u32(&S.mbar[tile]);
     c.cnt_saddr = umma::smem_u32(&S.arrive[tile]);
     c.full_saddr = umma::smem_u32(&S.full[tile]);
-    c.tmem_d = tmem_base + tile * HID;                                        // lane 0, this tile's 64 columns
+    c.tmem_d = tmem_base + tile * TCOLS;                                      // lane 0, this tile's columns
     c.tmem_row = c.tmem_d + ((unsigned)((warp & 3) * 32) << 16);              // this warp's 32-lane slice
+    c.h_row = c.tmem_row + 64u;
+    c.x_row = c.tmem_row + 96u;
+    if constexpr (AT) {
+        c.x_lo = c.tmem_d + 96u;
+        c.h_lo = c.tmem_d + 64u;
+        if (env_thread) {      // K padding of X (columns 40..47 = words 20..23) and the spare words start as zeros
+            tmem_st4(c.x_row + 20u, 0u, 0u, 0u, 0u);
+            tmem_st4(c.x_row + 24u, 0u, 0u, 0u, 0u);
+            tmem_st4(c.x_row + 28u, 0u, 0u, 0u, 0u);
+            tmem_st_wait();
+        }
+    }
 
     if constexpr (ISS) {
         if (!env_thread) {   // ---- issuer warp: serve two tiles through both phases, keep step with the CTA barriers
@@ -321,20 +355,21 @@ kin_rollout_tc16_kernel(const __grid_constant__ KinEnvParams PA, const __grid_co
                 unsigned char* X = tiles + (size_t)t * 2 * TILE_BYTES;
                 it[j].x_lo = desc_lo(umma::smem_u32(X));
                 it[j].h_lo = desc_lo(umma::smem_u32(X + TILE_BYTES));
-                it[j].tmem_d = tmem_base + t * HID;
+                it[j].tmem_d = tmem_base + t * TCOLS;
+                if constexpr (AT) { it[j].x_lo = it[j].tmem_d + 96u; it[j].h_lo = it[j].tmem_d + 64u; }
                 it[j].full_saddr = umma::smem_u32(&S.full[t]);
                 it[j].mbar_saddr = umma::smem_u32(&S.mbar[t]);
                 it[j].stamp = &S.run_stamp[t];
                 it[j].parity = 0u;
                 it[j].sid = 0;
             }
-            issuer_phase(it[0], it[1], c.w0_lo, c.w1_lo, c.wo_lo, c.wob_lo);
+            issuer_phase<AT>(it[0], it[1], c.w0_lo, c.w1_lo, c.wo_lo, c.wob_lo);
             __syncthreads();
             if (has_finisher) {
                 load_weights(S, pol_f, KIN_MODE_DOCK, tid, (int)blockDim.x);
                 umma::fence_async_smem();
                 __syncthreads();
-                issuer_phase(it[0], it[1], c.w0_lo, c.w1_lo, c.wo_lo, c.wob_lo);
+                issuer_phase<AT>(it[0], it[1], c.w0_lo, c.w1_lo, c.wo_lo, c.wob_lo);
             }
             umma::fence_before();
             __syncthreads();
@@ -378,7 +413,7 @@ kin_rollout_tc16_kernel(const __grid_constant__ KinEnvParams PA, const __grid_co
         unsigned w[X_DYN / 2];
         float act[NJ];
         obs_pack(PA, s, so, w);
-        if (!mlp16<ISS>(c, w, act, running)) break;
+        if (!mlp16<ISS, AT>(c, w, act, running)) break;
         if (running) {
             step_core<KIN_MODE_APPROACH, false, FAST>(PA, s, act, so, nullptr);
             const float an = so.action_l2;
@@ -450,7 +485,7 @@ kin_rollout_tc16_kernel(const __grid_constant__ KinEnvParams PA, const __grid_co
             unsigned w[X_DYN / 2];
             float act[NJ];
             obs_pack(PF, s, so, w);
-            if (!mlp16<ISS>(c, w, act, running)) break;
+            if (!mlp16<ISS, AT>(c, w, act, running)) break;
             if (running) {
                 float an2 = 0.0f;   // the policy's own action (the step clips it to the dock limit before it reports action_l2)
 #pragma unroll
@@ -511,13 +546,15 @@ int kin_rollout_tc16_launch(const KinHandle* ha, const KinHandle* hf, const KinP
                             int confirm, uint32_t* result, unsigned long long* env_steps, cudaStream_t st) {
     using Kernel = void (*)(KinEnvParams, KinEnvParams, tc16::DevPolicy, tc16::DevPolicy, int, const float*, const float*, const float*, const float*,
                             const float*, int, int, int, uint32_t*, unsigned long long*);
-    static const Kernel kernels[2][2] = {{kin_rollout_tc16_kernel<1, false>, kin_rollout_tc16_kernel<1, true>},
-                                         {kin_rollout_tc16_kernel<2, false>, kin_rollout_tc16_kernel<2, true>}};
+    static const Kernel kernels[2][2][2] = {{{kin_rollout_tc16_kernel<1, false, false>, kin_rollout_tc16_kernel<1, false, true>},
+                                             {kin_rollout_tc16_kernel<1, true, false>, kin_rollout_tc16_kernel<1, true, true>}},
+                                            {{kin_rollout_tc16_kernel<2, false, false>, kin_rollout_tc16_kernel<2, false, true>},
+                                             {kin_rollout_tc16_kernel<2, true, false>, kin_rollout_tc16_kernel<2, true, true>}}};
     static bool attr_set[KIN_MAX_DEVICES] = {};
     const int dev_slot = kin_device_slot();
     if (!attr_set[dev_slot]) {
-        for (int i = 0; i < 4; ++i) {
-            cudaError_t e = cudaFuncSetAttribute(kernels[i >> 1][i & 1], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc16::smem_bytes(tc16::MAX_TILES));
+        for (int i = 0; i < 8; ++i) {
+            cudaError_t e = cudaFuncSetAttribute(kernels[i >> 2][(i >> 1) & 1][i & 1], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc16::smem_bytes(tc16::MAX_TILES));
             if (e != cudaSuccess) return kin_fail_cuda(e, "kin_rollout_approach_finisher(tc16): smem attribute");
         }
         attr_set[dev_slot] = true;
@@ -525,6 +562,7 @@ int kin_rollout_tc16_launch(const KinHandle* ha, const KinHandle* hf, const KinP
     // KIN_TC16_EXACT_SINCOS=1: polynomial sine / cosine in the FK instead of the MUFU units (the default: 6 % faster, same flip count)
     static const bool exact_sincos = kin_env_flag("KIN_TC16_EXACT_SINCOS");
     static const bool no_issuer = kin_env_flag("KIN_TC16_NO_ISSUER_WARPS");
+    static const bool tmem_a = !kin_env_flag("KIN_TC16_SMEM_A");       // default: activations as TMEM A operands (+5 %, bitwise the same results)
     static bool hint_set = false;
     if (!hint_set) {
         if (const char* v = getenv("KIN_TC16_POLL_HINT")) { const unsigned h = (unsigned)atoi(v); cudaMemcpyToSymbol(kin_tc16_poll_hint, &h, sizeof(h)); }
@@ -548,7 +586,7 @@ int kin_rollout_tc16_launch(const KinHandle* ha, const KinHandle* hf, const KinP
     const int env_threads = 32 * w_per_cta;
     const int threads = env_threads + (iss ? 64 : 0);
     const size_t smem = tc16::smem_bytes((env_threads + tc16::TILE - 1) / tc16::TILE);
-    kernels[exact_sincos ? 0 : 1][iss ? 1 : 0]<<<(n + env_threads - 1) / env_threads, threads, smem, st>>>(
+    kernels[exact_sincos ? 0 : 1][iss ? 1 : 0][tmem_a ? 1 : 0]<<<(n + env_threads - 1) / env_threads, threads, smem, st>>>(
         ha->params, PF, da, df, (hf && pf) ? 1 : 0, iq, idq, ipa, gq, gpose, n, stride, confirm, result, env_steps);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? KIN_OK : kin_fail_cuda(e, "kin_rollout_approach_finisher(tc16)");

@@ -115,6 +115,25 @@ __device__ __forceinline__ void mma_f16(unsigned tmem_d, unsigned a_lo, unsigned
         "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
         ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(DESC_HI) : "memory");
 }
+// the same MMA with the A operand in tensor memory (lane = row, each 32-bit column = two consecutive K halves): no shared-memory
+// round trip and no generic -> async proxy fence for the activations
+__device__ __forceinline__ void mma_f16_ts(unsigned tmem_d, unsigned a_taddr, unsigned b_lo, unsigned idesc, unsigned accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_taddr), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(DESC_HI) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(unsigned taddr, const unsigned* r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_st4(unsigned taddr, unsigned a, unsigned b, unsigned c, unsigned d) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 __device__ __forceinline__ bool elect_one() {
     unsigned pred;
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
@@ -203,6 +222,30 @@ __device__ __forceinline__ void tanh_store16(const unsigned* r, unsigned char* H
             w[j] = pack_h2(umma::tanh_fast(__uint_as_float(r[8 * h + 2 * j])), umma::tanh_fast(__uint_as_float(r[8 * h + 2 * j + 1])));
         st_chunk(H, row, 2 * ch2 + h, w[0], w[1], w[2], w[3]);
     }
+}
+
+// 16 accumulator columns -> tanh -> 8 packed words -> columns [8 * piece, 8 * piece + 8) of this thread's lane of the H operand in TMEM
+__device__ __forceinline__ void tanh_store16_tmem(const unsigned* r, unsigned h_taddr, int piece) {
+    unsigned w[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) w[j] = pack_h2(umma::tanh_fast(__uint_as_float(r[2 * j])), umma::tanh_fast(__uint_as_float(r[2 * j + 1])));
+    tmem_st8(h_taddr + 8u * piece, w);
+}
+// the epilogue with the H operand in tensor memory
+__device__ __forceinline__ void epilogue_tanh_tmem(unsigned tmem_row, unsigned h_taddr) {
+    unsigned a[16], b[16];
+    tmem_ld16_raw(tmem_row, a);
+    tmem_wait16(a);
+    tmem_ld16_raw(tmem_row + 16u, b);
+    tanh_store16_tmem(a, h_taddr, 0);
+    tmem_wait16(b);
+    tmem_ld16_raw(tmem_row + 32u, a);
+    tanh_store16_tmem(b, h_taddr, 1);
+    tmem_wait16(a);
+    tmem_ld16_raw(tmem_row + 48u, b);
+    tanh_store16_tmem(a, h_taddr, 2);
+    tmem_wait16(b);
+    tanh_store16_tmem(b, h_taddr, 3);
 }
 
 // hidden-layer epilogue: this thread's 64 accumulator columns -> tanh -> fp16 -> its row of the H image, in four 16-column

@@ -712,6 +712,15 @@ int kin_ppo_grad_tc_exchange(const float *params, int in_dim, const KinPpoHyper 
                              const float *adv_stats, const void *weight_image, void *const *peer_buffers, int rank, int world, unsigned epoch,
                              int *timed_out, void *stream);
 
+/* Experimental variant switch of kin_ppo_grad_tc / kin_ppo_grad_tc_exchange.  When enabled, 56-input policies on operand images with
+ * minibatches of at least one 128-sample tile per CTA (n_tiles / 2 >= grid, 2 <= grid <= SM count) run the gradient pass on the
+ * three-tile-streams-per-SM kernel (csrc/kin_ppo_tc3.cu: one CTA per SM, grid split between actor and critic CTAs); everything else, and
+ * everything by default, runs the two-CTAs-per-SM kernel (the three-stream kernel measured 4 % slower: both are bound by the
+ * shared-memory data pipe).  enabled: 0 / 1, negative = leave; actor_pct: share of the CTAs that work on the actor (10..90),
+ * else leave.  Defaults: off, 52 %, or the environment (KIN_PPO_TC3=1, KIN_PPO_TC3_ACTOR_PCT).  Returns enabled | actor_pct << 8 after
+ * the change.  Same reference call replaced as kin_ppo_grad_tc (SB3 ppo.py train(), one minibatch).                                 */
+int kin_ppo_tc3_config(int enabled, int actor_pct);
+
 /* Replaces: OnPolicyAlgorithm.collect_rollouts (SB3 on_policy_algorithm.py) over a VecEnv of ArmKinematicEnv, fused into ONE
  * launch: n_steps x (actor + critic forward on tcgen05, a = mean + exp(log_std) * eps, log-prob, env step with reward and
  * termination, in-register auto-reset from the device sampler).  n_envs must be a multiple of 128.  Outputs, time-major:

@@ -70,4 +70,13 @@ __host__ __device__ inline int wimg_offset(const PpoOffsets& o, int in_dim, int 
 // grad[p] = sum over CTAs of partials[c][p] (rows of P + KIN_PPO_STATS + 8 floats); stats (nullable) likewise, scaled
 int kin_ppo_reduce_launch(const float* partials, int n_cta, int P, float* grad, float* stats, float inv_global_batch, cudaStream_t st);
 
+
+// kin_ppo_tc3.cu: the three-streams-per-SM form of the tensor-core gradient kernel.  Returns 0 when the call is not eligible (the caller
+// launches the two-chain kernel), 1 when it was handled (*rc = KIN_OK or the error)
+struct PeerFused;
+int kin_ppo_grad_tc3_try(const float* params, const KinPpoHyper* hp, const void* images, const float* action, const float* old_logp,
+                         const float* advantage, const float* returns, const double* tile_sums, const int* tile_ids, int n_pairs, float inv_global_batch,
+                         float* partials, int grid, const float* adv_stats, const void* weight_image, const PeerFused& px, bool fused, cudaStream_t st,
+                         int* rc);
+
 }  // namespace kin

@@ -682,10 +682,17 @@ static int grad_tc_launch(const float* params, int in_dim, const KinPpoHyper* hp
     const unsigned char* wimg = static_cast<const unsigned char*>(weight_image);
     const bool fused = px.world > 0 && !forward_only;
     if (fused && (int)(dg.x * dg.y) > PEER_MAX_CTA) return kin_fail(KIN_ERR_INVALID_ARG, "kin_ppo_grad_tc_exchange: at most 512 CTAs");
+    // 56-input policies on operand images, full-size minibatches: the three-streams-per-SM kernel (kin_ppo_tc3.cu)
+    int rc3 = KIN_OK;
+    const bool tc3_done = !forward_only && obs_is_image && in_dim == 56 &&
+                          kin_ppo_grad_tc3_try(params, hp, obs_any, action, old_logp, advantage, returns, tile_sums, tile_ids, n_pairs, inv, partials, grid,
+                                               adv_stats, weight_image, px, fused, st, &rc3);
+    if (tc3_done && rc3 != KIN_OK) return rc3;
 #define KIN_GRAD_TC_LAUNCH(IMG, IN, PEER)                                                                                                        \
     kin_ppo_grad_tc_kernel<IMG, IN, PEER><<<dg, TCG_THREADS, smem, st>>>(params, *hp, obs, action, old_logp, advantage, returns, tile_sums, tile_ids, n_pairs, \
                                                                          inv, partials, logp_out, value_out, forward_only, net_base, adv_stats, wimg, px)
-    if (fused) {
+    if (tc3_done) {
+    } else if (fused) {
         if (in_dim == 80) KIN_GRAD_TC_LAUNCH(true, 80, true);
         else if (obs_is_image) KIN_GRAD_TC_LAUNCH(true, 56, true);
         else KIN_GRAD_TC_LAUNCH(false, 56, true);

@@ -669,6 +669,23 @@ def decode_obs_images(images: torch.Tensor) -> torch.Tensor:
     return rows.view(torch.bfloat16).float()
 
 
+def encode_obs_images(obs: torch.Tensor) -> torch.Tensor:
+    """``[n, 56]`` float observations (n a multiple of 128) -> ``[n / 128, 16384]`` uint8 operand images in the layout ``kin_ppo_collect``
+    writes and ``kin_ppo_grad_tc(obs_is_image=1)`` reads: rows ``[bf16(obs56) | 1 | 0 x 7]``, SWIZZLE_128B (the inverse of
+    ``decode_obs_images``; the chunk swizzle is an involution)."""
+    n, d = obs.shape
+    if n % 128 or d != 56:
+        raise ValueError("encode_obs_images: [n, 56] observations, n a multiple of 128")
+    rows = torch.zeros((n // 128, 128, 64), dtype=torch.bfloat16, device=obs.device)
+    rows[..., :56] = obs.reshape(n // 128, 128, 56).to(torch.bfloat16)
+    rows[..., 56] = 1.0
+    chunks = rows.view(torch.uint8).reshape(n // 128, 128, 8, 16)
+    r = torch.arange(128, device=obs.device)[:, None]
+    c = torch.arange(8, device=obs.device)[None, :]
+    slot = (c ^ (r & 7)).reshape(1, 128, 8, 1).expand(n // 128, 128, 8, 16)
+    return torch.gather(chunks, -2, slot).reshape(n // 128, 16384).contiguous()
+
+
 def numpy_gae(rewards: np.ndarray, values: np.ndarray, episode_starts: np.ndarray, last_values: np.ndarray, last_dones: np.ndarray,
               gamma: float, gae_lambda: float) -> tuple[np.ndarray, np.ndarray]:
     """Plain restatement of SB3 ``RolloutBuffer.compute_returns_and_advantage`` (host-side reference for tests)."""

@@ -242,6 +242,81 @@ def test_minibatch_gradient_tc_matches_autograd(in_dim):
         assert torch.equal(g2, grad)
 
 
+def test_minibatch_gradient_three_stream_kernel_matches_autograd_and_the_two_chain_kernel():
+    """kin_ppo_tc3.cu (three tile streams per SM, dO in the spare X columns, one M = 128 GEMM for dW0 | db0 | db1): same tolerances
+    against fp32 autograd as the two-chain kernel, agreement with the two-chain kernel on the same inputs to summation-order level,
+    bitwise reproducible, for grids where streams idle (more streams than tiles), where every stream has one tile and several."""
+    from rl_brain_trainer_b200 import _lib
+
+    ppo, pol, flat = _setup(seed=4, in_dim=56)
+    S = 128 * 512
+    g = torch.Generator(device="cuda").manual_seed(5)
+    obs = (torch.rand((S, 56), device="cuda", generator=g) * 2 - 1).contiguous()
+    with torch.no_grad():
+        mean, value = _torch_forward(pol, obs)
+    sigma = pol.tensors["log_std"].exp()
+    act = (mean + sigma * torch.randn((S, 7), device="cuda", generator=g)).contiguous()
+    exact_logp = torch.distributions.Normal(mean, sigma).log_prob(act).sum(-1)
+    old_logp = (exact_logp + 0.3 * torch.randn(S, device="cuda", generator=g)).contiguous()
+    adv = torch.randn(S, device="cuda", generator=g).contiguous()
+    ret = (value + torch.randn(S, device="cuda", generator=g)).contiguous()
+    sums = torch.stack([adv.reshape(-1, 64).double().sum(1), (adv.reshape(-1, 64).double() ** 2).sum(1)], dim=1).contiguous()
+    images = ppo.encode_obs_images(obs)
+    P = flat.numel()
+    L = _lib.lib()
+    stream = torch.cuda.current_stream().cuda_stream
+    wimg = torch.zeros(36864, dtype=torch.uint8, device="cuda")
+    _lib.check(L.kin_ppo_pack_weights(flat.data_ptr(), 56, wimg.data_ptr(), stream))
+    hp = ppo.PPOHyper(clip_range=50.0, ent_coef=0.01, vf_coef=0.5, normalize_advantage=True)
+    c_hp = hp.c()
+    perm = torch.randperm(S // 128, generator=torch.Generator().manual_seed(9))
+
+    def run(tile_ids, ctas, enabled, pct=-1):
+        L.kin_ppo_tc3_config(enabled, pct)
+        partials = torch.full((ctas, P + 16), 7.0, device="cuda")      # stale rows must not leak into the sum
+        grad, stats = torch.zeros(P, device="cuda"), torch.zeros(8, device="cuda")
+        _lib.check(L.kin_ppo_grad_tc(flat.data_ptr(), 56, ctypes.byref(c_hp), images.data_ptr(), act.data_ptr(), old_logp.data_ptr(), adv.data_ptr(),
+                                     ret.data_ptr(), sums.data_ptr(), tile_ids.data_ptr(), tile_ids.numel(), tile_ids.numel() * 64,
+                                     partials.data_ptr(), ctas, grad.data_ptr(), stats.data_ptr(), None, None, 0, 1, None, wimg.data_ptr(), stream))
+        torch.cuda.synchronize()
+        return grad, stats
+
+    try:
+        # (pairs, CTAs): streams without a tile; exactly one tile per stream; ragged; the trainer's shape (148 CTAs, several tiles per stream)
+        for n_pairs, ctas in ((5, 4), (12, 4), (37, 6), (512, 148)):
+            img_ids = perm[:n_pairs].to(torch.int32)
+            tile_ids = torch.stack((2 * img_ids, 2 * img_ids + 1), dim=1).reshape(-1).contiguous().cuda()
+            idx = (tile_ids.long()[:, None] * 64 + torch.arange(64, device="cuda")[None]).reshape(-1)
+            for t in pol.tensors.values():
+                t.requires_grad_(True)
+            loss, ref_stats = _torch_ppo_loss(pol, hp, obs[idx], act[idx], old_logp[idx], adv[idx], ret[idx])
+            grads = torch.autograd.grad(loss, [pol.tensors[k] for k in ppo.PARAM_ORDER])
+            ref = torch.cat([gk.reshape(-1) for gk in grads])
+            for t in pol.tensors.values():
+                t.requires_grad_(False)
+            g2, s2 = run(tile_ids, ctas, 0)
+            for pct in (52, 30, 75):
+                g3, s3 = run(tile_ids, ctas, 1, pct)
+                off = 0
+                for k, gk in zip(ppo.PARAM_ORDER, grads):
+                    n = gk.numel()
+                    rel = float((g3[off:off + n] - gk.reshape(-1)).norm() / (gk.norm() + 1e-12))
+                    # (a single-element tensor -- val_b -- is a signed sum over all samples with full cancellation: its bf16 noise is
+                    # checked against the two-chain kernel below, not against fp32 autograd)
+                    assert n == 1 or rel < (5e-2 if n > 64 else 0.15), (n_pairs, ctas, pct, k, rel)
+                    # against the two-chain kernel: the same per-element arithmetic, sums in another order
+                    rel2 = float((g3[off:off + n] - g2[off:off + n]).norm() / (g2[off:off + n].norm() + 1e-12))
+                    assert rel2 < (2e-4 if n > 1 else 5e-3), (n_pairs, ctas, pct, k, rel2)
+                    off += n
+                cos = float(torch.dot(g3, ref) / (g3.norm() * ref.norm()))
+                assert cos > 0.9999 and float((g3 - ref).norm() / ref.norm()) < 1.2e-2, (n_pairs, ctas, pct, cos)
+                assert float((s3[:5] - s2[:5]).abs().max()) < 1e-4 * max(1.0, float(s2[:5].abs().max())), (s3, s2)
+                g3b, s3b = run(tile_ids, ctas, 1, pct)
+                assert torch.equal(g3, g3b) and torch.equal(s3, s3b)
+    finally:
+        L.kin_ppo_tc3_config(0, 52)
+
+
 def test_adam_matches_torch():
     from rl_brain_trainer_b200 import _lib, ppo
 

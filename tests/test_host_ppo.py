@@ -31,6 +31,8 @@ def test_decode_obs_images_inverts_the_swizzle():
     assert torch.equal(back, rows.bfloat16().float())
     # leading dimensions are kept ([T, tiles, bytes] in the trainer)
     assert ppo.decode_obs_images(img.reshape(1, 3, 16384)).shape == (1, 3, 128, 64)
+    # the product-side encoder (fp32 observations -> the images kin_ppo_collect would have written) agrees with the test's scalar one
+    assert torch.equal(ppo.encode_obs_images(rows[..., :56].reshape(-1, 56)), img)
 
 
 def test_numpy_gae_matches_a_scalar_loop():

@@ -452,6 +452,10 @@ typedef struct KinRouteTable {
  * library
  * ------------------------------------------------------------------------------------------- */
 int kin_abi_version(void);
+/* sha256 (hex) of the sources this library was compiled from (rl_brain_trainer_b200/build.py::source_hash: every csrc .cu / .cuh / .h and
+ * this header), "unstamped" for a build outside build.py.  The Python loader refuses (after one rebuild attempt) a library whose hash
+ * differs from the tree it sits in.  No reference counterpart: the reference is interpreted Python.                                  */
+const char *kin_source_hash(void);
 const char *kin_last_error_string(void);
 /* number of SMs / device name of the current device (for grid sizing and bench metadata) */
 int kin_device_info(int *sm_count, int *cc_major, int *cc_minor, char *name, int name_len);

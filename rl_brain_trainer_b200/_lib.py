@@ -75,6 +75,41 @@ class KinError(RuntimeError):
     """A C-ABI call returned a non-zero code (message from kin_last_error_string)."""
 
 
+def library_source_hash(path: Path | None = None) -> str:
+    """``kin_source_hash()`` of a built library, read through a throw-away handle (``"missing"`` if the symbol is absent)."""
+    h = ctypes.CDLL(str(path or LIB_PATH))
+    try:
+        fn = h.kin_source_hash
+    except AttributeError:
+        return "missing"
+    fn.restype = ctypes.c_char_p
+    return fn().decode()
+
+
+def _check_source_hash() -> None:
+    """The in-tree library must have been compiled from the sources it sits next to (``build.source_hash``).  A stale library is
+    rebuilt once when nvcc is there (the GPU box has the same image); otherwise, or if the rebuild does not fix it, loading fails.
+    ``KIN_B200_ALLOW_STALE=1`` turns the refusal into a warning (experiments with hand-built libraries)."""
+    from . import build as kbuild
+
+    want = kbuild.source_hash()
+    got = library_source_hash()
+    if got == want:
+        return
+    if os.environ.get("KIN_B200_ALLOW_STALE"):
+        import warnings
+
+        warnings.warn(f"libkin_b200.so was built from other sources (library {got[:12]}, tree {want[:12]})")
+        return
+    try:
+        kbuild.build()
+    except Exception as exc:  # no nvcc, compile error ...
+        raise KinError(f"libkin_b200.so was built from other sources (library {got[:12]}, tree {want[:12]}) and the rebuild failed: {exc}") from exc
+    got = library_source_hash()
+    if got != want:
+        raise KinError(f"libkin_b200.so does not match its sources after a rebuild (library {got[:12]}, tree {want[:12]})")
+
+
 def lib() -> ctypes.CDLL:
     global _lib
     if _lib is not None:
@@ -82,6 +117,9 @@ def lib() -> ctypes.CDLL:
     if not LIB_PATH.exists():
         raise KinError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                        "(nvcc, sm_100a). There is no CPU fallback.")
+    default_lib = not os.environ.get("KIN_B200_LIB") and LIB_PATH == PKG_DIR / "libkin_b200.so"
+    if default_lib:
+        _check_source_hash()
     L = ctypes.CDLL(str(LIB_PATH))
     vp, i32, u64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64
     L.kin_abi_version.restype = i32
@@ -129,8 +167,9 @@ def lib() -> ctypes.CDLL:
     L.kin_peer_grad_gather.argtypes = [vp, i32, i32, u32, vp, vp, vp, vp]
     for name in declared_functions():
         fn = getattr(L, name)  # raises AttributeError if the .so lacks a declared symbol
-        if name not in ("kin_last_error_string",):
+        if name not in ("kin_last_error_string", "kin_source_hash"):
             fn.restype = i32
+    L.kin_source_hash.restype = ctypes.c_char_p
     if L.kin_abi_version() != define("KIN_ABI_VERSION"):
         raise KinError("libkin_b200.so ABI version does not match include/kin_b200.h; rebuild")
     _lib = L

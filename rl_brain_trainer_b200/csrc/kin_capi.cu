@@ -32,6 +32,11 @@ using namespace kin;
 
 extern "C" int kin_abi_version(void) { return KIN_ABI_VERSION; }
 
+#ifndef KIN_SOURCE_HASH
+#define KIN_SOURCE_HASH "unstamped"
+#endif
+extern "C" const char* kin_source_hash(void) { return KIN_SOURCE_HASH; }
+
 extern "C" const char* kin_last_error_string(void) { return g_err; }
 
 extern "C" int kin_device_info(int* sm_count, int* cc_major, int* cc_minor, char* name, int name_len) {

@@ -47,6 +47,16 @@ def test_library_exports_every_declared_symbol():
     assert _lib.lib().kin_ppo_param_count(56) == 16143     # 8 270 actor (incl. log_std) + 7 873 critic
 
 
+def test_library_is_built_from_the_sources_in_the_tree():
+    """The library carries the sha256 of the sources it was compiled from; the loader refuses (after one rebuild) a stale one."""
+    from rl_brain_trainer_b200 import build as kbuild
+
+    want = kbuild.source_hash()
+    assert len(want) == 64 and _lib.lib().kin_source_hash().decode() == want == _lib.library_source_hash()
+    files = [f.name for f in kbuild.source_files()]
+    assert "kin_b200.h" in files and "kin_step.cu" in files and "kin_rollout_tc16.cu" in files and "kin_ppo_tc.cu" in files
+
+
 def test_header_structs_parse_and_params_fill():
     from rl_brain_trainer_b200 import params
 

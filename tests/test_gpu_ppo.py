@@ -387,6 +387,43 @@ def test_trainer_runs_and_improves_value_fit(variant):
     assert torch.equal(tr2.params, q0)
 
 
+def test_bf16_and_fp32_update_variants_train_equivalently():
+    """The tensor-core (bf16 operand) update is accepted at bf16-level gradient tolerances; this is the check that it TRAINS like the strict
+    fp32 update: from one random init and seed, the reference's from-scratch config (approach_default, 6 stages, promotion at a windowed
+    success rate of 0.8) through the whole curriculum with either variant -- both reach the last stage in a similar number of rollouts and
+    the policies they produce score the same (+- 3 points) on every stage under ONE evaluator (the strict-fp32 fused rollout)."""
+    from dataclasses import replace
+
+    from rl_brain_trainer_b200 import gate, ppo
+    from rl_brain_trainer_b200.rollout import VARIANT_FFMA
+
+    cfg = env_config("approach_default")
+    cfg = replace(cfg, curriculum_config=replace(cfg.curriculum_config, window_episodes=2048, min_episodes_per_stage=2048))
+    n_stages = len(cfg.curriculum_config.stages)
+    envs, n_steps = 8192, 64
+    result = {}
+    for variant in ("tc", "fp32"):
+        pol = ppo.random_policy(56, seed=0, log_std_init=-0.5, device="cuda")
+        hp = ppo.PPOHyper(learning_rate=3e-4, n_steps=n_steps, batch_size=envs * n_steps // 16, n_epochs=8, gamma=0.98, gae_lambda=0.95, clip_range=0.2)
+        tr = ppo.PPOTrainer(cfg, pol, num_envs=envs, hyper=hp, seed=1, stage_index=0, update_variant=variant)
+        iters, rate = 0, 0.0
+        while iters < 120:
+            row = tr.learn(1)[0]
+            iters += 1
+            rate = row["successes"] / max(row["episodes"], 1.0)
+            assert np.isfinite(list(row.values())).all()
+            if int(row["stage"]) >= n_stages - 1 and rate >= 0.95:
+                break
+        ev = gate.evaluate_workspace_expansion(cfg, pol, None, None, episodes=1024, seed=720001, stage_indices=list(range(n_stages)), variant=VARIANT_FFMA)
+        result[variant] = (iters, int(tr.env.get_curriculum_stage()), rate, [ev["stage_metrics"][s]["success_rate"] for s in range(n_stages)])
+    (it_tc, st_tc, rate_tc, ev_tc), (it_f, st_f, rate_f, ev_f) = result["tc"], result["fp32"]
+    assert st_tc == st_f == n_stages - 1, result
+    assert rate_tc >= 0.95 and rate_f >= 0.95, result
+    assert abs(it_tc - it_f) <= 0.4 * max(it_tc, it_f) + 2, result
+    assert min(ev_tc) > 0.9 and min(ev_f) > 0.9, result
+    assert max(abs(a - b) for a, b in zip(ev_tc, ev_f)) < 0.03, result
+
+
 def test_route_policy_training_runs_end_to_end():
     """train_route_curriculum.py on the device: the 80-input route policy on the batched RouteSequence env -- rollout with sampled
     route resets, TimeLimit bootstrap, tensor-core update (fp32 route observations), prefix curriculum promotion."""

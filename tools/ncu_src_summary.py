@@ -5,7 +5,12 @@ top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 hdr = rows[hdr_i]
 col = {h: i for i, h in enumerate(hdr)}
-data = [r for r in rows[hdr_i + 1:] if len(r) == len(hdr)]
+data = []
+for r in rows[hdr_i + 1:]:          # the first captured launch only (a second launch repeats the header)
+    if r and r[0] == "Address":
+        break
+    if len(r) == len(hdr):
+        data.append(r)
 f = lambda r, h: float(r[col[h]] or 0)
 tot_samples = sum(f(r, "# Samples") for r in data)
 tot_inst = sum(f(r, "Instructions Executed") for r in data)

@@ -366,6 +366,7 @@ def measure_training(torch, dist, device, world: int, envs: int = 65536, n_steps
         dist.all_gather(allp, mine)
         check["params_bitwise_identical_across_ranks"] = all(bool(torch.equal(allp[0], q)) for q in allp)
         check["param_checksums"] = [float(q.double().sum()) for q in allp]
+    fused_update = bool(tr.fused_update)
     tr.close()
     if world > 1:
         side = {}
@@ -381,7 +382,8 @@ def measure_training(torch, dist, device, world: int, envs: int = 65536, n_steps
         check["peer_vs_nccl_rel_diff"] = float((side["peer"] - side["nccl"]).norm() / side["nccl"].norm())
     return {"workload": "stage10_ppo_train", "exchange_check": check, "envs_per_gpu": envs, "n_steps": n_steps, "epochs": 8, "minibatches_per_epoch": 16, "iters": iters,
             "rollout_env_steps_per_s": steps / float(t[0]), "update_env_steps_per_s": steps / float(t[1]),
-            "e2e_env_steps_per_s": steps / float(t[0] + t[1]), "collect": "kin_ppo_collect (fused, tcgen05 bf16)", "update": "kin_ppo_grad_tc (tcgen05 bf16)",
+            "e2e_env_steps_per_s": steps / float(t[0] + t[1]), "collect": "kin_ppo_collect (fused, tcgen05 bf16)",
+            "update": "kin_ppo_grad_tc_update (tcgen05 bf16; gradient + exchange + clip + Adam in one launch)" if fused_update else "kin_ppo_grad_tc (tcgen05 bf16) + kin_ppo_adam",
             "grad_exchange": (grad_exchange if world > 1 else "none"), "approx_kl": stats["approx_kl"], "value_loss": stats["value_loss"]}
 
 

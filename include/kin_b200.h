@@ -727,6 +727,19 @@ int kin_ppo_grad_tc_exchange(const float *params, int in_dim, const KinPpoHyper 
                              const float *adv_stats, const void *weight_image, void *const *peer_buffers, int rank, int world, unsigned epoch,
                              int *timed_out, void *stream);
 
+/* kin_ppo_grad_tc_exchange + kin_ppo_adam in ONE launch: after the rank-ordered sum every CTA also applies clip_grad_norm_ + Adam
+ * (SB3 ppo.py train(): th.nn.utils.clip_grad_norm_ + optimizer.step, kin_ppo_adam's arithmetic) to the slice of the summed gradient it
+ * owns -- per-CTA sums of squares, a second grid barrier, the same clip coefficient in every CTA and on every rank -- and keeps the bf16
+ * weight image (56-input policies) in step.  params_rw must be params (updated in place; the kernel reads the weights only in its
+ * prologue), step counts optimiser steps from 1, norm_scratch holds 2 * grid floats, stats_accum (nullable) receives the running sums of
+ * kin_ppo_adam.  A minibatch whose exchange timed out leaves the parameters untouched.  With world == 1 the peer buffer is the rank's own
+ * (kin_peer_buffer_create(n_params, 1, ..)): single-GPU training runs one launch per minibatch too.                                  */
+int kin_ppo_grad_tc_update(const float *params, int in_dim, const KinPpoHyper *host_hyper, const void *obs, const float *action, const float *old_logp,
+                           const float *advantage, const float *returns, const double *tile_sums, const int *tile_ids, int n_tiles,
+                           long long global_batch, float *partials, int grid, float *grad, float *stats, int obs_is_image, const float *adv_stats,
+                           void *weight_image, void *const *peer_buffers, int rank, int world, unsigned epoch, int *timed_out, float *params_rw,
+                           float *adam_m, float *adam_v, int step, float *stats_accum, float *norm_scratch, void *stream);
+
 /* Experimental variant switch of kin_ppo_grad_tc / kin_ppo_grad_tc_exchange.  When enabled, 56-input policies on operand images with
  * minibatches of at least one 128-sample tile per CTA (n_tiles / 2 >= grid, 2 <= grid <= SM count) run the gradient pass on the
  * three-tile-streams-per-SM kernel (csrc/kin_ppo_tc3.cu: one CTA per SM, grid split between actor and critic CTAs); everything else, and

@@ -153,6 +153,7 @@ def lib() -> ctypes.CDLL:
     L.kin_ppo_grad_tc.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, i64, vp, i32, vp, vp, vp, vp, i32, i32, vp, vp, vp]
     L.kin_ppo_grad_tc_exchange.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, i64, vp, i32, vp, vp, i32, vp, vp, vp, i32, i32, u32, vp, vp]
     L.kin_ppo_tc3_config.argtypes = [i32, i32]
+    L.kin_ppo_grad_tc_update.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, i64, vp, i32, vp, vp, i32, vp, vp, vp, i32, i32, u32, vp, vp, vp, vp, i32, vp, vp, vp]
     L.kin_ppo_shuffle.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp]
     L.kin_ppo_adv_stats.argtypes = [vp, vp, i32, i32, i32, vp, vp]
     L.kin_ppo_collect.argtypes = [vp, vp, i32, i32, i32, vp, vp, i32, i32, u64, u32, u64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp]

@@ -6,9 +6,12 @@
 //     [0]      unsigned arrived[8]            two-kernel form: arrived[s] = pushes of sender s that have fully landed here
 //     [64]     unsigned local_count           two-kernel form: CTAs of this rank's push kernel that have finished
 //     [68]     unsigned grid_count            fused form: CTAs of this rank's gradient kernel whose partial row is complete (monotonic)
+//     [72]     unsigned adam_count            fused update: CTAs whose slice of the summed gradient and its sum of squares are written (monotonic)
 //     [128]    unsigned slice_flag[8][512]    fused form: slice_flag[s][c] = last exchange whose slice c sender s has delivered here
 //     [16512]  float    slot[2][world][row]   row = n_params + 8 (gradient, then the 5 loss statistics); slot = exchange parity
 #pragma once
+
+#include <cuda_bf16.h>
 
 #include "kin_internal.h"
 #include "kin_ppo_layout.cuh"
@@ -24,6 +27,18 @@ struct PeerTable {
     unsigned char* base[PEER_MAX];
 };
 
+// optional clip + Adam step in the same tail (params == nullptr: the caller launches kin_ppo_adam)
+struct AdamFused {
+    float* params;                    // [P] flat parameters, updated in place
+    float* m;                         // [P] Adam first moments
+    float* v;                         // [P] Adam second moments
+    unsigned short* wimg;             // bf16 operand image of the 56-input weights kept in step (nullable)
+    float* stats_accum;               // [KIN_PPO_STATS] running sums over the minibatches of an update (nullable)
+    float* norm_part;                 // [n_cta] scratch: sum of squares of each CTA's gradient slice
+    float bc1, bc2;                   // 1 - beta^step
+    int in_dim;
+};
+
 // arguments of the fused exchange (world == 0: no exchange, the caller reduces `partials` itself)
 struct PeerFused {
     PeerTable peers;
@@ -33,6 +48,7 @@ struct PeerFused {
     float* stats;                     // [KIN_PPO_STATS] (5 summed loss statistics, slot KIN_PPO_STAT_SKIP on a timeout)
     int* timed_out;                   // sticky device flag
     unsigned long long timeout_cycles;
+    AdamFused adam;
 };
 
 unsigned long long kin_peer_timeout_cycles();      // kin_peer.cu
@@ -142,6 +158,90 @@ __device__ __forceinline__ void peer_exchange_tail(const PeerFused& px, const fl
         else if (px.stats) px.stats[p - P] = a;
     }
     if (cta == 0 && tid == 0 && px.stats) px.stats[KIN_PPO_STAT_SKIP] = *reinterpret_cast<volatile int*>(px.timed_out) ? 1.0f : 0.0f;
+}
+
+// Second half of the fused update, called by ALL threads of EVERY CTA right after peer_exchange_tail when px.adam.params is set:
+// clip_grad_norm_ + Adam (kin_ppo_adam's arithmetic) on the slice of the summed gradient this CTA has just written, so a minibatch is ONE
+// launch (gradient, reduction, exchange, optimiser step) instead of three.
+//   1. every CTA writes the sum of squares of its slice (fixed order) to norm_part[cta]; grid barrier (adam_count);
+//   2. every CTA adds the n_cta partial sums in the same fixed order -> the same clip coefficient everywhere (and on every rank: the
+//      summed gradient is bitwise identical on all ranks);
+//   3. Adam on the slice: m, v, params, and the bf16 weight image the next launch's TMA copies read.
+// The parameters are only read in the gradient kernel's prologue and every CTA is past the first grid barrier, so updating them here
+// races with nothing.  A timed-out exchange leaves them untouched (same rule as kin_ppo_adam with KIN_PPO_STAT_SKIP).
+__device__ __forceinline__ void peer_adam_tail(const PeerFused& px, const KinPpoHyper& hp, int P, float* red /* >= 40 floats of smem */) {
+    const AdamFused& A = px.adam;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = (int)(blockDim.x + 31) >> 5;
+    const int n_cta = (int)(gridDim.x * gridDim.y), cta = (int)(blockIdx.y * gridDim.x + blockIdx.x);
+    unsigned char* own = px.peers.base[px.rank];
+    const int cols = P + 5;
+    const int per = ((cols + n_cta - 1) / n_cta + 31) & ~31;
+    const int p0 = min(cta * per, P), p1 = min(cta * per + per, P);       // the gradient part of this CTA's slice
+    __syncthreads();                 // px.grad[p0 .. p1) was written by this CTA's threads
+    float ss = 0.0f;
+    for (int p = p0 + tid; p < p1; p += (int)blockDim.x) {
+        const float g = px.grad[p];
+        ss = fmaf(g, g, ss);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+    if (lane == 0) red[w] = ss;
+    __syncthreads();
+    if (tid == 0) {
+        float t = 0.0f;
+        for (int k = 0; k < nw; ++k) t += red[k];
+        A.norm_part[cta] = t;
+        __threadfence();
+        unsigned* cnt = reinterpret_cast<unsigned*>(own + 72);
+        atomicAdd(cnt, 1u);
+        const unsigned target = px.epoch * (unsigned)n_cta;
+        const long long t0 = clock64();
+        while ((int)(ld_acquire_gpu(cnt) - target) < 0) {
+            if ((unsigned long long)(clock64() - t0) > px.timeout_cycles) { atomicExch(px.timed_out, 1); break; }
+        }
+    }
+    __syncthreads();
+    if (w == 0) {
+        float t = 0.0f;
+        for (int k = lane; k < n_cta; k += 32) t += __ldcg(A.norm_part + k);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+        if (lane == 0) {
+            const float norm = sqrtf(t);
+            const float c = hp.max_grad_norm > 0.0f ? hp.max_grad_norm / (norm + 1e-6f) : 1.0f;
+            red[32] = c < 1.0f ? c : 1.0f;
+            red[33] = norm;
+        }
+    }
+    __syncthreads();
+    const bool skip = *reinterpret_cast<volatile int*>(px.timed_out) != 0;
+    if (cta == 0 && tid == 0 && px.stats) {
+        px.stats[KIN_PPO_STAT_GRAD_NORM] = red[33];
+        px.stats[KIN_PPO_STAT_SKIP] = skip ? 1.0f : 0.0f;
+        if (A.stats_accum && !skip) {
+#pragma unroll
+            for (int q = 0; q < 5; ++q) A.stats_accum[q] += __ldcg(px.stats + q);
+            A.stats_accum[KIN_PPO_STAT_GRAD_NORM] += red[33];
+            A.stats_accum[7] += 1.0f;
+        }
+    }
+    if (skip) return;
+    const float cf = red[32];
+    const PpoOffsets O = ppo_offsets(A.in_dim);
+    for (int p = p0 + tid; p < p1; p += (int)blockDim.x) {
+        const float g = px.grad[p] * cf;
+        const float mm = fmaf(hp.adam_beta1, A.m[p], (1.0f - hp.adam_beta1) * g);
+        const float vv = fmaf(hp.adam_beta2, A.v[p], (1.0f - hp.adam_beta2) * g * g);
+        A.m[p] = mm;
+        A.v[p] = vv;
+        const float denom = sqrtf(vv) / sqrtf(A.bc2) + hp.adam_eps;
+        const float np = A.params[p] - (hp.learning_rate / A.bc1) * (mm / denom);
+        A.params[p] = np;
+        if (A.wimg) {
+            const int off = wimg_offset(O, A.in_dim, p);
+            if (off >= 0) A.wimg[off >> 1] = __bfloat16_as_ushort(__float2bfloat16_rn(np));
+        }
+    }
 }
 
 }  // namespace kin

@@ -620,6 +620,7 @@ kin_ppo_grad_tc_kernel(const float* __restrict__ params, KinPpoHyper hp, const f
         if constexpr (PEER) {       // every tile buffer is dead by now: the exchange borrows the X tile for its 1 KB of scratch
             float(*part)[32] = reinterpret_cast<float(*)[32]>(S.X[0]);
             peer_exchange_tail(px, partials, (int)gridDim.x, P, inv_global_batch, part, reinterpret_cast<int*>(S.X[0] + 2048));
+            if (px.adam.params) peer_adam_tail(px, hp, P, reinterpret_cast<float*>(S.X[0] + 4096));      // clip + Adam on this CTA's slice
         }
     }
     fence_before();
@@ -738,3 +739,41 @@ extern "C" int kin_ppo_grad_tc_exchange(const float* params, int in_dim, const K
     return grad_tc_launch(params, in_dim, hp, obs_any, action, old_logp, advantage, returns, tile_sums, tile_ids, n_tiles, global_batch, partials, grid, grad,
                           stats, nullptr, nullptr, 0, obs_is_image, adv_stats, weight_image, px, stream);
 }
+
+// gradient + exchange + clip + Adam in ONE launch (peer_adam_tail): the optimiser step of kin_ppo_adam runs in the kernel's tail on the
+// slice of the summed gradient each CTA owns
+extern "C" int kin_ppo_grad_tc_update(const float* params, int in_dim, const KinPpoHyper* hp, const void* obs_any, const float* action, const float* old_logp,
+                                      const float* advantage, const float* returns, const double* tile_sums, const int* tile_ids, int n_tiles,
+                                      long long global_batch, float* partials, int grid, float* grad, float* stats, int obs_is_image,
+                                      const float* adv_stats, void* weight_image, void* const* peer_buffers, int rank, int world, unsigned epoch,
+                                      int* timed_out, float* params_rw, float* adam_m, float* adam_v, int step, float* stats_accum, float* norm_scratch,
+                                      void* stream) {
+    if (!peer_buffers || !grad || !timed_out || world < 1 || world > PEER_MAX || rank < 0 || rank >= world || epoch == 0u)
+        return kin_fail(KIN_ERR_INVALID_ARG, "kin_ppo_grad_tc_update: bad exchange arguments (epoch counts exchanges from 1)");
+    if (!params_rw || params_rw != params || !adam_m || !adam_v || !norm_scratch || !stats || step < 1 || !hp)
+        return kin_fail(KIN_ERR_INVALID_ARG, "kin_ppo_grad_tc_update: bad optimiser arguments (params_rw must be params; norm_scratch holds 2 * grid floats)");
+    PeerFused px{};
+    for (int i = 0; i < world; ++i) {
+        if (!peer_buffers[i]) return kin_fail(KIN_ERR_INVALID_ARG, "kin_ppo_grad_tc_update: null peer buffer");
+        px.peers.base[i] = static_cast<unsigned char*>(peer_buffers[i]);
+    }
+    px.rank = rank;
+    px.world = world;
+    px.epoch = epoch;
+    px.grad = grad;
+    px.stats = stats;
+    px.timed_out = timed_out;
+    px.timeout_cycles = kin_peer_timeout_cycles();
+    px.adam.params = params_rw;
+    px.adam.m = adam_m;
+    px.adam.v = adam_v;
+    px.adam.wimg = in_dim == 56 ? static_cast<unsigned short*>(weight_image) : nullptr;      // the folded route image is rebuilt by kin_ppo_pack_weights
+    px.adam.stats_accum = stats_accum;
+    px.adam.norm_part = norm_scratch;
+    px.adam.bc1 = 1.0f - powf(hp->adam_beta1, (float)step);
+    px.adam.bc2 = 1.0f - powf(hp->adam_beta2, (float)step);
+    px.adam.in_dim = in_dim;
+    return grad_tc_launch(params, in_dim, hp, obs_any, action, old_logp, advantage, returns, tile_sums, tile_ids, n_tiles, global_batch, partials, grid, grad,
+                          stats, nullptr, nullptr, 0, obs_is_image, adv_stats, weight_image, px, stream);
+}
+

@@ -636,6 +636,7 @@ kin_ppo_grad_tc3_kernel(const float* __restrict__ params, KinPpoHyper hp, const 
     if constexpr (PEER) {       // every tile buffer is dead by now: the exchange borrows an X tile for its 1 KB of scratch
         float(*part)[32] = reinterpret_cast<float(*)[32]>(S.st[0].X[0]);
         peer_exchange_tail(px, partials, (int)gridDim.x, P, inv_global_batch, part, reinterpret_cast<int*>(S.st[0].X[0] + 2048));
+        if (px.adam.params) peer_adam_tail(px, hp, P, reinterpret_cast<float*>(S.st[0].X[0] + 4096));      // clip + Adam on this CTA's slice
     }
     fence_before();
     __syncthreads();

@@ -114,7 +114,7 @@ class PPOTrainer:
                  seed: int = 0, stage_index: int = 0, process_group: Any = None, grad_ctas: int | None = None,
                  update_variant: str = "tc", collect_variant: str | None = None, handoff_states: torch.Tensor | None = None,
                  grad_exchange: str = "nccl", route: Any = None, route_sequence_config: Any = None, route_curriculum: Any = None,
-                 shuffle: str = "tile") -> None:
+                 shuffle: str = "tile", fused_update: bool | None = None) -> None:
         if not torch.cuda.is_available():
             raise _lib.KinError("PPOTrainer needs a CUDA device; there is no CPU fallback")
         self.in_dim = int(policy.in_dim)
@@ -184,6 +184,20 @@ class PPOTrainer:
             self.partials = torch.zeros((self.grad_ctas, self.P + _D("KIN_PPO_STATS") + 8), dtype=torch.float32, device=self.device)
             # several ranks: the per-minibatch gradient sum goes through NCCL or through NVLink peer buffers (distributed.PeerGradExchange)
             self.peer = PeerGradExchange(self.P, self.device, process_group) if grad_exchange == "peer" else None
+            # One launch per minibatch (kin_ppo_grad_tc_update): gradient, reduction, rank-ordered exchange, clip + Adam all in the tensor-core
+            # gradient kernel's tail.  Default with several ranks on the peer-memory exchange, where the tail already holds the grid barrier
+            # and the summed slice (2 x B200: update 19.21 ms vs 19.51 ms with a separate Adam launch, NCCL 19.76 ms).  A single rank can ask
+            # for it too (it then owns a one-rank exchange buffer) but gains nothing: 18.6 vs 18.4 ms -- the two grid barriers and the slice
+            # reduction cost what the two small launches did.
+            if fused_update is None:
+                fused_update = update_variant == "tc" and self.peer is not None and self.world > 1
+            if fused_update and (update_variant != "tc" or (self.peer is None and self.world > 1)):
+                raise ValueError("fused_update needs update_variant='tc' and, with several ranks, grad_exchange='peer'")
+            self.fused_update = bool(fused_update)
+            if self.fused_update and self.peer is None:
+                self.peer = PeerGradExchange(self.P, self.device, None)
+            self._norm_scratch = torch.zeros(2 * self.grad_ctas, dtype=torch.float32, device=self.device)
+            self._adam_done = False
             self.route_curriculum = None
             if self.is_route:
                 from .route import BatchedRouteKinematicEnv
@@ -470,7 +484,7 @@ class PPOTrainer:
         self._sample_perm = perm
         self._use_shadow = True
 
-    def _grad_launch(self, tile_ptr: int, n_tiles: int, adv_ptr: int | None) -> None:
+    def _grad_launch(self, tile_ptr: int, n_tiles: int, adv_ptr: int | None, with_update: bool = False) -> None:
         stream = torch.cuda.current_stream(self.device).cuda_stream
         hp = self._c_hyper
         global_batch = n_tiles * _D("KIN_PPO_TILE") * self.world
@@ -478,6 +492,15 @@ class PPOTrainer:
         if self.update_variant == "tc":
             img = self._img
             wimg = self.weight_image.data_ptr()
+            if self.peer and self.fused_exchange and self.fused_update and with_update:      # ... and clip + Adam: ONE launch per minibatch
+                _lib.check(self._L.kin_ppo_grad_tc_update(self.params.data_ptr(), self.in_dim, ctypes.byref(hp), obs, act, logp, adv, ret, sums,
+                                                          tile_ptr, n_tiles, global_batch, self.partials.data_ptr(), self.grad_ctas, self.grad.data_ptr(),
+                                                          self.stats.data_ptr(), int(img), adv_ptr, wimg, self.peer.buffers, self.peer.rank, self.peer.world,
+                                                          self.peer.next_epoch(), self.peer.timed_out.data_ptr(), self.params.data_ptr(),
+                                                          self.adam_m.data_ptr(), self.adam_v.data_ptr(), self.update_count + 1, self.stats_accum.data_ptr(),
+                                                          self._norm_scratch.data_ptr(), stream))
+                self._adam_done = True
+                return
             if self.peer and self.fused_exchange:     # reduce + push + rank-ordered gather inside the gradient kernel's tail
                 _lib.check(self._L.kin_ppo_grad_tc_exchange(self.params.data_ptr(), self.in_dim, ctypes.byref(hp), obs, act, logp, adv, ret, sums,
                                                             tile_ptr, n_tiles, global_batch, self.partials.data_ptr(), self.grad_ctas, self.grad.data_ptr(),
@@ -514,6 +537,13 @@ class PPOTrainer:
 
     def apply_update(self) -> None:
         """All-reduce the gradient (sum over ranks), clip by global norm, Adam step -- identical on every rank."""
+        if self._adam_done:          # kin_ppo_grad_tc_update already did all of it in the gradient kernel's tail
+            self._adam_done = False
+            self.update_count += 1
+            if self.is_route:        # the folded bias column mixes three parameters: rebuild the image
+                _lib.check(self._L.kin_ppo_pack_weights(self.params.data_ptr(), self.in_dim, self.weight_image.data_ptr(),
+                                                        torch.cuda.current_stream(self.device).cuda_stream))
+            return
         if self.peer:
             if not (self.fused_exchange and self.update_variant == "tc"):  # (the fused form already left the rank-ordered sum in self.grad)
                 self.peer.gather(self.grad, self.stats)                    # waits for every rank's push, rank-ordered sum
@@ -564,7 +594,7 @@ class PPOTrainer:
                 _lib.check(self._L.kin_ppo_adv_stats(self._buffers()[5], perm.data_ptr(), tiles_per_mb, mb_per_epoch,
                                                      int(self.hp.normalize_advantage), adv.data_ptr(), stream))
                 for m in range(mb_per_epoch):
-                    self._grad_launch(perm.data_ptr() + 4 * m * tiles_per_mb, tiles_per_mb, adv.data_ptr() + 8 * m)
+                    self._grad_launch(perm.data_ptr() + 4 * m * tiles_per_mb, tiles_per_mb, adv.data_ptr() + 8 * m, with_update=True)
                     self.apply_update()
                 if self.peer:
                     self.peer.poll()         # once per epoch, without a host sync: a dead peer surfaces after at most two epochs of skipped updates

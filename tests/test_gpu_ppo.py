@@ -389,6 +389,37 @@ def test_trainer_runs_and_improves_value_fit(variant):
     assert torch.equal(tr2.params, q0)
 
 
+def test_fused_update_is_the_three_launch_update():
+    """kin_ppo_grad_tc_update (gradient + reduction + exchange + clip + Adam in one launch) against the same update as gradient kernel
+    + kin_ppo_adam: same parameters, Adam moments, weight image and statistics (the clip norm is summed in another order: a few ulp)."""
+    from rl_brain_trainer_b200 import ppo
+
+    cfg = env_config("approach_dynamic_scale_big")
+    out = {}
+    for fused in (True, False):
+        pol = ppo.random_policy(56, seed=1, log_std_init=-1.0, device="cuda")
+        hp = ppo.PPOHyper(learning_rate=1e-3, n_steps=32, batch_size=4096, n_epochs=3, gamma=0.98, clip_range=0.2, max_grad_norm=0.05)
+        tr = ppo.PPOTrainer(cfg, pol, num_envs=1024, hyper=hp, seed=3, update_variant="tc", fused_update=fused)
+        assert tr.fused_update == fused and (tr.peer is not None) == fused
+        tr.collect()
+        stats = tr.update()
+        torch.cuda.synchronize()
+        out[fused] = (tr.params.clone(), tr.adam_m.clone(), tr.adam_v.clone(), tr.weight_image.clone(), stats, tr.update_count)
+        kept = tr.weight_image.clone()
+        tr.pack_weights()
+        assert torch.equal(kept, tr.weight_image)
+        tr.close()
+    (p1, m1, v1, w1, s1, c1), (p0, m0, v0, w0, s0, c0) = out[True], out[False]
+    assert c1 == c0 == 3 * (1024 * 32 // 4096)
+    assert s1["grad_norm"] > 0.05                      # the clip is active: the coefficient matters
+    assert float((p1 - p0).abs().max()) < 2e-6 and float((m1 - m0).abs().max()) < 1e-6 * float(m0.abs().max()) + 1e-9
+    assert float((v1 - v0).abs().max()) < 1e-5 * float(v0.abs().max()) + 1e-12
+    assert (w1 != w0).float().mean() < 0.01            # bf16 image: at most a few last-bit differences
+    for k in ("policy_loss", "value_loss", "entropy", "approx_kl", "clip_fraction", "grad_norm"):
+        assert abs(s1[k] - s0[k]) < 1e-4 * max(1.0, abs(s0[k])), (k, s1[k], s0[k])
+    assert s1["minibatches"] == s0["minibatches"]
+
+
 def test_per_sample_shuffle_is_sb3_rollout_buffer_get():
     """kin_ppo_shuffle = SB3's RolloutBuffer.get: every array of the rollout permuted by one per-sample permutation (bit-exact, operand
     images included: rows move between swizzle phases), tile sums of the new order; PPOTrainer(shuffle="sample") then runs the gradient

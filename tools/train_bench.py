@@ -25,6 +25,7 @@ ap.add_argument("--grad-exchange", default="peer", choices=("peer", "nccl"), hel
 ap.add_argument("--force-peer", action="store_true", help="use the peer-memory exchange even with one rank (it then pushes into its own buffer)")
 ap.add_argument("--two-kernel", action="store_true", help="peer exchange as separate push + gather kernels instead of the gradient kernel's fused tail")
 ap.add_argument("--route", action="store_true", help="train the 80-input route policy on the batched RouteSequence env (train_route_curriculum.py)")
+ap.add_argument("--fused-update", default="auto", choices=("auto", "on", "off"), help="kin_ppo_grad_tc_update: gradient + reduction + exchange + clip + Adam in one launch per minibatch (auto: with several ranks on the peer exchange)")
 ap.add_argument("--shuffle", default="tile", choices=("tile", "sample", "sample_once"), help="minibatch composition: tile unions, SB3's per-sample permutation every epoch, or one per rollout")
 ap.add_argument("--from-checkpoint", action="store_true", help="fine-tune the bundled approach checkpoint instead of a random init")
 a = ap.parse_args()
@@ -47,7 +48,8 @@ else:
 S = a.envs * a.n_steps
 hp = ppo.PPOHyper(learning_rate=4e-6, n_steps=a.n_steps, batch_size=S // 16, n_epochs=a.epochs, gamma=0.995, gae_lambda=0.95, clip_range=0.1, ent_coef=0.0003)
 tr = ppo.PPOTrainer(cfg, pol, num_envs=a.envs, hyper=hp, device=dev, seed=1, stage_index=a.stage, update_variant=a.update,
-                    grad_exchange=a.grad_exchange if (world > 1 or a.force_peer) else "nccl", shuffle=a.shuffle, **route_kw)
+                    grad_exchange=a.grad_exchange if (world > 1 or a.force_peer) else "nccl", shuffle=a.shuffle,
+                    fused_update={"auto": None, "on": True, "off": False}[a.fused_update], **route_kw)
 if a.two_kernel:
     tr.fused_exchange = False
 tr.collect(); tr.update()          # warm-up

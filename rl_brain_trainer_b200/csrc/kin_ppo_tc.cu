@@ -62,7 +62,15 @@ constexpr unsigned COL_Z = 0;         // 64 (layer 3's O aliases columns 0..15)
 constexpr unsigned COL_WO = 64;       // 16
 constexpr unsigned COL_W1 = 80;       // 64 + 16: the N = 80 GEMM's columns 64..79 come from the dO tile, column 64 + 8 = db1
 constexpr unsigned COL_W0 = 160;      // 64 (column 56 = db0)
+constexpr unsigned COL_A = 224;       // 32: the A operand of the next chain GEMM (H1, then H2, then G2: bf16 pairs, 8 columns per K = 16 step)
 constexpr unsigned TMEM_COLS_G = 256;
+// Chain GEMMs whose A operand the epilogue threads have just produced (layer 2: H1, layer 3: H2, Z = G2 W1: G2) take it from tensor
+// memory: the kernel is bound by the shared-memory data pipe (tensor-core operand fetch 37 % + epilogue LDS / STS 30 % of its peak,
+// profiles/r2_ppo_tc3_raw.csv), and an SS-mode N = 64 MMA fetches 4 KB of A + 2 KB of B per 32 cycles of math.  The tiles are still
+// stored to shared memory -- the weight-gradient GEMMs read them MN-major -- so this removes 48 of ~196 KB of operand fetch per tile.
+#ifndef KIN_PPO_A_TMEM
+#define KIN_PPO_A_TMEM 1
+#endif
 
 #ifdef KIN_PPO_TRACE
 // phase profiler (debug builds only, tools/ppo_trace.py): cycles per phase of the per-tile chain, summed over the tiles of a CTA,
@@ -326,7 +334,10 @@ kin_ppo_grad_tc_kernel(const float* __restrict__ params, KinPpoHyper hp, const f
             fence_after();
             if (lead) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) mma_bf16(tb + COL_Z, desc_k(aH1 + k * 32), desc_k(aW1 + k * 32), id_fwd, k > 0);
+                for (int k = 0; k < 4; ++k) {
+                    if (KIN_PPO_A_TMEM) mma_bf16_ts(tb + COL_Z, tb + COL_A + 8 * k, desc_k(aW1 + k * 32), id_fwd, k > 0);
+                    else mma_bf16(tb + COL_Z, desc_k(aH1 + k * 32), desc_k(aW1 + k * 32), id_fwd, k > 0);
+                }
                 commit(mb_main);
             }
             // ---- layer 3: action means (cols 0..6) or value (col 7) ----------------------------------------------------------
@@ -335,7 +346,10 @@ kin_ppo_grad_tc_kernel(const float* __restrict__ params, KinPpoHyper hp, const f
             fence_after();
             if (lead) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) mma_bf16(tb + COL_Z, desc_k(aH2 + k * 32), desc_k(aWO + k * 32), id_out, k > 0);
+                for (int k = 0; k < 4; ++k) {
+                    if (KIN_PPO_A_TMEM) mma_bf16_ts(tb + COL_Z, tb + COL_A + 8 * k, desc_k(aWO + k * 32), id_out, k > 0);
+                    else mma_bf16(tb + COL_Z, desc_k(aH2 + k * 32), desc_k(aWO + k * 32), id_out, k > 0);
+                }
                 commit(mb_main);
             }
             if (forward_only) continue;
@@ -357,7 +371,10 @@ kin_ppo_grad_tc_kernel(const float* __restrict__ params, KinPpoHyper hp, const f
             fence_after();
             if (lead) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) mma_bf16(tb + COL_Z, desc_k(aH2 + k * 32), desc_mn(aW1 + k * 2048), id_bwd, k > 0);
+                for (int k = 0; k < 4; ++k) {
+                    if (KIN_PPO_A_TMEM) mma_bf16_ts(tb + COL_Z, tb + COL_A + 8 * k, desc_mn(aW1 + k * 2048), id_bwd, k > 0);
+                    else mma_bf16(tb + COL_Z, desc_k(aH2 + k * 32), desc_mn(aW1 + k * 2048), id_bwd, k > 0);
+                }
                 commit(mb_main);
 #pragma unroll
                 for (int k = 0; k < 8; ++k) mma_bf16(tb + COL_W1, desc_mn(aH2 + k * 2048), desc_mn(aH1 + k * 2048), id_w80, acc0 | (k > 0));
@@ -415,6 +432,7 @@ kin_ppo_grad_tc_kernel(const float* __restrict__ params, KinPpoHyper hp, const f
             TRACE_MARK(1);
             epilogue_math<0>(tz, half, nullptr, h1p, p);
             epilogue_store(S.H1, row, half, p);
+            if (KIN_PPO_A_TMEM) tmem_st16(tlane + COL_A + half * 16, p);
             fence_async_smem();
             fence_before();
             ready_arrive();
@@ -426,6 +444,7 @@ kin_ppo_grad_tc_kernel(const float* __restrict__ params, KinPpoHyper hp, const f
             TRACE_MARK(3);
             epilogue_math<1>(tz, half, S.b1, h2p, p);
             epilogue_store(S.H2, row, half, p);
+            if (KIN_PPO_A_TMEM) tmem_st16(tlane + COL_A + half * 16, p);
             fence_async_smem();
             fence_before();
             ready_arrive();
@@ -500,6 +519,7 @@ kin_ppo_grad_tc_kernel(const float* __restrict__ params, KinPpoHyper hp, const f
             fence_after();
             TRACE_MARK(7);
             epilogue_math<2>(tz, half, nullptr, h2p, p);
+            if (KIN_PPO_A_TMEM) tmem_st16(tlane + COL_A + half * 16, p);      // (layer 3, the last reader of these columns, has completed)
             mbar_wait(mb_ride, 0u);
             TRACE_MARK(8);
             epilogue_store(S.H2, row, half, p);

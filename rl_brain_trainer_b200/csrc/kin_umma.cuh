@@ -40,6 +40,22 @@ __device__ __forceinline__ void mma_bf16(unsigned tmem_d, unsigned long long da,
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
+// the same MMA with the A operand in tensor memory (lane = row, each 32-bit column = two consecutive K elements, 8 columns per K = 16
+// step): the tensor core fetches only B from shared memory
+__device__ __forceinline__ void mma_bf16_ts(unsigned tmem_d, unsigned a_taddr, unsigned long long db, unsigned idesc, unsigned accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_taddr), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+// 16 packed bf16x2 words -> 16 consecutive columns of this thread's TMEM lane (an A operand for mma_bf16_ts), completed before returning
+__device__ __forceinline__ void tmem_st16(unsigned taddr, const unsigned* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+          "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void commit(unsigned mbar_saddr) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar_saddr) : "memory");
 }

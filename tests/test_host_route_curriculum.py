@@ -82,3 +82,94 @@ def test_route_eval_summaries_reproduce_the_reference_on_its_own_rows():
     assert route_chunk_metrics(ref["rows"]) == ref["chunk_metrics"]
     assert [None if r["success"] else route_failure_reason(r) for r in ref["rows"]] == ref["failure_reasons"]
     assert summarize_route_rows([], route) == {"target_count": 0}
+
+
+def test_prefix_curriculum_matches_the_reference_callback_on_random_streams():
+    """``RoutePrefixCurriculum.record`` against the reference's ``RoutePrefixCurriculumCallback._on_step`` (route/route_curriculum.py:85-111)
+    on random episode streams cut into random per-step groups: same stage after every step, same promotion history (stage names, prefix
+    ends, timesteps, the four windowed rates), same summary.  With /root/reference present the LIVE class is driven (its SB3 base class is
+    absent here, so the instance is built without ``__init__`` and given the attributes that constructor sets); everywhere, a sequential
+    restatement of the same lines."""
+    import os
+    import sys
+    from collections import deque
+
+    class Restated:
+        def __init__(self, stages, thr, window, min_ep):
+            self.stages, self.thr, self.window, self.min_ep = stages, thr, window, min_ep
+            self.idx, self.count, self.history = 0, 0, []
+            self.w = [deque(maxlen=window) for _ in range(4)]
+
+        def step(self, dones, infos, t):
+            for done, info in zip(dones, infos):
+                if not done:
+                    continue
+                self.count += 1
+                for d, k in zip(self.w, ("success", "route_ready", "route_orientation_hit", "route_regression")):
+                    d.append(1 if info.get(k, False) else 0)
+                if self.count < self.min_ep or len(self.w[0]) < self.window:
+                    continue
+                m = [sum(d) / len(d) for d in self.w]
+                if m[0] >= self.thr[0] and m[1] >= self.thr[1] and m[2] >= self.thr[2] and m[3] <= self.thr[3] and self.idx < len(self.stages) - 1:
+                    self.history.append((self.stages[self.idx].name, self.stages[self.idx + 1].name, t, *m))
+                    self.idx += 1
+                    self.count = 0
+                    for d in self.w:
+                        d.clear()
+
+    live_cls = None
+    if os.path.isdir("/root/reference/hrl_ws/src/hrl_trainer"):
+        sys.path.insert(0, "/root/reference/hrl_ws/src/hrl_trainer")
+        try:
+            from hrl_trainer.kinematic_phase1.route.route_curriculum import RoutePrefixCurriculumCallback as live_cls
+        finally:
+            sys.path.pop(0)
+
+    class FakeVecEnv:
+        def __init__(self):
+            self.calls = []
+
+        def env_method(self, name, **kw):
+            self.calls.append((name, kw))
+
+    rng = np.random.default_rng(42)
+    for case in range(12):
+        n_stage = int(rng.integers(1, 5))
+        stages = [RouteCurriculumStage(name=f"prefix_{20 * (i + 1)}", prefix_end_index=20 * (i + 1)) for i in range(n_stage)]
+        thr = (float(rng.choice([0.5, 0.7, 0.9])), float(rng.choice([0.4, 0.8])), float(rng.choice([0.3, 0.6])), float(rng.choice([0.05, 0.3])))
+        window, min_ep = int(rng.integers(1, 24)), int(rng.integers(1, 40))
+        mine = RoutePrefixCurriculum(stages, promotion_success_rate=thr[0], promotion_route_ready_hit_rate=thr[1], promotion_orientation_hit_rate=thr[2],
+                                     promotion_max_regression_rate=thr[3], window_episodes=window, min_episodes_per_stage=min_ep)
+        rest = Restated(stages, thr, window, min_ep)
+        live = None
+        if live_cls is not None:
+            live = object.__new__(live_cls)
+            live.stages, live.window_episodes, live.min_episodes_per_stage = list(stages), window, min_ep
+            (live.promotion_success_rate, live.promotion_route_ready_hit_rate, live.promotion_orientation_hit_rate,
+             live.promotion_max_regression_rate) = thr
+            live.current_stage_index, live.stage_episode_count, live.history = 0, 0, []
+            live.successes, live.ready_hits, live.orientation_hits, live.regressions = (deque(maxlen=window) for _ in range(4))
+            live.training_env, live.num_timesteps, live.locals = FakeVecEnv(), 0, {}
+        p_good = float(rng.choice([0.6, 0.85, 0.97]))
+        t = 0
+        for _ in range(int(rng.integers(50, 400))):
+            n_env = int(rng.integers(1, 9))
+            t += n_env
+            dones = rng.random(n_env) < 0.4
+            infos = [{"success": bool(rng.random() < p_good), "route_ready": bool(rng.random() < p_good), "route_orientation_hit": bool(rng.random() < p_good),
+                      "route_regression": bool(rng.random() < 0.1)} for _ in range(n_env)]
+            fin = [i for i in range(n_env) if dones[i]]
+            mine.record([infos[i]["success"] for i in fin], [infos[i]["route_ready"] for i in fin], [infos[i]["route_orientation_hit"] for i in fin],
+                        [infos[i]["route_regression"] for i in fin], total_timesteps=t)
+            rest.step(dones, infos, t)
+            assert mine.current_stage_index == rest.idx and mine.stage_episode_count == rest.count
+            if live is not None:
+                live.num_timesteps, live.locals = t, {"dones": dones, "infos": infos}
+                assert live._on_step() is True
+                assert live.current_stage_index == mine.current_stage_index and live.stage_episode_count == mine.stage_episode_count
+        assert [(h["from_stage"], h["to_stage"], h["total_timesteps"], h["recent_success_rate"], h["recent_route_ready_hit_rate"],
+                 h["recent_orientation_hit_rate"], h["recent_regression_rate"]) for h in mine.history] == rest.history
+        if live is not None:
+            assert live.history == mine.history and live.summary() == mine.summary()
+            assert [kw["max_route_index"] for _, kw in live.training_env.calls] == [h["to_prefix_end_index"] for h in mine.history]
+

@@ -524,6 +524,14 @@ def main() -> None:
         del flush
         torch.cuda.empty_cache()
         train = measure_training(torch, dist, device, world, grad_exchange=args.grad_exchange)
+        # the update kernel against the tensor peak (a long step: the sustained figure) -- its binder is the shared-memory data pipe, not the
+        # tensor pipe: 95.2 kFLOP per sample and epoch (forward, data gradients, weight gradients of both nets)
+        upd_tf = 95.2e3 * 8 * train["update_env_steps_per_s"] / world / 1e12
+        train["update_roofline"] = {"kernel": "kin_ppo_grad_tc_kernel (+ reduction, Adam, exchange: the whole update is timed)", "bound": "tensor",
+                                    "achieved": upd_tf, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": upd_tf / pk["bf16_tflops_sustained"],
+                                    "peak_kind": "sustained (bf16_tflops_sustained): 128 back-to-back launches per update", "peak_source": pk["source"],
+                                    "limiter": "shared-memory data pipe (tensor-core operand fetch 29 % + epilogue LDS/STS 24 % of its peak) and the 11-phase "
+                                               "per-tile dependency chain at two chains per SM; ncu: profiles/r2_ppo_tc_atmem_raw.csv"}
 
     # ---- the strict-fp32 variant of the same rollout, timed the same way (rank 0, a few launches): the parity path beside the headline
     strict = None

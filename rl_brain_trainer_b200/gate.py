@@ -44,49 +44,61 @@ def gate_config_from_dict(payload: Mapping[str, Any] | None) -> WorkspaceGateCon
     return WorkspaceGateConfig(**{k: v for k, v in data.items() if k in names})
 
 
-def _rate(metrics: Mapping[str, Any], key: str, default: float) -> float:
-    return float(metrics.get(key, default))
+# A stage "passes" when every rule holds: (metric key, value assumed when the key is missing, config bound, +1: at least / -1: at most).
+# Known answers of the reference's helpers (workspace_curriculum.py) are pinned in tests/golden/gate_cases.json.
+_PASS_RULES = (("success_rate", 0.0, "promotion_stage_success", +1.0),
+               ("finisher_ready_hit_rate", 0.0, "promotion_ready_rate", +1.0),
+               ("mean_final_position_error", 999.0, "max_mean_position_error_m", -1.0),
+               ("mean_final_orientation_error", 999.0, "max_mean_orientation_error_rad", -1.0))
+
+
+def _metric(row: Mapping[str, Any] | None, key: str, missing: float) -> float:
+    return float((row or {}).get(key, missing))
 
 
 def stage_passed(metrics: Mapping[str, Any], cfg: WorkspaceGateConfig) -> bool:
-    return (_rate(metrics, "success_rate", 0.0) >= cfg.promotion_stage_success
-            and _rate(metrics, "finisher_ready_hit_rate", 0.0) >= cfg.promotion_ready_rate
-            and _rate(metrics, "mean_final_position_error", 999.0) <= cfg.max_mean_position_error_m
-            and _rate(metrics, "mean_final_orientation_error", 999.0) <= cfg.max_mean_orientation_error_rad)
+    return all((_metric(metrics, key, missing) >= getattr(cfg, bound)) if sense > 0 else (_metric(metrics, key, missing) <= getattr(cfg, bound))
+               for key, missing, bound, sense in _PASS_RULES)
+
+
+def _retention_requirements(present: Sequence[int], cfg: WorkspaceGateConfig) -> list[tuple[int, float]]:
+    """(stage, minimum success rate) pairs the retention check enforces: an explicit per-stage list binds only the evaluated stages,
+    the default binds stages 0-4 and stage 5 whether evaluated or not (a missing stage counts as success 0)."""
+    if cfg.retention_stage_thresholds:
+        return [(i, float(t)) for i, t in enumerate(cfg.retention_stage_thresholds) if i in present]
+    return [(i, cfg.retention_stage0_4_success) for i in range(5)] + [(5, cfg.retention_stage5_success)]
 
 
 def retention_ok(stage_metrics: Mapping[int, Mapping[str, Any]], cfg: WorkspaceGateConfig) -> bool:
-    if cfg.retention_stage_thresholds:
-        return all(_rate(stage_metrics[i], "success_rate", 0.0) >= float(thr)
-                   for i, thr in enumerate(cfg.retention_stage_thresholds) if i in stage_metrics)
-    if any(_rate(stage_metrics.get(i, {}), "success_rate", 0.0) < cfg.retention_stage0_4_success for i in range(5)):
-        return False
-    return _rate(stage_metrics.get(5, {}), "success_rate", 0.0) >= cfg.retention_stage5_success
+    return all(_metric(stage_metrics.get(i), "success_rate", 0.0) >= need for i, need in _retention_requirements(list(stage_metrics), cfg))
 
 
 def highest_passed_stage(stage_metrics: Mapping[int, Mapping[str, Any]], cfg: WorkspaceGateConfig) -> int:
-    best = -1
-    for idx in sorted(stage_metrics):
-        if stage_passed(stage_metrics[idx], cfg):
-            best = idx
-        elif idx >= 6:
-            break
-    return best
+    """Largest passing stage index before the first failing frontier stage (index >= 6); -1 if none."""
+    order = sorted(stage_metrics)
+    verdicts = [stage_passed(stage_metrics[i], cfg) for i in order]
+    cut = next((k for k, (i, ok) in enumerate(zip(order, verdicts)) if i >= 6 and not ok), len(order))
+    passing = [i for i, ok in zip(order[:cut], verdicts[:cut]) if ok]
+    return passing[-1] if passing else -1
 
 
 def gated_score(stage_metrics: Mapping[int, Mapping[str, Any]], current_stage: int, cfg: WorkspaceGateConfig) -> dict[str, Any]:
-    cur = stage_metrics.get(current_stage, {})
-    kept = [_rate(stage_metrics.get(i, {}), "success_rate", 0.0) for i in range(0, min(6, current_stage + 1))]
-    retention = sum(kept) / len(kept) if kept else 0.0
-    pos_score = max(0.0, 1.0 - _rate(cur, "mean_final_position_error", 1.0) / max(cfg.max_mean_position_error_m, 1e-6))
-    ori_score = max(0.0, 1.0 - _rate(cur, "mean_final_orientation_error", 1.0) / max(cfg.max_mean_orientation_error_rad, 1e-6))
-    error_score = 0.5 * (pos_score + ori_score)
-    score = (_rate(cur, "success_rate", 0.0) * cfg.score_current_success_weight + _rate(cur, "finisher_ready_hit_rate", 0.0) * cfg.score_current_ready_weight
-             + retention * cfg.score_retention_weight + error_score * cfg.score_error_weight)
+    here = stage_metrics.get(current_stage)
+    success, ready = _metric(here, "success_rate", 0.0), _metric(here, "finisher_ready_hit_rate", 0.0)
+    old_stages = range(0, min(6, current_stage + 1))
+    retention = sum(_metric(stage_metrics.get(i), "success_rate", 0.0) for i in old_stages) / len(old_stages) if len(old_stages) else 0.0
+    closeness = [max(0.0, 1.0 - _metric(here, key, 1.0) / max(getattr(cfg, bound), 1e-6))
+                 for key, bound in (("mean_final_position_error", "max_mean_position_error_m"),
+                                    ("mean_final_orientation_error", "max_mean_orientation_error_rad"))]
+    error_score = 0.5 * (closeness[0] + closeness[1])
+    terms = ((success, cfg.score_current_success_weight), (ready, cfg.score_current_ready_weight), (retention, cfg.score_retention_weight),
+             (error_score, cfg.score_error_weight))
+    score = 0.0
+    for value, weight in terms:
+        score += value * weight
     return {"score": float(score), "current_stage": int(current_stage), "retention_ok": retention_ok(stage_metrics, cfg),
-            "highest_passed_stage": int(highest_passed_stage(stage_metrics, cfg)), "current_stage_success_rate": _rate(cur, "success_rate", 0.0),
-            "current_stage_ready_rate": _rate(cur, "finisher_ready_hit_rate", 0.0), "retention_mean_success_rate": float(retention),
-            "error_score": float(error_score)}
+            "highest_passed_stage": int(highest_passed_stage(stage_metrics, cfg)), "current_stage_success_rate": success,
+            "current_stage_ready_rate": ready, "retention_mean_success_rate": float(retention), "error_score": float(error_score)}
 
 
 def summarize_stages(result: RolloutResult, stage_of_episode: torch.Tensor, stages: Sequence[int]) -> dict[int, dict[str, float]]:

@@ -110,7 +110,7 @@ unsigned long long kin::kin_peer_timeout_cycles() {
 using namespace kin;
 
 extern "C" int kin_peer_buffer_bytes(int n_params, int world) {
-    return (int)(PEER_HEADER + sizeof(float) * 2 * (size_t)world * peer_row(n_params));
+    return (int)peer_buffer_size(n_params, world);
 }
 
 extern "C" int kin_peer_buffer_create(int n_params, int world, void** buffer, unsigned char* ipc_handle) {

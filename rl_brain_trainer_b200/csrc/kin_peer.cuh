@@ -8,7 +8,9 @@
 //     [68]     unsigned grid_count            fused form: CTAs of this rank's gradient kernel whose partial row is complete (monotonic)
 //     [72]     unsigned adam_count            fused update: CTAs whose slice of the summed gradient and its sum of squares are written (monotonic)
 //     [128]    unsigned slice_flag[8][512]    fused form: slice_flag[s][c] = last exchange whose slice c sender s has delivered here
-//     [16512]  float    slot[2][world][row]   row = n_params + 8 (gradient, then the 5 loss statistics); slot = exchange parity
+//     [16512]  float    slot[2][world][row]   row = n_params + 8 (gradient, then the 5 loss statistics); slot = exchange parity (two-kernel form)
+//     [...]    uint2    ll[2][world][row]     fused form: (value bits, exchange number) pairs -- the flag travels IN the 8-byte store that
+//                                             carries the value, so the sender needs no release fence and the receiver no flag round trip
 #pragma once
 
 #include <cuda_bf16.h>
@@ -53,7 +55,31 @@ struct PeerFused {
 
 unsigned long long kin_peer_timeout_cycles();      // kin_peer.cu
 
+#ifdef KIN_PPO_TRACE
+// phase profiler of the fused tail (debug builds only, tools/ppo_trace.py --tail): cycles per phase summed over launches, thread 0 of CTAs 0 and 150
+static __device__ unsigned long long kin_peer_trace_buf[2][12];
+#define PT_DECL long long pt_t = clock64(); const bool pt_on = threadIdx.x == 0 && (cta == 0 || cta == 150); unsigned long long* pt_o = kin_peer_trace_buf[cta ? 1 : 0];
+#define PT_MARK(i) do { if (pt_on) { const long long t_ = clock64(); pt_o[i] += (unsigned long long)(t_ - pt_t); pt_t = t_; } } while (0)
+#define PT_COUNT() do { if (pt_on) pt_o[11] += 1ull; } while (0)
+#else
+#define PT_DECL
+#define PT_MARK(i)
+#define PT_COUNT()
+#endif
+
 __host__ __device__ inline int peer_row(int P) { return (P + KIN_PPO_STATS + 3) & ~3; }
+// byte offset of the fused form's (value, exchange) pairs behind the two-kernel form's float slots
+__host__ __device__ inline size_t peer_ll_offset(int P, int world) { return PEER_HEADER + sizeof(float) * 2 * (size_t)world * peer_row(P); }
+__host__ __device__ inline size_t peer_buffer_size(int P, int world) { return peer_ll_offset(P, world) + sizeof(uint2) * 2 * (size_t)world * peer_row(P); }
+
+__device__ __forceinline__ void st_ll(uint2* p, float value, unsigned epoch) {      // one 8-byte store: value and flag land together
+    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(value)), "r"(epoch) : "memory");
+}
+__device__ __forceinline__ uint2 ld_ll(const uint2* p) {
+    uint2 v;
+    asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+    return v;
+}
 
 __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
     unsigned v;
@@ -70,15 +96,22 @@ __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
 // global memory.  Needs every CTA of the grid co-resident (it contains a grid barrier): the gradient kernel's grid is <= 2 CTAs / SM.
 //   1. grid barrier: all partial rows of this rank are complete;
 //   2. CTA c reduces its slice of the P + 5 columns over the rows -- in the order kin_peer_push_kernel / kin_ppo_reduce_kernel use
-//      (8 interleaved row groups, folded in warp order), so the result is bitwise the two-kernel path's -- and stores it into
-//      slot[epoch & 1][rank] of every peer (posted NVLink stores), then publishes slice_flag[rank][c] = epoch at every peer;
-//   3. waits for slice_flag[r][c] >= epoch from every rank r and writes grad / stats = sum over ranks in RANK ORDER (bitwise
-//      identical on every rank).  A peer that never delivers sets the sticky timeout flag and marks the minibatch to be skipped.
+//      (8 interleaved row groups, folded in warp order), so the result is bitwise the two-kernel path's -- and stores every value
+//      TOGETHER WITH THE EXCHANGE NUMBER as one 8-byte word into ll[epoch & 1][rank] of every peer (posted NVLink stores; an aligned
+//      8-byte store lands atomically, the protocol NCCL calls LL): no release fence, no separate flag.  A trace of the first version
+//      (per-slice flags published with st.release.sys: tools/peer_tail_trace.py) showed 6 us in the release -- it waits for the
+//      acknowledgements of all the CTA's peer stores -- and 9 us in the flag wait per minibatch at 2 GPUs;
+//   3. polls its own copy of ll[epoch & 1][r][p] until the exchange number matches, for every rank r, and writes grad / stats = sum over
+//      ranks in RANK ORDER (bitwise identical on every rank).  A peer that never delivers sets the sticky timeout flag and marks the
+//      minibatch to be skipped.  Two parities suffice: a word is rewritten two exchanges later, and a sender only gets there after its own
+//      step 3 of the exchange in between, which waited for every rank's step 2 of that exchange.
 __device__ __forceinline__ void peer_exchange_tail(const PeerFused& px, const float* __restrict__ partials, int n_rows, int P, float inv_global_batch,
                                                    float (*part)[32], int* flag_smem) {
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int n_cta = (int)(gridDim.x * gridDim.y), cta = (int)(blockIdx.y * gridDim.x + blockIdx.x);
     unsigned char* own = px.peers.base[px.rank];
+    PT_DECL
+    PT_COUNT();
     // ---- 1. grid barrier (monotonic counter: exchange e completes at e * n_cta)
     __threadfence();
     __syncthreads();
@@ -92,6 +125,7 @@ __device__ __forceinline__ void peer_exchange_tail(const PeerFused& px, const fl
         }
     }
     __syncthreads();
+    PT_MARK(0);
     // ---- 2. this CTA's column slice: reduce over the rows, push to every peer
     const int cols = P + 5, prow = P + KIN_PPO_STATS + 8;
     const int per = ((cols + n_cta - 1) / n_cta + 31) & ~31;      // whole 32-column blocks per CTA
@@ -128,36 +162,38 @@ __device__ __forceinline__ void peer_exchange_tail(const PeerFused& px, const fl
 #pragma unroll
             for (int k = 1; k < 8; ++k) a += part[k][lane];
             if (p >= P) a *= inv_global_batch;
-            float* slot = reinterpret_cast<float*>(px.peers.base[w] + PEER_HEADER) + ((size_t)(px.epoch & 1u) * px.world + px.rank) * peer_row(P);
-            slot[p] = a;
+            uint2* ll = reinterpret_cast<uint2*>(px.peers.base[w] + peer_ll_offset(P, px.world)) + ((size_t)(px.epoch & 1u) * px.world + px.rank) * peer_row(P);
+            st_ll(ll + p, a, px.epoch);
         }
         __syncthreads();
     }
-    // the release stores below are the only system-scope fences of the CTA: release is cumulative, so coming after the CTA barrier it
-    // also orders the other threads' slot stores before the flag
-    if (tid < px.world) {
-        unsigned* flag = reinterpret_cast<unsigned*>(px.peers.base[tid] + PEER_FLAGS) + px.rank * PEER_MAX_CTA + cta;
-        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(px.epoch) : "memory");
-    }
-    // ---- 3. wait for the same slice from every rank, rank-ordered sum
-    if (tid == 0) *flag_smem = 0;
-    __syncthreads();
-    if (tid < px.world && p0 < p1 && *reinterpret_cast<volatile int*>(px.timed_out) == 0) {
-        const unsigned* flag = reinterpret_cast<const unsigned*>(own + PEER_FLAGS) + tid * PEER_MAX_CTA + cta;
-        const long long t0 = clock64();
-        while ((int)(ld_acquire_sys(flag) - px.epoch) < 0) {
-            if ((unsigned long long)(clock64() - t0) > px.timeout_cycles) { atomicExch(px.timed_out, 1); break; }
-        }
-    }
-    __syncthreads();
-    const float* slot = reinterpret_cast<const float*>(own + PEER_HEADER) + (size_t)(px.epoch & 1u) * px.world * peer_row(P);
+    PT_MARK(1);
+    PT_MARK(2);
+    // ---- 3. every rank's value of this CTA's columns (the exchange number in the same word says it has landed), rank-ordered sum
+    (void)flag_smem;
+    const uint2* ll = reinterpret_cast<const uint2*>(own + peer_ll_offset(P, px.world)) + (size_t)(px.epoch & 1u) * px.world * peer_row(P);
     for (int p = p0 + tid; p < p1; p += (int)blockDim.x) {
         float a = 0.0f;
-        for (int r = 0; r < px.world; ++r) a += __ldcg(slot + (size_t)r * peer_row(P) + p);      // L2 is where the peers' stores land
+        bool ok = *reinterpret_cast<volatile int*>(px.timed_out) == 0;
+        for (int r = 0; r < px.world; ++r) {
+            const uint2* src = ll + (size_t)r * peer_row(P) + p;
+            uint2 v = ld_ll(src);
+            if (ok && v.y != px.epoch) {
+                const long long t0 = clock64();
+                do {
+                    v = ld_ll(src);
+                    if (v.y == px.epoch) break;
+                    if ((unsigned long long)(clock64() - t0) > px.timeout_cycles) { atomicExch(px.timed_out, 1); ok = false; break; }
+                } while (true);
+            }
+            a += __uint_as_float(v.x);
+        }
         if (p < P) px.grad[p] = a;
         else if (px.stats) px.stats[p - P] = a;
     }
+    PT_MARK(3);
     if (cta == 0 && tid == 0 && px.stats) px.stats[KIN_PPO_STAT_SKIP] = *reinterpret_cast<volatile int*>(px.timed_out) ? 1.0f : 0.0f;
+    PT_MARK(4);
 }
 
 // Second half of the fused update, called by ALL threads of EVERY CTA right after peer_exchange_tail when px.adam.params is set:
@@ -177,6 +213,11 @@ __device__ __forceinline__ void peer_adam_tail(const PeerFused& px, const KinPpo
     const int cols = P + 5;
     const int per = ((cols + n_cta - 1) / n_cta + 31) & ~31;
     const int p0 = min(cta * per, P), p1 = min(cta * per + per, P);       // the gradient part of this CTA's slice
+    PT_DECL
+    // this thread's first parameter: fetch its optimiser state now, so the loads fly while the norm goes through the grid barrier
+    const int own_p = p0 + tid;
+    float own_m = 0.0f, own_v = 0.0f, own_w = 0.0f;
+    if (own_p < p1) { own_m = A.m[own_p]; own_v = A.v[own_p]; own_w = A.params[own_p]; }
     __syncthreads();                 // px.grad[p0 .. p1) was written by this CTA's threads
     float ss = 0.0f;
     for (int p = p0 + tid; p < p1; p += (int)blockDim.x) {
@@ -201,6 +242,7 @@ __device__ __forceinline__ void peer_adam_tail(const PeerFused& px, const KinPpo
         }
     }
     __syncthreads();
+    PT_MARK(5);
     if (w == 0) {
         float t = 0.0f;
         for (int k = lane; k < n_cta; k += 32) t += __ldcg(A.norm_part + k);
@@ -230,18 +272,20 @@ __device__ __forceinline__ void peer_adam_tail(const PeerFused& px, const KinPpo
     const PpoOffsets O = ppo_offsets(A.in_dim);
     for (int p = p0 + tid; p < p1; p += (int)blockDim.x) {
         const float g = px.grad[p] * cf;
-        const float mm = fmaf(hp.adam_beta1, A.m[p], (1.0f - hp.adam_beta1) * g);
-        const float vv = fmaf(hp.adam_beta2, A.v[p], (1.0f - hp.adam_beta2) * g * g);
+        const bool first = p == own_p;
+        const float mm = fmaf(hp.adam_beta1, first ? own_m : A.m[p], (1.0f - hp.adam_beta1) * g);
+        const float vv = fmaf(hp.adam_beta2, first ? own_v : A.v[p], (1.0f - hp.adam_beta2) * g * g);
         A.m[p] = mm;
         A.v[p] = vv;
         const float denom = sqrtf(vv) / sqrtf(A.bc2) + hp.adam_eps;
-        const float np = A.params[p] - (hp.learning_rate / A.bc1) * (mm / denom);
+        const float np = (first ? own_w : A.params[p]) - (hp.learning_rate / A.bc1) * (mm / denom);
         A.params[p] = np;
         if (A.wimg) {
             const int off = wimg_offset(O, A.in_dim, p);
             if (off >= 0) A.wimg[off >> 1] = __bfloat16_as_ushort(__float2bfloat16_rn(np));
         }
     }
+    PT_MARK(6);
 }
 
 }  // namespace kin

@@ -24,9 +24,12 @@ N, T = 4096, 32
 hp = ppo.PPOHyper(learning_rate=3e-4, n_steps=T, batch_size=N * T // 4, n_epochs=2, gamma=0.995, gae_lambda=0.95, clip_range=0.1, ent_coef=0.0003)
 out = {}
 params = {}
-for ex in ("nccl", "peer", "peer_two_kernel"):
+# "peer": the default -- one launch per minibatch (exchange + clip + Adam in the gradient kernel's tail); "peer_separate_adam": the same
+# in-kernel exchange followed by a kin_ppo_adam launch; "peer_two_kernel": push + gather kernels, then kin_ppo_adam
+for ex in ("nccl", "peer", "peer_separate_adam", "peer_two_kernel"):
     pol = ppo.random_policy(56, seed=0, log_std_init=-1.0, device=dev)
-    tr = ppo.PPOTrainer(cfg, pol, num_envs=N, hyper=hp, device=dev, seed=1, stage_index=10, update_variant="tc", grad_exchange=ex.split("_")[0])
+    tr = ppo.PPOTrainer(cfg, pol, num_envs=N, hyper=hp, device=dev, seed=1, stage_index=10, update_variant="tc", grad_exchange=ex.split("_")[0],
+                        fused_update=None if ex in ("nccl", "peer") else False)
     tr.fused_exchange = not ex.endswith("two_kernel")
     for _ in range(2):
         tr.collect()
@@ -36,12 +39,15 @@ for ex in ("nccl", "peer", "peer_two_kernel"):
     out[ex] = {"approx_kl": u["approx_kl"], "grad_norm": u["grad_norm"], "value_loss": u["value_loss"]}
     tr.close()
 rel = float((params["peer"] - params["nccl"]).norm() / params["nccl"].norm())
-fused_equal = bool(torch.equal(params["peer"], params["peer_two_kernel"]))      # same summation orders: bitwise the two-kernel form
+# the in-kernel exchange sums in the two-kernel form's orders: bitwise equal with the same (separate) Adam; the one-launch form adds the
+# squares for the clip norm in another order (a few ulp of the coefficient)
+fused_equal = bool(torch.equal(params["peer_separate_adam"], params["peer_two_kernel"]))
+rel_one_launch = float((params["peer"] - params["peer_two_kernel"]).norm() / params["peer_two_kernel"].norm())
 gathered = [torch.zeros_like(params["peer"]) for _ in range(world)]
 dist.all_gather(gathered, params["peer"])
 identical = all(bool(torch.equal(gathered[0], g)) for g in gathered)
 if rank == 0:
     print(json.dumps({"world": world, "peer_vs_nccl_rel_diff": rel, "peer_params_bitwise_identical_across_ranks": identical,
-                      "fused_tail_bitwise_equals_two_kernel": fused_equal, **out}))
+                      "fused_tail_bitwise_equals_two_kernel": fused_equal, "one_launch_vs_two_kernel_rel_diff": rel_one_launch, **out}))
 dist.destroy_process_group()
-assert rel < 1e-5 and identical and fused_equal
+assert rel < 1e-5 and identical and fused_equal and rel_one_launch < 1e-6

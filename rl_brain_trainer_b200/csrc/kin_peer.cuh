@@ -136,7 +136,7 @@ __device__ __forceinline__ void peer_exchange_tail(const PeerFused& px, const fl
         if (w < 8 && p < cols) {
             // rows w, w + 16, ... into a0 and w + 8, w + 24, ... into a1, added in that order (kin_ppo_reduce_kernel's order); the loads
             // of a batch are all issued before the first add, so the L2 latency is paid once per batch, not once per row
-            constexpr int B = 6;
+            constexpr int B = 10;      // 160 rows per pass: the 148 partial rows of a B200 in ONE batch of loads
             int c = w;
             while (c < n_rows) {
                 float v0[B], v1[B];
@@ -173,20 +173,34 @@ __device__ __forceinline__ void peer_exchange_tail(const PeerFused& px, const fl
     (void)flag_smem;
     const uint2* ll = reinterpret_cast<const uint2*>(own + peer_ll_offset(P, px.world)) + (size_t)(px.epoch & 1u) * px.world * peer_row(P);
     for (int p = p0 + tid; p < p1; p += (int)blockDim.x) {
-        float a = 0.0f;
-        bool ok = *reinterpret_cast<volatile int*>(px.timed_out) == 0;
-        for (int r = 0; r < px.world; ++r) {
-            const uint2* src = ll + (size_t)r * peer_row(P) + p;
-            uint2 v = ld_ll(src);
-            if (ok && v.y != px.epoch) {
-                const long long t0 = clock64();
-                do {
-                    v = ld_ll(src);
-                    if (v.y == px.epoch) break;
-                    if ((unsigned long long)(clock64() - t0) > px.timeout_cycles) { atomicExch(px.timed_out, 1); ok = false; break; }
-                } while (true);
+        // all ranks' words are requested at once (independent loads), then only the ones whose exchange number is still old are polled
+        uint2 v[PEER_MAX];
+        unsigned pending = 0u;
+#pragma unroll
+        for (int r = 0; r < PEER_MAX; ++r) {
+            if (r < px.world) v[r] = ld_ll(ll + (size_t)r * peer_row(P) + p);
+        }
+#pragma unroll
+        for (int r = 0; r < PEER_MAX; ++r) {
+            if (r < px.world && v[r].y != px.epoch) pending |= 1u << r;
+        }
+        if (pending && *reinterpret_cast<volatile int*>(px.timed_out) == 0) {
+            const long long t0 = clock64();
+            while (pending) {
+#pragma unroll
+                for (int r = 0; r < PEER_MAX; ++r) {
+                    if (pending & (1u << r)) {
+                        v[r] = ld_ll(ll + (size_t)r * peer_row(P) + p);
+                        if (v[r].y == px.epoch) pending &= ~(1u << r);
+                    }
+                }
+                if (pending && (unsigned long long)(clock64() - t0) > px.timeout_cycles) { atomicExch(px.timed_out, 1); break; }
             }
-            a += __uint_as_float(v.x);
+        }
+        float a = 0.0f;
+#pragma unroll
+        for (int r = 0; r < PEER_MAX; ++r) {
+            if (r < px.world) a += __uint_as_float(v[r].x);      // rank order
         }
         if (p < P) px.grad[p] = a;
         else if (px.stats) px.stats[p - P] = a;

@@ -122,7 +122,15 @@ class DeviceRoute:
         t = _lib.c_struct("KinRouteTable")()
         t.n_waypoints = len(route)
         t.q_goal, t.pose6, t.next_q_delta, t.progress_m = self.q.data_ptr(), self.pose.data_ptr(), self.tan.data_ptr(), self.prog.data_ptr()
-        self.nearest_lb = f(nearest_scan_bounds(route.q_goal))
+        # pruning bounds of the nearest-waypoint scan: a property of the route, computed once per RouteDataset object
+        lb = getattr(route, "_nearest_lb_cache", None)
+        if lb is None:
+            lb = nearest_scan_bounds(route.q_goal)
+            try:
+                object.__setattr__(route, "_nearest_lb_cache", lb)
+            except (AttributeError, TypeError):
+                pass
+        self.nearest_lb = f(lb)
         t.nearest_lb, t.nearest_lb_k = self.nearest_lb.data_ptr(), int(self.nearest_lb.shape[1])
         self.c = t
 
@@ -138,8 +146,16 @@ def nearest_scan_bounds(q_goal: np.ndarray, k_max: int = 64) -> np.ndarray:
     d = np.linalg.norm(q[:, None, :] - q[None, :, :], axis=2)
     off = np.abs(np.arange(n)[:, None] - np.arange(n)[None, :])
     lb = np.full((n, k_max), np.inf)
-    for k in range(k_max):
-        lb[:, k] = np.where(off >= k, d, np.inf).min(axis=1)
+    # min over offsets >= k  =  min(min over offsets >= k + 1, the two waypoints at offset exactly k): one masked pass for the last
+    # column, then a backwards sweep over the diagonals (min is exact, so this equals the masked minimum per column)
+    lb[:, k_max - 1] = np.where(off >= k_max - 1, d, np.inf).min(axis=1)
+    idx = np.arange(n)
+    for k in range(k_max - 2, -1, -1):
+        at_k = np.full(n, np.inf)
+        lo, hi = idx - k, idx + k
+        at_k[lo >= 0] = d[idx[lo >= 0], lo[lo >= 0]]
+        at_k[hi < n] = np.minimum(at_k[hi < n], d[idx[hi < n], hi[hi < n]])
+        lb[:, k] = np.minimum(lb[:, k + 1], at_k)
     lb32 = lb.astype(np.float32)
     lb32 = np.where(lb32.astype(np.float64) > lb, np.nextafter(lb32, np.float32(-np.inf)), lb32)
     return lb32

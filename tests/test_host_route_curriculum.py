@@ -173,3 +173,31 @@ def test_prefix_curriculum_matches_the_reference_callback_on_random_streams():
             assert live.history == mine.history and live.summary() == mine.summary()
             assert [kw["max_route_index"] for _, kw in live.training_env.calls] == [h["to_prefix_end_index"] for h in mine.history]
 
+
+def test_nearest_scan_bounds_equal_their_definition():
+    """``nearest_scan_bounds`` (diagonal sweep) against the definition ``lb[i, k] = min_{|j - i| >= k} |q_j - q_i|`` evaluated by brute force,
+    rounded down to fp32 -- the pruned nearest-waypoint scan of the route kernels is exact only if these are true lower bounds."""
+    from rl_brain_trainer_b200.route import nearest_scan_bounds, synthetic_route
+
+    def brute(q, k_max=64):
+        q = np.asarray(q, dtype=np.float64)
+        n = q.shape[0]
+        k_max = int(min(k_max, max(n, 2)))
+        out = np.full((n, k_max), np.inf)
+        for i in range(n):
+            for k in range(k_max):
+                js = [j for j in range(n) if abs(j - i) >= k]
+                if js:
+                    out[i, k] = min(float(np.linalg.norm(q[j] - q[i])) for j in js)
+        return out
+
+    rng = np.random.default_rng(3)
+    for n in (1, 2, 3, 9, 40):
+        q = rng.normal(size=(n, 7))
+        got, want = nearest_scan_bounds(q), brute(q)
+        assert got.dtype == np.float32 and got.shape == want.shape
+        assert np.all(got.astype(np.float64) <= want) and np.allclose(got, want, rtol=2e-7, atol=0.0, equal_nan=True)
+    route = synthetic_route(120, seed=7)
+    lb = nearest_scan_bounds(route.q_goal)
+    assert lb.shape == (120, 64) and np.all(lb[:, 0] == 0.0) and np.all(lb[:, 1:] >= lb[:, :-1])      # k = 0 includes j = i; monotone in k
+

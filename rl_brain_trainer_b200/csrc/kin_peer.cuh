@@ -58,6 +58,7 @@ unsigned long long kin_peer_timeout_cycles();      // kin_peer.cu
 #ifdef KIN_PPO_TRACE
 // phase profiler of the fused tail (debug builds only, tools/ppo_trace.py --tail): cycles per phase summed over launches, thread 0 of CTAs 0 and 150
 static __device__ unsigned long long kin_peer_trace_buf[2][12];
+static __device__ unsigned long long kin_peer_trace_wait[PEER_MAX_CTA][2];      // per CTA: cycles spent in grid barrier 1 (summed), SM id
 #define PT_DECL long long pt_t = clock64(); const bool pt_on = threadIdx.x == 0 && (cta == 0 || cta == 150); unsigned long long* pt_o = kin_peer_trace_buf[cta ? 1 : 0];
 #define PT_MARK(i) do { if (pt_on) { const long long t_ = clock64(); pt_o[i] += (unsigned long long)(t_ - pt_t); pt_t = t_; } } while (0)
 #define PT_COUNT() do { if (pt_on) pt_o[11] += 1ull; } while (0)
@@ -125,6 +126,14 @@ __device__ __forceinline__ void peer_exchange_tail(const PeerFused& px, const fl
         }
     }
     __syncthreads();
+#ifdef KIN_PPO_TRACE
+    if (tid == 0 && cta < PEER_MAX_CTA) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        kin_peer_trace_wait[cta][0] += (unsigned long long)(clock64() - pt_t);
+        kin_peer_trace_wait[cta][1] = smid;
+    }
+#endif
     PT_MARK(0);
     // ---- 2. this CTA's column slice: reduce over the rows, push to every peer
     const int cols = P + 5, prow = P + KIN_PPO_STATS + 8;

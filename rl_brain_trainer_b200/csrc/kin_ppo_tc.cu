@@ -656,6 +656,9 @@ using namespace kin;
 extern "C" int kin_debug_peer_trace(unsigned long long* out) {      // 2 x 12 counters of the fused tail, see PT_DECL (this TU's copy: the
     return cudaMemcpyFromSymbol(out, kin_peer_trace_buf, sizeof(kin_peer_trace_buf)) == cudaSuccess ? KIN_OK : KIN_ERR_INVALID_ARG;   // two-chain kernel's)
 }
+extern "C" int kin_debug_peer_wait(unsigned long long* out) {       // [512][2]: barrier-1 wait cycles (summed over launches), SM id
+    return cudaMemcpyFromSymbol(out, kin_peer_trace_wait, sizeof(kin_peer_trace_wait)) == cudaSuccess ? KIN_OK : KIN_ERR_INVALID_ARG;
+}
 extern "C" int kin_debug_ppo_trace(unsigned long long* out) {      // 4 x 16 counters, see TRACE_DECL
     return cudaMemcpyFromSymbol(out, kin_ppo_trace_buf, sizeof(kin_ppo_trace_buf)) == cudaSuccess ? KIN_OK : KIN_ERR_INVALID_ARG;
 }

@@ -46,6 +46,25 @@ if rank == 0:
         print(f"{who}: {n} launches, world {world}: {sum(row[:7]) / n:.0f} cycles per launch in the tail")
         for i, nm in enumerate(names):
             print(f"   {nm:50s} {row[i] / n:9.0f}")
+if rank == 0 and hasattr(L, "kin_debug_peer_wait"):
+    import numpy as np
+    wbuf = (ctypes.c_ulonglong * 1024)()
+    L.kin_debug_peer_wait.argtypes = [ctypes.c_void_p]
+    assert L.kin_debug_peer_wait(wbuf) == 0
+    w = np.array(list(wbuf), dtype=np.float64).reshape(512, 2)[:296]
+    n = max(buf[11], 1)
+    wait, sm = w[:, 0] / n, w[:, 1].astype(int)
+    order = np.argsort(wait)
+    print("barrier-1 wait per CTA (cycles per launch): min %.0f  median %.0f  max %.0f" % (wait.min(), np.median(wait), wait.max()))
+    print("actor CTAs (0..147): mean wait %.0f; critic CTAs (148..295): mean wait %.0f" % (wait[:148].mean(), wait[148:].mean()))
+    print("CTAs with 28 tiles (x < 100): mean wait %.0f; 27 tiles: %.0f" % (np.concatenate([wait[:100], wait[148:248]]).mean(), np.concatenate([wait[100:148], wait[248:]]).mean()))
+    print("the 12 CTAs that wait least (= finish last): " + ", ".join(f"cta {c} sm {sm[c]} {wait[c]:.0f}" for c in order[:12]))
+    per_sm = {}
+    for c in range(296):
+        per_sm.setdefault(sm[c], []).append(wait[c])
+    sm_wait = sorted((min(v), k, len(v)) for k, v in per_sm.items())
+    print("SMs whose CTAs finish last: " + ", ".join(f"sm {k} ({n_} CTAs) {w_:.0f}" for w_, k, n_ in sm_wait[:10]))
+    print("SMs whose CTAs finish first: " + ", ".join(f"sm {k} ({n_} CTAs) {w_:.0f}" for w_, k, n_ in sm_wait[-6:]))
 tr.close()
 if world > 1:
     dist.barrier()

@@ -5,7 +5,7 @@
 //   * the actor and the critic are independent networks with independent parameter gradients, so each CTA works on ONE
 //     of them (blockIdx.y): 256 threads, threads r and r + 128 <-> sample row r of a 128-sample GEMM tile <-> TMEM lane r (each
 //     owns 32 of the row's 64 accumulator columns, halving every epilogue on the per-tile dependency chain).  A CTA needs
-//     98 KB of shared memory and 256 TMEM columns, so an actor CTA and a critic CTA (or two of a kind) share every SM and
+//     112 KB of shared memory and 256 TMEM columns, so an actor CTA and a critic CTA (or two of a kind) share every SM and
 //     one's epilogue arithmetic overlaps the other's GEMMs and barrier round trips.
 //   * every operand lives in shared memory as a [rows][64 bf16] SWIZZLE_128B tile (kin_umma.cuh).  The tiles written for
 //     the forward pass (X, H1, H2 as K-major A operands with M = sample) are re-read UNCHANGED as MN-major operands
@@ -20,7 +20,9 @@
 //                                                    spans the adjacent H1 and dO tiles     (G1 then replaces H1 in place)
 //       weights   dW0|db0 += G1^T X                  M = 64, K = 128 samples
 //     The weight-gradient accumulators (and the bias gradients b0 / b1, which fall out of the constant-one columns) stay in TMEM
-//     across all tiles of the CTA: 224 of 256 columns = Z/O 64 | dWO 16 | dW1 64 + db1 16 | dW0 64.  The output-bias gradient is
+//     across all tiles of the CTA: 224 of 256 columns = Z/O 64 | dWO 16 | dW1 64 + db1 16 | dW0 64; the last 32 columns hold the bf16
+//     A operand of the next chain GEMM (H1, H2, G2: written by the epilogue threads with tcgen05.st, read by TS-mode MMAs -- the kernel
+//     is bound by the shared-memory data pipe, and this removes a quarter of the tensor core's operand fetch).  The output-bias gradient is
 //     a per-thread fp32 sum of dO, reduced once per CTA.
 //   * a dedicated ninth warp issues the MMAs from warp-uniform control flow (one elected lane executes the tcgen05 instructions,
 //     descriptors stay in uniform registers); the 256 epilogue threads never issue and never block on a CTA-wide barrier: they

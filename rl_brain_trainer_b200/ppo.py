@@ -3,8 +3,10 @@
 Replaces ``model.learn`` of the reference's trainers (``kinematic_phase1/train_workspace_expansion.py:144-270``), whose
 arithmetic is stable-baselines3 2.8.0 PPO (third-party, absent from the reference tree; restated in ``csrc/kin_ppo.cu`` and
 checked against a PyTorch autograd restatement in ``tests/test_gpu_ppo.py``).  Differences that are deliberate and
-documented in DESIGN.md: minibatches are random unions of 64-sample tiles (64 consecutive envs of one time step) instead
-of a per-sample permutation, and with several ranks the advantage normalisation is per rank-local minibatch.
+documented in DESIGN.md: by default minibatches are random unions of 64-sample tiles (64 consecutive envs of one time step);
+``PPOTrainer(shuffle="sample")`` gives SB3's per-sample permutation (``RolloutBuffer.get``, ``kin_ppo_shuffle``); with several ranks
+the advantage normalisation is per rank-local minibatch and every minibatch's gradient is summed over the ranks (NVLink peer memory
+in the gradient kernel's tail, or NCCL) before the identical clip + Adam step on every rank.
 """
 
 from __future__ import annotations
@@ -106,8 +108,9 @@ class PPOTrainer:
 
     Two env families: the 56-input Approach / Finisher policies on ``BatchedArmKinematicEnv`` (``config`` = ``Phase1EnvConfig``;
     ``train_workspace_expansion.py:144-270``), and -- with ``route=`` -- the 80-input route policy on ``BatchedRouteKinematicEnv``
-    (``config`` = ``RouteEnvConfig``; ``train_route_curriculum.py``), which collects step by step (policy, route step, TimeLimit
-    bootstrap, sampled route resets of the finished slots) and updates with the tensor-core kernel's fp32-observation path.
+    (``config`` = ``RouteEnvConfig``; ``train_route_curriculum.py``): one fused ``kin_route_collect`` launch per rollout (or per
+    ``route_chunk_steps`` steps under a prefix curriculum; ``collect_variant="steps"`` is the five-launches-per-step restatement) and the
+    tensor-core update on constant-folded observation images.
     """
 
     def __init__(self, config: Any, policy: PolicyWeights, *, num_envs: int, hyper: PPOHyper, device: str | torch.device = "cuda",

@@ -53,6 +53,11 @@ struct StepOut {
 };
 
 __device__ __forceinline__ float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
+// Quotients of the rewards' shaping terms (value / configured radius or threshold): MUFU reciprocal + multiply (2 ulp) instead of
+// the IEEE division sequence -- reward terms only, never a predicate, so flags and counters are untouched and the reward stays inside
+// its 2e-4 relative tolerance by three orders of magnitude.  (The approach reward gets the same saving from host-side reciprocals.)
+__device__ __forceinline__ float qdiv(float x, float y) { return __fdividef(x, y); }
+
 __device__ __forceinline__ float norm3(float a, float b, float c) { return sqrtf(fmaf(a, a, fmaf(b, b, c * c))); }
 __device__ __forceinline__ float norm7(const float* v) {
     float acc = v[0] * v[0];
@@ -459,8 +464,8 @@ __device__ __forceinline__ float approach_reward(const KinEnvParams& P, const Re
         // python `a or b` fallbacks (reward_approach.py:253-254)
         float a_thr = P.ar_finisher_ready_action_threshold != 0.0f ? P.ar_finisher_ready_action_threshold : P.ar_dock_coarse_ready_action_threshold;
         float d_thr = P.ar_finisher_ready_dq_threshold != 0.0f ? P.ar_finisher_ready_dq_threshold : P.ar_dock_coarse_ready_dq_threshold;
-        float a_clean = a_thr > 0.0f ? fmaxf(1.0f - an / fmaxf(a_thr, 1e-9f), 0.0f) : 0.0f;
-        float d_clean = d_thr > 0.0f ? fmaxf(1.0f - dqn / fmaxf(d_thr, 1e-9f), 0.0f) : 0.0f;
+        float a_clean = a_thr > 0.0f ? fmaxf(1.0f - qdiv(an, fmaxf(a_thr, 1e-9f)), 0.0f) : 0.0f;
+        float d_clean = d_thr > 0.0f ? fmaxf(1.0f - qdiv(dqn, fmaxf(d_thr, 1e-9f)), 0.0f) : 0.0f;
         nh_motion = P.ar_near_handoff_motion_bonus_weight * (0.5f * a_clean + 0.5f * d_clean);
         nh_settle = P.ar_near_handoff_settle_bonus_weight * (0.5f * fmaxf(pan - an, 0.0f) + 0.5f * fmaxf(pdqn - dqn, 0.0f));
     }
@@ -500,7 +505,7 @@ __device__ __forceinline__ float entry_penalty_scale(float pos, float near_thr, 
     if (near_thr <= 0.0f || far_thr <= near_thr) return 1.0f;
     if (pos <= near_thr) return near_m;
     if (pos >= far_thr) return far_m;
-    float alpha = (pos - near_thr) / fmaxf(far_thr - near_thr, 1e-9f);
+    float alpha = qdiv(pos - near_thr, fmaxf(far_thr - near_thr, 1e-9f));
     return fmaf(alpha, far_m - near_m, near_m);
 }
 
@@ -528,7 +533,7 @@ __device__ __forceinline__ float dock_reward(const KinEnvParams& P, const Reward
     const float ns_ori = P.dr_near_strict_ori_threshold_rad != 0.0f ? P.dr_near_strict_ori_threshold_rad : to * 3.0f;
     const bool curr_ns = curr_pos <= ns_pos && curr_ori <= ns_ori;
     const bool prev_ns = prev_pos <= ns_pos && prev_ori <= ns_ori;
-    const float r_p = curr_pos / fmaxf(tp, 1e-9f), r_o = curr_ori / fmaxf(to, 1e-9f);
+    const float r_p = qdiv(curr_pos, fmaxf(tp, 1e-9f)), r_o = qdiv(curr_ori, fmaxf(to, 1e-9f));
     float s_close = 0.8f * fmaxf(1.0f - r_p, 0.0f) + 0.2f * fmaxf(1.0f - r_o, 0.0f);
     s_close *= s_close;
     float tight_bonus = curr_tight ? P.dr_tight_pose_bonus : 0.0f;
@@ -541,10 +546,10 @@ __device__ __forceinline__ float dock_reward(const KinEnvParams& P, const Reward
     float sc_small = 0.0f;
     if (curr_tight && P.dr_strict_center_small_action_bonus_weight > 0.0f && P.dr_strict_center_small_action_pos_radius_m > 0.0f &&
         P.dr_strict_center_small_action_ori_radius_rad > 0.0f && P.dr_strict_center_small_action_scale > 0.0f) {
-        float cpc = fmaxf(1.0f - curr_pos / P.dr_strict_center_small_action_pos_radius_m, 0.0f);
-        float coc = fmaxf(1.0f - curr_ori / P.dr_strict_center_small_action_ori_radius_rad, 0.0f);
+        float cpc = fmaxf(1.0f - qdiv(curr_pos, P.dr_strict_center_small_action_pos_radius_m), 0.0f);
+        float coc = fmaxf(1.0f - qdiv(curr_ori, P.dr_strict_center_small_action_ori_radius_rad), 0.0f);
         float cc = powf(0.8f * cpc + 0.2f * coc, P.dr_strict_center_small_action_power);
-        float smallness = fmaxf(1.0f - action_rms / P.dr_strict_center_small_action_scale, 0.0f);
+        float smallness = fmaxf(1.0f - qdiv(action_rms, P.dr_strict_center_small_action_scale), 0.0f);
         sc_small = P.dr_strict_center_small_action_bonus_weight * cc * smallness;
     }
     float sc_dwell = 0.0f;
@@ -553,9 +558,9 @@ __device__ __forceinline__ float dock_reward(const KinEnvParams& P, const Reward
         sc_dwell = P.dr_strict_center_dwell_bonus_weight * s_close * dscale;
     }
     float tp_shape = P.dr_tight_position_shaping_radius_m > 0.0f
-                         ? P.dr_tight_position_shaping_weight * fmaxf(1.0f - curr_pos / fmaxf(P.dr_tight_position_shaping_radius_m, 1e-9f), 0.0f) : 0.0f;
+                         ? P.dr_tight_position_shaping_weight * fmaxf(1.0f - qdiv(curr_pos, fmaxf(P.dr_tight_position_shaping_radius_m, 1e-9f)), 0.0f) : 0.0f;
     float to_shape = P.dr_tight_orientation_shaping_radius_rad > 0.0f
-                         ? P.dr_tight_orientation_shaping_weight * fmaxf(1.0f - curr_ori / fmaxf(P.dr_tight_orientation_shaping_radius_rad, 1e-9f), 0.0f) : 0.0f;
+                         ? P.dr_tight_orientation_shaping_weight * fmaxf(1.0f - qdiv(curr_ori, fmaxf(P.dr_tight_orientation_shaping_radius_rad, 1e-9f)), 0.0f) : 0.0f;
     float conv_pos = (P.dr_convergence_position_radius_m > 0.0f && fminf(prev_pos, curr_pos) <= P.dr_convergence_position_radius_m)
                          ? P.dr_convergence_position_progress_weight * dpos : 0.0f;
     float gate_scale = (P.dr_position_first_orientation_pos_threshold_m > 0.0f && curr_pos > P.dr_position_first_orientation_pos_threshold_m)
@@ -614,9 +619,9 @@ __device__ __forceinline__ float dock_reward(const KinEnvParams& P, const Reward
         const bool po = prev_pos <= outer_r, pi = prev_pos <= inner_r, pd = prev_pos <= dwell_r;
         const bool co = curr_pos <= outer_r, ci = curr_pos <= inner_r, cd = curr_pos <= dwell_r;
         zone = cd ? 3 : (ci ? 2 : (co ? 1 : 0));
-        if (co) b_outer = P.dr_basin_outer_bonus * (1.0f + fmaxf(1.0f - curr_pos / outer_r, 0.0f));
-        if (ci) b_inner = P.dr_basin_inner_bonus * (1.0f + fmaxf(1.0f - curr_pos / inner_r, 0.0f));
-        if (cd) b_dwell = P.dr_basin_dwell_bonus * (1.0f + fmaxf(1.0f - curr_pos / dwell_r, 0.0f));
+        if (co) b_outer = P.dr_basin_outer_bonus * (1.0f + fmaxf(1.0f - qdiv(curr_pos, outer_r), 0.0f));
+        if (ci) b_inner = P.dr_basin_inner_bonus * (1.0f + fmaxf(1.0f - qdiv(curr_pos, inner_r), 0.0f));
+        if (cd) b_dwell = P.dr_basin_dwell_bonus * (1.0f + fmaxf(1.0f - qdiv(curr_pos, dwell_r), 0.0f));
         b_outer_exit = (po && !co) ? -P.dr_basin_outer_exit_penalty : 0.0f;
         b_inner_exit = (pi && !ci) ? -P.dr_basin_inner_exit_penalty : 0.0f;
         b_break = (pd && !cd) ? -P.dr_basin_dwell_break_penalty : 0.0f;

@@ -39,6 +39,7 @@ ap.add_argument("--stop-at-success", type=float, default=None, help="stop once t
 ap.add_argument("--gate-every", type=int, default=0, help="evaluate with the reference's gate (gated_score / retention_ok) every this many iterations and "
                 "finish on the best checkpoint (WorkspaceEvalGateCallback, train_workspace_expansion.py:54-129)")
 ap.add_argument("--load", default=None, help="start from a checkpoint written by --save")
+ap.add_argument("--shuffle", default="tile", choices=("tile", "sample", "sample_once"), help="minibatch composition (sample = SB3's per-sample permutation every epoch)")
 a = ap.parse_args()
 
 dev = torch.device("cuda", 0)
@@ -85,7 +86,7 @@ if a.from_checkpoint:
 S = a.envs * a.n_steps
 hp = ppo.PPOHyper(learning_rate=a.lr, n_steps=a.n_steps, batch_size=S // a.minibatches, n_epochs=a.epochs, gamma=a.gamma, gae_lambda=0.95, clip_range=a.clip,
                   ent_coef=a.ent, target_kl=a.target_kl)
-tr = ppo.PPOTrainer(cfg, pol, num_envs=a.envs, hyper=hp, device=dev, seed=1, stage_index=a.stage)
+tr = ppo.PPOTrainer(cfg, pol, num_envs=a.envs, hyper=hp, device=dev, seed=1, stage_index=a.stage, shuffle=a.shuffle)
 eg = None
 if a.gate_every:
     we = kcfg.preset_dict(a.preset).get("workspace_expansion", {})

@@ -321,9 +321,11 @@ class BatchedArmKinematicEnv:
             _lib.check(self._L.kin_env_step(self._params.handle, _ptr(self.state), self.stride, self.num_envs, hint, _ptr(a), _ptr(self.obs),
                                             _ptr(self.reward), _ptr(self.done), _ptr(self.aux), _ptr(self.components), int(self.auto_reset),
                                             self._seed, _ptr(self.terminal_obs), _stream()))
-        terminated = (self.done & _D("KIN_DONE_TERMINATED")) != 0
-        truncated = (self.done & _D("KIN_DONE_TRUNCATED")) != 0
-        return self.obs, self.reward, terminated, truncated, self._info(reset=False)
+        masks = getattr(self, "_done_masks", None)
+        if masks is None:
+            masks = self._done_masks = torch.tensor([[_D("KIN_DONE_TERMINATED")], [_D("KIN_DONE_TRUNCATED")]], dtype=self.done.dtype, device=self.device)
+        tt = (self.done.unsqueeze(0) & masks) != 0          # both done-bit tests in two launches: [2, n]
+        return self.obs, self.reward, tt[0], tt[1], self._info(reset=False)
 
     def step_raw(self, actions: torch.Tensor) -> None:
         """One fused-kernel step with no host-side post-processing: results land in ``self.obs / reward / done / aux``.
@@ -384,6 +386,11 @@ class BatchedArmKinematicEnv:
         plus the two done-bit tests; a key costs its one or two elementwise ops only when somebody reads it.  Values are views of
         (or derived from) the env's buffers as they are at first access, valid until the next ``step`` / ``reset``."""
         n, st, d = self.num_envs, self.state, self.done
+        # the thunks only close over the env's buffers: built once per (reset, buffer set), shared by every LazyInfo (each has its own cache)
+        key_ = (bool(reset), id(st), id(d), id(self.aux), id(self.components), id(self.terminal_obs))
+        cached = getattr(self, "_info_thunks", None)
+        if cached is not None and cached[0] == key_:
+            return LazyInfo(cached[1])
         e = _D("KIN_ROW_ENTRY")
         t: dict[str, Any] = {
             "q": lambda: self.q, "dq": lambda: self.dq, "goal_q": lambda: self.goal_q, "goal_pose6": lambda: self.goal_pose6,
@@ -414,6 +421,7 @@ class BatchedArmKinematicEnv:
                 t["terminal_observation"] = lambda: self.terminal_obs
         for key in ("step_count", "dwell_count", "near_goal_entry_count", "near_goal_drift_count", "pre_near_goal_hit", "near_goal_hit", "mode", "stage"):
             t[key] = (lambda k: (lambda: self.counters()[k]))(key)
+        self._info_thunks = (key_, t)
         return LazyInfo(t)
 
     # ------------------------------------------------------------------ helpers

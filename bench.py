@@ -309,6 +309,15 @@ def measure_step_variants(torch, device, pk, n_envs: int = 1 << 21, launches: in
     out["step_api_65536"] = {"call": "BatchedArmKinematicEnv.step (auto-reset, lazy info)", "n_envs": 65536, "us_per_call": t_small * 1e6,
                              "env_steps_per_sec": 65536 / t_small, "note": "35 MB working set: L2-resident, launch-latency bound"}
     del small
+    gsmall = BatchedArmKinematicEnv(acfg, 65536, device, with_aux=False, seed=3, host_sampler=False, auto_reset=True, graph_step=True)
+    gsmall.set_curriculum_stage(STAGE)
+    gsmall.reset()
+    for _ in range(3):
+        gsmall.step(a_small)
+    t_graph = _time_launches(torch, device, lambda: gsmall.step(a_small), 50)
+    out["step_api_65536_graph"] = {"call": "BatchedArmKinematicEnv.step(graph_step=True): CUDA graph of the step kernel + done-bit ops", "n_envs": 65536,
+                                   "us_per_call": t_graph * 1e6, "env_steps_per_sec": 65536 / t_graph}
+    del gsmall
     route = synthetic_route(483, seed=7)
     renv, _ = kcfg.to_route_env_config(kcfg.preset_dict("route_prefix120"), max_route_index=len(route) - 1)
     n_route = n_envs // 2

@@ -166,8 +166,14 @@ class BatchedArmKinematicEnv:
 
     def __init__(self, config: Phase1EnvConfig | None = None, num_envs: int = 1, device: str | torch.device = "cuda", *,
                  auto_reset: bool = False, seed: int = 0, host_sampler: bool | None = None, with_aux: bool = True,
-                 with_components: bool = False, route_reward: Any | None = None) -> None:
+                 with_components: bool = False, route_reward: Any | None = None, graph_step: bool = False) -> None:
         self.config = config or Phase1EnvConfig()
+        # graph_step: ``step()`` replays a CUDA graph of [kin_env_step, the two done-bit ops] instead of launching them from Python -- for
+        # callers that drive the env step by step at sizes where the launch path, not the kernel, is the cost (65 536 envs: 57 us per
+        # call eager).  The graph bakes the config / mode / seed in and is re-captured when one of them changes.
+        self.graph_step = bool(graph_step)
+        self._graph: Any = None
+        self._graph_key: Any = None
         if len(self.config.joint_specs) != self.config.n_joints:
             raise ValueError("joint_specs length must match n_joints")
         if num_envs <= 0:
@@ -317,13 +323,28 @@ class BatchedArmKinematicEnv:
         if self.auto_reset:
             self._ensure_sampler()
         self._step_calls += 1
+        masks = getattr(self, "_done_masks", None)
+        if masks is None:
+            masks = self._done_masks = torch.tensor([[_D("KIN_DONE_TERMINATED")], [_D("KIN_DONE_TRUNCATED")]], dtype=self.done.dtype, device=self.device)
+        if self.graph_step and self._step_calls > 1:       # (the first call runs eagerly: one-off attribute / sampler set-up happens there)
+            key = (id(self._params), hint, self._seed, bool(self.auto_reset))
+            if self._graph is None or self._graph_key != key:
+                self._g_act = torch.empty_like(a)
+                torch.cuda.synchronize(self.device)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.device(self.device), torch.cuda.graph(g):
+                    _lib.check(self._L.kin_env_step(self._params.handle, _ptr(self.state), self.stride, self.num_envs, hint, _ptr(self._g_act),
+                                                    _ptr(self.obs), _ptr(self.reward), _ptr(self.done), _ptr(self.aux), _ptr(self.components),
+                                                    int(self.auto_reset), self._seed, _ptr(self.terminal_obs), _stream()))
+                    self._g_tt = (self.done.unsqueeze(0) & masks) != 0
+                self._graph, self._graph_key = g, key
+            self._g_act.copy_(a, non_blocking=True)
+            self._graph.replay()
+            return self.obs, self.reward, self._g_tt[0], self._g_tt[1], self._info(reset=False)
         with torch.cuda.device(self.device):
             _lib.check(self._L.kin_env_step(self._params.handle, _ptr(self.state), self.stride, self.num_envs, hint, _ptr(a), _ptr(self.obs),
                                             _ptr(self.reward), _ptr(self.done), _ptr(self.aux), _ptr(self.components), int(self.auto_reset),
                                             self._seed, _ptr(self.terminal_obs), _stream()))
-        masks = getattr(self, "_done_masks", None)
-        if masks is None:
-            masks = self._done_masks = torch.tensor([[_D("KIN_DONE_TERMINATED")], [_D("KIN_DONE_TRUNCATED")]], dtype=self.done.dtype, device=self.device)
         tt = (self.done.unsqueeze(0) & masks) != 0          # both done-bit tests in two launches: [2, n]
         return self.obs, self.reward, tt[0], tt[1], self._info(reset=False)
 

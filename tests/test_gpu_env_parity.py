@@ -366,3 +366,32 @@ def test_invalid_state_terminates():
     env.reset(options={"initial_q": np.zeros((32, 7)), "goal_q": np.zeros((32, 7)), "goal_pose6": gp})
     _, _, term, trunc, info = env.step(torch.zeros(32, 7))
     assert bool(term[5]) and int(info["reason_code"][5]) == 3 and not bool(term[4])
+
+
+def test_graph_step_replays_the_eager_step():
+    """``graph_step=True`` (a CUDA graph of the step kernel + the done-bit ops) gives bit for bit the eager ``step()``: observations,
+    rewards, flags, lazily decoded info, through auto-resets, a curriculum-stage change and a policy-mode change (the graph is re-captured
+    when a baked-in argument changes)."""
+    from rl_brain_trainer_b200.env import BatchedArmKinematicEnv
+
+    cfg = env_config("approach_dynamic_scale_big")
+    n = 2048
+    envs = [BatchedArmKinematicEnv(cfg, n, "cuda", auto_reset=True, seed=11, host_sampler=False, graph_step=g) for g in (False, True)]
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    for e in envs:
+        e.set_curriculum_stage(3)
+        e.reset()
+    for t in range(150):
+        a = torch.rand((n, 7), device="cuda", generator=gen) * 2 - 1
+        if t == 60:
+            for e in envs:
+                e.set_curriculum_stage(7)
+        outs = [e.step(a.clone()) for e in envs]
+        (o0, r0, te0, tr0, i0), (o1, r1, te1, tr1, i1) = outs
+        assert torch.equal(o0, o1) and torch.equal(r0, r1) and torch.equal(te0, te1) and torch.equal(tr0, tr1)
+        if t % 37 == 0:
+            for k in ("success", "position_error_norm", "step_count", "reason_code"):
+                assert torch.equal(i0[k], i1[k]), k
+    assert envs[1]._graph is not None and int((envs[0].state != envs[1].state).sum()) == 0
+    assert bool(te0.any() or tr0.any() or (envs[0].state[48] > 0).any())      # episodes did end and were reset inside the kernel
+

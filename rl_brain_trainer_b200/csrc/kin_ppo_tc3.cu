@@ -26,7 +26,7 @@
 // different order (tile -> CTA assignment), so gradients agree to fp32 rounding, and the kernel is bitwise reproducible run to run.
 //
 // MEASURED (B200, 524 288-sample minibatches): 134 us per launch under ncu against 126 us for the two-chain kernel, update 19.2 ms vs
-// 18.4 ms -- NOT faster, so it is OFF by default (KIN_PPO_TC3=1 / kin_ppo_tc3_config(1, ..) turn it on).  The ncu capture
+// 18.4 ms; with the chain GEMMs' A operands in tensor memory (both kernels): 18.96 ms vs 17.45 ms -- NOT faster, so it is OFF by default (KIN_PPO_TC3=1 / kin_ppo_tc3_config(1, ..) turn it on).  The ncu capture
 // (profiles/r2_ppo_tc3_raw.csv) shows why a third chain cannot pay: the kernel is bound by the shared-memory data pipe, which the tensor
 // core's operand fetch (l1tex__data_pipe_tc_wavefronts_mem_shared 36.7 % of peak: every activation tile is read 2-3 times, SS-mode MMAs
 // with N = 64 fetch 6 KB per 32-cycle MMA) shares with the epilogues' LDS / STS (30.0 %): 67 % busy on average with a per-tile chain of
@@ -58,6 +58,8 @@ constexpr unsigned COL_Z = 0;          // 3 x 64: the chain accumulator of strea
 constexpr unsigned COL_WO = 192;       // 16 (M = 64): columns 9..15 = dWO rows
 constexpr unsigned COL_W1 = 208;       // 64 (M = 64)
 constexpr unsigned COL_W0 = 272;       // 64 (M = 128): lanes 64..127 = dW0 | db0 (column 56), lanes 0..63 column 56 = db1
+constexpr unsigned COL_A = 336;        // 3 x 32: the bf16 A operand of stream s's next chain GEMM (H1, H2, G2) at 336 + 32 s -- TS-mode MMAs, as in
+                                       // the two-chain kernel: the tiles are still stored to shared memory for the MN-major readers
 constexpr unsigned TMEM_COLS = 512;
 
 struct __align__(1024) StreamTiles {
@@ -269,7 +271,7 @@ kin_ppo_grad_tc3_kernel(const float* __restrict__ params, KinPpoHyper hp, const 
             const int cs = warp - ISSUER_WARP;
             const unsigned mb = smem_u32(&S.mbar[cs][0]);       // main +0, X buffers +24 / +32, tile written +48
             const unsigned aT = aS0 + cs * (unsigned)sizeof(StreamTiles), aH2 = aT + 2 * TILE, aH1 = aT + 3 * TILE;
-            const unsigned tz = tb + COL_Z + 64 * cs;
+            const unsigned tz = tb + COL_Z + 64 * cs, ta = tb + COL_A + 32 * cs;
             constexpr unsigned id_fwd = idesc_bf16(128, 64, false, false), id_out = idesc_bf16(128, 16, false, false);
             constexpr unsigned id_bwd = idesc_bf16(128, 64, false, true);
             unsigned pr = 0u;
@@ -290,7 +292,7 @@ kin_ppo_grad_tc3_kernel(const float* __restrict__ params, KinPpoHyper hp, const 
                 T3_MARK(2);
                 if (lead) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) mma_bf16(tz, desc_k(aH1 + k * 32), desc_k(aW1 + k * 32), id_fwd, k > 0);
+                    for (int k = 0; k < 4; ++k) mma_bf16_ts(tz, ta + 8 * k, desc_k(aW1 + k * 32), id_fwd, k > 0);
                     commit(mb);
                 }
                 mbar_wait(mb + 48, pr); pr ^= 1u;        // H2 written -> layer 3: action means (columns 9..15) or value (column 9)
@@ -298,7 +300,7 @@ kin_ppo_grad_tc3_kernel(const float* __restrict__ params, KinPpoHyper hp, const 
                 T3_MARK(3);
                 if (lead) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) mma_bf16(tz, desc_k(aH2 + k * 32), desc_k(aWO + k * 32), id_out, k > 0);
+                    for (int k = 0; k < 4; ++k) mma_bf16_ts(tz, ta + 8 * k, desc_k(aWO + k * 32), id_out, k > 0);
                     commit(mb);
                 }
                 mbar_wait(mb + 48, pr); pr ^= 1u;        // dO written (X columns 57..63) -> Z = dO WO
@@ -313,7 +315,7 @@ kin_ppo_grad_tc3_kernel(const float* __restrict__ params, KinPpoHyper hp, const 
                 T3_MARK(5);
                 if (lead) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) mma_bf16(tz, desc_k(aH2 + k * 32), desc_mn(aW1 + k * 2048), id_bwd, k > 0);
+                    for (int k = 0; k < 4; ++k) mma_bf16_ts(tz, ta + 8 * k, desc_mn(aW1 + k * 2048), id_bwd, k > 0);
                     commit(mb);
                 }
                 mbar_wait(mb + 48, pr); pr ^= 1u;        // G1 written: the epilogue threads have read Z, the next tile's layer 1 may overwrite it
@@ -440,7 +442,7 @@ kin_ppo_grad_tc3_kernel(const float* __restrict__ params, KinPpoHyper hp, const 
         // ================= epilogue threads of stream `sid` ==============================================================================
         StreamTiles& T = S.st[sid];
         const unsigned tlane = tb + ((unsigned)((warp & 3) * 32) << 16);     // this warp's lane quadrant, column 0
-        const unsigned tz = tlane + COL_Z + 64 * sid;
+        const unsigned tz = tlane + COL_Z + 64 * sid, ta = tlane + COL_A + 32 * sid + 16 * half;
         const unsigned mb_main = smem_u32(&S.mbar[sid][0]), mb_ride = mb_main + 8, mb_wg = mb_main + 16, mb_loss = mb_main + 40, mb_rdy = mb_main + 48;
         unsigned par_main = 0u;
         float dls[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, dbo[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, st[4] = {0.f, 0.f, 0.f, 0.f};
@@ -459,6 +461,7 @@ kin_ppo_grad_tc3_kernel(const float* __restrict__ params, KinPpoHyper hp, const 
             T3_MARK(1);
             if (it > 0) mbar_wait(mb_wg, (unsigned)(it - 1) & 1u);
             epilogue_store(T.H1, row, half, p);
+            tmem_st16(ta, p);
             tile_written<false>(mb_rdy, lane);
             T3_MARK(2);
             // ---- layer 2 -------------------------------------------------------------------------------------------------------------
@@ -468,6 +471,7 @@ kin_ppo_grad_tc3_kernel(const float* __restrict__ params, KinPpoHyper hp, const 
             T3_MARK(3);
             epilogue_fwd_math<true>(tz, half, S.b1, p);
             epilogue_store(T.H2, row, half, p);
+            tmem_st16(ta, p);
             tile_written<false>(mb_rdy, lane);
             T3_MARK(4);
             // ---- layer 3 -> loss and d(loss)/d(outputs), one thread per sample -----------------------------------------------------------
@@ -525,6 +529,7 @@ kin_ppo_grad_tc3_kernel(const float* __restrict__ params, KinPpoHyper hp, const 
             fence_after();
             T3_MARK(7);
             epilogue_bwd_math(tz, half, T.H2, row, p);
+            tmem_st16(ta, p);            // (layer 3, the last reader of these columns, has completed)
             T3_MARK(8);
             mbar_wait(mb_ride, 0u);
             T3_MARK(9);

@@ -53,8 +53,10 @@ class KinVecEnv(_VecEnvBase):
     """``num_envs`` kinematic envs behind SB3's ``VecEnv`` interface (see the module docstring)."""
 
     def __init__(self, config: Phase1EnvConfig | None = None, num_envs: int = 1, device: str | torch.device = "cuda", *, seed: int = 0,
-                 stage_index: int = 0, handoff_states: torch.Tensor | None = None, info_keys: Sequence[str] = _INFO_SCALARS) -> None:
-        self.env = BatchedArmKinematicEnv(config, num_envs, device, auto_reset=True, seed=seed, host_sampler=False, with_aux=True)
+                 stage_index: int = 0, handoff_states: torch.Tensor | None = None, info_keys: Sequence[str] = _INFO_SCALARS,
+                 graph_step: bool = False) -> None:
+        self.env = BatchedArmKinematicEnv(config, num_envs, device, auto_reset=True, seed=seed, host_sampler=False, with_aux=True,
+                                          graph_step=graph_step)
         self.env.set_curriculum_stage(stage_index)
         if handoff_states is not None:
             self.env.set_handoff_states(handoff_states)
